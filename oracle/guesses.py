@@ -1,0 +1,163 @@
+"""Guess preparation that feeds the fit (oracle).  TEST INFRASTRUCTURE.
+
+Restates (numpy, reference operation order):
+  * moment_guess.moment_guesses          mufasa/moment_guess.py:388-518  (LineSetup :27-58)
+  * moment_guess.get_tex/get_tau/peakT   mufasa/moment_guess.py:774-800
+  * guess_refine.tautex_renorm           mufasa/guess_refine.py:183-213
+  * clamp rules of cubefit_gen           mufasa/multi_v_fit.py:335-342
+  * impose_lim / velocity window of cubefit_simp   mufasa/multi_v_fit.py:163-190, get_vstats :634-644
+Pinned by tests/golden/make_golden.py (guess_*.npz).
+"""
+import numpy as np
+
+from . import constants as K
+
+# moment_guess.py:15 takes h, kb from pyspeckit's ammonia_constants (not in the reference tree).  [RECALLED: that
+# module derives them from astropy constants; older releases carried CODATA-2006 literals that differ at 2e-8
+# relative, which moves these guess helpers by the same factor -- irrelevant for initial guesses.]
+H_PYSPECKIT = K.H_CGS
+KB_PYSPECKIT = K.KB_CGS
+
+
+def _line_setup(linetype):
+    """moment_guess.LineSetup (:27-58): guessing limits per line species."""
+    if linetype == 'nh3':
+        return dict(tex_max=8.0, tau_max=5.0, tex_min=3.0, tau_min=0.1)
+    if linetype == 'n2hp':
+        return dict(tex_max=8.0, tau_max=5.0, tex_min=3.0, tau_min=0.1)
+    raise ValueError(linetype)
+
+
+def get_tex(Ta, tau=0.5, nu=23.722634):
+    background_tb = 2.7315
+    T0 = (H_PYSPECKIT * nu * 1e9 / KB_PYSPECKIT)
+    term1 = Ta / T0 / (1 - np.exp(-tau))
+    term2 = 1.0 / (np.exp(T0 / background_tb) - 1)
+    term3 = 1.0 / (term1 + term2) + 1
+    term4 = T0 / np.log(term3)
+    return term4
+
+
+def get_tau(Ta, tex=6.0, nu=23.722634):
+    background_tb = 2.7315
+    T0 = (H_PYSPECKIT * nu * 1e9 / KB_PYSPECKIT)
+    term1 = 1 / (np.exp(T0 / tex) - 1) - 1 / (np.exp(T0 / background_tb) - 1)
+    term2 = -Ta / T0 / term1 + 1
+    return -np.log(term2)
+
+
+def peakT(tex, tau, nu=23.722634):
+    background_tb = 2.7315
+    T0 = (H_PYSPECKIT * nu * 1e9 / KB_PYSPECKIT)
+    return (T0 / (np.exp(T0 / tex) - 1) - T0 / (np.exp(T0 / background_tb) - 1)) * (1 - np.exp(-tau))
+
+
+def moment_guesses(moment1, moment2, ncomp, sigmin=0.07, tex_guess=3.2, tau_guess=0.5, moment0=None,
+                   linetype='nh3', mom0_floor=None):
+    ls = _line_setup(linetype)
+    tex_max, tau_max, tex_min, tau_min = ls['tex_max'], ls['tau_max'], ls['tex_min'], ls['tau_min']
+    if moment0 is not None:
+        norm_ref = 99.73
+        mom0high = np.percentile(moment0[np.isfinite(moment0)], norm_ref)
+        if mom0_floor is None:
+            m0Norm = moment0.copy() * norm_ref / 100.0 / mom0high
+            tex_guess = m0Norm * tex_max
+            tau_guess = m0Norm * tau_max
+        else:
+            m0Norm = moment0.copy() * norm_ref / 100.0 / (mom0high - mom0_floor)
+            tex_guess = m0Norm * (tex_max - tex_min) + tex_min
+            tau_guess = m0Norm * (tau_max - tau_min) + tau_min
+    m1 = moment1
+    m2 = moment2
+    gs_sig = m2 / ncomp
+    gs_sig[gs_sig < sigmin] = sigmin
+    gg = np.zeros((ncomp * 4,) + m1.shape)
+    if ncomp == 1:
+        gg[0, :] = m1
+        gg[1, :] = gs_sig
+        gg[2, :] = tex_guess
+        gg[3, :] = tau_guess
+    if ncomp == 2:
+        sigmaoff = 0.4
+        tau2_frac = 0.25
+        gg[0, :] = m1 - sigmaoff * m2
+        gg[1, :] = gs_sig
+        gg[2, :] = tex_guess
+        gg[3, :] = tau_guess * (1 - tau2_frac)
+        gg[4, :] = m1 + sigmaoff * m2
+        gg[5, :] = gs_sig
+        gg[6, :] = tex_guess * 0.8
+        gg[7, :] = tau_guess * tau2_frac
+    # (the reference clamps tex_guess/tau_guess AFTER copying them into gg -> no effect on gg; :513-516)
+    return gg
+
+
+def tautex_renorm(taumap, texmap, tau_thresh=0.21, tex_thresh=15.0, nu=23.6944955):
+    """guess_refine.py:183-213; mutates and returns (taumap, texmap).  Only the thin-tau branch has an
+    effect: the high-Tex branch assigns through chained fancy indexing (:209-210), a no-op."""
+    f_tau = 0.5
+    isthin = np.logical_and(taumap < tau_thresh, np.isfinite(taumap))
+    TA_lowtau = peakT(texmap[isthin], taumap[isthin] * f_tau, nu=nu)
+    # NB the reference does NOT forward nu here (guess_refine.py:199) -> get_tex's default 23.722634 GHz
+    texmap[isthin] = get_tex(TA_lowtau, tau=tau_thresh * f_tau)
+    taumap[isthin] = tau_thresh
+    return taumap, texmap
+
+
+def clamp_gen(guesses, vmin, vmax, fittype):
+    """multi_v_fit.py:335-342 (in place)."""
+    L = K.limits(fittype)
+    g = guesses
+    g[::4][g[::4] > vmax] = vmax
+    g[::4][g[::4] < vmin] = vmin
+    g[1::4][g[1::4] > L['sigmax']] = L['sigmax']
+    g[1::4][g[1::4] < L['sigmin']] = L['sigmin'] + L['eps']
+    g[2::4][g[2::4] > L['Texmax']] = L['Texmax']
+    g[2::4][g[2::4] < L['Texmin']] = L['Texmin']
+    g[3::4][g[3::4] > L['taumax']] = L['taumax']
+    g[3::4][g[3::4] < L['taumin']] = L['taumin']
+    return g
+
+
+def vlimits_gen(m1, fittype):
+    """multi_v_fit.py:253-254."""
+    L = K.limits(fittype)
+    return np.nanmin(m1) - L['sigmax'] / 2, np.nanmax(m1) + L['sigmax'] / 2
+
+
+def get_vstats(velocities):
+    m1_good = velocities[np.isfinite(velocities)]
+    return np.median(m1_good), np.percentile(m1_good, 99), np.percentile(m1_good, 1)
+
+
+def vlimits_simp(guesses, fittype):
+    """multi_v_fit.py:163-176 (sets zero velocity guesses to NaN in place, like the reference)."""
+    L = K.limits(fittype)
+    v_guess = guesses[::4]
+    v_guess[v_guess == 0] = np.nan
+    v_median, v_99p, v_1p = get_vstats(v_guess)
+    vmax = v_median + 10
+    vmin = v_median - 10
+    if v_99p + L['sigmax'] > vmax:
+        vmax = v_99p + L['sigmax']
+    if v_1p - L['sigmax'] < vmin:
+        vmin = v_1p - L['sigmax']
+    return vmin, vmax
+
+
+def impose_lim_simp(guesses, vmin, vmax, fittype):
+    """multi_v_fit.py:178-190 (in place)."""
+    L = K.limits(fittype)
+    eps = L['eps']
+
+    def impose_lim(data, lo, hi):
+        mask = data < lo
+        data[mask] = lo + eps
+        mask = data > hi
+        data[mask] = hi - eps
+
+    impose_lim(guesses[::4], vmin, vmax)
+    impose_lim(guesses[1::4], L['sigmin'], L['sigmax'])
+    impose_lim(guesses[2::4], L['Texmin'], L['Texmax'])
+    impose_lim(guesses[3::4], L['taumin'], L['taumax'])
+    return guesses
