@@ -1,0 +1,145 @@
+/* b200fit.h -- C ABI of the B200-native per-pixel spectral fitter (libb200fit.so).
+ *
+ * The reference (mcyc/mufasa) is pure Python and has no FFI for this path; its plugin boundary is
+ *     pcube.specfit.Registry.add_fitter(fittype, fitter, npars)        mufasa/multi_v_fit.py:119-120
+ *     pcube.fiteach(fittype=, guesses=, limitedmin/max=, minpars/maxpars=, maskmap=, ...)
+ *                                                                       mufasa/multi_v_fit.py:374-393, :192-206
+ *     pcube.get_modelcube()                                             mufasa/UltraCube.py:324, :978
+ *     UltraCube.get_rss / get_AICc / get_all_lnk_maps / get_best_2c_parcube
+ *                                                                       mufasa/UltraCube.py:432-498, :1218-1379
+ * Each entry point below names the reference call it stands in for.  A reference-side binding is a
+ * ctypes stub.  Plain pointers and sizes only; no torch / CUDA types in signatures
+ * (``stream`` is a cudaStream_t passed as void*; NULL = default stream).
+ *
+ * Conventions
+ *   - Every function returns 0 on success, <0 on error (B200FIT_E_*).  Errors are per call, never per pixel:
+ *     per-pixel outcomes are reported in ``status[]`` (MINPACK-style, see b200fit_fit).
+ *   - Pointers named d_* are DEVICE pointers owned by the caller; h_* are HOST pointers.
+ *   - Pixel-major device layout: spectra[npix][nchan_stride] fp32, velocity ascending,
+ *     nchan_stride = b200fit_nchan_stride(nchan) (multiple of 32; pad channels hold NaN).
+ *   - Parameter order per pixel: [v1, sigma1, Tex1, tau1, (v2, sigma2, Tex2, tau2)]   BaseModel.py:71-73;
+ *     component 1 is the rear slab (HyperfineModel.py:46-56).
+ */
+#ifndef B200FIT_H
+#define B200FIT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FIT_ABI_VERSION 1
+
+enum {
+    B200FIT_OK = 0,
+    B200FIT_E_ARG = -1,      /* bad argument (NULL pointer, ncomp not in {1,2}, nchan too large, ...) */
+    B200FIT_E_CUDA = -2,     /* a CUDA runtime call failed; see b200fit_last_error()                  */
+    B200FIT_E_NOGPU = -3,    /* no usable CUDA device: there is NO CPU fallback                        */
+    B200FIT_E_MODEL = -4     /* unknown model_id (FitTypeError on the Python side, meta_model.py:135) */
+};
+
+enum { B200FIT_MODEL_NH3_11 = 0, B200FIT_MODEL_N2HP_10 = 1 };
+#define B200FIT_MAX_NCHAN 2048
+#define B200FIT_MAX_PAR 8
+
+typedef struct b200fit_ctx b200fit_ctx;      /* one per device */
+
+/* Context: replaces the implicit per-process state of pyspeckit's fitter Registry (multi_v_fit.py:119-120). */
+int b200fit_create(b200fit_ctx** out, int device);
+void b200fit_destroy(b200fit_ctx* ctx);
+const char* b200fit_last_error(const b200fit_ctx* ctx);
+int b200fit_abi_version(void);
+int b200fit_num_sms(const b200fit_ctx* ctx);
+
+/* Description of one fit call == the arguments MUFASA hands to pcube.fiteach (multi_v_fit.py:374-383) plus the
+ * spectral axis pyspeckit takes from pcube.xarr. */
+typedef struct {
+    int32_t model_id;        /* B200FIT_MODEL_*  ('nh3_multi_v' / 'n2hp_multi_v', meta_model.py:107,118)   */
+    int32_t ncomp;           /* 1 or 2 -> P = 4*ncomp                                                        */
+    int32_t nchan;           /* channels per spectrum (<= B200FIT_MAX_NCHAN)                                 */
+    int32_t max_iter;        /* accepted-step cap, mpfit maxiter = 200                                       */
+    int64_t npix;            /* spectra in this call (already masked / compacted)                            */
+    double v0, dv;           /* V_i = v0 + i*dv, km/s, radio convention, dv > 0 (ascending; the transpose
+                                kernel flips descending cubes)                                               */
+    double nu_ref_ghz;       /* rest frequency of the cube's velocity axis (0 => the model's nu0,
+                                multi_v_fit.py:109-113)                                                      */
+    double lo[B200FIT_MAX_PAR], hi[B200FIT_MAX_PAR];   /* minpars / maxpars, all limits active (:376-379)    */
+    double ftol;             /* stop when predicted chi2 reduction <= ftol*chi2 (mpfit ftol = 1e-10)         */
+    double signal_cut;       /* pyspeckit fiteach signal_cut: skip a pixel whose max(y/err) < cut; 0 = off   */
+    int32_t weight_mode;     /* 0 = err := std(finite channels) per pixel (what fiteach does for MUFASA);
+                                1 = use d_err[pix]                                                           */
+    int32_t reserved;
+} b200fit_problem;
+
+int64_t b200fit_nchan_stride(int32_t nchan);
+size_t b200fit_workspace_bytes(const b200fit_problem* prob);
+
+/* Cube layout pass: FITS order [nchan][ny][nx] (channel-major) -> compacted pixel-major rows.
+ * Replaces pcube.get_spectrum(x, y) per pixel inside Cube.fiteach.  pix_index[k] = flat index y*nx+x of the
+ * k-th selected pixel (host builds it from maskmap, multi_v_fit.py:347-350).  flip != 0 reverses the channel
+ * order (descending-velocity cubes). */
+int b200fit_gather_spectra(b200fit_ctx* ctx, const float* d_cube, int32_t nchan, int64_t nplane,
+                           const int64_t* d_pix_index, int64_t npix, int32_t flip,
+                           float* d_spectra, int64_t nchan_stride, void* stream);
+
+/* The fit: replaces pcube.fiteach(...) -> Specfit -> SpectralModel.fitter -> mpfit for every pixel.
+ *   d_guesses [npix][P] fp64   must lie inside [lo,hi] (else status 0 like mpfit); NaN => status 0
+ *   d_err     [npix] fp64 or NULL (weight_mode 0)
+ *   d_params  [npix][P] fp64   zeros on failure              (parcube)
+ *   d_perr    [npix][P] fp64   0 for pegged parameters       (errcube = mpfit perror)
+ *   d_chi2    [npix] fp64      sum(((y-M)/err)^2) at the solution (mpfit fnorm)
+ *   d_err_used[npix] fp64      the weight actually used
+ *   d_status  [npix] int32     1,2,3 converged (MINPACK meaning), 5 = max_iter, 0 = not fitted / bad guess,
+ *                              -16 = non-finite; has_fit = status > 0
+ *   d_counts  [npix][4] uint32 {evaluations, rejected steps, executed gaussian-lane evals / 32, active chunks}
+ *                              (roofline accounting); may be NULL */
+int b200fit_fit(b200fit_ctx* ctx, const b200fit_problem* prob,
+                const float* d_spectra, int64_t nchan_stride,
+                const double* d_guesses, const double* d_err,
+                double* d_params, double* d_perr, double* d_chi2, double* d_err_used,
+                int32_t* d_status, uint32_t* d_counts,
+                void* d_workspace, void* stream);
+
+/* Model evaluation: replaces pcube.get_modelcube() (one multi_v_spectrum call per pixel,
+ * HyperfineModel.py:22-109), in fp64 with the reference's frequency-space operation order.
+ *   d_params [npix][P]; all-zero or non-finite rows produce NaN rows (pyspeckit convention)
+ *   d_model  [npix][nchan_stride] fp64 */
+int b200fit_model(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d_params,
+                  double* d_model, int64_t nchan_stride, void* stream);
+
+/* Model selection: replaces UltraCube.get_all_lnk_maps + get_best_2c_parcube's selection
+ * (UltraCube.py:1218-1379 => get_rss :1384-1475, expand_mask :1658-1698, aic.py:136-201).
+ *   d_params1 [npix][4], d_params2 [npix][8]  (all-zero row = no fit)
+ *   h_fill_mask: nchan bytes (0/1) = spectral mask used for pixels whose own model mask is empty
+ *                (include_nosamp rule, UltraCube.py:1423-1438); NULL => such pixels get N = NaN.
+ *                Obtain it with b200fit_mask_counts + one host argmax over ALL pixels (global rule).
+ *   model_f32: != 0 => model cube takes the data cube's dtype (fp32), as pyspeckit's full_like does
+ *   d_rss [npix][3] (ncomp 0,1,2), d_nsamp [npix], d_lnk [npix][3] (lnk10, lnk20, lnk21),
+ *   d_ncomp [npix] int8 (0/1/2 with thresholds thr[3] = {lnk10, lnk20, lnk21}) */
+int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob,
+                 const float* d_spectra, int64_t nchan_stride,
+                 const double* d_params1, const double* d_params2,
+                 const unsigned char* h_fill_mask, int32_t expand, int32_t model_f32, const double* thr,
+                 double* d_rss, double* d_nsamp, double* d_lnk, signed char* d_ncomp, void* stream);
+
+/* Per-pixel size of the un-dilated union mask (model1 > 0) | (model2 > 0) and, for one pixel, the mask
+ * itself; the two pieces the host needs for the global include_nosamp rule. */
+int b200fit_mask_counts(b200fit_ctx* ctx, const b200fit_problem* prob,
+                        const double* d_params1, const double* d_params2, int32_t model_f32,
+                        int32_t* d_counts, void* stream);
+int b200fit_mask_of_pixel(b200fit_ctx* ctx, const b200fit_problem* prob,
+                          const double* d_params1, const double* d_params2, int32_t model_f32,
+                          int64_t pix, unsigned char* h_mask_out, void* stream);
+
+/* Residual statistics: replaces UltraCube.get_chisq / get_rms (UltraCube.py:1478-1565, 1701-1740).
+ *   d_rms [npix] = 1.4826*median(|r - roll(r,2)|)/sqrt(2);  d_chisq_red [npix] */
+int b200fit_resid_stats(b200fit_ctx* ctx, const b200fit_problem* prob,
+                        const float* d_spectra, int64_t nchan_stride, const double* d_params,
+                        int32_t expand, int32_t model_f32, double* d_rms, double* d_chisq_red, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FIT_H */

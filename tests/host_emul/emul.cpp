@@ -1,0 +1,224 @@
+// TEST-ONLY host emulation of the CUDA fit kernel (mufasa_b200/csrc/b200fit_kernels.cu).
+// It runs the SAME shared source (b200fit_common.h: line set-up, per-channel RT + Jacobian, LM state machine)
+// over 32 "virtual lanes" with the kernel's chunking, fp32 per-lane partial sums and fp64 cross-lane reduction,
+// so the numerical algorithm can be checked against the oracle in a container without a GPU.
+// It is never built into libb200fit.so and never imported by the mufasa_b200 package.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../mufasa_b200/csrc/b200fit_host.h"
+
+using namespace b200fit;
+
+namespace {
+
+template <int NC>
+struct Eval {
+    static constexpr int P = 4 * NC;
+    static constexpr int NH = P * (P + 1) / 2;
+    static constexpr int NACC = NH + P + 1;
+
+    const DeviceProblem& pr;
+    const float* spec;
+    std::vector<float> chunkY2;
+    int nchunks;
+    uint64_t n_gauss = 0, n_chunks = 0;
+
+    Eval(const DeviceProblem& p, const float* s) : pr(p), spec(s) {
+        nchunks = (pr.nchan + 31) / 32;
+        chunkY2.assign(nchunks, 0.f);
+        for (int j = 0; j < nchunks; ++j) {
+            float acc = 0.f;
+            for (int m = 0; m < 32; ++m) {
+                const int i = 32 * j + m;
+                if (i < pr.nchan && spec[i] == spec[i]) acc = fmaf(spec[i], spec[i], acc);
+            }
+            chunkY2[j] = acc;
+        }
+    }
+
+    void run(const double* p, double* H, double* b, double& chi2) {
+        CompCoef cc[NC];
+        LineCoef lc[NC][MAXHF_FIT];
+        float ic[NC][MAXHF_FIT], hw[NC][MAXHF_FIT];
+        for (int c = 0; c < NC; ++c) {
+            comp_coefs(pr, p + 4 * c, cc[c]);
+            for (int k = 0; k < pr.nhf; ++k) line_coef(pr, p + 4 * c, k, lc[c][k], ic[c][k], hw[c][k]);
+        }
+        std::vector<float> acc(32 * NACC, 0.f);
+        for (int j = 0; j < nchunks; ++j) {
+            int klo[NC], khi[NC];
+            bool active = false;
+            const float lo_edge = 32.f * j, hi_edge = 32.f * j + 31.f;
+            for (int c = 0; c < NC; ++c) {
+                klo[c] = 0;
+                khi[c] = 0;
+                for (int k = 0; k < pr.nhf; ++k) {
+                    klo[c] += (ic[c][k] + hw[c][k] < lo_edge) ? 1 : 0;
+                    khi[c] += (ic[c][k] - hw[c][k] <= hi_edge) ? 1 : 0;
+                }
+                if (klo[c] < khi[c]) active = true;
+            }
+            if (!active) {
+                acc[(j & 31) * NACC + NACC - 1] += chunkY2[j];
+                continue;
+            }
+            n_chunks++;
+            for (int lane = 0; lane < 32; ++lane) {
+                const int i = 32 * j + lane;
+                if (i >= pr.nchan) continue;
+                const float y = spec[i];
+                if (!(y == y)) continue;
+                const float fi = (float)i;
+                float G[NC], A[NC], B[NC];
+                for (int c = 0; c < NC; ++c) {
+                    G[c] = A[c] = B[c] = 0.f;
+                    for (int k = klo[c]; k < khi[c]; ++k) gauss_accum(fi, lc[c][k], G[c], A[c], B[c]);
+                }
+                float m, J[P];
+                rt_channel<NC>(G, A, B, fi - (float)pr.ic0, cc, m, J);
+                const float r = y - m;
+                float* a = &acc[lane * NACC];
+                int q = 0;
+                for (int u = 0; u < P; ++u)
+                    for (int v = u; v < P; ++v) a[q] = fmaf(J[u], J[v], a[q]), ++q;
+                for (int u = 0; u < P; ++u) a[NH + u] = fmaf(J[u], r, a[NH + u]);
+                a[NACC - 1] = fmaf(r, r, a[NACC - 1]);
+            }
+            for (int c = 0; c < NC; ++c) n_gauss += (uint64_t)(khi[c] > klo[c] ? khi[c] - klo[c] : 0);
+        }
+        for (int e = 0; e < NACC; ++e) {
+            double s = 0.0;
+            for (int lane = 0; lane < 32; ++lane) s += (double)acc[lane * NACC + e];
+            if (e < NH)
+                H[e] = s;
+            else if (e < NH + P)
+                b[e - NH] = s;
+            else
+                chi2 = s;
+        }
+    }
+};
+
+template <int NC>
+void fit_pixel(const DeviceProblem& pr, const float* spec, const double* guess, const double* err_in, double* params,
+               double* perr, double* chi2_out, double* err_used, int32_t* status, uint32_t* counts) {
+    constexpr int P = 4 * NC;
+    for (int j = 0; j < P; ++j) params[j] = perr[j] = 0.0;
+    *chi2_out = 0.0;
+    *status = 0;
+    if (counts) counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    // weights (Cube.fiteach: std of the finite channels) + peak for signal_cut
+    double sum = 0.0, ymax = -INFINITY;
+    int n = 0;
+    for (int i = 0; i < pr.nchan; ++i)
+        if (spec[i] == spec[i]) {
+            sum += spec[i];
+            ++n;
+            ymax = fmax(ymax, (double)spec[i]);
+        }
+    double err = NAN;
+    if (n > 0) {
+        const double mean = sum / n;
+        double ss = 0.0;
+        for (int i = 0; i < pr.nchan; ++i)
+            if (spec[i] == spec[i]) ss += ((double)spec[i] - mean) * ((double)spec[i] - mean);
+        err = sqrt(ss / n);
+    }
+    if (pr.weight_mode == 1 && err_in) err = *err_in;
+    *err_used = err;
+    if (!(err > 0.0) || std::isinf(err)) return;
+    if (pr.signal_cut > 0.0 && !(ymax / err >= pr.signal_cut)) return;
+
+    LMState<P> s;
+    if (!lm_init<P>(s, guess, pr.lo, pr.hi, pr.max_iter, pr.ftol)) return;
+    Eval<NC> ev(pr, spec);
+    ev.run(s.pt, s.Ht, s.bt, s.chi2t);
+    int done = lm_adopt_first<P>(s);
+    while (!done) {
+        done = lm_propose<P>(s);
+        if (done) break;
+        ev.run(s.pt, s.Ht, s.bt, s.chi2t);
+        done = lm_update<P>(s);
+    }
+    *status = s.status;
+    if (counts) {
+        counts[0] = (uint32_t)s.nevals;
+        counts[1] = (uint32_t)s.nrej;
+        counts[2] = (uint32_t)ev.n_gauss;
+        counts[3] = (uint32_t)ev.n_chunks;
+    }
+    if (s.status > 0) {
+        const double err2 = err * err;
+        for (int j = 0; j < P; ++j) params[j] = s.p[j];
+        lm_errors<P>(s, err2, perr);
+        *chi2_out = lm_reported_chi2<P>(s) / err2;
+    }
+}
+
+}  // namespace
+
+extern "C" int emul_fit(const b200fit_problem* prob, const float* spectra, int64_t nchan_stride, const double* guesses,
+                        const double* err, double* params, double* perr, double* chi2, double* err_used,
+                        int32_t* status, uint32_t* counts) {
+    DeviceProblem pr;
+    const int rc = make_device_problem(*prob, pr);
+    if (rc) return rc;
+    const int P = 4 * pr.ncomp;
+    for (int64_t i = 0; i < pr.npix; ++i) {
+        const float* sp = spectra + i * nchan_stride;
+        if (pr.ncomp == 1)
+            fit_pixel<1>(pr, sp, guesses + i * P, err ? err + i : nullptr, params + i * P, perr + i * P, chi2 + i,
+                         err_used + i, status + i, counts ? counts + 4 * i : nullptr);
+        else
+            fit_pixel<2>(pr, sp, guesses + i * P, err ? err + i : nullptr, params + i * P, perr + i * P, chi2 + i,
+                         err_used + i, status + i, counts ? counts + 4 * i : nullptr);
+    }
+    return 0;
+}
+
+// model + Jacobian of one spectrum through the fp32 kernel math (for unit tests of the shared header)
+extern "C" int emul_eval(const b200fit_problem* prob, const float* spec, const double* p, double* H, double* b,
+                         double* chi2) {
+    DeviceProblem pr;
+    const int rc = make_device_problem(*prob, pr);
+    if (rc) return rc;
+    if (pr.ncomp == 1) {
+        Eval<1> ev(pr, spec);
+        ev.run(p, H, b, *chi2);
+    } else {
+        Eval<2> ev(pr, spec);
+        ev.run(p, H, b, *chi2);
+    }
+    return 0;
+}
+
+// debugging aid: trace of one 2-component fit (iteration log to stderr)
+#include <cstdio>
+extern "C" int emul_trace2(const b200fit_problem* prob, const float* spec, const double* guess) {
+    DeviceProblem pr;
+    const int rc = make_device_problem(*prob, pr);
+    if (rc) return rc;
+    constexpr int P = 8;
+    LMState<P> s;
+    if (!lm_init<P>(s, guess, pr.lo, pr.hi, pr.max_iter, pr.ftol)) return -1;
+    Eval<2> ev(pr, spec);
+    ev.run(s.pt, s.Ht, s.bt, s.chi2t);
+    int done = lm_adopt_first<P>(s);
+    while (!done) {
+        done = lm_propose<P>(s);
+        if (done) break;
+        ev.run(s.pt, s.Ht, s.bt, s.chi2t);
+        const double c0 = s.chi2;
+        const int it0 = s.iters;
+        done = lm_update<P>(s);
+        fprintf(stderr, "ev %3d it %3d %s chi2 %.9f -> %.9f act %.3e par %.3e delta %.3e alpha %.3g pnorm %.3e peg %02x pt:", s.nevals,
+                s.iters, s.iters > it0 ? "ACC" : "rej", c0, s.chi2t, 1 - s.chi2t / c0, s.par, s.delta, s.alpha, s.pnorm, s.peg);
+        for (int j = 0; j < P; ++j) fprintf(stderr, " %.6g", s.pt[j]);
+        fprintf(stderr, "\n");
+    }
+    fprintf(stderr, "status %d\n", s.status);
+    return 0;
+}
