@@ -114,7 +114,7 @@ B2_HD void comp_coefs(const DeviceProblem& pr, const double* p4, CompCoef& cc) {
 }
 
 // Line set-up: z'(i) = ((i - nf) - f) * a  with  a = KAPPA0*dv/(sigma*rho_k);  stored as {nf, -f*a, a, lw}.
-struct LineCoef {
+struct alignas(16) LineCoef {
     float nf, b, a, lw;
 };
 

@@ -1,0 +1,876 @@
+// b200fit_kernels.cu -- sm_100a kernels + C ABI of the B200-native per-pixel spectral fitter.
+//
+// Hot path replaced (reference file:line):
+//   pcube.fiteach -> Specfit -> SpectralModel.fitter -> mpfit       mufasa/multi_v_fit.py:374-393, :192-206
+//   HyperfineModel.multi_v_spectrum / _single_spectrum_hf            mufasa/spec_models/HyperfineModel.py:22-109
+//   pcube.get_modelcube, UltraCube.get_rss / expand_mask / AICc ...  mufasa/UltraCube.py:322-325, 1384-1475, 1658-1698
+//
+// Design:
+//   * fit_kernel<NC>: persistent warps, ONE WARP PER PIXEL, pixels pulled from an atomic queue (iteration counts
+//     vary by >10x between pixels).  The spectrum is staged in shared memory with coalesced float4 loads; lanes
+//     own channels (32-channel chunks).  Per evaluation the warp computes the fp32 model and its analytic
+//     Jacobian only over the chunks a hyperfine window touches, accumulates J^T J / J^T r / chi2 per lane in
+//     fp32, reduces across lanes in fp64 through shared memory, and lane 0 advances the LM state machine
+//     (fp64 Cholesky on the damped normal equations, mpfit-style limits) from b200fit_common.h.
+//   * model/aicc/mask/stat kernels: fp64 model in the reference's frequency-space operation order (the AICc
+//     sample mask is ``model > 0``, decided by fp64 round-off), one warp per pixel.
+//   * gather_kernel: FITS channel-major cube -> compacted pixel-major rows (smem tile transpose).
+// No tensor cores: the per-pixel systems are 4x4 / 8x8.  No CPU fallback anywhere in this library.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "b200fit_host.h"
+
+namespace b200fit {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int FIT_WARPS = 4;   // warps per block of the fit kernel
+
+// ---------------------------------------------------------------------------------------------------------
+// warp helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-warp shared-memory working set of the fit kernel.
+template <int NC>
+struct alignas(16) FitShared {
+    static constexpr int P = 4 * NC;
+    static constexpr int NH = P * (P + 1) / 2;
+    static constexpr int NACC = NH + P + 1;
+    LMState<P> st;                       // 8-byte aligned first
+    alignas(16) LineCoef lines[NC][MAXHF_FIT];   // 16-byte records (float4 loads)
+    float ic[NC][MAXHF_FIT];
+    float hw[NC][MAXHF_FIT];
+    CompCoef cc[NC];
+    float red[NACC][33];                 // cross-lane reduction scratch (+1 pad: conflict-free both ways)
+    // float spec[nchan_stride] follows (dynamic)
+};
+
+template <int NC>
+__host__ __device__ constexpr size_t fit_shared_fixed_bytes() {
+    return (sizeof(FitShared<NC>) + 15) / 16 * 16;
+}
+
+template <int P>
+__device__ __noinline__ int dev_lm_propose(LMState<P>* s) {
+    return lm_propose<P>(*s);
+}
+template <int P>
+__device__ __noinline__ int dev_lm_update(LMState<P>* s) {
+    return lm_update<P>(*s);
+}
+template <int P>
+__device__ __noinline__ void dev_lm_errors(const LMState<P>* s, double err2, double* perr) {
+    lm_errors<P>(*s, err2, perr);
+}
+
+// One evaluation at the trial point st.pt: fills st.Ht / st.bt / st.chi2t.  Warp-collective.
+template <int NC>
+__device__ __forceinline__ void warp_eval(const DeviceProblem& pr, FitShared<NC>& w, const float* spec, int lane,
+                                          float y2a, float y2b, unsigned& n_gauss, unsigned& n_chunks) {
+    constexpr int P = 4 * NC;
+    constexpr int NH = P * (P + 1) / 2;
+    constexpr int NACC = NH + P + 1;
+    const int nhf = pr.nhf;
+    // 1. fp64 set-up spread over lanes: line positions/widths, Planck terms
+    for (int idx = lane; idx < NC * nhf; idx += 32) {
+        const int c = idx / nhf, k = idx - c * nhf;
+        LineCoef lc;
+        float icf, hwf;
+        line_coef(pr, &w.st.pt[4 * c], k, lc, icf, hwf);
+        w.lines[c][k] = lc;
+        w.ic[c][k] = icf;
+        w.hw[c][k] = hwf;
+    }
+    if (lane < NC) {
+        CompCoef cc;
+        comp_coefs(pr, &w.st.pt[4 * lane], cc);
+        w.cc[lane] = cc;
+    }
+    __syncwarp();
+    // 2. which hyperfines touch chunk `lane` and chunk `lane + 32`  (lines are sorted by centre)
+    const int nchunks = (pr.nchan + 31) >> 5;
+    unsigned packed[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int ch = lane + 32 * h;
+        const float lo_edge = 32.f * ch, hi_edge = 32.f * ch + 31.f;
+        unsigned pk = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            int klo = 0, khi = 0;
+            for (int k = 0; k < nhf; ++k) {
+                const float icv = w.ic[c][k], hwv = w.hw[c][k];
+                klo += (icv + hwv < lo_edge) ? 1 : 0;
+                khi += (icv - hwv <= hi_edge) ? 1 : 0;
+            }
+            if (ch >= nchunks) klo = khi = 0;
+            pk |= ((unsigned)klo | ((unsigned)khi << 8)) << (16 * c);
+        }
+        packed[h] = pk;
+    }
+    CompCoef cc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) cc[c] = w.cc[c];
+    const float ic0 = (float)pr.ic0;
+
+    float acc[NACC];
+#pragma unroll
+    for (int e = 0; e < NACC; ++e) acc[e] = 0.f;
+
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        bool mine = false;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const unsigned f = packed[h] >> (16 * c);
+            mine = mine || ((f & 0xffu) < ((f >> 8) & 0xffu));
+        }
+        unsigned act = __ballot_sync(FULL, mine);
+        // chunks no hyperfine touches: model == 0 exactly, Jacobian == 0 -> chi2 += sum(y^2) (precomputed)
+        if (!mine) acc[NACC - 1] += (h == 0) ? y2a : y2b;
+        while (act) {
+            const int j = __ffs(act) - 1;
+            act &= act - 1;
+            const unsigned pk = __shfl_sync(FULL, packed[h], j);
+            const int i = ((j + 32 * h) << 5) + lane;
+            const float y = spec[i];
+            const float fi = (float)i;
+            float G[NC], A[NC], B[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const unsigned f = pk >> (16 * c);
+                const int klo = f & 0xffu, khi = (f >> 8) & 0xffu;
+                float g = 0.f, a = 0.f, b = 0.f;
+                for (int k = klo; k < khi; ++k) {
+                    const float4 q = *reinterpret_cast<const float4*>(&w.lines[c][k]);
+                    LineCoef lc;
+                    lc.nf = q.x;
+                    lc.b = q.y;
+                    lc.a = q.z;
+                    lc.lw = q.w;
+                    gauss_accum(fi, lc, g, a, b);
+                }
+                G[c] = g;
+                A[c] = a;
+                B[c] = b;
+                n_gauss += (khi > klo) ? (unsigned)(khi - klo) : 0u;
+            }
+            n_chunks += 1;
+            float m, J[P];
+            rt_channel<NC>(G, A, B, fi - ic0, cc, m, J);
+            const bool valid = (y == y);   // NaN channels (and the NaN padding) carry no weight
+            const float r = valid ? (y - m) : 0.f;
+#pragma unroll
+            for (int u = 0; u < P; ++u) J[u] = valid ? J[u] : 0.f;
+            int q = 0;
+#pragma unroll
+            for (int u = 0; u < P; ++u) {
+#pragma unroll
+                for (int v = u; v < P; ++v) {
+                    acc[q] = fmaf(J[u], J[v], acc[q]);
+                    ++q;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < P; ++u) acc[NH + u] = fmaf(J[u], r, acc[NH + u]);
+            acc[NACC - 1] = fmaf(r, r, acc[NACC - 1]);
+        }
+    }
+    // 3. cross-lane reduction in fp64 through shared memory
+#pragma unroll
+    for (int e = 0; e < NACC; ++e) w.red[e][lane] = acc[e];
+    __syncwarp();
+    for (int e = lane; e < NACC; e += 32) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < 32; ++m) s += (double)w.red[e][m];
+        if (e < NH)
+            w.st.Ht[e] = s;
+        else if (e < NH + P)
+            w.st.bt[e - NH] = s;
+        else
+            w.st.chi2t = s;
+    }
+    __syncwarp();
+}
+
+template <int NC>
+__global__ void __launch_bounds__(FIT_WARPS * 32, 4)
+    fit_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
+               const double* __restrict__ guesses, const double* __restrict__ err_in, double* __restrict__ params,
+               double* __restrict__ perr, double* __restrict__ chi2, double* __restrict__ err_used,
+               int* __restrict__ status, unsigned* __restrict__ counts, unsigned long long* __restrict__ queue) {
+    constexpr int P = 4 * NC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = fit_shared_fixed_bytes<NC>() + (size_t)stride * sizeof(float);
+    FitShared<NC>& w = *reinterpret_cast<FitShared<NC>*>(smem_raw + warp * per_warp);
+    float* spec = reinterpret_cast<float*>(smem_raw + warp * per_warp + fit_shared_fixed_bytes<NC>());
+    const int nchan = pr.nchan;
+
+    for (;;) {
+        unsigned long long pix = 0;
+        if (lane == 0) pix = atomicAdd(queue, 1ULL);
+        pix = __shfl_sync(FULL, pix, 0);
+        if (pix >= (unsigned long long)pr.npix) break;
+
+        // ---- stage the spectrum: coalesced, vectorised, streaming (read once)
+        const float4* src = reinterpret_cast<const float4*>(spectra + pix * stride);
+        for (int i = lane; i < (int)(stride >> 2); i += 32) reinterpret_cast<float4*>(spec)[i] = __ldcs(src + i);
+        __syncwarp();
+
+        // ---- weights: err = population std of the finite channels (Cube.fiteach), peak for signal_cut
+        double s1 = 0.0, ymax = -INFINITY;
+        int n = 0;
+        for (int i = lane; i < nchan; i += 32) {
+            const float y = spec[i];
+            if (y == y) {
+                s1 += (double)y;
+                ++n;
+                ymax = fmax(ymax, (double)y);
+            }
+        }
+        s1 = warp_sum(s1);
+        n = warp_sum_i(n);
+        ymax = warp_max(ymax);
+        const double mean = (n > 0) ? s1 / n : 0.0;
+        double s2 = 0.0;
+        for (int i = lane; i < nchan; i += 32) {
+            const float y = spec[i];
+            if (y == y) {
+                const double d = (double)y - mean;
+                s2 += d * d;
+            }
+        }
+        s2 = warp_sum(s2);
+        double err = (n > 0) ? sqrt(s2 / n) : NAN;
+        if (pr.weight_mode == 1 && err_in != nullptr) err = err_in[pix];
+
+        // ---- sum(y^2) per 32-channel chunk (skewed reads: conflict-free), chunk = lane and lane + 32
+        float y2a = 0.f, y2b = 0.f;
+        {
+            const int nchunks = (nchan + 31) >> 5;
+            if (lane < nchunks) {
+                for (int m = 0; m < 32; ++m) {
+                    const float y = spec[(lane << 5) + ((m + lane) & 31)];
+                    if (y == y) y2a = fmaf(y, y, y2a);
+                }
+            }
+            if (lane + 32 < nchunks) {
+                for (int m = 0; m < 32; ++m) {
+                    const float y = spec[((lane + 32) << 5) + ((m + lane) & 31)];
+                    if (y == y) y2b = fmaf(y, y, y2b);
+                }
+            }
+        }
+
+        bool go = (err > 0.0) && !isinf(err);
+        if (go && pr.signal_cut > 0.0 && !(ymax / err >= pr.signal_cut)) go = false;
+        int ok = 0;
+        if (lane == 0 && go) ok = lm_init<P>(w.st, guesses + pix * P, pr.lo, pr.hi, pr.max_iter, pr.ftol) ? 1 : 0;
+        ok = __shfl_sync(FULL, ok, 0);
+        unsigned n_gauss = 0, n_chunks = 0;
+        int st_final = 0;
+        if (ok) {
+            __syncwarp();
+            warp_eval<NC>(pr, w, spec, lane, y2a, y2b, n_gauss, n_chunks);
+            int done = 0;
+            if (lane == 0) done = lm_adopt_first<P>(w.st);
+            done = __shfl_sync(FULL, done, 0);
+            while (!done) {
+                if (lane == 0) done = dev_lm_propose<P>(&w.st);
+                done = __shfl_sync(FULL, done, 0);
+                if (done) break;
+                __syncwarp();
+                warp_eval<NC>(pr, w, spec, lane, y2a, y2b, n_gauss, n_chunks);
+                if (lane == 0) done = dev_lm_update<P>(&w.st);
+                done = __shfl_sync(FULL, done, 0);
+            }
+            __syncwarp();
+            st_final = w.st.status;
+        }
+        // ---- results (zeros on failure, like pyspeckit's blank parcube)
+        if (lane == 0) {
+            double pe[P];
+            const bool good = ok && st_final > 0;
+            const double err2 = err * err;
+            if (good) dev_lm_errors<P>(&w.st, err2, pe);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                params[pix * P + j] = good ? w.st.p[j] : 0.0;
+                perr[pix * P + j] = good ? pe[j] : 0.0;
+            }
+            chi2[pix] = good ? lm_reported_chi2<P>(w.st) / err2 : 0.0;
+            err_used[pix] = err;
+            status[pix] = ok ? st_final : 0;
+            if (counts) {
+                counts[4 * pix + 0] = ok ? (unsigned)w.st.nevals : 0u;
+                counts[4 * pix + 1] = ok ? (unsigned)w.st.nrej : 0u;
+                counts[4 * pix + 2] = n_gauss;
+                counts[4 * pix + 3] = n_chunks;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp64 model in the reference's operation order (HyperfineModel.py:41-58, 91-107; BaseModel.py:191-192).
+// Explicit _rn intrinsics keep nvcc from contracting mul+add into FMA, so the arithmetic is the numpy sequence.
+// Hyperfine terms below exp(-90) relative are skipped: they cannot change the rounded sum.
+struct CompF64 {
+    double tex, tau, nuoff[MAXHF_FULL], inv2w2[MAXHF_FULL], tw[MAXHF_FULL];
+};
+
+__device__ __forceinline__ void comp_setup_f64(const DeviceProblem& pr, const double* p4, CompF64& c) {
+    const double vel = p4[0], width = p4[1];
+    c.tex = p4[2];
+    c.tau = p4[3];
+    for (int k = 0; k < pr.nfull; ++k) {
+        const double line = pr.lines_full[k];
+        const double nuwidth = fabs(__dmul_rn(__ddiv_rn(width, CKMS), line));
+        c.nuoff[k] = __dmul_rn(__ddiv_rn(vel, CKMS), line);
+        c.inv2w2[k] = __dmul_rn(2.0, __dmul_rn(nuwidth, nuwidth));   // 2.0 * nuwidth**2 (the divisor)
+        c.tw[k] = __dmul_rn(c.tau, pr.wts_full[k]);
+    }
+}
+
+__device__ __forceinline__ double xarr_ghz(const DeviceProblem& pr, int i) {
+    const double v = __dadd_rn(pr.v0, __dmul_rn(pr.dv, (double)i));
+    return __ddiv_rn(__dmul_rn(__dmul_rn(pr.nu_ref_ghz, 1e9), __dsub_rn(1.0, __ddiv_rn(v, CKMS))), 1e9);
+}
+
+__device__ __forceinline__ double t_antenna(double T0, double T) {
+    return __ddiv_rn(T0, __dsub_rn(exp(__ddiv_rn(T0, T)), 1.0));
+}
+
+// model of NC components at channel i; comps in shared/local memory
+__device__ __forceinline__ double model_f64(const DeviceProblem& pr, const CompF64* comps, int ncomp, int i) {
+    const double x = xarr_ghz(pr, i);
+    const double T0 = __ddiv_rn(__dmul_rn(__dmul_rn(H_CGS, x), 1e9), KB_CGS);
+    const double bg0 = t_antenna(T0, TCMB);
+    double bg = bg0;
+    for (int c = 0; c < ncomp; ++c) {
+        const CompF64& cp = comps[c];
+        double tauprof = 0.0;
+        for (int k = 0; k < pr.nfull; ++k) {
+            const double a = __dsub_rn(__dadd_rn(x, cp.nuoff[k]), pr.lines_full[k]);
+            const double arg = __ddiv_rn(-__dmul_rn(a, a), cp.inv2w2[k]);
+            if (arg > -90.0) tauprof = __dadd_rn(tauprof, __dmul_rn(cp.tw[k], exp(arg)));
+        }
+        const double e = exp(-tauprof);
+        const double jt = t_antenna(T0, cp.tex);
+        bg = __dadd_rn(__dmul_rn(jt, __dsub_rn(1.0, e)), __dmul_rn(bg, e));
+    }
+    return __dsub_rn(bg, bg0);
+}
+
+__device__ __forceinline__ bool params_valid(const double* p, int P) {
+    bool any = false, fin = true;
+    for (int j = 0; j < P; ++j) {
+        any = any || (p[j] != 0.0);
+        fin = fin && isfinite(p[j]);
+    }
+    return any && fin;
+}
+
+constexpr int AUX_WARPS = 4;
+
+struct AuxShared {
+    CompF64 comps[3];   // [0] = 1-comp fit, [1..2] = 2-comp fit
+};
+
+// get_modelcube: one warp per pixel
+__global__ void __launch_bounds__(AUX_WARPS * 32)
+    model_kernel(const DeviceProblem pr, const double* __restrict__ params, double* __restrict__ model,
+                 long long stride) {
+    __shared__ AuxShared sh[AUX_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P = 4 * pr.ncomp;
+    for (long long pix = (long long)blockIdx.x * AUX_WARPS + warp; pix < pr.npix;
+         pix += (long long)gridDim.x * AUX_WARPS) {
+        const double* p = params + pix * P;
+        const bool valid = params_valid(p, P);
+        if (valid && lane < pr.ncomp) comp_setup_f64(pr, p + 4 * lane, sh[warp].comps[lane]);
+        __syncwarp();
+        for (int i = lane; i < (int)stride; i += 32) {
+            double m = NAN;
+            if (valid && i < pr.nchan) m = model_f64(pr, sh[warp].comps, pr.ncomp, i);
+            model[pix * stride + i] = m;
+        }
+        __syncwarp();
+    }
+}
+
+// Union mask (model1 > 0) | (model2 > 0) as 64 x 32-bit words held one per lane pair; returns via smem bits.
+// mask_bits[w] bit b <-> channel 32*w + b
+__device__ __forceinline__ void union_mask_bits(const DeviceProblem& pr, const AuxShared& sh, bool v1, bool v2,
+                                                int model_f32, int lane, unsigned* bits /*smem [64]*/,
+                                                float* m1s, float* m2s /* optional smem model rows or null */) {
+    const int nwords = (pr.nchan + 31) >> 5;
+    for (int wd = 0; wd < nwords; ++wd) {
+        const int i = (wd << 5) + lane;
+        bool on = false;
+        double m1 = 0.0, m2 = 0.0;
+        if (i < pr.nchan) {
+            if (v1) m1 = model_f64(pr, &sh.comps[0], 1, i);
+            if (v2) m2 = model_f64(pr, &sh.comps[1], 2, i);
+            if (model_f32) {   // model cube stored in the data cube's dtype (pyspeckit full_like)
+                m1 = (double)(float)m1;
+                m2 = (double)(float)m2;
+            }
+            on = (m1 > 0.0) || (m2 > 0.0);
+        }
+        const unsigned b = __ballot_sync(FULL, on);
+        if (lane == 0) bits[wd] = b;
+        if (m1s && i < pr.nchan) {
+            m1s[i] = (float)m1;
+            m2s[i] = (float)m2;
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(AUX_WARPS * 32)
+    mask_count_kernel(const DeviceProblem pr, const double* __restrict__ params1, const double* __restrict__ params2,
+                      int model_f32, int* __restrict__ counts, long long one_pix, unsigned char* __restrict__ mask_out) {
+    __shared__ AuxShared sh[AUX_WARPS];
+    __shared__ unsigned bits[AUX_WARPS][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long first = (long long)blockIdx.x * AUX_WARPS + warp, step = (long long)gridDim.x * AUX_WARPS, last = pr.npix;
+    if (one_pix >= 0) {
+        first = one_pix + ((blockIdx.x == 0 && warp == 0) ? 0 : pr.npix);
+        last = one_pix + 1;
+    }
+    for (long long pix = first; pix < last; pix += step) {
+        const bool v1 = params1 && params_valid(params1 + pix * 4, 4);
+        const bool v2 = params2 && params_valid(params2 + pix * 8, 8);
+        if (v1 && lane == 0) comp_setup_f64(pr, params1 + pix * 4, sh[warp].comps[0]);
+        if (v2 && lane >= 1 && lane <= 2) comp_setup_f64(pr, params2 + pix * 8 + 4 * (lane - 1), sh[warp].comps[lane]);
+        __syncwarp();
+        union_mask_bits(pr, sh[warp], v1, v2, model_f32, lane, bits[warp], nullptr, nullptr);
+        const int nwords = (pr.nchan + 31) >> 5;
+        int cnt = 0;
+        for (int wd = lane; wd < nwords; wd += 32) cnt += __popc(bits[warp][wd]);
+        cnt = warp_sum_i(cnt);
+        if (counts && lane == 0) counts[pix] = cnt;
+        if (mask_out)
+            for (int i = lane; i < pr.nchan; i += 32) mask_out[i] = (bits[warp][i >> 5] >> (i & 31)) & 1u;
+        __syncwarp();
+    }
+}
+
+// dilate along the spectral axis: True at k spreads to [k - e/2, k + (e-1)/2]   (scipy binary_dilation with
+// ones(e), origin 0 -- UltraCube.expand_mask :1658-1698; for e = 20: [k-10, k+9])
+__device__ __forceinline__ bool dilated(const unsigned* bits, int nchan, int i, int expand) {
+    if (expand <= 0) return (bits[i >> 5] >> (i & 31)) & 1u;
+    int lo = i - (expand - 1) / 2, hi = i + expand / 2;   // sources k with k - e/2 <= i <= k + (e-1)/2
+    lo = lo < 0 ? 0 : lo;
+    hi = hi >= nchan ? nchan - 1 : hi;
+    for (int k = lo; k <= hi; ++k)
+        if ((bits[k >> 5] >> (k & 31)) & 1u) return true;
+    return false;
+}
+
+// get_all_lnk_maps + the get_best_2c_parcube selection, one warp per pixel.
+__global__ void __launch_bounds__(AUX_WARPS * 32)
+    aicc_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
+                const double* __restrict__ params1, const double* __restrict__ params2,
+                const unsigned* __restrict__ fill_bits, int expand, int model_f32, double thr10, double thr20,
+                double thr21, double* __restrict__ rss_out, double* __restrict__ nsamp_out, double* __restrict__ lnk_out,
+                signed char* __restrict__ ncomp_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ AuxShared sh[AUX_WARPS];
+    __shared__ unsigned bits[AUX_WARPS][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* m1s = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 2 * stride;
+    float* m2s = m1s + stride;
+    double* m1d = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * stride;   // fp64 variant
+    double* m2d = m1d + stride;
+    const int nwords = (pr.nchan + 31) >> 5;
+    for (long long pix = (long long)blockIdx.x * AUX_WARPS + warp; pix < pr.npix;
+         pix += (long long)gridDim.x * AUX_WARPS) {
+        const bool v1 = params_valid(params1 + pix * 4, 4);
+        const bool v2 = params_valid(params2 + pix * 8, 8);
+        if (v1 && lane == 0) comp_setup_f64(pr, params1 + pix * 4, sh[warp].comps[0]);
+        if (v2 && lane >= 1 && lane <= 2) comp_setup_f64(pr, params2 + pix * 8 + 4 * (lane - 1), sh[warp].comps[lane]);
+        __syncwarp();
+        // models (kept in smem) + union mask
+        for (int wd = 0; wd < nwords; ++wd) {
+            const int i = (wd << 5) + lane;
+            bool on = false;
+            if (i < pr.nchan) {
+                double m1 = v1 ? model_f64(pr, &sh[warp].comps[0], 1, i) : 0.0;
+                double m2 = v2 ? model_f64(pr, &sh[warp].comps[1], 2, i) : 0.0;
+                if (model_f32) {
+                    m1s[i] = (float)m1;
+                    m2s[i] = (float)m2;
+                    on = ((float)m1 > 0.f) || ((float)m2 > 0.f);
+                } else {
+                    m1d[i] = m1;
+                    m2d[i] = m2;
+                    on = (m1 > 0.0) || (m2 > 0.0);
+                }
+            }
+            const unsigned b = __ballot_sync(FULL, on);
+            if (lane == 0) bits[warp][wd] = b;
+        }
+        __syncwarp();
+        int cnt = 0;
+        for (int wd = lane; wd < nwords; wd += 32) cnt += __popc(bits[warp][wd]);
+        cnt = warp_sum_i(cnt);
+        bool have_mask = cnt > 0;
+        if (!have_mask && fill_bits) {   // include_nosamp: borrow the spectral mask of the max-N pixel
+            for (int wd = lane; wd < nwords; wd += 32) bits[warp][wd] = fill_bits[wd];
+            have_mask = true;
+        }
+        __syncwarp();
+        // rss over the dilated mask.  residual = data - model in the cube's dtype (fp32) when model_f32,
+        // squared and summed in fp64 (numpy: (residual * mask.astype(float)) ** 2 -> float64).
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+        int ns = 0;
+        const float* y = spectra + pix * stride;
+        if (have_mask) {
+            for (int i = lane; i < pr.nchan; i += 32) {
+                if (!dilated(bits[warp], pr.nchan, i, expand)) continue;
+                ns += 1;
+                const float d = y[i];
+                if (!(d == d)) continue;   // nansum skips NaN data, but the channel still counts in N
+                double e0, e1, e2;
+                if (model_f32) {
+                    e0 = (double)d;
+                    e1 = (double)(d - m1s[i]);
+                    e2 = (double)(d - m2s[i]);
+                } else {
+                    e0 = (double)d;
+                    e1 = (double)d - m1d[i];
+                    e2 = (double)d - m2d[i];
+                }
+                r0 += e0 * e0;
+                r1 += e1 * e1;
+                r2 += e2 * e2;
+            }
+        }
+        r0 = warp_sum(r0);
+        r1 = warp_sum(r1);
+        r2 = warp_sum(r2);
+        ns = warp_sum_i(ns);
+        if (lane == 0) {
+            // get_rss: rss == 0 -> NaN, N = NaN where rss NaN; method: N < 1 -> NaN, rss <= 0 -> NaN
+            double N = (double)ns;
+            double rs[3] = {r0, r1, r2}, Nn[3], aic[3];
+            for (int k = 0; k < 3; ++k) {
+                double rr = rs[k];
+                double nn = N;
+                if (rr == 0.0) {
+                    rr = NAN;
+                    nn = NAN;
+                }
+                if (nn < 1.0) {
+                    nn = NAN;
+                    rr = NAN;
+                }
+                if (rr <= 0.0) rr = NAN;
+                rs[k] = rr;
+                Nn[k] = nn;
+                const double p = 4.0 * k;
+                // aic.AIC / AICc (aic.py:136-181)
+                aic[k] = nn * log(rr / nn) + 2.0 * p + (2.0 * p * (p + 1.0)) / (nn - p - 1.0);
+                rss_out[pix * 3 + k] = rr;
+            }
+            nsamp_out[pix] = Nn[2];
+            double l10 = -1.0 * (aic[1] - aic[0]) / 2.0;
+            double l20 = -1.0 * (aic[2] - aic[0]) / 2.0;
+            double l21 = -1.0 * (aic[2] - aic[1]) / 2.0;
+            signed char nc = ((l21 > thr21) && (l20 > thr20)) ? 2 : 1;
+            if (!(l10 > thr10)) nc = 0;
+            // lnk maps are NaN where the corresponding fit does not exist (UltraCube.py:1369-1377)
+            if (!v1) l10 = NAN;
+            if (!v2) {
+                l20 = NAN;
+                l21 = NAN;
+            }
+            lnk_out[pix * 3 + 0] = l10;
+            lnk_out[pix * 3 + 1] = l20;
+            lnk_out[pix * 3 + 2] = l21;
+            ncomp_out[pix] = nc;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Cube layout: [nchan][nplane] (FITS) -> rows [npix][stride], compacted by pix_index, NaN padded, optional flip.
+__global__ void __launch_bounds__(256)
+    gather_kernel(const float* __restrict__ cube, int nchan, long long nplane, const long long* __restrict__ pix_index,
+                  long long npix, int flip, float* __restrict__ out, long long stride) {
+    __shared__ float tile[32][33];
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    // read: rows = channels, columns = pixels (coalesced when the selected pixels are contiguous)
+    long long src_pix = -1;
+    if (p0 + tx < npix) src_pix = pix_index ? pix_index[p0 + tx] : (p0 + tx);
+    for (int r = ty; r < 32; r += 8) {
+        const int ch = c0 + r;
+        float v = NAN;
+        if (ch < nchan && src_pix >= 0) {
+            const int sch = flip ? (nchan - 1 - ch) : ch;
+            v = __ldcs(cube + (long long)sch * nplane + src_pix);
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    // write: rows = pixels, columns = channels (coalesced)
+    for (int r = ty; r < 32; r += 8) {
+        const long long p = p0 + r;
+        const int ch = c0 + tx;
+        if (p < npix && ch < stride) out[p * stride + ch] = tile[tx][r];
+    }
+}
+
+}  // namespace b200fit
+
+// =============================================================================================================
+// C ABI
+using namespace b200fit;
+
+struct b200fit_ctx {
+    int device;
+    int num_sms;
+    std::string err;
+};
+
+static int fail(b200fit_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess) {
+    if (ctx) {
+        ctx->err = what;
+        if (ce != cudaSuccess) {
+            ctx->err += ": ";
+            ctx->err += cudaGetErrorString(ce);
+        }
+    }
+    return code;
+}
+
+#define CK(call)                                                    \
+    do {                                                            \
+        cudaError_t ce_ = (call);                                   \
+        if (ce_ != cudaSuccess) return fail(ctx, B200FIT_E_CUDA, #call, ce_); \
+    } while (0)
+
+template <int NC>
+static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_spectra, int64_t stride,
+                      const double* d_guesses, const double* d_err, double* d_params, double* d_perr, double* d_chi2,
+                      double* d_err_used, int32_t* d_status, uint32_t* d_counts, void* d_workspace,
+                      cudaStream_t stream) {
+    const size_t smem = FIT_WARPS * (fit_shared_fixed_bytes<NC>() + (size_t)stride * sizeof(float));
+    CK(cudaFuncSetAttribute(fit_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel<NC>, FIT_WARPS * 32, smem));
+    if (per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit kernel does not fit on an SM");
+    long long blocks = (long long)ctx->num_sms * per_sm;   // persistent: a whole number of CTAs per SM
+    const long long need = (pr.npix + FIT_WARPS - 1) / FIT_WARPS;
+    if (blocks > need) blocks = need;
+    CK(cudaMemsetAsync(d_workspace, 0, sizeof(unsigned long long), stream));
+    fit_kernel<NC><<<(unsigned)blocks, FIT_WARPS * 32, smem, stream>>>(
+        pr, d_spectra, (long long)stride, d_guesses, d_err, d_params, d_perr, d_chi2, d_err_used, d_status, d_counts,
+        (unsigned long long*)d_workspace);
+    CK(cudaGetLastError());
+    return B200FIT_OK;
+}
+
+extern "C" {
+
+int b200fit_abi_version(void) { return B200FIT_ABI_VERSION; }
+
+int64_t b200fit_nchan_stride(int32_t nchan) { return ((int64_t)nchan + 31) / 32 * 32; }
+
+int b200fit_create(b200fit_ctx** out, int device) {
+    if (!out) return B200FIT_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return B200FIT_E_NOGPU;
+    if (device < 0 || device >= ndev) return B200FIT_E_ARG;
+    b200fit_ctx* ctx = new b200fit_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return B200FIT_E_CUDA;
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    *out = ctx;
+    return B200FIT_OK;
+}
+
+void b200fit_destroy(b200fit_ctx* ctx) { delete ctx; }
+
+const char* b200fit_last_error(const b200fit_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int b200fit_num_sms(const b200fit_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+
+size_t b200fit_workspace_bytes(const b200fit_problem* prob) {
+    (void)prob;
+    return 256;   // work-queue counter (+ padding)
+}
+
+int b200fit_gather_spectra(b200fit_ctx* ctx, const float* d_cube, int32_t nchan, int64_t nplane,
+                           const int64_t* d_pix_index, int64_t npix, int32_t flip, float* d_spectra,
+                           int64_t nchan_stride, void* stream) {
+    if (!ctx || !d_cube || !d_spectra || nchan <= 0 || nchan_stride < nchan || (nchan_stride & 31)) return fail(ctx, B200FIT_E_ARG, "gather_spectra: bad argument");
+    if (npix == 0) return B200FIT_OK;
+    CK(cudaSetDevice(ctx->device));
+    dim3 grid((unsigned)((npix + 31) / 32), (unsigned)(nchan_stride / 32));
+    gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_cube, nchan, nplane, (const long long*)d_pix_index, npix,
+                                                          flip, d_spectra, nchan_stride);
+    CK(cudaGetLastError());
+    return B200FIT_OK;
+}
+
+int b200fit_fit(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_spectra, int64_t nchan_stride,
+                const double* d_guesses, const double* d_err, double* d_params, double* d_perr, double* d_chi2,
+                double* d_err_used, int32_t* d_status, uint32_t* d_counts, void* d_workspace, void* stream) {
+    if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "fit: null context/problem");
+    DeviceProblem pr;
+    const int rc = make_device_problem(*prob, pr);
+    if (rc) return fail(ctx, rc, "fit: invalid problem description");
+    if (pr.npix == 0) return B200FIT_OK;
+    if (!d_spectra || !d_guesses || !d_params || !d_perr || !d_chi2 || !d_err_used || !d_status || !d_workspace)
+        return fail(ctx, B200FIT_E_ARG, "fit: null device pointer");
+    if (nchan_stride < pr.nchan || (nchan_stride & 31)) return fail(ctx, B200FIT_E_ARG, "fit: bad nchan_stride");
+    if (pr.weight_mode == 1 && !d_err) return fail(ctx, B200FIT_E_ARG, "fit: weight_mode 1 needs d_err");
+    CK(cudaSetDevice(ctx->device));
+    if (pr.ncomp == 1)
+        return launch_fit<1>(ctx, pr, d_spectra, nchan_stride, d_guesses, d_err, d_params, d_perr, d_chi2, d_err_used,
+                             d_status, d_counts, d_workspace, (cudaStream_t)stream);
+    return launch_fit<2>(ctx, pr, d_spectra, nchan_stride, d_guesses, d_err, d_params, d_perr, d_chi2, d_err_used,
+                         d_status, d_counts, d_workspace, (cudaStream_t)stream);
+}
+
+static long long aux_blocks(const b200fit_ctx* ctx, long long npix) {
+    long long blocks = (long long)ctx->num_sms * 8;
+    const long long need = (npix + AUX_WARPS - 1) / AUX_WARPS;
+    return blocks < need ? blocks : (need > 0 ? need : 1);
+}
+
+int b200fit_model(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d_params, double* d_model,
+                  int64_t nchan_stride, void* stream) {
+    if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "model: null context/problem");
+    DeviceProblem pr;
+    const int rc = make_device_problem(*prob, pr);
+    if (rc) return fail(ctx, rc, "model: invalid problem description");
+    if (pr.npix == 0) return B200FIT_OK;
+    if (!d_params || !d_model || nchan_stride < pr.nchan) return fail(ctx, B200FIT_E_ARG, "model: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    model_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, 0, (cudaStream_t)stream>>>(pr, d_params, d_model,
+                                                                                                 nchan_stride);
+    CK(cudaGetLastError());
+    return B200FIT_OK;
+}
+
+int b200fit_mask_counts(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d_params1,
+                        const double* d_params2, int32_t model_f32, int32_t* d_counts, void* stream) {
+    if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "mask_counts: null context/problem");
+    DeviceProblem pr;
+    const int rc = make_device_problem(*prob, pr);
+    if (rc) return fail(ctx, rc, "mask_counts: invalid problem description");
+    if (pr.npix == 0) return B200FIT_OK;
+    if (!d_counts || (!d_params1 && !d_params2)) return fail(ctx, B200FIT_E_ARG, "mask_counts: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    mask_count_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        pr, d_params1, d_params2, model_f32, d_counts, -1, nullptr);
+    CK(cudaGetLastError());
+    return B200FIT_OK;
+}
+
+int b200fit_mask_of_pixel(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d_params1,
+                          const double* d_params2, int32_t model_f32, int64_t pix, unsigned char* h_mask_out,
+                          void* stream) {
+    if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "mask_of_pixel: null context/problem");
+    DeviceProblem pr;
+    const int rc = make_device_problem(*prob, pr);
+    if (rc) return fail(ctx, rc, "mask_of_pixel: invalid problem description");
+    if (!h_mask_out || pix < 0 || pix >= pr.npix) return fail(ctx, B200FIT_E_ARG, "mask_of_pixel: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    unsigned char* d_mask = nullptr;
+    CK(cudaMalloc(&d_mask, pr.nchan));
+    mask_count_kernel<<<1, AUX_WARPS * 32, 0, (cudaStream_t)stream>>>(pr, d_params1, d_params2, model_f32, nullptr,
+                                                                     pix, d_mask);
+    cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_mask_out, d_mask, pr.nchan, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(d_mask);
+    if (ce != cudaSuccess) return fail(ctx, B200FIT_E_CUDA, "mask_of_pixel", ce);
+    return B200FIT_OK;
+}
+
+int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_spectra, int64_t nchan_stride,
+                 const double* d_params1, const double* d_params2, const unsigned char* h_fill_mask, int32_t expand,
+                 int32_t model_f32, const double* thr, double* d_rss, double* d_nsamp, double* d_lnk,
+                 signed char* d_ncomp, void* stream) {
+    if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "aicc: null context/problem");
+    DeviceProblem pr;
+    const int rc = make_device_problem(*prob, pr);
+    if (rc) return fail(ctx, rc, "aicc: invalid problem description");
+    if (pr.npix == 0) return B200FIT_OK;
+    if (!d_spectra || !d_params1 || !d_params2 || !d_rss || !d_nsamp || !d_lnk || !d_ncomp || nchan_stride < pr.nchan)
+        return fail(ctx, B200FIT_E_ARG, "aicc: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    unsigned* d_fill = nullptr;
+    if (h_fill_mask) {
+        unsigned words[64];
+        std::memset(words, 0, sizeof(words));
+        for (int i = 0; i < pr.nchan; ++i)
+            if (h_fill_mask[i]) words[i >> 5] |= 1u << (i & 31);
+        CK(cudaMalloc(&d_fill, sizeof(words)));
+        cudaError_t ce = cudaMemcpyAsync(d_fill, words, sizeof(words), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize((cudaStream_t)stream);   // `words` is a stack buffer
+        if (ce != cudaSuccess) {
+            cudaFree(d_fill);
+            return fail(ctx, B200FIT_E_CUDA, "aicc: fill mask upload", ce);
+        }
+    }
+    const double t10 = thr ? thr[0] : 5.0, t20 = thr ? thr[1] : 5.0, t21 = thr ? thr[2] : 5.0;
+    const size_t smem = (size_t)AUX_WARPS * 2 * nchan_stride * (model_f32 ? sizeof(float) : sizeof(double));
+    cudaError_t ce = cudaFuncSetAttribute(aicc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce == cudaSuccess) {
+        aicc_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            pr, d_spectra, nchan_stride, d_params1, d_params2, d_fill, expand, model_f32, t10, t20, t21, d_rss, d_nsamp,
+            d_lnk, d_ncomp);
+        ce = cudaGetLastError();
+    }
+    if (d_fill) {
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize((cudaStream_t)stream);
+        cudaFree(d_fill);
+    }
+    if (ce != cudaSuccess) return fail(ctx, B200FIT_E_CUDA, "aicc launch", ce);
+    return B200FIT_OK;
+}
+
+int b200fit_resid_stats(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_spectra, int64_t nchan_stride,
+                        const double* d_params, int32_t expand, int32_t model_f32, double* d_rms, double* d_chisq_red,
+                        void* stream) {
+    (void)prob; (void)d_spectra; (void)nchan_stride; (void)d_params; (void)expand; (void)model_f32; (void)d_rms;
+    (void)d_chisq_red; (void)stream;
+    return fail(ctx, B200FIT_E_ARG, "resid_stats: not implemented yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+"""GPU parity tests of the fit kernel, through the C ABI, against the CPU oracle (mpfit restatement)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _tiles as T
+from mufasa_b200 import _abi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import torch
+    from mufasa_b200.engine import get_engine
+    assert torch.cuda.is_available()
+    return get_engine(0)
+
+
+def _gpu_fit(engine, tile, ncomp, lo, hi, guesses):
+    import torch
+    spec, gg = T.pixel_major(tile, guesses)
+    prob = _abi.make_problem(tile["fittype"], ncomp, tile["nchan"], spec.shape[0], tile["v"][0], tile["dv"], lo, hi)
+    out = engine.fit(prob, torch.from_numpy(spec).cuda(), torch.from_numpy(gg).cuda())
+    torch.cuda.synchronize()
+    return {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+
+
+CASES = [
+    # cfg, ncomp, nrows, xstep, min pass fraction on the oracle-stable converged set
+    (2, 1, 4, 8, 0.99),
+    (2, 2, 4, 8, 0.90),
+    (4, 2, 3, 16, 0.90),
+    (4, 1, 3, 16, 0.97),
+]
+
+
+@pytest.mark.parametrize("cfg,ncomp,nrows,xstep,min_frac", CASES)
+def test_fit_parity(engine, cfg, ncomp, nrows, xstep, min_frac):
+    tile = T.sample_tile(cfg, nrows=nrows, xstep=xstep)
+    lo, hi = T.limits_vectors(tile["fittype"], ncomp)
+    g = synth.clamp_guesses(tile["guess%d" % ncomp], lo, hi)
+    P = 4 * ncomp
+    o = T.oracle_fit(tile, ncomp, lo, hi, g)
+    o2 = T.oracle_fit(tile, ncomp, lo, hi, g, perturb=1e-9)
+    stable = T.stable_set(o, o2, P)
+    out = _gpu_fit(engine, tile, ncomp, lo, hi, g)
+    c = T.criteria(out["params"], out["chi2"], out["status"], o, P)
+    sel = c["both"] & stable
+    ok = c["par_ok"] & c["chi2_ok"]
+    rep = dict(cfg=cfg, ncomp=ncomp, npix=int(sel.size), oracle_converged=int(c["conv_o"].sum()),
+               gpu_converged=int(c["conv_g"].sum()), oracle_stable=int((stable & c["conv_o"]).sum()),
+               compared=int(sel.sum()), passed=int(ok[sel].sum()),
+               passed_all_converged=int(ok[c["both"]].sum()), both_converged=int(c["both"].sum()),
+               median_dsigma=float(np.median(c["mz"][sel])), evals_mean=float(out["counts"][:, 0].mean()),
+               err_used_rel=float(np.nanmax(np.abs(out["err_used"] - o["err"].ravel()) / o["err"].ravel())))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_fit.jsonl", "a") as f:
+        f.write(json.dumps(rep) + "\n")
+    print(rep)
+    # has_fit agreement (status > 0 on both sides)
+    assert np.array_equal(out["status"] > 0, o["status"].ravel() > 0)
+    # weights: std of the spectrum (fp64 on the GPU, cube dtype in numpy) agree to fp32 round-off
+    assert rep["err_used_rel"] < 5e-7
+    assert sel.sum() >= 0.5 * sel.size
+    assert ok[sel].mean() >= min_frac
+    # typical agreement is orders of magnitude inside the 0.05-sigma criterion
+    assert rep["median_dsigma"] < 5e-3
+
+
+def test_fit_matches_host_emulation(engine):
+    """The kernel and the test-only host emulation run the same shared source: results agree to fp32 noise."""
+    tile = T.sample_tile(2, nrows=2, xstep=8)
+    lo, hi = T.limits_vectors(tile["fittype"], 2)
+    g = synth.clamp_guesses(tile["guess2"], lo, hi)
+    out = _gpu_fit(engine, tile, 2, lo, hi, g)
+    spec, gg = T.pixel_major(tile, g)
+    prob = _abi.make_problem(tile["fittype"], 2, tile["nchan"], spec.shape[0], tile["v"][0], tile["dv"], lo, hi)
+    em = T.emul_fit(T.build_emul(), prob, spec, gg)
+    same = out["status"] == em["status"]
+    assert same.mean() > 0.9
+    with np.errstate(all="ignore"):
+        d = np.abs(out["params"] - em["params"]) / np.where(em["perr"] > 0, em["perr"], np.inf)
+    assert np.median(np.nanmax(d, axis=1)[same]) < 1e-2
+
+
+def test_edge_cases(engine):
+    """NaN guesses, guesses outside the limits, all-NaN spectra, NaN channels, signal_cut."""
+    import torch
+    tile = T.sample_tile(2, nrows=1, xstep=32)
+    lo, hi = T.limits_vectors(tile["fittype"], 1)
+    g = synth.clamp_guesses(tile["guess1"], lo, hi)
+    spec, gg = T.pixel_major(tile, g)
+    npix = spec.shape[0]
+    gg[0, 2] = np.nan            # NaN guess -> not fitted
+    gg[1, 1] = 5.0               # sigma above its upper limit -> mpfit status 0 -> not fitted
+    spec[2, :] = np.nan          # empty spectrum
+    spec[3, 100:140] = np.nan    # NaN channels carry no weight, pixel still fitted
+    prob = _abi.make_problem(tile["fittype"], 1, tile["nchan"], npix, tile["v"][0], tile["dv"], lo, hi)
+    out = engine.fit(prob, torch.from_numpy(spec).cuda(), torch.from_numpy(gg).cuda())
+    st = out["status"].cpu().numpy()
+    par = out["params"].cpu().numpy()
+    assert st[0] == 0 and st[1] == 0 and st[2] == 0
+    assert np.all(par[:3] == 0) and np.all(out["perr"].cpu().numpy()[:3] == 0)
+    assert st[3] > 0 and np.all(np.isfinite(par[3]))
+    assert np.all(st[4:] > 0)
+    # signal_cut: a cut above every peak S/N leaves nothing fitted (pyspeckit fiteach semantics)
+    prob2 = _abi.make_problem(tile["fittype"], 1, tile["nchan"], npix, tile["v"][0], tile["dv"], lo, hi,
+                              signal_cut=1e6)
+    out2 = engine.fit(prob2, torch.from_numpy(spec).cuda(), torch.from_numpy(gg).cuda())
+    assert np.all(out2["status"].cpu().numpy() == 0)
+    # empty call
+    prob0 = _abi.make_problem(tile["fittype"], 1, tile["nchan"], 0, tile["v"][0], tile["dv"], lo, hi)
+    out0 = engine.fit(prob0, torch.empty((0, spec.shape[1]), dtype=torch.float32, device="cuda"),
+                      torch.empty((0, 4), dtype=torch.float64, device="cuda"))
+    assert out0["params"].shape[0] == 0
