@@ -1,0 +1,249 @@
+"""PCube: the object MUFASA's drivers talk to where the reference uses ``pyspeckit.Cube``.
+
+Same attribute names / shapes / dtypes the reference reads back:
+  parcube[P, ny, nx], errcube[P, ny, nx] (float64, zeros where not fitted), has_fit[ny, nx] (bool),
+  get_modelcube() -> [nchan, ny, nx] cached in ``_modelcube`` (NaN where no fit), cube, xarr, maskmap,
+  specfit.Registry.add_fitter(...), fiteach(...) with pyspeckit's keyword names.
+The per-pixel work -- what ``Cube.fiteach`` does in forked worker processes -- is one call into the CUDA library
+(b200fit_gather_spectra + b200fit_fit).  Extra maps the reference does not keep are exposed too: chi2map,
+statusmap, nevalmap, errmap_used.
+"""
+import numpy as np
+import torch
+
+from . import _abi
+from .engine import get_engine
+from .exceptions import FitTypeError
+from .spec_models.meta_model import FITTYPE_ALIASES, MetaModel
+
+
+class _Registry(object):
+    """pyspeckit's fitter registry: MUFASA calls ``pcube.specfit.Registry.add_fitter(fittype, fitter, npars)``
+    (multi_v_fit.py:119-120; UltraCube.py:851-854).  Here it maps fittype -> model id of the CUDA library."""
+
+    def __init__(self):
+        self.multifitters = {}
+        self.npars = {}
+
+    def add_fitter(self, name, function, npars, **kwargs):
+        name = FITTYPE_ALIASES.get(name, name)
+        if name not in _abi.MODEL_IDS:
+            raise FitTypeError("\'{}\' is an invalid fittype".format(name))
+        self.multifitters[name] = function
+        self.npars[name] = npars
+
+
+class _Specfit(object):
+    def __init__(self):
+        self.Registry = _Registry()
+
+
+class VelocityAxis(object):
+    """Uniform velocity axis in km/s, radio convention about ``refX`` (Hz).  Carries the two attributes
+    register_pcube inspects (multi_v_fit.py:107-116)."""
+
+    def __init__(self, v_kms, refX=None, velocity_convention='radio'):
+        v = np.asarray(v_kms, dtype=np.float64)
+        if v.ndim != 1 or v.size < 8:
+            raise ValueError("spectral axis must be 1-D with at least 8 channels")
+        dv = np.diff(v)
+        if not np.all(np.isfinite(v)) or dv[0] == 0 or np.max(np.abs(dv - dv[0])) > 1e-6 * abs(dv[0]):
+            raise ValueError("the CUDA fitter needs a uniform velocity axis")
+        self.value = v
+        self.refX = refX
+        self.velocity_convention = velocity_convention
+        self.unit = 'km/s'
+
+    def __len__(self):
+        return self.value.size
+
+    @property
+    def v0_dv_flip(self):
+        """(v0, dv, flip) of the ascending axis the device works on."""
+        v = self.value
+        dv = (v[-1] - v[0]) / (v.size - 1)
+        if dv > 0:
+            return float(v[0]), float(dv), False
+        return float(v[-1]), float(-dv), True
+
+
+class PCube(object):
+    def __init__(self, cube, xarr, header=None, unit='K', maskmap=None, device=None):
+        cube = np.asarray(cube)
+        if cube.ndim != 3:
+            raise ValueError("cube must be [nchan, ny, nx]")
+        self.cube = cube
+        self.xarr = xarr if isinstance(xarr, VelocityAxis) else VelocityAxis(xarr)
+        if len(self.xarr) != cube.shape[0]:
+            raise ValueError("spectral axis length does not match the cube")
+        self.header = header
+        self.wcs = None
+        self.unit = unit
+        self.maskmap = maskmap
+        self.specfit = _Specfit()
+        self.parcube = None
+        self.errcube = None
+        self.has_fit = np.zeros(cube.shape[1:], dtype=bool)
+        self._modelcube = None
+        self.chi2map = None
+        self.statusmap = None
+        self.nevalmap = None
+        self.errmap_used = None
+        self.fittype = None
+        self.npars = None
+        self._device = device
+        self._cube_dev = None
+        self.timing = {}
+
+    # ---------------------------------------------------------------------------------------------------
+    @property
+    def engine(self):
+        return get_engine(self._device)
+
+    def cube_on_device(self):
+        """[nchan, ny*nx] fp32 on the GPU (uploaded once per PCube, from pinned memory)."""
+        if self._cube_dev is None:
+            nchan, ny, nx = self.cube.shape
+            host = np.ascontiguousarray(self.cube, dtype=np.float32).reshape(nchan, ny * nx)
+            t = torch.from_numpy(host)
+            try:
+                t = t.pin_memory()
+            except RuntimeError:
+                pass
+            self._cube_dev = t.to(self.engine.device, non_blocking=True)
+        return self._cube_dev
+
+    def release_device(self):
+        self._cube_dev = None
+
+    def copy(self):
+        new = PCube(self.cube, self.xarr, header=self.header, unit=self.unit, maskmap=self.maskmap,
+                    device=self._device)
+        new._cube_dev = self._cube_dev
+        for k in ("parcube", "errcube", "has_fit", "_modelcube", "chi2map", "statusmap", "nevalmap", "errmap_used"):
+            v = getattr(self, k)
+            setattr(new, k, None if v is None else v.copy())
+        new.fittype, new.npars = self.fittype, self.npars
+        new.specfit = self.specfit
+        return new
+
+    def _problem(self, fittype, ncomp, npix, minpars, maxpars, signal_cut=0.0, maxiter=200):
+        v0, dv, _ = self.xarr.v0_dv_flip
+        nu_ref = 0.0 if self.xarr.refX is None else float(self.xarr.refX) / 1e9
+        return _abi.make_problem(fittype, ncomp, self.cube.shape[0], npix, v0, dv, minpars, maxpars,
+                                 nu_ref_ghz=nu_ref, max_iter=maxiter, signal_cut=signal_cut)
+
+    # ---------------------------------------------------------------------------------------------------
+    def fiteach(self, fittype='nh3_multi_v', guesses=None, limitedmin=None, limitedmax=None, minpars=None,
+                maxpars=None, multicore=1, maskmap=None, start_from_point=None, use_neighbor_as_guess=False,
+                guesses_are_moments=False, signal_cut=3, errmap=None, verbose_level=0, verbose=False,
+                maxiter=200, **kwargs):
+        """pyspeckit ``Cube.fiteach`` for the call MUFASA makes (multi_v_fit.py:374-393, :192-206).
+
+        Every valid pixel (maskmap & finite guesses & a finite channel) is fitted on the GPU in one launch.
+        ``multicore``, ``start_from_point`` and the verbosity switches are accepted and ignored: pixel order does
+        not matter because use_neighbor_as_guess=False (multi_v_fit.py:381).  ``signal_cut`` keeps pyspeckit's
+        default of 3; the MUFASA drivers pass 0."""
+        fittype = FITTYPE_ALIASES.get(fittype, fittype)
+        if fittype not in _abi.MODEL_IDS:
+            raise FitTypeError("\'{}\' is an invalid fittype".format(fittype))
+        if use_neighbor_as_guess or guesses_are_moments:
+            raise NotImplementedError("MUFASA always passes use_neighbor_as_guess=False, guesses_are_moments=False")
+        if errmap is not None:
+            raise NotImplementedError("MUFASA never forwards an errmap to fiteach (multi_v_fit.py:234-238)")
+        guesses = np.asarray(guesses, dtype=np.float64)
+        nchan, ny, nx = self.cube.shape
+        if guesses.ndim != 3 or guesses.shape[1:] != (ny, nx) or guesses.shape[0] % 4:
+            raise ValueError("guesses must be [4*ncomp, ny, nx]")
+        P = guesses.shape[0]
+        ncomp = P // 4
+        if ncomp not in (1, 2):
+            raise NotImplementedError("the CUDA fitter covers 1- and 2-component models")
+        for lim in (limitedmin, limitedmax):
+            if lim is not None and not all(lim):
+                raise NotImplementedError("all parameter limits are active in MUFASA's calls")
+        if minpars is None or maxpars is None or len(minpars) != P or len(maxpars) != P:
+            raise ValueError("minpars/maxpars must have one entry per parameter")
+
+        ok = np.all(np.isfinite(guesses), axis=0)
+        if maskmap is not None:
+            ok &= np.asarray(maskmap, dtype=bool)
+        if self.maskmap is not None:
+            ok &= np.asarray(self.maskmap, dtype=bool)
+        if start_from_point is not None:
+            sx, sy = int(start_from_point[0]), int(start_from_point[1])
+            if not (0 <= sx < nx and 0 <= sy < ny) or not ok[sy, sx]:
+                raise ValueError("The starting fit position is not among the valid pixels")   # pyspeckit contract
+        pix = np.flatnonzero(ok.ravel())
+        npix = pix.size
+
+        self.parcube = np.zeros((P, ny, nx), dtype=np.float64)
+        self.errcube = np.zeros((P, ny, nx), dtype=np.float64)
+        self.has_fit = np.zeros((ny, nx), dtype=bool)
+        self.chi2map = np.zeros((ny, nx), dtype=np.float64)
+        self.statusmap = np.zeros((ny, nx), dtype=np.int32)
+        self.nevalmap = np.zeros((ny, nx), dtype=np.int32)
+        self.errmap_used = np.full((ny, nx), np.nan)
+        self._modelcube = None
+        self.fittype, self.npars = fittype, P
+        if npix == 0:
+            return
+
+        eng = self.engine
+        dev = eng.device
+        _, _, flip = self.xarr.v0_dv_flip
+        prob = self._problem(fittype, ncomp, npix, list(minpars), list(maxpars), signal_cut=float(signal_cut or 0.0),
+                             maxiter=maxiter)
+        cube_dev = self.cube_on_device()
+        gsel = np.ascontiguousarray(guesses.reshape(P, ny * nx)[:, pix].T)
+        g_dev = torch.from_numpy(gsel).to(dev, non_blocking=True)
+        idx_dev = None if npix == ny * nx else torch.from_numpy(pix.astype(np.int64)).to(dev, non_blocking=True)
+        spectra = eng.gather(cube_dev, idx_dev, flip=flip)
+        out = eng.fit(prob, spectra, g_dev)
+        packed = torch.cat([out["params"], out["perr"], out["chi2"][:, None], out["err_used"][:, None],
+                            out["status"].to(torch.float64)[:, None],
+                            out["counts"][:, 0].to(torch.float64)[:, None]], dim=1).cpu().numpy()
+        flat = lambda a: a.reshape(a.shape[0], ny * nx) if a.ndim == 3 else a.reshape(ny * nx)
+        flat(self.parcube)[:, pix] = packed[:, :P].T
+        flat(self.errcube)[:, pix] = packed[:, P:2 * P].T
+        flat(self.chi2map)[pix] = packed[:, 2 * P]
+        flat(self.errmap_used)[pix] = packed[:, 2 * P + 1]
+        st = packed[:, 2 * P + 2].astype(np.int32)
+        flat(self.statusmap)[pix] = st
+        flat(self.nevalmap)[pix] = packed[:, 2 * P + 3].astype(np.int32)
+        flat(self.has_fit)[pix] = st > 0
+        self._last = dict(prob=prob, pix=pix, spectra=spectra)
+        if not self.has_fit.any():
+            # pyspeckit: "The first fitted pixel did not yield a fit" -> AssertionError, which cubefit_gen turns
+            # into a retry / StartFitError (multi_v_fit.py:388-403)
+            raise AssertionError("No pixel yielded a fit. Please check the guesses, limits and mask.")
+
+    # ---------------------------------------------------------------------------------------------------
+    def get_modelcube(self, update=False, multicore=1, mask=None):
+        """Model cube from parcube (pyspeckit get_modelcube: NaN where there is no fit), dtype of the data cube,
+        cached in ``_modelcube``; callers may mutate the returned array (master_fitter.py:2516-2520)."""
+        if self._modelcube is not None and not update:
+            return self._modelcube
+        if self.parcube is None:
+            raise AttributeError("no fit has been performed")
+        P, ny, nx = self.parcube.shape
+        nchan = self.cube.shape[0]
+        valid = np.any(self.parcube != 0, axis=0) & np.all(np.isfinite(self.parcube), axis=0)
+        if mask is not None:
+            valid &= np.asarray(mask, dtype=bool)
+        out = np.full((nchan, ny, nx), np.nan, dtype=self.cube.dtype if self.cube.dtype.kind == 'f' else np.float64)
+        pix = np.flatnonzero(valid.ravel())
+        if pix.size:
+            eng = self.engine
+            lo = [-1e30] * P
+            hi = [1e30] * P
+            prob = self._problem(self.fittype, P // 4, pix.size, lo, hi)
+            par = np.ascontiguousarray(self.parcube.reshape(P, ny * nx)[:, pix].T)
+            m = eng.model(prob, torch.from_numpy(par).to(eng.device))[:, :nchan]
+            _, _, flip = self.xarr.v0_dv_flip
+            if flip:
+                m = torch.flip(m, dims=[1])
+            out.reshape(nchan, ny * nx)[:, pix] = m.to(torch.float32 if out.dtype == np.float32 else torch.float64
+                                                      ).cpu().numpy().T
+        self._modelcube = out
+        return out
