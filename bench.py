@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the B200 per-pixel spectral fitter on BASELINE.json's metric.
+
+metric   : spectra fitted / second, 2-component NH3(1,1) model selection workload
+workload : BASELINE.json configs[1] -- synthetic NH3(1,1) cube 256 x 256 x 800 channels; one STEP = the whole job
+           on one cube: 1-component fit + 2-component fit of every spectrum + AICc 0/1/2-component selection
+           (UltraCube.fit_cube(1), fit_cube(2), get_best_2c_parcube in the reference's terms).
+           N GPUs: every rank owns one such cube (independent noise realisation) -- pixels are independent, no
+           collective on the data path -> "scaling": "weak".
+value    : (spectra of all ranks) / (max-over-ranks device time per step), cube rows already resident in HBM.
+e2e      : the same job through the public host API (mufasa_b200.UltraCube) starting from HOST (pinned) buffers:
+           H2D of the cube and guesses, all kernels, D2H of parameter / error / lnk / ncomp maps, host bookkeeping.
+roofline : dominant kernel = fit_kernel<2> (2-component LM fit).  The path is compute bound: the
+           fraction reported is algorithmic pipe work / time / pipe peak for the binding pipe (FP32 FMA, XU ex2,
+           FP64), with the HBM figure alongside.
+cpu_baseline / --impl reference: the CPU oracle (numpy restatement of the reference's pyspeckit/mpfit path; the
+           reference itself is pure Python on un-vendored pyspeckit and cannot be installed here) timed on this
+           box's host cores on a bounded sample of the same cube.
+
+Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = 2
+METRIC = "spectra fitted/sec, 2-comp NH3(1,1)"
+UNIT = "spectra/s"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), power_w_max=float(max(power)),
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def oracle_modelcube(parcube, v, fittype):
+    from oracle import model as M
+    return M.modelcube(v, parcube, fittype)
+
+
+def sample_rows(ny, nrows):
+    return [int(y) for y in np.linspace(20, ny - 21, nrows)]
+
+
+def cpu_job(cfg, rows, xstep, cores, seed_offset=0):
+    """The reference's job on a sample of the workload cube, on the host: 1c fit + 2c fit (cubefit_simp semantics:
+    guesses clamped into the limits, err = std(spectrum), mpfit) + get_all_lnk_maps / get_best_2c_parcube.
+    Returns (nspectra, seconds)."""
+    from mufasa_b200 import synth
+    from oracle import constants as K
+    from oracle import fiteach as F
+    from oracle import model as M
+    from oracle import stats as ST
+    parts = [synth.make_cube(cfg, oracle_modelcube, rows=(y, y + 1), seed_offset=seed_offset) for y in rows]
+    cube = np.ascontiguousarray(np.concatenate([p["cube"][:, :, ::xstep] for p in parts], axis=1))
+    g1 = np.concatenate([p["guess1"][:, :, ::xstep] for p in parts], axis=1)
+    g2 = np.concatenate([p["guess2"][:, :, ::xstep] for p in parts], axis=1)
+    v, fittype = parts[0]["v"], parts[0]["fittype"]
+    L = K.limits(fittype)
+    lo1 = [-3.5, L["sigmin"], L["Texmin"], L["taumin"]]
+    hi1 = [4.5, L["sigmax"], L["Texmax"], L["taumax"]]
+    g1 = synth.clamp_guesses(g1, lo1, hi1)
+    g2 = synth.clamp_guesses(g2, lo1 * 2, hi1 * 2)
+    t0 = time.perf_counter()
+    o1 = F.fiteach(cube, v, g1, lo1, hi1, fittype, multicore=cores)
+    o2 = F.fiteach(cube, v, g2, lo1 * 2, hi1 * 2, fittype, multicore=cores)
+    m1 = M.modelcube(v, o1["parcube"], fittype, dtype=np.float32)
+    m2 = M.modelcube(v, o2["parcube"], fittype, dtype=np.float32)
+    with np.errstate(all="ignore"):
+        Lk = ST.all_lnk_maps(cube, m1, m2, expand=20)
+        ST.best_2c_parcube(o1["parcube"], o1["errcube"], o2["parcube"], o2["errcube"], Lk["lnk10"], Lk["lnk20"],
+                           Lk["lnk21"])
+    dt = time.perf_counter() - t0
+    return cube.shape[1] * cube.shape[2], dt
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle restatement) on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from mufasa_b200 import synth
+    fittype, ny, nx, nchan, dv = synth.CONFIGS[CFG]
+    cores = host_cores()
+    # pilot: one short row sample to size the per-step sample so that the whole run stays within ~3 minutes
+    n0, t0 = cpu_job(CFG, sample_rows(ny, 2), 16, cores)
+    rate = n0 / t0
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    want = int(min(2048, max(32, rate * budget)))
+    nrows = max(2, min(16, want // 32))
+    xstep = max(1, nx // max(1, want // nrows))
+    rows = sample_rows(ny, nrows)
+    times = []
+    nspec = 0
+    for it in range(args.warmup + args.steps):
+        nspec, dt = cpu_job(CFG, rows, xstep, cores)
+        if it >= args.warmup:
+            times.append(dt)
+    tstep = float(np.mean(times))
+    value = nspec / tstep
+    sample = "%d spectra per step (%d rows x every %d-th column of the %dx%dx%d cube); 1c fit + 2c fit + AICc" % (
+        nspec, nrows, xstep, ny, nx, nchan)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tstep * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = pure-Python MUFASA on un-vendored pyspeckit/mpfit (not installable offline); timed "
+                    "here: the numpy oracle restatement of that path (oracle/), multiprocessing over all host cores"}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n):
+    return {"workload": "BASELINE configs[1]: synthetic NH3(1,1) cube 256x256x800 ch per GPU; step = 1-comp fit + "
+                        "2-comp fit + AICc ncomp selection of all 65536 spectra",
+            "spectra_per_gpu": 65536, "nchan": 800, "fittype": "nh3_multi_v",
+            "partition": "one cube per rank (pixels independent, no data-path collective)" if n > 1 else "single GPU",
+            "cache": "inputs larger than L2 (210 MB of spectra per GPU vs 126 MB L2), streamed once per kernel"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from mufasa_b200 import _abi, synth
+    from mufasa_b200.cube import SpecCube
+    from mufasa_b200.engine import get_engine
+    from mufasa_b200.spec_models.meta_model import MetaModel
+    from mufasa_b200.UltraCube import UltraCube
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = get_engine(local)
+    dev = eng.device
+
+    fittype, ny, nx, nchan, dv = synth.CONFIGS[CFG]
+    npix = ny * nx
+
+    def gpu_modelcube(parcube, v, ft):
+        P, ry, rx = parcube.shape
+        prob = _abi.make_problem(ft, P // 4, len(v), ry * rx, v[0], v[1] - v[0], [-1e30] * P, [1e30] * P)
+        par = torch.from_numpy(np.ascontiguousarray(parcube.reshape(P, ry * rx).T)).to(dev)
+        m = eng.model(prob, par)[:, :len(v)]
+        return m.cpu().numpy().T.reshape(len(v), ry, rx)
+
+    pinned = torch.empty((nchan, ny, nx), dtype=torch.float32).pin_memory()
+    syn = synth.make_cube(CFG, gpu_modelcube, seed_offset=rank, out=pinned.numpy())
+    cube_host = syn["cube"]                       # numpy view of the pinned buffer
+    v = syn["v"]
+    mm = MetaModel(fittype, 1)
+    spec = SpecCube(cube_host, v)
+
+    # ---------------- end-to-end arm: the public API from host buffers ----------------------------------------
+    def e2e_step():
+        uc = UltraCube(cube=spec, fittype=fittype, device=local)
+        uc.fit_cube(ncomp=1, simpfit=True, guesses=syn["guess1"].copy())
+        uc.fit_cube(ncomp=2, simpfit=True, guesses=syn["guess2"].copy())
+        res = uc.get_best_2c_parcube()
+        return uc, res
+
+    uc, res = e2e_step()                           # also the source of the limits the device arm uses
+    torch.cuda.synchronize()
+    h2d = cube_host.nbytes + syn["guess1"].nbytes + syn["guess2"].nbytes + npix * 12 * 8
+    d2h = sum(uc.pcubes[k].parcube.nbytes * 2 + npix * (8 + 8 + 8 + 8) for k in ("1", "2")) + npix * (3 + 1 + 3) * 8 \
+        + npix
+    e2e_times = []
+    n_e2e = max(2, min(args.steps, 5))
+    for it in range(1 + n_e2e):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        uc_i, res_i = e2e_step()
+        torch.cuda.synchronize()
+        if it >= 1:
+            e2e_times.append(time.perf_counter() - t0)
+        del uc_i, res_i
+    e2e_t = torch.tensor([float(np.mean(e2e_times))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = npix * world / float(e2e_t.item())
+
+    # ---------------- device arm: rows resident in HBM --------------------------------------------------------
+    rows = uc._ref_pcube.rows_on_device()
+    p1h, p2h = uc.pcubes["1"], uc.pcubes["2"]
+    # same guesses / limits the drivers produced (cubefit_simp clamps + velocity window)
+    lims = {}
+    for nc in (1, 2):
+        g = syn["guess%d" % nc].copy()
+        from mufasa_b200 import multi_v_fit as mvf
+        vg = g[::4]
+        vmed, v99, v1p = mvf.get_vstats(vg)
+        vmax = max(vmed + 10, v99 + mm.sigmax)
+        vmin = min(vmed - 10, v1p - mm.sigmax)
+        lo = [vmin, mm.sigmin, mm.Texmin, mm.taumin] * nc
+        hi = [vmax, mm.sigmax, mm.Texmax, mm.taumax] * nc
+        g = synth.clamp_guesses(g, lo, hi, eps=mm.eps)
+        lims[nc] = (lo, hi, torch.from_numpy(np.ascontiguousarray(g.reshape(4 * nc, npix).T)).to(dev))
+    prob1 = _abi.make_problem(fittype, 1, nchan, npix, v[0], dv, lims[1][0], lims[1][1])
+    prob2 = _abi.make_problem(fittype, 2, nchan, npix, v[0], dv, lims[2][0], lims[2][1])
+    out1 = eng.fit(prob1, rows, lims[1][2])
+    out2 = eng.fit(prob2, rows, lims[2][2])
+    aout = eng.aicc_alloc(npix)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def dev_step(timers=None):
+        if timers is not None:
+            ev[0].record()
+        eng.fit(prob1, rows, lims[1][2], out=out1)
+        if timers is not None:
+            ev[1].record()
+        eng.fit(prob2, rows, lims[2][2], out=out2)
+        if timers is not None:
+            ev[2].record()
+        eng.aicc_pass(prob1, rows, out1["params"], out2["params"], aout)
+        best = eng.mask_argmax(aout["mask_counts"])
+        bits = eng.mask_bits(prob1, out1["params"], out2["params"], best=best)
+        eng.aicc_pass(prob1, rows, out1["params"], out2["params"], aout, fill_bits=bits, only_empty=True)
+        if timers is not None:
+            ev[3].record()
+
+    for _ in range(max(3, args.warmup)):
+        dev_step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_fit1 = t_fit2 = t_aicc = 0.0
+    start.record()
+    per = []
+    for _ in range(args.steps):
+        dev_step(timers=True)
+        per.append(list(ev))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    stop.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = start.elapsed_time(stop)
+    for e in per:
+        t_fit1 += e[0].elapsed_time(e[1])
+        t_fit2 += e[1].elapsed_time(e[2])
+        t_aicc += e[2].elapsed_time(e[3])
+    tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tt.item()) / args.steps
+    value = npix * world / (ms_per_step * 1e-3)
+
+    # ---------------- roofline of the dominant kernel (fit_kernel<2>) on rank 0 -------------------------------
+    peaks = measured_peaks()
+    cnt = out2["counts"].to(torch.float64)
+    evals = float(cnt[:, 0].sum().item())                 # fused model + Jacobian evaluations, summed over pixels
+    exec_gauss = float(cnt[:, 2].sum().item()) * 32.0      # gaussians actually evaluated (windowed)
+    H, C, P = 18, 2, 8
+    sfu = evals * nchan * C * (H + 2)                      # SFU_J = N*C*(H+2)
+    f32 = evals * nchan * C * (12 * H + 30)                # F32_J = N*C*(12H+30)
+    f64 = evals * nchan * (P * (P + 1) + 2 * P + 2)        # F64_J = N*(P(P+1)+2P+2)
+    t2 = t_fit2 * 1e-3 / args.steps                        # seconds per launch
+    clk = peaks["sm_max_mhz"] * 1e6
+    nsm = eng.num_sms
+    pk = {"fp32": nsm * 128 * 2 * clk, "xu": nsm * 16 * clk, "fp64": nsm * 64 * 2 * clk}
+    ach = {"fp32": f32 / t2, "xu": sfu / t2, "fp64": f64 / t2}
+    frac = {k: ach[k] / pk[k] for k in pk}
+    bound = max(frac, key=lambda k: frac[k])
+    hbm_bytes = npix * (nchan * 4 + P * 8 + (2 * P + 2) * 8 + 4 + 16)
+    roofline = {"bound": bound, "kernel": "fit_kernel<2>", "achieved": ach[bound] / 1e12, "peak": pk[bound] / 1e12,
+                "unit": "TFLOP/s" if bound != "xu" else "Top/s", "frac": frac[bound], "traffic": None,
+                "pipes": {k: {"achieved_T": ach[k] / 1e12, "peak_T": pk[k] / 1e12, "frac": frac[k]} for k in pk},
+                "peak_source": "derived: %d SMs x lanes x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json, %s)" % (
+                    nsm, peaks["sm_max_mhz"], peaks["source"]),
+                "hbm": {"achieved": hbm_bytes / t2 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": hbm_bytes / t2 / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"]},
+                "algorithmic_per_launch": {"evaluations": evals, "xu_ops": sfu, "fp32_flop": f32, "fp64_flop": f64,
+                                           "executed_gaussians": exec_gauss,
+                                           "algorithmic_gaussians": evals * nchan * C * H},
+                "launch_ms": t2 * 1e3,
+                "share_of_step": {"fit_1c": t_fit1 / total_ms, "fit_2c": t_fit2 / total_ms,
+                                  "aicc": t_aicc / total_ms}}
+
+    line = None
+    if rank == 0:
+        st2 = out2["status"].cpu().numpy()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 model+Jacobian, f64 normal equations/solve",
+                "data": "synthetic", "config": workload_config(world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": float(e2e_t.item()) * 1e3,
+                        "api": "UltraCube.fit_cube(1, simpfit) + fit_cube(2, simpfit) + get_best_2c_parcube()"},
+                "gpu_launches": 7 * args.steps,
+                "fit2c_only": {"value": npix / t2, "unit": UNIT, "ms": t2 * 1e3},
+                "roofline": roofline, "clocks": clocks,
+                "fit_stats": {"converged_2c": float(np.isin(st2, [1, 2, 3, 4]).mean()),
+                              "maxiter_2c": float((st2 == 5).mean()),
+                              "mean_evals_2c": evals / npix,
+                              "mean_evals_1c": float(out1["counts"][:, 0].to(torch.float64).mean().item())}}
+    if world > 1:
+        dist.barrier()
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        rows_s = sample_rows(ny, 8)
+        nspec, dt = cpu_job(CFG, rows_s, 8, cores)
+        line["cpu_baseline"] = {"value": nspec / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d spectra (8 rows x every 8th column of the same cube), 1c fit + 2c fit + "
+                                          "AICc with the numpy oracle (mpfit restatement), %d processes, %.1f s" % (
+                                              nspec, cores, dt)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

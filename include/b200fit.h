@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200FIT_ABI_VERSION 1
+#define B200FIT_ABI_VERSION 2
 
 enum {
     B200FIT_OK = 0,
@@ -85,18 +85,21 @@ int b200fit_gather_spectra(b200fit_ctx* ctx, const float* d_cube, int32_t nchan,
                            float* d_spectra, int64_t nchan_stride, void* stream);
 
 /* The fit: replaces pcube.fiteach(...) -> Specfit -> SpectralModel.fitter -> mpfit for every pixel.
+ *   d_row_index [npix] int64 or NULL: pixel k reads spectrum row d_row_index[k] (NULL = row k).  Lets masked refits
+ *              (cubefit_simp on a maskmap, multi_v_fit.py:126-208) run on the resident rows without a re-gather.
  *   d_guesses [npix][P] fp64   must lie inside [lo,hi] (else status 0 like mpfit); NaN => status 0
  *   d_err     [npix] fp64 or NULL (weight_mode 0)
  *   d_params  [npix][P] fp64   zeros on failure              (parcube)
  *   d_perr    [npix][P] fp64   0 for pegged parameters       (errcube = mpfit perror)
  *   d_chi2    [npix] fp64      sum(((y-M)/err)^2) at the solution (mpfit fnorm)
  *   d_err_used[npix] fp64      the weight actually used
- *   d_status  [npix] int32     1,2,3 converged (MINPACK meaning), 5 = max_iter, 0 = not fitted / bad guess,
+ *   d_status  [npix] int32     1,2,3,4 converged (MINPACK meaning), 5 = max_iter, 0 = not fitted / bad guess,
  *                              -16 = non-finite; has_fit = status > 0
  *   d_counts  [npix][4] uint32 {evaluations, rejected steps, executed gaussian-lane evals / 32, active chunks}
- *                              (roofline accounting); may be NULL */
+ *                              (roofline accounting); may be NULL
+ *   d_workspace: b200fit_workspace_bytes() bytes of device scratch */
 int b200fit_fit(b200fit_ctx* ctx, const b200fit_problem* prob,
-                const float* d_spectra, int64_t nchan_stride,
+                const float* d_spectra, int64_t nchan_stride, const int64_t* d_row_index,
                 const double* d_guesses, const double* d_err,
                 double* d_params, double* d_perr, double* d_chi2, double* d_err_used,
                 int32_t* d_status, uint32_t* d_counts,
@@ -111,33 +114,43 @@ int b200fit_model(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d
 
 /* Model selection: replaces UltraCube.get_all_lnk_maps + get_best_2c_parcube's selection
  * (UltraCube.py:1218-1379 => get_rss :1384-1475, expand_mask :1658-1698, aic.py:136-201).
- *   d_params1 [npix][4], d_params2 [npix][8]  (all-zero row = no fit)
- *   h_fill_mask: nchan bytes (0/1) = spectral mask used for pixels whose own model mask is empty
- *                (include_nosamp rule, UltraCube.py:1423-1438); NULL => such pixels get N = NaN.
- *                Obtain it with b200fit_mask_counts + one host argmax over ALL pixels (global rule).
+ *   d_params1 [npix][4], d_params2 [npix][8]  (all-zero row = no fit); d_row_index as in b200fit_fit
  *   model_f32: != 0 => model cube takes the data cube's dtype (fp32), as pyspeckit's full_like does
  *   d_rss [npix][3] (ncomp 0,1,2), d_nsamp [npix], d_lnk [npix][3] (lnk10, lnk20, lnk21),
- *   d_ncomp [npix] int8 (0/1/2 with thresholds thr[3] = {lnk10, lnk20, lnk21}) */
+ *   d_ncomp [npix] int8 (0/1/2 with thresholds thr[3] = {lnk10, lnk20, lnk21}; NULL = 5,5,5)
+ * The include_nosamp rule (UltraCube.py:1423-1438) is GLOBAL: pixels whose own model mask is empty borrow the
+ * spectral mask of the first (row-major) pixel with the largest mask.  It is therefore split in two passes:
+ *   pass 1  only_empty = 0, d_fill_bits = NULL: all pixels; d_mask_counts[npix] (int32, out) = own mask sizes;
+ *           empty-mask pixels get NaN statistics for now
+ *   ......  b200fit_mask_argmax over d_mask_counts (and over all ranks on the host side), b200fit_mask_bits
+ *   pass 2  only_empty = 1, d_fill_bits = the 64-word bit set: only pixels with d_mask_counts == 0 are redone.
+ * Passing d_fill_bits in pass 1 applies a caller-chosen fill mask directly. */
 int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob,
-                 const float* d_spectra, int64_t nchan_stride,
+                 const float* d_spectra, int64_t nchan_stride, const int64_t* d_row_index,
                  const double* d_params1, const double* d_params2,
-                 const unsigned char* h_fill_mask, int32_t expand, int32_t model_f32, const double* thr,
-                 double* d_rss, double* d_nsamp, double* d_lnk, signed char* d_ncomp, void* stream);
+                 const uint32_t* d_fill_bits, int32_t only_empty, int32_t expand, int32_t model_f32, const double* thr,
+                 double* d_rss, double* d_nsamp, double* d_lnk, signed char* d_ncomp, int32_t* d_mask_counts,
+                 void* stream);
 
-/* Per-pixel size of the un-dilated union mask (model1 > 0) | (model2 > 0) and, for one pixel, the mask
- * itself; the two pieces the host needs for the global include_nosamp rule. */
-int b200fit_mask_counts(b200fit_ctx* ctx, const b200fit_problem* prob,
-                        const double* d_params1, const double* d_params2, int32_t model_f32,
-                        int32_t* d_counts, void* stream);
-int b200fit_mask_of_pixel(b200fit_ctx* ctx, const b200fit_problem* prob,
-                          const double* d_params1, const double* d_params2, int32_t model_f32,
-                          int64_t pix, unsigned char* h_mask_out, void* stream);
+/* d_best[2] (int64, device) = {largest mask count, index_offset + lowest pixel index holding it} -- the argmax the
+ * reference takes with np.where(nsamp_map == nanmax(nsamp_map)) (UltraCube.py:1428-1429).  index_offset lets
+ * each rank of a partitioned cube report global pixel indices. */
+int b200fit_mask_argmax(b200fit_ctx* ctx, const int32_t* d_mask_counts, int64_t npix, int64_t index_offset,
+                        int64_t* d_best, void* d_workspace, void* stream);
 
-/* Residual statistics: replaces UltraCube.get_chisq / get_rms (UltraCube.py:1478-1565, 1701-1740).
- *   d_rms [npix] = 1.4826*median(|r - roll(r,2)|)/sqrt(2);  d_chisq_red [npix] */
+/* Un-dilated union mask (model1 > 0) | (model2 > 0) of one pixel as a bit set d_bits[64] (bit b of word w =
+ * channel 32 w + b).  The pixel is d_best[1] when d_best != NULL (empty set if d_best[0] == 0), else ``pix``. */
+int b200fit_mask_bits(b200fit_ctx* ctx, const b200fit_problem* prob,
+                      const double* d_params1, const double* d_params2, int32_t model_f32,
+                      const int64_t* d_best, int64_t pix, uint32_t* d_bits, void* stream);
+
+/* Residual statistics of one fitted model: replaces UltraCube.get_rms / get_chisq(reduced=True)
+ * (UltraCube.py:1701-1740, :1478-1565; prob->ncomp selects the model, d_params [npix][4*ncomp]).
+ *   d_rms [npix] = 1.4826*nanmedian(|r - roll(r,2)|)/sqrt(2);  d_chisq_red [npix]; NaN where there is no fit */
 int b200fit_resid_stats(b200fit_ctx* ctx, const b200fit_problem* prob,
-                        const float* d_spectra, int64_t nchan_stride, const double* d_params,
-                        int32_t expand, int32_t model_f32, double* d_rms, double* d_chisq_red, void* stream);
+                        const float* d_spectra, int64_t nchan_stride, const int64_t* d_row_index,
+                        const double* d_params, int32_t expand, int32_t model_f32,
+                        double* d_rms, double* d_chisq_red, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,286 @@
+"""UltraCube: host-side mirror of mufasa/UltraCube.py for the B200 fitter.
+
+Keeps the reference's method names and result conventions
+  * UltraCube.fit_cube                      UltraCube.py:272-326 (+ module fit_cube :777-801)
+  * has_fit / include_model_mask / reset_model_mask           :328-368
+  * get_rss / get_AICc / get_AICc_likelihood / get_all_lnk_maps / get_best_2c_parcube   :432-498, :1120-1379
+  * get_residual / get_rms / get_reduced_chisq                :403-471, :1478-1565, :1701-1800
+while every per-pixel computation is a kernel of libb200fit.so.  Differences that come from living on a GPU:
+  * the cube is uploaded once and kept resident as pixel-major rows (the reference re-reads the FITS file for every
+    ncomp, UltraCube.py:191) -- both fits and the AICc pass stream the same device buffer;
+  * ``master_model_mask`` (a [nchan, ny, nx] bool cube, 1 GB at 1024x1024x1000) is materialised only when a caller
+    asks for it; the AICc kernels rebuild the per-pixel mask from the fitted parameters on the fly.
+"""
+import gc
+import logging
+from collections.abc import Iterable
+from copy import copy
+
+import numpy as np
+import torch
+
+from . import multi_v_fit as mvf
+from .cube import SpecCube
+from .pcube import PCube
+from .spec_models.meta_model import MetaModel
+
+logger = logging.getLogger(__name__)
+
+
+class UltraCube(object):
+    def __init__(self, cubefile=None, cube=None, fittype=None, snr_min=None, rmsfile=None, cnv_factor=2,
+                 n_cores=True, device=None):
+        self.pcubes = {}
+        self.residual_cubes = {}
+        self.rms_maps = {}
+        self.Tpeak_maps = {}
+        self.chisq_maps = {}
+        self.rchisq_maps = {}
+        self.rss_maps = {}
+        self.NSamp_maps = {}
+        self.AICc_maps = {}
+        self.lnk_maps = {}
+        self.ncomp_map = None
+        self._master_model_mask = None
+        self._mask_ncomps = []            # which fits feed the lazily built master_model_mask
+        self.snr_min = 0.0
+        self.cnv_factor = cnv_factor
+        self.n_cores = mvf.validate_n_cores(n_cores)
+        self.fittype = fittype
+        self.meta_model = None
+        self.device = device
+        if cubefile is not None:
+            raise NotImplementedError("FITS I/O is outside the fit path (SURVEY.md 8f #2): pass cube=SpecCube(...)")
+        if not isinstance(cube, SpecCube):
+            raise TypeError("cube must be a mufasa_b200.cube.SpecCube")
+        self.cube = cube
+        if fittype is not None:
+            self.meta_model = MetaModel(fittype=fittype, ncomp=1)
+        if snr_min is not None:
+            self.snr_min = snr_min
+        if rmsfile is not None:
+            self.rmsfile = rmsfile
+        self._ref_pcube = None
+
+    # ---- pcube handling ---------------------------------------------------------------------------------
+    def load_pcube(self, pcube_ref=None):
+        """UltraCube.py:173-214: a fresh fit container on the same data.  The device copy of the cube is shared."""
+        p = PCube(self.cube._data, self.cube.xarr(), header=self.cube.header, unit=self.cube.unit,
+                  device=self.device)
+        ref = pcube_ref if pcube_ref is not None else self._ref_pcube
+        if ref is not None:
+            p.share_device(ref)
+        if self._ref_pcube is None:
+            self._ref_pcube = p
+        return p
+
+    def fit_cube(self, ncomp, simpfit=False, **kwargs):
+        """UltraCube.py:272-326."""
+        if 'multicore' not in kwargs:
+            kwargs['multicore'] = self.n_cores
+        if 'snr_min' not in kwargs:
+            kwargs['snr_min'] = self.snr_min
+        if not isinstance(ncomp, Iterable):
+            ncomp = [ncomp]
+        for nc in ncomp:
+            if self.pcubes:
+                _, pcube_ref = next(iter(self.pcubes.items()))
+                self.pcubes[str(nc)] = self.load_pcube(pcube_ref=pcube_ref)
+            else:
+                self.pcubes[str(nc)] = self.load_pcube()
+            self.pcubes[str(nc)] = fit_cube(self.cube, self.pcubes[str(nc)], fittype=self.fittype, simpfit=simpfit,
+                                            ncomp=nc, **kwargs)
+            p = self.pcubes[str(nc)]
+            if p.has_fit.sum() > 0 and p.parcube is not None:
+                self._include_fit_in_mask(nc)
+            self._invalidate_stats()
+
+    def _invalidate_stats(self):
+        for d in (self.rss_maps, self.NSamp_maps, self.AICc_maps, self.lnk_maps, self.residual_cubes, self.rms_maps,
+                  self.rchisq_maps):
+            d.clear()
+        self.ncomp_map = None
+
+    def has_fit(self, ncomp):
+        """UltraCube.py:328-348."""
+        parcube = self.pcubes[str(ncomp)].parcube
+        mask = np.any(parcube != 0, axis=0)
+        return mask & np.any(np.isfinite(parcube), axis=0)
+
+    # ---- model mask (lazy) --------------------------------------------------------------------------------
+    def _include_fit_in_mask(self, nc):
+        if nc not in self._mask_ncomps:
+            self._mask_ncomps.append(nc)
+        self._master_model_mask = None
+
+    @property
+    def master_model_mask(self):
+        """(model_nc > 0) OR-ed over the fits performed so far (UltraCube.py:351-368), built on demand."""
+        if self._master_model_mask is None and self._mask_ncomps:
+            m = None
+            for nc in self._mask_ncomps:
+                with np.errstate(invalid="ignore"):
+                    mm = self.pcubes[str(nc)].get_modelcube() > 0
+                m = mm if m is None else np.logical_or(m, mm)
+            self._master_model_mask = m
+        return self._master_model_mask
+
+    @master_model_mask.setter
+    def master_model_mask(self, value):
+        self._master_model_mask = value
+        if value is None:
+            self._mask_ncomps = []
+
+    def include_model_mask(self, mask):
+        cur = self.master_model_mask
+        self._master_model_mask = mask if cur is None else np.logical_or(cur, mask)
+
+    def reset_model_mask(self, ncomps, multicore=True):
+        self._master_model_mask = None
+        self._mask_ncomps = [nc for nc in ncomps if nc > 0 and str(nc) in self.pcubes
+                             and self.pcubes[str(nc)].parcube is not None]
+
+    # ---- statistics: one GPU pass gives rss_0/1/2, N, AICc_0/1/2 and the three lnk maps --------------------------
+    def _params_dev(self, nc, eng):
+        ny, nx = self.cube.shape[1:]
+        P = 4 * nc
+        if str(nc) in self.pcubes and self.pcubes[str(nc)].parcube is not None:
+            par = np.ascontiguousarray(self.pcubes[str(nc)].parcube.reshape(P, ny * nx).T)
+            par = np.nan_to_num(par, nan=0.0, posinf=0.0, neginf=0.0) if not np.all(np.isfinite(par)) else par
+        else:
+            par = np.zeros((ny * nx, P))
+        return torch.from_numpy(par).to(eng.device, non_blocking=True)
+
+    def _run_aicc(self, expand=20, thr=(5.0, 5.0, 5.0)):
+        key = (int(expand), tuple(float(t) for t in thr))
+        if self.lnk_maps.get("_key") == key:
+            return
+        ref = self._ref_pcube if self._ref_pcube is not None else self.load_pcube()
+        eng = ref.engine
+        ny, nx = self.cube.shape[1:]
+        rows = ref.rows_on_device()
+        prob = ref._problem(self.fittype, 1, ny * nx, [-1e30] * 4, [1e30] * 4)
+        p1 = self._params_dev(1, eng)
+        p2 = self._params_dev(2, eng)
+        model_f32 = self.cube._data.dtype == np.float32
+        out = eng.aicc_global(prob, rows, p1, p2, expand=expand, model_f32=model_f32, thr=thr)
+        rss = out["rss"].cpu().numpy().reshape(ny, nx, 3)
+        nsamp = out["nsamp"].cpu().numpy().reshape(ny, nx)
+        lnk = out["lnk"].cpu().numpy().reshape(ny, nx, 3)
+        with np.errstate(all="ignore"):
+            for nc in (0, 1, 2):
+                self.rss_maps[str(nc)] = np.ascontiguousarray(rss[:, :, nc])
+                ns = np.where(np.isnan(rss[:, :, nc]), np.nan, nsamp)
+                self.NSamp_maps[str(nc)] = ns
+                p = 4 * nc
+                self.AICc_maps[str(nc)] = ns * np.log(self.rss_maps[str(nc)] / ns) + 2 * p + \
+                    (2 * p * (p + 1)) / (ns - p - 1)
+        self.lnk_maps = {"_key": key, "10": np.ascontiguousarray(lnk[:, :, 0]),
+                         "20": np.ascontiguousarray(lnk[:, :, 1]), "21": np.ascontiguousarray(lnk[:, :, 2])}
+        self.ncomp_map = out["ncomp"].cpu().numpy().reshape(ny, nx)
+
+    def get_rss(self, ncomp, mask=None, planemask=None, update=True, expand=20):
+        """Residual sum of squares over the dilated union model mask (UltraCube.py:432-451)."""
+        if mask is not None or planemask is not None:
+            raise NotImplementedError("custom masks belong to the refit loop (SURVEY.md 8f #3)")
+        self._run_aicc(expand=expand)
+        return self.rss_maps[str(ncomp)]
+
+    def get_AICc(self, ncomp, update=False, planemask=None, expand=20, **kwargs):
+        """UltraCube.py:474-486 (p = 4 * ncomp; ncomp = 0: model == 0, no free parameter)."""
+        if planemask is not None:
+            raise NotImplementedError("planemask updates belong to the refit loop (SURVEY.md 8f #3)")
+        if update:
+            self.lnk_maps.clear()
+        self._run_aicc(expand=expand)
+        return self.AICc_maps[str(ncomp)]
+
+    def get_AICc_likelihood(self, ncomp1, ncomp2, **kwargs):
+        """ln(L_A / L_B) = (AICc_B - AICc_A) / 2  (calc_AICc_likelihood, UltraCube.py:1120-1216)."""
+        if kwargs.get("ucube_B") is not None or kwargs.get("planemask") is not None:
+            raise NotImplementedError("two-cube comparison belongs to the refit loop (SURVEY.md 8f #3)")
+        self._run_aicc()
+        return -1.0 * (self.AICc_maps[str(ncomp1)] - self.AICc_maps[str(ncomp2)]) / 2.0
+
+    def get_all_lnk_maps(self, ncomp_max=2, rest_model_mask=True, multicore=True):
+        """UltraCube.py:1218-1280."""
+        if rest_model_mask:
+            self.reset_model_mask(ncomps=[2, 1], multicore=multicore)
+        self._run_aicc()
+        lnk10 = self.get_AICc_likelihood(1, 0)
+        if ncomp_max <= 1:
+            return lnk10
+        return lnk10, self.get_AICc_likelihood(2, 0), self.get_AICc_likelihood(2, 1)
+
+    def get_best_2c_parcube(self, multicore=True, lnk21_thres=5, lnk20_thres=5, lnk10_thres=5, return_lnks=True,
+                            include_1c=True):
+        """UltraCube.py:1283-1379.  The integer 0/1/2 selection map is kept in ``self.ncomp_map``."""
+        self.reset_model_mask(ncomps=[2, 1], multicore=multicore)
+        self._run_aicc(thr=(lnk10_thres, lnk20_thres, lnk21_thres))
+        lnk10, lnk20, lnk21 = (self.get_AICc_likelihood(1, 0), self.get_AICc_likelihood(2, 0),
+                               self.get_AICc_likelihood(2, 1))
+        parcube = copy(self.pcubes['2'].parcube)
+        errcube = copy(self.pcubes['2'].errcube)
+        mask = self.ncomp_map == 2
+        if include_1c:
+            parcube[:4, ~mask] = self.pcubes['1'].parcube[:4, ~mask]
+            errcube[:4, ~mask] = self.pcubes['1'].errcube[:4, ~mask]
+            parcube[4:8, ~mask] = np.nan
+            errcube[4:8, ~mask] = np.nan
+        else:
+            parcube[:, ~mask] = np.nan
+            errcube[:, ~mask] = np.nan
+        mask = self.ncomp_map >= 1
+        parcube[:, ~mask] = np.nan
+        errcube[:, ~mask] = np.nan
+        if return_lnks:
+            lnk10[~self.has_fit(ncomp=1)] = np.nan
+            m2 = self.has_fit(ncomp=2)
+            lnk20[~m2] = np.nan
+            lnk21[~m2] = np.nan
+            return parcube, errcube, lnk10, lnk20, lnk21
+        return parcube, errcube
+
+    # ---- residual statistics ---------------------------------------------------------------------------------
+    def get_residual(self, ncomp, multicore=None):
+        compID = str(ncomp)
+        model = self.pcubes[compID].get_modelcube()
+        self.residual_cubes[compID] = get_residual(self.cube, model)
+        gc.collect()
+        return self.residual_cubes[compID]
+
+    def get_rms(self, ncomp):
+        self._run_resid_stats(ncomp)
+        return self.rms_maps[str(ncomp)]
+
+    def get_reduced_chisq(self, ncomp):
+        self._run_resid_stats(ncomp)
+        return self.rchisq_maps[str(ncomp)]
+
+    def _run_resid_stats(self, ncomp, expand=20):
+        compID = str(ncomp)
+        if compID in self.rms_maps and compID in self.rchisq_maps:
+            return
+        p = self.pcubes[compID]
+        eng = p.engine
+        ny, nx = self.cube.shape[1:]
+        rows = p.rows_on_device()
+        prob = p._problem(self.fittype, ncomp, ny * nx, [-1e30] * (4 * ncomp), [1e30] * (4 * ncomp))
+        par = self._params_dev(ncomp, eng)
+        out = eng.resid_stats(prob, rows, par, expand=expand, model_f32=self.cube._data.dtype == np.float32)
+        self.rms_maps[compID] = out["rms"].cpu().numpy().reshape(ny, nx)
+        self.rchisq_maps[compID] = out["chisq_red"].cpu().numpy().reshape(ny, nx)
+
+
+# ======================================================================================================================
+def fit_cube(cube, pcube, fittype, simpfit=False, **kwargs):
+    """Module-level dispatcher (UltraCube.py:777-801)."""
+    if simpfit:
+        return mvf.cubefit_simp(cube, pcube, fittype=fittype, **kwargs)
+    return mvf.cubefit_gen(cube, pcube, fittype=fittype, **kwargs)
+
+
+def get_residual(cube, model):
+    """data - model (UltraCube.py:1743-1800); NaN wherever the model cube has no fit."""
+    data = cube._data if hasattr(cube, "_data") else np.asarray(cube)
+    return data - model

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libb200fit.so")
 
 MODEL_IDS = {"nh3_multi_v": 0, "n2hp_multi_v": 1}
 MAX_NCHAN = 2048
+ABI_VERSION = 2
 
 
 class Problem(C.Structure):
@@ -51,12 +52,13 @@ SIGNATURES = {
     "b200fit_nchan_stride": (_i64, [_i32]),
     "b200fit_workspace_bytes": (_sz, [_PP]),
     "b200fit_gather_spectra": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
-    "b200fit_fit": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200fit_fit": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200fit_model": (C.c_int, [_vp, _PP, _vp, _vp, _i64, _vp]),
-    "b200fit_aicc": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "b200fit_mask_counts": (C.c_int, [_vp, _PP, _vp, _vp, _i32, _vp, _vp]),
-    "b200fit_mask_of_pixel": (C.c_int, [_vp, _PP, _vp, _vp, _i32, _i64, _vp, _vp]),
-    "b200fit_resid_stats": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "b200fit_aicc": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                               _vp, _vp]),
+    "b200fit_mask_argmax": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "b200fit_mask_bits": (C.c_int, [_vp, _PP, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
+    "b200fit_resid_stats": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
 }
 
 
@@ -73,7 +75,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.b200fit_abi_version() != 1:
+    if lib.b200fit_abi_version() != ABI_VERSION:
         raise B200FitError("ABI version mismatch")
     _lib = lib
     return lib

@@ -217,7 +217,8 @@ __global__ void __launch_bounds__(FIT_WARPS * 32, 4)
     fit_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
                const double* __restrict__ guesses, const double* __restrict__ err_in, double* __restrict__ params,
                double* __restrict__ perr, double* __restrict__ chi2, double* __restrict__ err_used,
-               int* __restrict__ status, unsigned* __restrict__ counts, unsigned long long* __restrict__ queue) {
+               int* __restrict__ status, unsigned* __restrict__ counts, unsigned long long* __restrict__ queue,
+               const long long* __restrict__ row_index) {
     constexpr int P = 4 * NC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -233,7 +234,8 @@ __global__ void __launch_bounds__(FIT_WARPS * 32, 4)
         if (pix >= (unsigned long long)pr.npix) break;
 
         // ---- stage the spectrum: coalesced, vectorised, streaming (read once)
-        const float4* src = reinterpret_cast<const float4*>(spectra + pix * stride);
+        const unsigned long long row = row_index ? (unsigned long long)row_index[pix] : pix;
+        const float4* src = reinterpret_cast<const float4*>(spectra + row * stride);
         for (int i = lane; i < (int)(stride >> 2); i += 32) reinterpret_cast<float4*>(spec)[i] = __ldcs(src + i);
         __syncwarp();
 
@@ -420,86 +422,113 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
     }
 }
 
-// Union mask (model1 > 0) | (model2 > 0) as 64 x 32-bit words held one per lane pair; returns via smem bits.
-// mask_bits[w] bit b <-> channel 32*w + b
-__device__ __forceinline__ void union_mask_bits(const DeviceProblem& pr, const AuxShared& sh, bool v1, bool v2,
-                                                int model_f32, int lane, unsigned* bits /*smem [64]*/,
-                                                float* m1s, float* m2s /* optional smem model rows or null */) {
-    const int nwords = (pr.nchan + 31) >> 5;
-    for (int wd = 0; wd < nwords; ++wd) {
-        const int i = (wd << 5) + lane;
-        bool on = false;
-        double m1 = 0.0, m2 = 0.0;
-        if (i < pr.nchan) {
-            if (v1) m1 = model_f64(pr, &sh.comps[0], 1, i);
-            if (v2) m2 = model_f64(pr, &sh.comps[1], 2, i);
-            if (model_f32) {   // model cube stored in the data cube's dtype (pyspeckit full_like)
-                m1 = (double)(float)m1;
-                m2 = (double)(float)m2;
-            }
-            on = (m1 > 0.0) || (m2 > 0.0);
-        }
-        const unsigned b = __ballot_sync(FULL, on);
-        if (lane == 0) bits[wd] = b;
-        if (m1s && i < pr.nchan) {
-            m1s[i] = (float)m1;
-            m2s[i] = (float)m2;
-        }
-    }
+// ---------------------------------------------------------------------------------------------------------
+// Spectral masks are bit sets: bits[w] bit b <-> channel 32*w + b, at most 64 words (B200FIT_MAX_NCHAN = 2048).
+constexpr int MASK_WORDS = B200FIT_MAX_NCHAN / 32;
+
+// Dilation along the spectral axis: True at k spreads to [k - e/2, k + (e-1)/2] (scipy binary_dilation with
+// ones(e), origin 0 -- UltraCube.expand_mask :1658-1698; e = 20: [k-10, k+9]).  Word-parallel, e <= 64.
+__device__ __forceinline__ unsigned dilate_word(const unsigned* bits, int nwords, int w, int expand) {
+    const unsigned cur = bits[w];
+    if (expand <= 1) return cur;
+    const int up = (expand - 1) / 2, dn = expand / 2;
+    const unsigned prev = (w > 0) ? bits[w - 1] : 0u, next = (w + 1 < nwords) ? bits[w + 1] : 0u;
+    const unsigned long long lo = ((unsigned long long)cur << 32) | prev;    // left shifts pull bits out of prev
+    const unsigned long long hi = ((unsigned long long)next << 32) | cur;    // right shifts pull bits out of next
+    unsigned out = cur;
+    for (int s = 1; s <= up; ++s) out |= (unsigned)((lo << s) >> 32);
+    for (int s = 1; s <= dn; ++s) out |= (unsigned)(hi >> s);
+    return out;
+}
+
+// In-place dilation of a warp's bit set (smem), clipped to [0, nchan).  Warp-collective.
+__device__ __forceinline__ void dilate_bits(unsigned* bits, int nchan, int expand, int lane) {
+    const int nwords = (nchan + 31) >> 5;
+    unsigned d0 = 0, d1 = 0;
+    if (lane < nwords) d0 = dilate_word(bits, nwords, lane, expand);
+    if (lane + 32 < nwords) d1 = dilate_word(bits, nwords, lane + 32, expand);
+    __syncwarp();
+    const int tail = nchan & 31;
+    if (lane < nwords) bits[lane] = (lane == nwords - 1 && tail) ? (d0 & ((1u << tail) - 1u)) : d0;
+    if (lane + 32 < nwords) bits[lane + 32] = (lane + 32 == nwords - 1 && tail) ? (d1 & ((1u << tail) - 1u)) : d1;
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(AUX_WARPS * 32)
-    mask_count_kernel(const DeviceProblem pr, const double* __restrict__ params1, const double* __restrict__ params2,
-                      int model_f32, int* __restrict__ counts, long long one_pix, unsigned char* __restrict__ mask_out) {
-    __shared__ AuxShared sh[AUX_WARPS];
-    __shared__ unsigned bits[AUX_WARPS][64];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    long long first = (long long)blockIdx.x * AUX_WARPS + warp, step = (long long)gridDim.x * AUX_WARPS, last = pr.npix;
-    if (one_pix >= 0) {
-        first = one_pix + ((blockIdx.x == 0 && warp == 0) ? 0 : pr.npix);
-        last = one_pix + 1;
+__device__ __forceinline__ void setup_pixel_models(const DeviceProblem& pr, AuxShared& sh, const double* p1,
+                                                   const double* p2, bool v1, bool v2, int lane) {
+    if (v1 && lane == 0) comp_setup_f64(pr, p1, sh.comps[0]);
+    if (v2 && lane >= 1 && lane <= 2) comp_setup_f64(pr, p2 + 4 * (lane - 1), sh.comps[lane]);
+    __syncwarp();
+}
+
+// Un-dilated union mask (model1 > 0) | (model2 > 0) of ONE pixel, written as a bit set: the spectral mask the
+// include_nosamp rule copies into pixels without samples (UltraCube.py:1423-1438).
+__global__ void __launch_bounds__(32)
+    mask_bits_kernel(const DeviceProblem pr, const double* __restrict__ params1, const double* __restrict__ params2,
+                     int model_f32, const long long* __restrict__ best /* {count, pix} or null */, long long pix_arg,
+                     unsigned* __restrict__ bits_out) {
+    __shared__ AuxShared sh;
+    const int lane = threadIdx.x;
+    long long pix = pix_arg;
+    if (best) pix = (best[0] > 0) ? best[1] : -1;   // nothing has a sample anywhere: the fill mask is empty
+    const int nwords = (pr.nchan + 31) >> 5;
+    if (pix < 0 || pix >= pr.npix) {
+        for (int wd = lane; wd < MASK_WORDS; wd += 32) bits_out[wd] = 0u;
+        return;
     }
-    for (long long pix = first; pix < last; pix += step) {
-        const bool v1 = params1 && params_valid(params1 + pix * 4, 4);
-        const bool v2 = params2 && params_valid(params2 + pix * 8, 8);
-        if (v1 && lane == 0) comp_setup_f64(pr, params1 + pix * 4, sh[warp].comps[0]);
-        if (v2 && lane >= 1 && lane <= 2) comp_setup_f64(pr, params2 + pix * 8 + 4 * (lane - 1), sh[warp].comps[lane]);
-        __syncwarp();
-        union_mask_bits(pr, sh[warp], v1, v2, model_f32, lane, bits[warp], nullptr, nullptr);
-        const int nwords = (pr.nchan + 31) >> 5;
-        int cnt = 0;
-        for (int wd = lane; wd < nwords; wd += 32) cnt += __popc(bits[warp][wd]);
-        cnt = warp_sum_i(cnt);
-        if (counts && lane == 0) counts[pix] = cnt;
-        if (mask_out)
-            for (int i = lane; i < pr.nchan; i += 32) mask_out[i] = (bits[warp][i >> 5] >> (i & 31)) & 1u;
-        __syncwarp();
+    const bool v1 = params1 && params_valid(params1 + pix * 4, 4);
+    const bool v2 = params2 && params_valid(params2 + pix * 8, 8);
+    setup_pixel_models(pr, sh, params1 + pix * 4, params2 + pix * 8, v1, v2, lane);
+    for (int wd = 0; wd < MASK_WORDS; ++wd) {
+        const int i = (wd << 5) + lane;
+        bool on = false;
+        if (wd < nwords && i < pr.nchan) {
+            double m1 = v1 ? model_f64(pr, &sh.comps[0], 1, i) : 0.0;
+            double m2 = v2 ? model_f64(pr, &sh.comps[1], 2, i) : 0.0;
+            on = model_f32 ? (((float)m1 > 0.f) || ((float)m2 > 0.f)) : ((m1 > 0.0) || (m2 > 0.0));
+        }
+        const unsigned b = __ballot_sync(FULL, on);
+        if (lane == 0) bits_out[wd] = b;
     }
 }
 
-// dilate along the spectral axis: True at k spreads to [k - e/2, k + (e-1)/2]   (scipy binary_dilation with
-// ones(e), origin 0 -- UltraCube.expand_mask :1658-1698; for e = 20: [k-10, k+9])
-__device__ __forceinline__ bool dilated(const unsigned* bits, int nchan, int i, int expand) {
-    if (expand <= 0) return (bits[i >> 5] >> (i & 31)) & 1u;
-    int lo = i - (expand - 1) / 2, hi = i + expand / 2;   // sources k with k - e/2 <= i <= k + (e-1)/2
-    lo = lo < 0 ? 0 : lo;
-    hi = hi >= nchan ? nchan - 1 : hi;
-    for (int k = lo; k <= hi; ++k)
-        if ((bits[k >> 5] >> (k & 31)) & 1u) return true;
-    return false;
+// First (lowest index) pixel with the largest mask count: key = count << 40 | (2^40 - 1 - index), atomicMax.
+__global__ void __launch_bounds__(256)
+    mask_argmax_kernel(const int* __restrict__ counts, long long npix, long long index_offset,
+                       unsigned long long* __restrict__ key_out) {
+    unsigned long long best = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k =
+            ((unsigned long long)(unsigned)counts[i] << 40) | (0xFFFFFFFFFFull - (unsigned long long)(i + index_offset));
+        best = k > best ? k : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(FULL, best, o);
+        best = other > best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(key_out, best);
+}
+__global__ void mask_argmax_finish_kernel(const unsigned long long* __restrict__ key, long long* __restrict__ best) {
+    best[0] = (long long)(key[0] >> 40);
+    best[1] = (long long)(0xFFFFFFFFFFull - (key[0] & 0xFFFFFFFFFFull));
 }
 
 // get_all_lnk_maps + the get_best_2c_parcube selection, one warp per pixel.
+//   pass 1 (only_empty = 0): every pixel; pixels whose own mask is empty use fill_bits when given, else they get
+//                            NaN statistics; mask_counts[pix] (if given) receives the un-dilated mask size.
+//   pass 2 (only_empty = 1): only the pixels with mask_counts[pix] == 0, with fill_bits (the global include_nosamp
+//                            mask, known only after pass 1 has seen every pixel of every rank).
 __global__ void __launch_bounds__(AUX_WARPS * 32)
     aicc_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
-                const double* __restrict__ params1, const double* __restrict__ params2,
-                const unsigned* __restrict__ fill_bits, int expand, int model_f32, double thr10, double thr20,
-                double thr21, double* __restrict__ rss_out, double* __restrict__ nsamp_out, double* __restrict__ lnk_out,
-                signed char* __restrict__ ncomp_out) {
+                const long long* __restrict__ row_index, const double* __restrict__ params1,
+                const double* __restrict__ params2, const unsigned* __restrict__ fill_bits, int only_empty, int expand,
+                int model_f32, double thr10, double thr20, double thr21, double* __restrict__ rss_out,
+                double* __restrict__ nsamp_out, double* __restrict__ lnk_out, signed char* __restrict__ ncomp_out,
+                int* __restrict__ mask_counts) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ AuxShared sh[AUX_WARPS];
-    __shared__ unsigned bits[AUX_WARPS][64];
+    __shared__ unsigned bits[AUX_WARPS][MASK_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* m1s = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 2 * stride;
     float* m2s = m1s + stride;
@@ -508,11 +537,10 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
     const int nwords = (pr.nchan + 31) >> 5;
     for (long long pix = (long long)blockIdx.x * AUX_WARPS + warp; pix < pr.npix;
          pix += (long long)gridDim.x * AUX_WARPS) {
+        if (only_empty && mask_counts[pix] != 0) continue;
         const bool v1 = params_valid(params1 + pix * 4, 4);
         const bool v2 = params_valid(params2 + pix * 8, 8);
-        if (v1 && lane == 0) comp_setup_f64(pr, params1 + pix * 4, sh[warp].comps[0]);
-        if (v2 && lane >= 1 && lane <= 2) comp_setup_f64(pr, params2 + pix * 8 + 4 * (lane - 1), sh[warp].comps[lane]);
-        __syncwarp();
+        setup_pixel_models(pr, sh[warp], params1 + pix * 4, params2 + pix * 8, v1, v2, lane);
         // models (kept in smem) + union mask
         for (int wd = 0; wd < nwords; ++wd) {
             const int i = (wd << 5) + lane;
@@ -537,30 +565,35 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
         int cnt = 0;
         for (int wd = lane; wd < nwords; wd += 32) cnt += __popc(bits[warp][wd]);
         cnt = warp_sum_i(cnt);
+        if (!only_empty && mask_counts && lane == 0) mask_counts[pix] = cnt;
         bool have_mask = cnt > 0;
         if (!have_mask && fill_bits) {   // include_nosamp: borrow the spectral mask of the max-N pixel
             for (int wd = lane; wd < nwords; wd += 32) bits[warp][wd] = fill_bits[wd];
             have_mask = true;
         }
         __syncwarp();
+        if (have_mask) dilate_bits(bits[warp], pr.nchan, expand, lane);
         // rss over the dilated mask.  residual = data - model in the cube's dtype (fp32) when model_f32,
         // squared and summed in fp64 (numpy: (residual * mask.astype(float)) ** 2 -> float64).
         double r0 = 0.0, r1 = 0.0, r2 = 0.0;
         int ns = 0;
-        const float* y = spectra + pix * stride;
+        const long long row = row_index ? row_index[pix] : pix;
+        const float* y = spectra + row * stride;
         if (have_mask) {
-            for (int i = lane; i < pr.nchan; i += 32) {
-                if (!dilated(bits[warp], pr.nchan, i, expand)) continue;
+            for (int wd = 0; wd < nwords; ++wd) {
+                const unsigned bw = bits[warp][wd];
+                if (!bw) continue;
+                if (!((bw >> lane) & 1u)) continue;
+                const int i = (wd << 5) + lane;
                 ns += 1;
                 const float d = y[i];
                 if (!(d == d)) continue;   // nansum skips NaN data, but the channel still counts in N
-                double e0, e1, e2;
+                double e1, e2;
+                const double e0 = (double)d;
                 if (model_f32) {
-                    e0 = (double)d;
                     e1 = (double)(d - m1s[i]);
                     e2 = (double)(d - m2s[i]);
                 } else {
-                    e0 = (double)d;
                     e1 = (double)d - m1d[i];
                     e2 = (double)d - m2d[i];
                 }
@@ -575,8 +608,8 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
         ns = warp_sum_i(ns);
         if (lane == 0) {
             // get_rss: rss == 0 -> NaN, N = NaN where rss NaN; method: N < 1 -> NaN, rss <= 0 -> NaN
-            double N = (double)ns;
-            double rs[3] = {r0, r1, r2}, Nn[3], aic[3];
+            const double N = (double)ns;
+            double rs[3] = {r0, r1, r2}, aic[3];
             for (int k = 0; k < 3; ++k) {
                 double rr = rs[k];
                 double nn = N;
@@ -590,13 +623,12 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
                 }
                 if (rr <= 0.0) rr = NAN;
                 rs[k] = rr;
-                Nn[k] = nn;
                 const double p = 4.0 * k;
                 // aic.AIC / AICc (aic.py:136-181)
                 aic[k] = nn * log(rr / nn) + 2.0 * p + (2.0 * p * (p + 1.0)) / (nn - p - 1.0);
                 rss_out[pix * 3 + k] = rr;
             }
-            nsamp_out[pix] = Nn[2];
+            nsamp_out[pix] = (N < 1.0) ? NAN : N;   // per-model NaNs follow from rss_out
             double l10 = -1.0 * (aic[1] - aic[0]) / 2.0;
             double l20 = -1.0 * (aic[2] - aic[0]) / 2.0;
             double l21 = -1.0 * (aic[2] - aic[1]) / 2.0;
@@ -612,6 +644,123 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
             lnk_out[pix * 3 + 1] = l20;
             lnk_out[pix * 3 + 2] = l21;
             ncomp_out[pix] = nc;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// get_rms + reduced get_chisq of one fitted model (UltraCube.py:1701-1740, :1478-1565), one warp per pixel:
+//   r = data - model;  rms = 1.4826 * nanmedian(|r - roll(r, 2)|) / sqrt(2);
+//   chisq_red = nansum((r * mask)^2) / sum(mask) / rms^2,  mask = dilate(model > 0, expand)
+// The median is taken with a warp-wide bitonic sort of |diff| in shared memory.
+__global__ void __launch_bounds__(AUX_WARPS * 32)
+    resid_stats_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
+                       const long long* __restrict__ row_index, const double* __restrict__ params, int expand,
+                       int model_f32, int npow2, double* __restrict__ rms_out, double* __restrict__ chisq_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ AuxShared sh[AUX_WARPS];
+    __shared__ unsigned bits[AUX_WARPS][MASK_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* res = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * npow2;   // residuals
+    double* key = res + npow2;                                                      // |diff| to sort
+    const int nchan = pr.nchan, nwords = (nchan + 31) >> 5;
+    const int P = 4 * pr.ncomp;
+    for (long long pix = (long long)blockIdx.x * AUX_WARPS + warp; pix < pr.npix;
+         pix += (long long)gridDim.x * AUX_WARPS) {
+        const double* p = params + pix * P;
+        const bool valid = params_valid(p, P);
+        if (!valid) {   // no model: residual NaN everywhere
+            if (lane == 0) {
+                rms_out[pix] = NAN;
+                chisq_out[pix] = NAN;
+            }
+            continue;
+        }
+        if (lane < pr.ncomp) comp_setup_f64(pr, p + 4 * lane, sh[warp].comps[lane]);
+        __syncwarp();
+        const long long row = row_index ? row_index[pix] : pix;
+        const float* y = spectra + row * stride;
+        for (int wd = 0; wd < nwords; ++wd) {
+            const int i = (wd << 5) + lane;
+            bool on = false;
+            if (i < nchan) {
+                const double m = model_f64(pr, sh[warp].comps, pr.ncomp, i);
+                const float d = y[i];
+                if (model_f32) {
+                    const float mf = (float)m;
+                    on = mf > 0.f;
+                    res[i] = (double)(d - mf);
+                } else {
+                    on = m > 0.0;
+                    res[i] = (double)d - m;
+                }
+            }
+            const unsigned b = __ballot_sync(FULL, on);
+            if (lane == 0) bits[warp][wd] = b;
+        }
+        __syncwarp();
+        dilate_bits(bits[warp], nchan, expand, lane);
+        double c2 = 0.0;
+        int ns = 0, nval = 0;
+        for (int i = lane; i < npow2; i += 32) {
+            double k = INFINITY;
+            if (i < nchan) {
+                const double r = res[i];
+                const double rb = res[(i >= 2) ? i - 2 : i - 2 + nchan];
+                double df = model_f32 ? (double)((float)r - (float)rb) : (r - rb);
+                df = fabs(df);
+                if (df == df) {
+                    k = df;
+                    ++nval;
+                }
+                if ((bits[warp][i >> 5] >> (i & 31)) & 1u) {
+                    ++ns;
+                    if (r == r) c2 += r * r;
+                }
+            }
+            key[i] = k;
+        }
+        c2 = warp_sum(c2);
+        ns = warp_sum_i(ns);
+        nval = warp_sum_i(nval);
+        __syncwarp();
+        for (int k = 2; k <= npow2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < (npow2 >> 1); t += 32) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+                    const int l = i | j;
+                    const bool up = ((i & k) == 0);
+                    const double a = key[i], b = key[l];
+                    if ((a > b) == up) {
+                        key[i] = b;
+                        key[l] = a;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            double med = NAN;
+            if (nval > 0) {
+                if (nval & 1)
+                    med = key[nval >> 1];
+                else
+                    med = model_f32 ? (double)(((float)key[(nval >> 1) - 1] + (float)key[nval >> 1]) * 0.5f)
+                                    : 0.5 * (key[(nval >> 1) - 1] + key[nval >> 1]);
+            }
+            double rms, rms2;
+            if (model_f32) {   // numpy keeps float32: 1.4826 * med / 2**0.5, then rms**2, all in float32
+                const float rf = (1.4826f * (float)med) / 1.4142135623730951f;
+                rms = (double)rf;
+                rms2 = (double)(rf * rf);
+            } else {
+                rms = 1.4826 * med / 1.4142135623730951;
+                rms2 = rms * rms;
+            }
+            rms_out[pix] = rms;
+            const double red = (ns == 0) ? NAN : (double)ns;
+            chisq_out[pix] = (c2 / red) / rms2;
         }
         __syncwarp();
     }
@@ -680,7 +829,7 @@ template <int NC>
 static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_spectra, int64_t stride,
                       const double* d_guesses, const double* d_err, double* d_params, double* d_perr, double* d_chi2,
                       double* d_err_used, int32_t* d_status, uint32_t* d_counts, void* d_workspace,
-                      cudaStream_t stream) {
+                      const int64_t* d_row_index, cudaStream_t stream) {
     const size_t smem = FIT_WARPS * (fit_shared_fixed_bytes<NC>() + (size_t)stride * sizeof(float));
     CK(cudaFuncSetAttribute(fit_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -692,7 +841,7 @@ static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_
     CK(cudaMemsetAsync(d_workspace, 0, sizeof(unsigned long long), stream));
     fit_kernel<NC><<<(unsigned)blocks, FIT_WARPS * 32, smem, stream>>>(
         pr, d_spectra, (long long)stride, d_guesses, d_err, d_params, d_perr, d_chi2, d_err_used, d_status, d_counts,
-        (unsigned long long*)d_workspace);
+        (unsigned long long*)d_workspace, (const long long*)d_row_index);
     CK(cudaGetLastError());
     return B200FIT_OK;
 }
@@ -746,7 +895,7 @@ int b200fit_gather_spectra(b200fit_ctx* ctx, const float* d_cube, int32_t nchan,
 }
 
 int b200fit_fit(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_spectra, int64_t nchan_stride,
-                const double* d_guesses, const double* d_err, double* d_params, double* d_perr, double* d_chi2,
+                const int64_t* d_row_index, const double* d_guesses, const double* d_err, double* d_params, double* d_perr, double* d_chi2,
                 double* d_err_used, int32_t* d_status, uint32_t* d_counts, void* d_workspace, void* stream) {
     if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "fit: null context/problem");
     DeviceProblem pr;
@@ -760,9 +909,9 @@ int b200fit_fit(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_sp
     CK(cudaSetDevice(ctx->device));
     if (pr.ncomp == 1)
         return launch_fit<1>(ctx, pr, d_spectra, nchan_stride, d_guesses, d_err, d_params, d_perr, d_chi2, d_err_used,
-                             d_status, d_counts, d_workspace, (cudaStream_t)stream);
+                             d_status, d_counts, d_workspace, d_row_index, (cudaStream_t)stream);
     return launch_fit<2>(ctx, pr, d_spectra, nchan_stride, d_guesses, d_err, d_params, d_perr, d_chi2, d_err_used,
-                         d_status, d_counts, d_workspace, (cudaStream_t)stream);
+                         d_status, d_counts, d_workspace, d_row_index, (cudaStream_t)stream);
 }
 
 static long long aux_blocks(const b200fit_ctx* ctx, long long npix) {
@@ -786,46 +935,44 @@ int b200fit_model(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d
     return B200FIT_OK;
 }
 
-int b200fit_mask_counts(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d_params1,
-                        const double* d_params2, int32_t model_f32, int32_t* d_counts, void* stream) {
-    if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "mask_counts: null context/problem");
-    DeviceProblem pr;
-    const int rc = make_device_problem(*prob, pr);
-    if (rc) return fail(ctx, rc, "mask_counts: invalid problem description");
-    if (pr.npix == 0) return B200FIT_OK;
-    if (!d_counts || (!d_params1 && !d_params2)) return fail(ctx, B200FIT_E_ARG, "mask_counts: bad argument");
+int b200fit_mask_argmax(b200fit_ctx* ctx, const int32_t* d_mask_counts, int64_t npix, int64_t index_offset,
+                        int64_t* d_best, void* d_workspace, void* stream) {
+    if (!ctx || !d_mask_counts || !d_best || !d_workspace || npix < 0)
+        return fail(ctx, B200FIT_E_ARG, "mask_argmax: bad argument");
     CK(cudaSetDevice(ctx->device));
-    mask_count_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        pr, d_params1, d_params2, model_f32, d_counts, -1, nullptr);
+    unsigned long long* key = (unsigned long long*)d_workspace + 8;   // slot 0 is the fit work queue
+    CK(cudaMemsetAsync(key, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    if (npix > 0) {
+        long long blocks = (npix + 255) / 256;
+        if (blocks > (long long)ctx->num_sms * 8) blocks = (long long)ctx->num_sms * 8;
+        mask_argmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_mask_counts, npix, index_offset, key);
+        CK(cudaGetLastError());
+    }
+    mask_argmax_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(key, (long long*)d_best);
     CK(cudaGetLastError());
     return B200FIT_OK;
 }
 
-int b200fit_mask_of_pixel(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d_params1,
-                          const double* d_params2, int32_t model_f32, int64_t pix, unsigned char* h_mask_out,
-                          void* stream) {
-    if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "mask_of_pixel: null context/problem");
+int b200fit_mask_bits(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d_params1,
+                      const double* d_params2, int32_t model_f32, const int64_t* d_best, int64_t pix,
+                      uint32_t* d_bits, void* stream) {
+    if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "mask_bits: null context/problem");
     DeviceProblem pr;
     const int rc = make_device_problem(*prob, pr);
-    if (rc) return fail(ctx, rc, "mask_of_pixel: invalid problem description");
-    if (!h_mask_out || pix < 0 || pix >= pr.npix) return fail(ctx, B200FIT_E_ARG, "mask_of_pixel: bad argument");
+    if (rc) return fail(ctx, rc, "mask_bits: invalid problem description");
+    if (!d_bits || (!d_params1 && !d_params2)) return fail(ctx, B200FIT_E_ARG, "mask_bits: bad argument");
     CK(cudaSetDevice(ctx->device));
-    unsigned char* d_mask = nullptr;
-    CK(cudaMalloc(&d_mask, pr.nchan));
-    mask_count_kernel<<<1, AUX_WARPS * 32, 0, (cudaStream_t)stream>>>(pr, d_params1, d_params2, model_f32, nullptr,
-                                                                     pix, d_mask);
-    cudaError_t ce = cudaGetLastError();
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_mask_out, d_mask, pr.nchan, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize((cudaStream_t)stream);
-    cudaFree(d_mask);
-    if (ce != cudaSuccess) return fail(ctx, B200FIT_E_CUDA, "mask_of_pixel", ce);
+    mask_bits_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pr, d_params1, d_params2, model_f32, (const long long*)d_best,
+                                                        pix, d_bits);
+    CK(cudaGetLastError());
     return B200FIT_OK;
 }
 
 int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_spectra, int64_t nchan_stride,
-                 const double* d_params1, const double* d_params2, const unsigned char* h_fill_mask, int32_t expand,
-                 int32_t model_f32, const double* thr, double* d_rss, double* d_nsamp, double* d_lnk,
-                 signed char* d_ncomp, void* stream) {
+                 const int64_t* d_row_index, const double* d_params1, const double* d_params2,
+                 const uint32_t* d_fill_bits, int32_t only_empty, int32_t expand, int32_t model_f32, const double* thr,
+                 double* d_rss, double* d_nsamp, double* d_lnk, signed char* d_ncomp, int32_t* d_mask_counts,
+                 void* stream) {
     if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "aicc: null context/problem");
     DeviceProblem pr;
     const int rc = make_device_problem(*prob, pr);
@@ -833,44 +980,41 @@ int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_s
     if (pr.npix == 0) return B200FIT_OK;
     if (!d_spectra || !d_params1 || !d_params2 || !d_rss || !d_nsamp || !d_lnk || !d_ncomp || nchan_stride < pr.nchan)
         return fail(ctx, B200FIT_E_ARG, "aicc: bad argument");
+    if (expand < 0 || expand > 64) return fail(ctx, B200FIT_E_ARG, "aicc: expand must be in [0, 64]");
+    if (only_empty && (!d_mask_counts || !d_fill_bits))
+        return fail(ctx, B200FIT_E_ARG, "aicc: pass 2 needs the mask counts of pass 1 and the fill mask");
     CK(cudaSetDevice(ctx->device));
-    unsigned* d_fill = nullptr;
-    if (h_fill_mask) {
-        unsigned words[64];
-        std::memset(words, 0, sizeof(words));
-        for (int i = 0; i < pr.nchan; ++i)
-            if (h_fill_mask[i]) words[i >> 5] |= 1u << (i & 31);
-        CK(cudaMalloc(&d_fill, sizeof(words)));
-        cudaError_t ce = cudaMemcpyAsync(d_fill, words, sizeof(words), cudaMemcpyHostToDevice, (cudaStream_t)stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize((cudaStream_t)stream);   // `words` is a stack buffer
-        if (ce != cudaSuccess) {
-            cudaFree(d_fill);
-            return fail(ctx, B200FIT_E_CUDA, "aicc: fill mask upload", ce);
-        }
-    }
     const double t10 = thr ? thr[0] : 5.0, t20 = thr ? thr[1] : 5.0, t21 = thr ? thr[2] : 5.0;
     const size_t smem = (size_t)AUX_WARPS * 2 * nchan_stride * (model_f32 ? sizeof(float) : sizeof(double));
-    cudaError_t ce = cudaFuncSetAttribute(aicc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce == cudaSuccess) {
-        aicc_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, smem, (cudaStream_t)stream>>>(
-            pr, d_spectra, nchan_stride, d_params1, d_params2, d_fill, expand, model_f32, t10, t20, t21, d_rss, d_nsamp,
-            d_lnk, d_ncomp);
-        ce = cudaGetLastError();
-    }
-    if (d_fill) {
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize((cudaStream_t)stream);
-        cudaFree(d_fill);
-    }
-    if (ce != cudaSuccess) return fail(ctx, B200FIT_E_CUDA, "aicc launch", ce);
+    CK(cudaFuncSetAttribute(aicc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    aicc_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        pr, d_spectra, nchan_stride, (const long long*)d_row_index, d_params1, d_params2, d_fill_bits, only_empty,
+        expand, model_f32, t10, t20, t21, d_rss, d_nsamp, d_lnk, d_ncomp, d_mask_counts);
+    CK(cudaGetLastError());
     return B200FIT_OK;
 }
 
 int b200fit_resid_stats(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_spectra, int64_t nchan_stride,
-                        const double* d_params, int32_t expand, int32_t model_f32, double* d_rms, double* d_chisq_red,
-                        void* stream) {
-    (void)prob; (void)d_spectra; (void)nchan_stride; (void)d_params; (void)expand; (void)model_f32; (void)d_rms;
-    (void)d_chisq_red; (void)stream;
-    return fail(ctx, B200FIT_E_ARG, "resid_stats: not implemented yet");
+                        const int64_t* d_row_index, const double* d_params, int32_t expand, int32_t model_f32,
+                        double* d_rms, double* d_chisq_red, void* stream) {
+    if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "resid_stats: null context/problem");
+    DeviceProblem pr;
+    const int rc = make_device_problem(*prob, pr);
+    if (rc) return fail(ctx, rc, "resid_stats: invalid problem description");
+    if (pr.npix == 0) return B200FIT_OK;
+    if (!d_spectra || !d_params || !d_rms || !d_chisq_red || nchan_stride < pr.nchan)
+        return fail(ctx, B200FIT_E_ARG, "resid_stats: bad argument");
+    if (expand < 0 || expand > 64) return fail(ctx, B200FIT_E_ARG, "resid_stats: expand must be in [0, 64]");
+    CK(cudaSetDevice(ctx->device));
+    int npow2 = 64;
+    while (npow2 < pr.nchan) npow2 <<= 1;
+    const size_t smem = (size_t)AUX_WARPS * 2 * npow2 * sizeof(double);
+    CK(cudaFuncSetAttribute(resid_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    resid_stats_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        pr, d_spectra, nchan_stride, (const long long*)d_row_index, d_params, expand, model_f32, npow2, d_rms,
+        d_chisq_red);
+    CK(cudaGetLastError());
+    return B200FIT_OK;
 }
 
 }  // extern "C"

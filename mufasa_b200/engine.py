@@ -74,20 +74,26 @@ class Engine(object):
         self._check(rc, "b200fit_gather_spectra")
         return out
 
-    def fit(self, prob, spectra, guesses, err=None, want_counts=True):
-        """Batched LM fit.  spectra [npix, stride] fp32, guesses [npix, P] fp64 (device).  Returns a dict of
-        device tensors: params, perr [npix, P]; chi2, err_used [npix]; status [npix] int32; counts [npix, 4]."""
+    def fit(self, prob, spectra, guesses, err=None, want_counts=True, row_index=None, out=None):
+        """Batched LM fit.  spectra [nrows, stride] fp32, guesses [npix, P] fp64 (device); ``row_index`` [npix] int64
+        maps pixel k to its spectrum row (None: row k).  Returns a dict of device tensors: params, perr [npix, P];
+        chi2, err_used [npix]; status [npix] int32; counts [npix, 4]."""
         npix, P = int(prob.npix), 4 * int(prob.ncomp)
-        assert spectra.dtype == torch.float32 and spectra.is_contiguous() and spectra.shape[0] == npix
+        assert spectra.dtype == torch.float32 and spectra.is_contiguous()
+        assert row_index is not None or spectra.shape[0] == npix
         assert guesses.dtype == torch.float64 and guesses.is_contiguous() and tuple(guesses.shape) == (npix, P)
+        if row_index is not None:
+            assert row_index.dtype == torch.int64 and row_index.is_contiguous() and row_index.numel() == npix
         dev = self.device
-        out = dict(params=torch.empty((npix, P), dtype=torch.float64, device=dev),
-                   perr=torch.empty((npix, P), dtype=torch.float64, device=dev),
-                   chi2=torch.empty(npix, dtype=torch.float64, device=dev),
-                   err_used=torch.empty(npix, dtype=torch.float64, device=dev),
-                   status=torch.empty(npix, dtype=torch.int32, device=dev),
-                   counts=torch.empty((npix, 4), dtype=torch.int32, device=dev) if want_counts else None)
-        rc = self.lib.b200fit_fit(self.ctx, C.byref(prob), _ptr(spectra), spectra.shape[1], _ptr(guesses), _ptr(err),
+        if out is None:
+            out = dict(params=torch.empty((npix, P), dtype=torch.float64, device=dev),
+                       perr=torch.empty((npix, P), dtype=torch.float64, device=dev),
+                       chi2=torch.empty(npix, dtype=torch.float64, device=dev),
+                       err_used=torch.empty(npix, dtype=torch.float64, device=dev),
+                       status=torch.empty(npix, dtype=torch.int32, device=dev),
+                       counts=torch.empty((npix, 4), dtype=torch.int32, device=dev) if want_counts else None)
+        rc = self.lib.b200fit_fit(self.ctx, C.byref(prob), _ptr(spectra), spectra.shape[1], _ptr(row_index),
+                                  _ptr(guesses), _ptr(err),
                                   _ptr(out["params"]), _ptr(out["perr"]), _ptr(out["chi2"]), _ptr(out["err_used"]),
                                   _ptr(out["status"]), _ptr(out["counts"]), _ptr(self._ws), self._stream())
         self._check(rc, "b200fit_fit")
@@ -102,38 +108,65 @@ class Engine(object):
         self._check(rc, "b200fit_model")
         return out
 
-    def mask_counts(self, prob, params1, params2, model_f32=True):
-        out = torch.empty(int(prob.npix), dtype=torch.int32, device=self.device)
-        rc = self.lib.b200fit_mask_counts(self.ctx, C.byref(prob), _ptr(params1), _ptr(params2),
-                                          1 if model_f32 else 0, _ptr(out), self._stream())
-        self._check(rc, "b200fit_mask_counts")
+    # -- model selection ---------------------------------------------------------------------------------------
+    def aicc_alloc(self, npix):
+        dev = self.device
+        return dict(rss=torch.empty((npix, 3), dtype=torch.float64, device=dev),
+                    nsamp=torch.empty(npix, dtype=torch.float64, device=dev),
+                    lnk=torch.empty((npix, 3), dtype=torch.float64, device=dev),
+                    ncomp=torch.empty(npix, dtype=torch.int8, device=dev),
+                    mask_counts=torch.empty(npix, dtype=torch.int32, device=dev))
+
+    def aicc_pass(self, prob, spectra, params1, params2, out, fill_bits=None, only_empty=False, expand=20,
+                  model_f32=True, thr=(5.0, 5.0, 5.0), row_index=None):
+        thr_arr = (C.c_double * 3)(*[float(t) for t in thr])
+        rc = self.lib.b200fit_aicc(self.ctx, C.byref(prob), _ptr(spectra), spectra.shape[1], _ptr(row_index),
+                                   _ptr(params1), _ptr(params2), _ptr(fill_bits), 1 if only_empty else 0, int(expand),
+                                   1 if model_f32 else 0, C.cast(thr_arr, C.c_void_p), _ptr(out["rss"]),
+                                   _ptr(out["nsamp"]), _ptr(out["lnk"]), _ptr(out["ncomp"]), _ptr(out["mask_counts"]),
+                                   self._stream())
+        self._check(rc, "b200fit_aicc")
         return out
 
-    def mask_of_pixel(self, prob, params1, params2, pix, model_f32=True):
-        out = np.zeros(int(prob.nchan), dtype=np.uint8)
-        rc = self.lib.b200fit_mask_of_pixel(self.ctx, C.byref(prob), _ptr(params1), _ptr(params2),
-                                            1 if model_f32 else 0, int(pix), out.ctypes.data_as(C.c_void_p),
-                                            self._stream())
-        self._check(rc, "b200fit_mask_of_pixel")
-        return out.astype(bool)
+    def mask_argmax(self, mask_counts, index_offset=0):
+        """device int64[2] = {largest mask count, index_offset + first pixel holding it}."""
+        best = torch.empty(2, dtype=torch.int64, device=self.device)
+        rc = self.lib.b200fit_mask_argmax(self.ctx, _ptr(mask_counts), int(mask_counts.numel()), int(index_offset),
+                                          _ptr(best), _ptr(self._ws), self._stream())
+        self._check(rc, "b200fit_mask_argmax")
+        return best
 
-    def aicc(self, prob, spectra, params1, params2, fill_mask=None, expand=20, model_f32=True, thr=(5.0, 5.0, 5.0)):
-        """lnk10/lnk20/lnk21, rss, N and the integer ncomp map for every pixel."""
+    def mask_bits(self, prob, params1, params2, best=None, pix=-1, model_f32=True):
+        """device uint32[64] bit set of the un-dilated union model mask of one pixel."""
+        bits = torch.empty(64, dtype=torch.int32, device=self.device)
+        rc = self.lib.b200fit_mask_bits(self.ctx, C.byref(prob), _ptr(params1), _ptr(params2), 1 if model_f32 else 0,
+                                        _ptr(best), int(pix), _ptr(bits), self._stream())
+        self._check(rc, "b200fit_mask_bits")
+        return bits
+
+    def aicc_global(self, prob, spectra, params1, params2, expand=20, model_f32=True, thr=(5.0, 5.0, 5.0),
+                    row_index=None):
+        """lnk10/lnk20/lnk21, rss, N and the integer ncomp map of every pixel of ONE device's pixel set, with the
+        include_nosamp rule applied over that set (single-GPU composition; dist.py composes it across ranks).
+        No host synchronisation between the passes."""
+        out = self.aicc_alloc(int(prob.npix))
+        self.aicc_pass(prob, spectra, params1, params2, out, expand=expand, model_f32=model_f32, thr=thr,
+                       row_index=row_index)
+        best = self.mask_argmax(out["mask_counts"])
+        bits = self.mask_bits(prob, params1, params2, best=best, model_f32=model_f32)
+        self.aicc_pass(prob, spectra, params1, params2, out, fill_bits=bits, only_empty=True, expand=expand,
+                       model_f32=model_f32, thr=thr, row_index=row_index)
+        out["fill_bits"] = bits
+        return out
+
+    def resid_stats(self, prob, spectra, params, expand=20, model_f32=True, row_index=None):
         npix = int(prob.npix)
-        dev = self.device
-        out = dict(rss=torch.empty((npix, 3), dtype=torch.float64, device=dev),
-                   nsamp=torch.empty(npix, dtype=torch.float64, device=dev),
-                   lnk=torch.empty((npix, 3), dtype=torch.float64, device=dev),
-                   ncomp=torch.empty(npix, dtype=torch.int8, device=dev))
-        fm = None
-        if fill_mask is not None:
-            fm = np.ascontiguousarray(fill_mask, dtype=np.uint8)
-        thr_arr = (C.c_double * 3)(*[float(t) for t in thr])
-        rc = self.lib.b200fit_aicc(self.ctx, C.byref(prob), _ptr(spectra), spectra.shape[1], _ptr(params1),
-                                   _ptr(params2), fm.ctypes.data_as(C.c_void_p) if fm is not None else None,
-                                   int(expand), 1 if model_f32 else 0, C.cast(thr_arr, C.c_void_p), _ptr(out["rss"]),
-                                   _ptr(out["nsamp"]), _ptr(out["lnk"]), _ptr(out["ncomp"]), self._stream())
-        self._check(rc, "b200fit_aicc")
+        out = dict(rms=torch.empty(npix, dtype=torch.float64, device=self.device),
+                   chisq_red=torch.empty(npix, dtype=torch.float64, device=self.device))
+        rc = self.lib.b200fit_resid_stats(self.ctx, C.byref(prob), _ptr(spectra), spectra.shape[1], _ptr(row_index),
+                                          _ptr(params), int(expand), 1 if model_f32 else 0, _ptr(out["rms"]),
+                                          _ptr(out["chisq_red"]), self._stream())
+        self._check(rc, "b200fit_resid_stats")
         return out
 
 

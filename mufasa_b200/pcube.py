@@ -92,7 +92,7 @@ class PCube(object):
         self.fittype = None
         self.npars = None
         self._device = device
-        self._cube_dev = None
+        self._dev = {}            # device-resident state, shared between PCubes of one data cube
         self.timing = {}
 
     # ---------------------------------------------------------------------------------------------------
@@ -100,26 +100,46 @@ class PCube(object):
     def engine(self):
         return get_engine(self._device)
 
-    def cube_on_device(self):
-        """[nchan, ny*nx] fp32 on the GPU (uploaded once per PCube, from pinned memory)."""
-        if self._cube_dev is None:
+    def rows_on_device(self):
+        """The cube as pixel-major rows [ny*nx, stride] fp32 on the GPU (NaN padded, velocity ascending).
+
+        Uploaded ONCE per data cube -- pinned host memory -> channel-major staging buffer -> ``b200fit_gather_spectra``
+        transpose -- and shared between the PCubes of one UltraCube (``share_device``).  The reference instead
+        re-reads the FITS file for every ncomp (UltraCube.py:191)."""
+        if self._dev.get("rows") is None:
             nchan, ny, nx = self.cube.shape
-            host = np.ascontiguousarray(self.cube, dtype=np.float32).reshape(nchan, ny * nx)
-            t = torch.from_numpy(host)
-            try:
-                t = t.pin_memory()
-            except RuntimeError:
-                pass
-            self._cube_dev = t.to(self.engine.device, non_blocking=True)
-        return self._cube_dev
+            eng = self.engine
+            host = self.cube if self.cube.dtype == np.float32 else self.cube.astype(np.float32)
+            t = torch.from_numpy(np.ascontiguousarray(host).reshape(nchan, ny * nx))
+            staging = t.to(eng.device, non_blocking=True)       # async when the cube lives in pinned memory
+            _, _, flip = self.xarr.v0_dv_flip
+            self._dev["rows"] = eng.gather(staging, None, flip=flip)
+            self._dev["h2d_bytes"] = t.numel() * 4
+            del staging
+        return self._dev["rows"]
+
+    def footprint(self):
+        """[ny, nx] bool: pixels with at least one finite channel (np.any(np.isfinite(cube), axis=0))."""
+        if self._dev.get("footprint") is None:
+            rows = self.rows_on_device()
+            nchan = self.cube.shape[0]
+            fp = torch.isfinite(rows[:, :nchan]).any(dim=1)
+            self._dev["footprint"] = fp.cpu().numpy().reshape(self.cube.shape[1:])
+        return self._dev["footprint"]
+
+    def share_device(self, other):
+        """Use the device-resident rows of another PCube built on the same data cube."""
+        if other.cube is not self.cube and other.cube.shape != self.cube.shape:
+            raise ValueError("cannot share device data between different cubes")
+        self._dev = other._dev
 
     def release_device(self):
-        self._cube_dev = None
+        self._dev.clear()
 
     def copy(self):
         new = PCube(self.cube, self.xarr, header=self.header, unit=self.unit, maskmap=self.maskmap,
                     device=self._device)
-        new._cube_dev = self._cube_dev
+        new._dev = self._dev
         for k in ("parcube", "errcube", "has_fit", "_modelcube", "chi2map", "statusmap", "nevalmap", "errmap_used"):
             v = getattr(self, k)
             setattr(new, k, None if v is None else v.copy())
@@ -186,20 +206,19 @@ class PCube(object):
         self.errmap_used = np.full((ny, nx), np.nan)
         self._modelcube = None
         self.fittype, self.npars = fittype, P
+        self.last_minpars, self.last_maxpars = list(minpars), list(maxpars)
         if npix == 0:
             return
 
         eng = self.engine
         dev = eng.device
-        _, _, flip = self.xarr.v0_dv_flip
         prob = self._problem(fittype, ncomp, npix, list(minpars), list(maxpars), signal_cut=float(signal_cut or 0.0),
                              maxiter=maxiter)
-        cube_dev = self.cube_on_device()
+        rows = self.rows_on_device()
         gsel = np.ascontiguousarray(guesses.reshape(P, ny * nx)[:, pix].T)
         g_dev = torch.from_numpy(gsel).to(dev, non_blocking=True)
         idx_dev = None if npix == ny * nx else torch.from_numpy(pix.astype(np.int64)).to(dev, non_blocking=True)
-        spectra = eng.gather(cube_dev, idx_dev, flip=flip)
-        out = eng.fit(prob, spectra, g_dev)
+        out = eng.fit(prob, rows, g_dev, row_index=idx_dev)
         packed = torch.cat([out["params"], out["perr"], out["chi2"][:, None], out["err_used"][:, None],
                             out["status"].to(torch.float64)[:, None],
                             out["counts"][:, 0].to(torch.float64)[:, None]], dim=1).cpu().numpy()
@@ -212,7 +231,6 @@ class PCube(object):
         flat(self.statusmap)[pix] = st
         flat(self.nevalmap)[pix] = packed[:, 2 * P + 3].astype(np.int32)
         flat(self.has_fit)[pix] = st > 0
-        self._last = dict(prob=prob, pix=pix, spectra=spectra)
         if not self.has_fit.any():
             # pyspeckit: "The first fitted pixel did not yield a fit" -> AssertionError, which cubefit_gen turns
             # into a retry / StartFitError (multi_v_fit.py:388-403)

@@ -71,12 +71,14 @@ def amplitude(cfg, ny, nx, rows=None):
     return 0.05 + 1.0 * t ** 2.2
 
 
-def make_cube(cfg, modelcube_fn, rows=None, shape=None, dtype=np.float32):
+def make_cube(cfg, modelcube_fn, rows=None, shape=None, dtype=np.float32, seed_offset=0, out=None):
     """Build (a row slab of) the synthetic cube of config ``cfg``.
 
     Returns dict(cube[nchan,ry,nx] float32, v[nchan], fittype, dv, truth1, truth2, ncomp_true,
                  guess1[4,ry,nx], guess2[8,ry,nx]).  ``shape=(ny,nx,nchan)`` overrides the config size
-    (reduced-size parity cases keep the config's species / channel width)."""
+    (reduced-size parity cases keep the config's species / channel width).  ``seed_offset`` selects an independent
+    noise realisation (one per rank in weak-scaling runs); ``out`` = preallocated [nchan, ry, nx] buffer for the
+    cube (e.g. a view of pinned memory)."""
     fittype, ny, nx, nchan, dv = CONFIGS[cfg]
     if shape is not None:
         ny, nx, nchan = shape
@@ -88,8 +90,8 @@ def make_cube(cfg, modelcube_fn, rows=None, shape=None, dtype=np.float32):
     m2 = modelcube_fn(np.concatenate([par1, par2]), v, fittype)
     m1 = modelcube_fn(par1, v, fittype)
     model = np.where(nct[None] == 2, m2, np.where(nct[None] == 1, m1, 0.0)) * amp[None]
-    children = np.random.SeedSequence(SEED0 + cfg).spawn(2 * ny)
-    cube = np.empty((nchan, y1 - y0, nx), dtype=dtype)
+    children = np.random.SeedSequence(SEED0 + cfg + 1000 * int(seed_offset)).spawn(2 * ny)
+    cube = out if out is not None else np.empty((nchan, y1 - y0, nx), dtype=dtype)
     g1 = np.empty((4, y1 - y0, nx))
     g2 = np.empty((8, y1 - y0, nx))
     truth = np.concatenate([par1, par2])
