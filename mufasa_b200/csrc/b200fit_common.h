@@ -6,7 +6,11 @@
 //  * per-component coefficient set-up and the per-channel radiative-transfer + analytic Jacobian assembly
 //    (velocity-space restatement of HyperfineModel.py:22-109)
 //  * LMState<P>: the Levenberg-Marquardt state machine (damped normal equations + Cholesky, mpfit-style box
-//    limits: pegged parameters, step clipping/truncation, snapping; zero error for pegged parameters)
+//    limits: pegged parameters, step clipping/truncation, snapping; zero error for pegged parameters).
+//    The solver is written with ROLLED loops over small arrays on purpose: in the fit kernel it runs SIMT (one
+//    lane per in-flight pixel of a warp's pixel group), and the first version of this file -- fully unrolled,
+//    16.5k SASS instructions -- spent 70 % of its stall samples waiting for the instruction cache
+//    (profiles/r1a_fit2c_source_summary.txt).
 //
 // Everything here is plain C++ so the same source is compiled by nvcc into the kernels and by g++ into the
 // test-only host emulation (tests/host_emul).  It is NOT a CPU fallback: libb200fit.so only exposes CUDA paths.
@@ -16,8 +20,12 @@
 
 #if defined(__CUDACC__)
 #define B2_HD __host__ __device__ __forceinline__
+#define B2_NOINL __host__ __device__ __noinline__
+#define B2_ROLL _Pragma("unroll 1")
 #else
 #define B2_HD inline
+#define B2_NOINL inline
+#define B2_ROLL
 #endif
 
 namespace b200fit {
@@ -61,13 +69,15 @@ struct DeviceProblem {
     int ncomp, nchan, max_iter, weight_mode;
     int nhf;                       // distinct hyperfines, sorted by ascending velocity offset
     int nfull;                     // reference-table entries (original order) for the fp64 model kernels
+    int ngroups;                   // groups of neighbouring hyperfines (windowing granularity of the fit kernel)
+    int gstart[MAXHF_FIT + 1];     // group g = lines [gstart[g], gstart[g+1])
     long long npix;
-    double v0, dv;                 // ascending velocity axis
+    double v0, dv, inv_dv;         // ascending velocity axis
     double ftol, signal_cut;
     double lo[8], hi[8];
     // fit kernel (velocity space): line k of a component at velocity v sits at  cen = c1mrho[k] + rho[k]*v,
-    // with width sigma*rho[k];  rho[k] = (1 - voff_k/c) * nu0/nu_ref
-    double rho[MAXHF_FIT], c1mrho[MAXHF_FIT];
+    // with width sigma*rho[k];  rho[k] = (1 - voff_k/c) * nu0/nu_ref;  kdv[k] = KAPPA0*dv/rho[k]
+    double rho[MAXHF_FIT], c1mrho[MAXHF_FIT], kdv[MAXHF_FIT];
     float lw[MAXHF_FIT];           // log2(normalised weight)
     // Planck terms, linear in channel offset di = i - ic0:  T0_i = T0c + dT0*di
     double ic0, T0c, dT0, Jbg0, Jbg1;
@@ -77,6 +87,15 @@ struct DeviceProblem {
     double wts_full[MAXHF_FULL];   // tau_wts / sum(tau_wts)
 };
 
+// The slice of DeviceProblem the fit kernel's per-evaluation set-up indexes with a lane-dependent subscript
+// (kept in shared memory: constant-bank reads with divergent indices serialise).
+struct FitTables {
+    double rho[MAXHF_FIT], c1mrho[MAXHF_FIT], kdv[MAXHF_FIT];
+    double lo[8], hi[8];
+    float lw[MAXHF_FIT];
+    int gstart[MAXHF_FIT + 1];
+};
+
 // ------------------------------------------------------------------------------------------------------------
 // Per-component coefficients for one evaluation (fp64 set-up, fp32 use).
 struct CompCoef {
@@ -84,6 +103,7 @@ struct CompCoef {
     float dJ0, dJ1;    // J(Tex) - J(Tbg), linear in di
     float dJT0, dJT1;  // dJ/dTex, linear in di
     float sA, sB;      // dtau/dv = sA * A,  dtau/dsigma = sB * B   (A = sum g z', B = sum g z'^2)
+    float pad;
 };
 
 B2_HD void planck_terms(double T, double T0c, double dT0, double& J0, double& J1, double& JT0, double& JT1) {
@@ -100,17 +120,18 @@ B2_HD void planck_terms(double T, double T0c, double dT0, double& J0, double& J1
     JT1 = dJTdx / T * dT0;
 }
 
-B2_HD void comp_coefs(const DeviceProblem& pr, const double* p4, CompCoef& cc) {
+B2_HD void comp_coefs(double T0c, double dT0, double Jbg0, double Jbg1, const double* p4, CompCoef& cc) {
     const double sigma = p4[1], tex = p4[2], tau0 = p4[3];
     double J0, J1, JT0, JT1;
-    planck_terms(tex, pr.T0c, pr.dT0, J0, J1, JT0, JT1);
+    planck_terms(tex, T0c, dT0, J0, J1, JT0, JT1);
     cc.tau0 = (float)tau0;
-    cc.dJ0 = (float)(J0 - pr.Jbg0);
-    cc.dJ1 = (float)(J1 - pr.Jbg1);
+    cc.dJ0 = (float)(J0 - Jbg0);
+    cc.dJ1 = (float)(J1 - Jbg1);
     cc.dJT0 = (float)JT0;
     cc.dJT1 = (float)JT1;
     cc.sA = (float)(tau0 / (sigma * KAPPA0));
     cc.sB = (float)(tau0 / (sigma * KAPPA0 * KAPPA0));
+    cc.pad = 0.f;
 }
 
 // Line set-up: z'(i) = ((i - nf) - f) * a  with  a = KAPPA0*dv/(sigma*rho_k);  stored as {nf, -f*a, a, lw}.
@@ -118,18 +139,20 @@ struct alignas(16) LineCoef {
     float nf, b, a, lw;
 };
 
-B2_HD void line_coef(const DeviceProblem& pr, const double* p4, int k, LineCoef& lc, float& ic_f, float& hw_f) {
-    const double v = p4[0], sigma = p4[1];
-    const double cen = pr.c1mrho[k] + pr.rho[k] * v;
-    const double ic = (cen - pr.v0) / pr.dv;
+// cen/rho/kdv of line k, component velocity v and 1/sigma -> coefficients + the line's channel window [wlo, whi]
+B2_HD void line_coef(double c1mrho_k, double rho_k, double kdv_k, float lw_k, double v0, double inv_dv, double v,
+                     double inv_sigma, LineCoef& lc, float& wlo, float& whi) {
+    const double cen = c1mrho_k + rho_k * v;
+    const double ic = (cen - v0) * inv_dv;
     const double nf = rint(ic);
-    const double a = KAPPA0 * pr.dv / (sigma * pr.rho[k]);
+    const double a = kdv_k * inv_sigma;
     lc.nf = (float)nf;
     lc.b = (float)(-(ic - nf) * a);
     lc.a = (float)a;
-    lc.lw = pr.lw[k];
-    ic_f = (float)ic;
-    hw_f = (float)((double)ZCUT / a);
+    lc.lw = lw_k;
+    const double hw = (double)ZCUT / a;
+    wlo = (float)(ic - hw);
+    whi = (float)(ic + hw);
 }
 
 #if defined(__CUDA_ARCH__)
@@ -195,19 +218,26 @@ constexpr double LM_MACHEP = 2.220446049250313e-16;
 constexpr double LM_DWARF = 2.2250738585072014e-308;
 constexpr double LM_XTOL = 1e-10, LM_GTOL = 1e-10, LM_FACTOR = 100.0;
 
-template <int P>
-struct LMState {
-    static constexpr int NH = P * (P + 1) / 2;
-    double p[P], H[NH], b[P], chi2;
-    double pt[P], Ht[NH], bt[P], chi2t;
-    double lo[P], hi[P], diag[P], step[P];
-    double delta, par, xnorm, pnorm, alpha, sHs, ftol, chi2_last;
-    int status, iters, nevals, nrej, max_iter, first, fresh, nnoise;
-    unsigned peg;
+// Per-call solver constants (limits live in shared memory in the kernel).
+struct LMConfig {
+    const double* lo;
+    const double* hi;
+    double ftol;
+    int max_iter;
 };
 
 template <int P>
-B2_HD int hidx(int i, int j) {   // i <= j
+struct LMState {
+    static constexpr int NH = P * (P + 1) / 2;
+    double p[P], pt[P], diag[P], b[P], bt[P];
+    double H[NH], Ht[NH];
+    double chi2, chi2t, chi2_last, delta, par, xnorm, pnorm, alpha, sHs;
+    int status, iters, nevals, nrej, first, fresh;
+    unsigned peg, pad_;
+};
+
+template <int P>
+B2_HD int hidx(int i, int j) {   // packed upper triangle, i <= j
     return i * P - (i * (i - 1)) / 2 + (j - i);
 }
 
@@ -216,132 +246,129 @@ B2_HD double hget(const double* H, int i, int j) {
     return H[(i <= j) ? hidx<P>(i, j) : hidx<P>(j, i)];
 }
 
-// Cholesky factor (lower, in L) of A = H_free + par*diag^2; fixed rows/cols are replaced by identity.
-// Returns false if A is not (numerically) positive definite.
+B2_HD int lidx(int i, int k) {   // packed lower triangle, k <= i
+    return (i * (i + 1)) / 2 + k;
+}
+
+// Cholesky factor (packed lower, L; reciprocal diagonal in Linv) of A = H_free + par*diag^2; fixed rows/cols are
+// replaced by identity.  Returns false if A is not (numerically) positive definite.
 template <int P>
-B2_HD bool lm_chol(const double* H, const double* dg, double par, unsigned fixed, double (&L)[P][P]) {
+B2_NOINL bool lm_chol(const double* H, const double* dg, double par, unsigned fixed, double* L, double* Linv) {
     bool ok = true;
-#pragma unroll
+    B2_ROLL
     for (int j = 0; j < P; ++j) {
         const bool fj = (fixed >> j) & 1u;
         double d = fj ? 1.0 : H[hidx<P>(j, j)] + par * dg[j] * dg[j];
         const double d0 = d;
-#pragma unroll
-        for (int k = 0; k < P; ++k)
-            if (k < j) d -= L[j][k] * L[j][k];
+        double* Lj = L + lidx(j, 0);
+        B2_ROLL
+        for (int k = 0; k < j; ++k) d -= Lj[k] * Lj[k];
         if (!(d > 1e-14 * d0)) {   // rank deficient in this direction
             ok = false;
             d = (d0 > 0.0) ? d0 : 1.0;
         }
         const double s = sqrt(d);
         const double inv = 1.0 / s;
-        L[j][j] = s;
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-            if (i <= j) continue;
+        Lj[j] = s;
+        Linv[j] = inv;
+        B2_ROLL
+        for (int i = j + 1; i < P; ++i) {
             const bool fi = (fixed >> i) & 1u;
             double v = (fi || fj) ? 0.0 : H[hidx<P>(j, i)];
-#pragma unroll
-            for (int k = 0; k < P; ++k)
-                if (k < j) v -= L[i][k] * L[j][k];
-            L[i][j] = v * inv;
+            const double* Li = L + lidx(i, 0);
+            B2_ROLL
+            for (int k = 0; k < j; ++k) v -= Li[k] * Lj[k];
+            L[lidx(i, j)] = v * inv;
         }
     }
     return ok;
 }
 
 template <int P>
-B2_HD void lm_fwd(const double (&L)[P][P], const double* rhs, double* y) {   // L y = rhs
-#pragma unroll
+B2_NOINL void lm_fwd(const double* L, const double* Linv, const double* rhs, double* y) {   // L y = rhs
+    B2_ROLL
     for (int i = 0; i < P; ++i) {
         double v = rhs[i];
-#pragma unroll
-        for (int k = 0; k < P; ++k)
-            if (k < i) v -= L[i][k] * y[k];
-        y[i] = v / L[i][i];
+        const double* Li = L + lidx(i, 0);
+        B2_ROLL
+        for (int k = 0; k < i; ++k) v -= Li[k] * y[k];
+        y[i] = v * Linv[i];
     }
 }
 
 template <int P>
-B2_HD void lm_bwd(const double (&L)[P][P], const double* y, double* x) {   // L^T x = y
-#pragma unroll
-    for (int ii = 0; ii < P; ++ii) {
-        const int i = P - 1 - ii;
+B2_NOINL void lm_bwd(const double* L, const double* Linv, const double* y, double* x) {   // L^T x = y
+    B2_ROLL
+    for (int i = P - 1; i >= 0; --i) {
         double v = y[i];
-#pragma unroll
-        for (int k = 0; k < P; ++k)
-            if (k > i) v -= L[k][i] * x[k];
-        x[i] = v / L[i][i];
+        B2_ROLL
+        for (int k = i + 1; k < P; ++k) v -= L[lidx(k, i)] * x[k];
+        x[i] = v * Linv[i];
     }
 }
 
 template <int P>
 B2_HD double lm_dnorm(const double* dg, const double* x) {
     double s = 0.0;
-#pragma unroll
+    B2_ROLL
     for (int j = 0; j < P; ++j) s += dg[j] * x[j] * dg[j] * x[j];
     return sqrt(s);
+}
+
+// |L^-1 (D^2 x / |D x|)|^2 : the Newton correction denominator of lmpar
+template <int P>
+B2_HD double lm_newton_den(const double* L, const double* Linv, const double* dg, const double* x, double dxnorm,
+                           unsigned fixed) {
+    double q[P], w[P];
+    B2_ROLL
+    for (int j = 0; j < P; ++j) q[j] = ((fixed >> j) & 1u) ? 0.0 : dg[j] * dg[j] * x[j] / dxnorm;
+    lm_fwd<P>(L, Linv, q, w);
+    double wn = 0.0;
+    B2_ROLL
+    for (int j = 0; j < P; ++j) wn += w[j] * w[j];
+    return wn;
 }
 
 // MINPACK lmpar on normal equations.  rhs = b with fixed entries zeroed.  Returns delta-step in x, updates par.
 template <int P>
 B2_HD void lm_par(const double* H, const double* dg, const double* rhs, unsigned fixed, double delta, double& par,
                   double* x) {
-    double L[P][P], y[P], w[P], q[P];
-    // Gauss-Newton direction
-    const bool spd = lm_chol<P>(H, dg, 0.0, fixed, L);
-    double dxnorm, fp;
-    if (spd) {
-        lm_fwd<P>(L, rhs, y);
-        lm_bwd<P>(L, y, x);
-        dxnorm = lm_dnorm<P>(dg, x);
-        fp = dxnorm - delta;
-        if (fp <= 0.1 * delta) {
-            par = 0.0;
-            return;
-        }
-    } else {
-        dxnorm = INFINITY;
-        fp = INFINITY;
-    }
-    double parl = 0.0;
-    if (spd) {
-#pragma unroll
-        for (int j = 0; j < P; ++j) q[j] = ((fixed >> j) & 1u) ? 0.0 : dg[j] * dg[j] * x[j] / dxnorm;
-        lm_fwd<P>(L, q, w);
-        double wn = 0.0;
-#pragma unroll
-        for (int j = 0; j < P; ++j) wn += w[j] * w[j];
-        parl = ((fp / delta) / wn);
-    }
-    double gn = 0.0;
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-        const double t = rhs[j] / dg[j];
-        gn += t * t;
-    }
-    const double gnorm = sqrt(gn);
-    double paru = gnorm / delta;
-    if (paru == 0.0) paru = LM_DWARF / fmin(delta, 0.1);
-    par = fmax(par, parl);
-    par = fmin(par, paru);
-    if (par == 0.0) par = gnorm / dxnorm;
-    for (int it = 1;; ++it) {
-        if (par == 0.0) par = fmax(LM_DWARF, 0.001 * paru);
-        lm_chol<P>(H, dg, par, fixed, L);
-        lm_fwd<P>(L, rhs, y);
-        lm_bwd<P>(L, y, x);
-        dxnorm = lm_dnorm<P>(dg, x);
+    double L[P * (P + 1) / 2], Linv[P], y[P];
+    double dxnorm = INFINITY, fp = INFINITY, parl = 0.0, paru = 0.0;
+    // it == 0: Gauss-Newton direction (par = 0); it >= 1: the lmpar iteration
+    B2_ROLL
+    for (int it = 0;; ++it) {
+        if (it > 0 && par == 0.0) par = fmax(LM_DWARF, 0.001 * paru);
+        const bool spd = lm_chol<P>(H, dg, (it == 0) ? 0.0 : par, fixed, L, Linv);
         const double temp = fp;
-        fp = dxnorm - delta;
+        if (it > 0 || spd) {
+            lm_fwd<P>(L, Linv, rhs, y);
+            lm_bwd<P>(L, Linv, y, x);
+            dxnorm = lm_dnorm<P>(dg, x);
+            fp = dxnorm - delta;
+        }
+        if (it == 0) {
+            if (spd && fp <= 0.1 * delta) {
+                par = 0.0;
+                return;
+            }
+            if (spd) parl = (fp / delta) / lm_newton_den<P>(L, Linv, dg, x, dxnorm, fixed);
+            double gn = 0.0;
+            B2_ROLL
+            for (int j = 0; j < P; ++j) {
+                const double t = rhs[j] / dg[j];
+                gn += t * t;
+            }
+            const double gnorm = sqrt(gn);
+            paru = gnorm / delta;
+            if (paru == 0.0) paru = LM_DWARF / fmin(delta, 0.1);
+            par = fmax(par, parl);
+            par = fmin(par, paru);
+            if (par == 0.0) par = gnorm / dxnorm;
+            continue;
+        }
         if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || it == 10) break;
-#pragma unroll
-        for (int j = 0; j < P; ++j) q[j] = ((fixed >> j) & 1u) ? 0.0 : dg[j] * dg[j] * x[j] / dxnorm;
-        lm_fwd<P>(L, q, w);
-        double wn = 0.0;
-#pragma unroll
-        for (int j = 0; j < P; ++j) wn += w[j] * w[j];
-        const double parc = ((fp / delta) / wn);
+        const double parc = (fp / delta) / lm_newton_den<P>(L, Linv, dg, x, dxnorm, fixed);
         if (fp > 0.0) parl = fmax(parl, par);
         if (fp < 0.0) paru = fmin(paru, par);
         par = fmax(parl, par + parc);
@@ -349,18 +376,18 @@ B2_HD void lm_par(const double* H, const double* dg, const double* rhs, unsigned
 }
 
 template <int P>
-B2_HD unsigned lm_pegged(const LMState<P>& s) {
+B2_HD unsigned lm_pegged(const LMState<P>& s, const LMConfig& cf) {
     // mpfit: a parameter sitting on a limit whose chi2 gradient points out of the box gets its Jacobian column
     // zeroed.  d(chi2)/dp_j = -2 b_j:  lower limit & b_j < 0, or upper limit & b_j > 0.
     // The gradient of an fp32-evaluated model carries noise of relative size ~LM_NOISE_REL in MINPACK's cosine
     // measure |b_j| / (|J_j| |r|); a parameter on a limit is released only by a gradient that is significant.
     unsigned peg = 0;
-#pragma unroll
+    B2_ROLL
     for (int j = 0; j < P; ++j) {
         const double hjj = s.H[hidx<P>(j, j)];
         const double thr = 3.0 * LM_NOISE_REL * sqrt((hjj > 0.0 ? hjj : 0.0) * s.chi2);
-        if (s.p[j] <= s.lo[j] && s.b[j] < thr) peg |= 1u << j;
-        if (s.p[j] >= s.hi[j] && s.b[j] > -thr) peg |= 1u << j;
+        if (s.p[j] <= cf.lo[j] && s.b[j] < thr) peg |= 1u << j;
+        if (s.p[j] >= cf.hi[j] && s.b[j] > -thr) peg |= 1u << j;
     }
     return peg;
 }
@@ -368,18 +395,15 @@ B2_HD unsigned lm_pegged(const LMState<P>& s) {
 // Start: returns false (status 0) when the guess is not finite or outside the box (mpfit: "parameters are not
 // within PARINFO limits" -> pyspeckit raises -> pixel not fitted).
 template <int P>
-B2_HD bool lm_init(LMState<P>& s, const double* guess, const double* lo, const double* hi, int max_iter,
-                   double ftol) {
+B2_HD bool lm_init(LMState<P>& s, const double* guess, const LMConfig& cf) {
     bool ok = true;
-#pragma unroll
+    B2_ROLL
     for (int j = 0; j < P; ++j) {
-        s.lo[j] = lo[j];
-        s.hi[j] = hi[j];
-        s.p[j] = guess[j];
-        s.pt[j] = guess[j];
+        const double g = guess[j];
+        s.p[j] = g;
+        s.pt[j] = g;
         s.diag[j] = 1.0;
-        s.step[j] = 0.0;
-        if (!(guess[j] >= lo[j] && guess[j] <= hi[j])) ok = false;   // also catches NaN
+        if (!(g >= cf.lo[j] && g <= cf.hi[j])) ok = false;   // also catches NaN
     }
     s.par = 0.0;
     s.delta = 0.0;
@@ -390,13 +414,10 @@ B2_HD bool lm_init(LMState<P>& s, const double* guess, const double* lo, const d
     s.iters = 0;
     s.nevals = 0;
     s.nrej = 0;
-    s.max_iter = max_iter;
-    s.ftol = ftol;
     s.status = 0;
     s.peg = 0;
     s.first = 1;
     s.fresh = 1;
-    s.nnoise = 0;
     s.chi2 = 0.0;
     s.chi2t = 0.0;
     s.chi2_last = 0.0;
@@ -413,22 +434,22 @@ B2_HD int lm_adopt_first(LMState<P>& s) {
     }
     s.chi2 = s.chi2t;
     s.chi2_last = s.chi2t;
-#pragma unroll
+    B2_ROLL
     for (int j = 0; j < P; ++j) s.b[j] = s.bt[j];
-#pragma unroll
+    B2_ROLL
     for (int q = 0; q < LMState<P>::NH; ++q) s.H[q] = s.Ht[q];
     return LM_CONTINUE;
 }
 
 // Propose the next trial point s.pt.  Returns LM_DONE when a convergence test fires (s.status set).
 template <int P>
-B2_HD int lm_propose(LMState<P>& s) {
+B2_HD int lm_propose(LMState<P>& s, const LMConfig& cf) {
     double rhs[P], dl[P];
     if (s.fresh) {   // start of an outer iteration: new Jacobian => new pegged set, scaling, gradient test
-        s.peg = lm_pegged(s);
+        s.peg = lm_pegged(s, cf);
         double gnorm = 0.0;
         const double fnorm = sqrt(s.chi2);
-#pragma unroll
+        B2_ROLL
         for (int j = 0; j < P; ++j) {
             const double hjj = s.H[hidx<P>(j, j)];
             const double cn = ((s.peg >> j) & 1u) ? 0.0 : sqrt(hjj > 0.0 ? hjj : 0.0);
@@ -450,54 +471,55 @@ B2_HD int lm_propose(LMState<P>& s) {
         s.fresh = 0;
     }
     unsigned fixed = s.peg;
-#pragma unroll
+    B2_ROLL
     for (int j = 0; j < P; ++j) {
         if (!(s.H[hidx<P>(j, j)] > 0.0)) fixed |= 1u << j;   // zero column: no information, leave untouched
         rhs[j] = ((fixed >> j) & 1u) ? 0.0 : s.b[j];
     }
-    lm_par<P>(s.H, s.diag, rhs, fixed, s.delta, s.par, dl);
-    // mpfit: parameters sitting on a limit may only step into the box ...
+    double par = s.par;
+    lm_par<P>(s.H, s.diag, rhs, fixed, s.delta, par, dl);
+    s.par = par;
+    // mpfit: parameters sitting on a limit may only step into the box, and the whole step is shortened so that
+    // no other parameter crosses a limit
     double alpha = 1.0;
-#pragma unroll
+    B2_ROLL
     for (int j = 0; j < P; ++j) {
-        if ((fixed >> j) & 1u) dl[j] = 0.0;
-        if (s.p[j] <= s.lo[j] && dl[j] < 0.0) dl[j] = 0.0;
-        if (s.p[j] >= s.hi[j] && dl[j] > 0.0) dl[j] = 0.0;
-    }
-    // ... and the whole step is shortened so that no other parameter crosses a limit
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-        if (fabs(dl[j]) > LM_MACHEP) {
-            if (s.p[j] + dl[j] < s.lo[j]) alpha = fmin(alpha, (s.lo[j] - s.p[j]) / dl[j]);
-            if (s.p[j] + dl[j] > s.hi[j]) alpha = fmin(alpha, (s.hi[j] - s.p[j]) / dl[j]);
+        const double pj = s.p[j], lo = cf.lo[j], hi = cf.hi[j];
+        double d = dl[j];
+        if ((fixed >> j) & 1u) d = 0.0;
+        if (pj <= lo && d < 0.0) d = 0.0;
+        if (pj >= hi && d > 0.0) d = 0.0;
+        dl[j] = d;
+        if (fabs(d) > LM_MACHEP) {
+            if (pj + d < lo) alpha = fmin(alpha, (lo - pj) / d);
+            if (pj + d > hi) alpha = fmin(alpha, (hi - pj) / d);
         }
     }
-#pragma unroll
+    B2_ROLL
     for (int j = 0; j < P; ++j) {
-        s.step[j] = alpha * dl[j];
-        double pn = s.p[j] + s.step[j];
+        const double lo = cf.lo[j], hi = cf.hi[j];
+        dl[j] *= alpha;
+        double pn = s.p[j] + dl[j];
         // snap to the limit when the step lands on it (mpfit ulim1/llim1 rule)
-        const double u1 =
-            s.hi[j] * (1.0 - (s.hi[j] >= 0 ? 1.0 : -1.0) * LM_MACHEP) - (s.hi[j] == 0.0 ? LM_MACHEP : 0.0);
-        const double l1 =
-            s.lo[j] * (1.0 + (s.lo[j] >= 0 ? 1.0 : -1.0) * LM_MACHEP) + (s.lo[j] == 0.0 ? LM_MACHEP : 0.0);
-        if (pn >= u1) pn = s.hi[j];
-        if (pn <= l1) pn = s.lo[j];
+        const double u1 = hi * (1.0 - (hi >= 0 ? 1.0 : -1.0) * LM_MACHEP) - (hi == 0.0 ? LM_MACHEP : 0.0);
+        const double l1 = lo * (1.0 + (lo >= 0 ? 1.0 : -1.0) * LM_MACHEP) + (lo == 0.0 ? LM_MACHEP : 0.0);
+        if (pn >= u1) pn = hi;
+        if (pn <= l1) pn = lo;
         s.pt[j] = pn;
     }
     s.alpha = alpha;
-    s.pnorm = lm_dnorm<P>(s.diag, s.step);
+    s.pnorm = lm_dnorm<P>(s.diag, dl);
     if (s.first) s.delta = fmin(s.delta, s.pnorm);
     // |J s|^2 with the pegged columns zeroed
     double sHs = 0.0;
-#pragma unroll
+    B2_ROLL
     for (int i = 0; i < P; ++i) {
         if ((s.peg >> i) & 1u) continue;
         double row = 0.0;
-#pragma unroll
+        B2_ROLL
         for (int j = 0; j < P; ++j)
-            if (!((s.peg >> j) & 1u)) row += hget<P>(s.H, i, j) * s.step[j];
-        sHs += s.step[i] * row;
+            if (!((s.peg >> j) & 1u)) row += hget<P>(s.H, i, j) * dl[j];
+        sHs += dl[i] * row;
     }
     s.sHs = sHs;
     return LM_CONTINUE;
@@ -505,7 +527,7 @@ B2_HD int lm_propose(LMState<P>& s) {
 
 // Judge the trial evaluation (chi2t/Ht/bt filled), MINPACK lmdif / mpfit bookkeeping.  Returns LM_DONE when finished.
 template <int P>
-B2_HD int lm_update(LMState<P>& s) {
+B2_HD int lm_update(LMState<P>& s, const LMConfig& cf) {
     s.nevals += 1;
     s.chi2_last = s.chi2t;
     const bool finite = (s.chi2t == s.chi2t) && !isinf(s.chi2t);
@@ -519,7 +541,7 @@ B2_HD int lm_update(LMState<P>& s) {
     // whose error is third order in the step.
     const double direct = s.chi2 - s.chi2t;
     double trap = 0.0;
-#pragma unroll
+    B2_ROLL
     for (int j = 0; j < P; ++j) trap += (s.pt[j] - s.p[j]) * (s.b[j] + s.bt[j]);
     const double act_abs = (fabs(direct) > 40.0 * LM_NOISE_REL * s.chi2) ? direct : trap;
     double actred = -1.0;
@@ -541,12 +563,12 @@ B2_HD int lm_update(LMState<P>& s) {
         s.par = 0.5 * s.par;
     }
     if (ratio >= 1e-4) {
-#pragma unroll
+        B2_ROLL
         for (int j = 0; j < P; ++j) {
             s.p[j] = s.pt[j];
             s.b[j] = s.bt[j];
         }
-#pragma unroll
+        B2_ROLL
         for (int q = 0; q < LMState<P>::NH; ++q) s.H[q] = s.Ht[q];
         s.chi2 = s.chi2t;
         s.xnorm = lm_dnorm<P>(s.diag, s.p);
@@ -557,13 +579,13 @@ B2_HD int lm_update(LMState<P>& s) {
         s.nrej += 1;
     }
     int st = 0;
-    if (fabs(actred) <= s.ftol && prered <= s.ftol && 0.5 * ratio <= 1.0) st = 1;
+    if (fabs(actred) <= cf.ftol && prered <= cf.ftol && 0.5 * ratio <= 1.0) st = 1;
     if (s.delta <= LM_XTOL * s.xnorm) st = (st == 1) ? 3 : 2;
     if (st != 0) {
         s.status = st;
         return LM_DONE;
     }
-    if (s.iters >= s.max_iter || s.nevals >= 2 * s.max_iter + 2) {
+    if (s.iters >= cf.max_iter || s.nevals >= 2 * cf.max_iter + 2) {
         s.status = 5;
         return LM_DONE;
     }
@@ -584,28 +606,26 @@ B2_HD double lm_reported_chi2(const LMState<P>& s) {
 // Parameter errors: sqrt(diag(err^2 (H_FF)^-1)), zero for pegged parameters (mpfit calc_covar on the
 // column-zeroed Jacobian); 0 as well for directions without sensitivity.
 template <int P>
-B2_HD void lm_errors(const LMState<P>& s, double err2, double* perr) {
-    unsigned fixed = lm_pegged(s);
+B2_HD void lm_errors(const LMState<P>& s, const LMConfig& cf, double err2, double* perr) {
+    unsigned fixed = lm_pegged(s, cf);
     double hmax = 0.0;
-#pragma unroll
+    B2_ROLL
     for (int j = 0; j < P; ++j) hmax = fmax(hmax, s.H[hidx<P>(j, j)]);
-#pragma unroll
+    B2_ROLL
     for (int j = 0; j < P; ++j)
         if (!(s.H[hidx<P>(j, j)] > 1e-28 * hmax)) fixed |= 1u << j;
-    double L[P][P], one[P];
-#pragma unroll
-    for (int j = 0; j < P; ++j) one[j] = 0.0;
-    const bool ok = lm_chol<P>(s.H, one, 0.0, fixed, L);
-    (void)ok;
-    // (H^-1)_jj = | L^-1 e_j |^2 restricted to rows >= j
-#pragma unroll
+    double L[P * (P + 1) / 2], Linv[P], rhs[P], y[P];
+    B2_ROLL
+    for (int j = 0; j < P; ++j) rhs[j] = 0.0;
+    lm_chol<P>(s.H, rhs /* zero scaling: par = 0 anyway */, 0.0, fixed, L, Linv);
+    // (H^-1)_jj = | L^-1 e_j |^2
+    B2_ROLL
     for (int j = 0; j < P; ++j) {
-        double rhs[P], y[P];
-#pragma unroll
+        B2_ROLL
         for (int k = 0; k < P; ++k) rhs[k] = (k == j) ? 1.0 : 0.0;
-        lm_fwd<P>(L, rhs, y);
+        lm_fwd<P>(L, Linv, rhs, y);
         double c = 0.0;
-#pragma unroll
+        B2_ROLL
         for (int k = 0; k < P; ++k) c += y[k] * y[k];
         c *= err2;
         perr[j] = (((fixed >> j) & 1u) || !(c > 0.0) || isinf(c)) ? 0.0 : sqrt(c);

@@ -32,6 +32,7 @@ inline int make_device_problem(const b200fit_problem& in, DeviceProblem& out) {
     out.npix = in.npix;
     out.v0 = in.v0;
     out.dv = in.dv;
+    out.inv_dv = 1.0 / in.dv;
     out.ftol = in.ftol > 0 ? in.ftol : 1e-10;
     out.signal_cut = in.signal_cut;
     for (int j = 0; j < 8; ++j) {
@@ -66,8 +67,15 @@ inline int make_device_problem(const b200fit_problem& in, DeviceProblem& out) {
         const double rho = (1.0 - v[k].first / CKMS) * nu0_ghz / nu_ref;
         out.rho[k] = rho;
         out.c1mrho[k] = CKMS * (1.0 - rho);
+        out.kdv[k] = KAPPA0 * in.dv / rho;
         out.lw[k] = (float)std::log2(v[k].second / wsum);
     }
+    // windowing groups: neighbouring hyperfines closer than GROUP_GAP km/s share one channel window
+    const double GROUP_GAP = 3.0;
+    out.ngroups = 0;
+    for (int k = 0; k < out.nhf; ++k)
+        if (k == 0 || v[k].first - v[k - 1].first > GROUP_GAP) out.gstart[out.ngroups++] = k;
+    for (int g = out.ngroups; g <= MAXHF_FIT; ++g) out.gstart[g] = out.nhf;
     // Planck terms about the band centre
     out.ic0 = 0.5 * (in.nchan - 1);
     const double vc = in.v0 + in.dv * out.ic0;

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -48,65 +49,78 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Per-warp shared-memory working set of the fit kernel.
+// fit_kernel<NC, G>: persistent warps; every warp keeps a GROUP of G pixels in flight ("slots").
+//   round := { refill empty slots from the atomic pixel queue (warp-cooperative prologue: weights, sum y^2);
+//              for each live slot: ONE warp-cooperative evaluation at its trial point (lanes = channels);
+//              SIMT solver step: lane s advances the LM state machine of slot s }.
+// The solver is branchy fp64 scalar code; running it on one lane per pixel with G pixels per warp amortises
+// its issue slots G-fold (v1 ran it on lane 0 only: 63 % of all executed instructions, profiles/r1a_*).
+// Slots finish independently (iteration counts differ by >10x) and are refilled at once, so a slow pixel never
+// holds the other G-1 slots back.  Spectra are NOT staged in shared memory: an evaluation touches only the
+// 32-channel chunks inside a hyperfine window (~half of the row) and the in-flight rows (148 SMs x 16 warps x G
+// x 3.2 KB ~ 60 MB) stay L2-resident (126 MB), so shared memory is spent on solver state instead.
+template <int P>
+struct alignas(8) FitSlot {
+    LMState<P> st;
+    CompCoef cc[P / 4];          // coefficients of the trial point st.pt (filled by the slot's solver lane)
+    double inv_sigma[P / 4];
+    double err, sumsq;           // weight (std of the finite channels); sum of y^2 over the finite channels
+    long long pix;
+    const float* spec;
+    unsigned n_gauss, n_chunks;
+};
+
+// slot stride in bytes: == 8 (mod 128), so that lanes s = 0..15 touching the same field of their own slot hit
+// distinct 8-byte bank pairs
+template <int P>
+__host__ __device__ constexpr size_t slot_stride() {
+    return (sizeof(FitSlot<P>) + 119) / 128 * 128 + 8;
+}
+
 template <int NC>
-struct alignas(16) FitShared {
+struct FitWarpScratch {
     static constexpr int P = 4 * NC;
     static constexpr int NH = P * (P + 1) / 2;
     static constexpr int NACC = NH + P + 1;
-    LMState<P> st;                       // 8-byte aligned first
+    static constexpr int RED_ROWS = (NACC < 24) ? NACC : 24;
     alignas(16) LineCoef lines[NC][MAXHF_FIT];   // 16-byte records (float4 loads)
-    float ic[NC][MAXHF_FIT];
-    float hw[NC][MAXHF_FIT];
-    CompCoef cc[NC];
-    float red[NACC][33];                 // cross-lane reduction scratch (+1 pad: conflict-free both ways)
-    // float spec[nchan_stride] follows (dynamic)
+    float wlo[NC][MAXHF_FIT], whi[NC][MAXHF_FIT];
+    float red[RED_ROWS][33];                     // cross-lane reduction scratch (+1 pad: conflict-free both ways)
 };
 
-template <int NC>
-__host__ __device__ constexpr size_t fit_shared_fixed_bytes() {
-    return (sizeof(FitShared<NC>) + 15) / 16 * 16;
+template <int NC, int G>
+__host__ __device__ constexpr size_t fit_warp_bytes() {
+    return (G * slot_stride<4 * NC>() + sizeof(FitWarpScratch<NC>) + 15) / 16 * 16;
 }
 
-template <int P>
-__device__ __noinline__ int dev_lm_propose(LMState<P>* s) {
-    return lm_propose<P>(*s);
-}
-template <int P>
-__device__ __noinline__ int dev_lm_update(LMState<P>* s) {
-    return lm_update<P>(*s);
-}
-template <int P>
-__device__ __noinline__ void dev_lm_errors(const LMState<P>* s, double err2, double* perr) {
-    lm_errors<P>(*s, err2, perr);
-}
-
-// One evaluation at the trial point st.pt: fills st.Ht / st.bt / st.chi2t.  Warp-collective.
+// One evaluation of slot `sl` at its trial point st.pt: fills st.Ht / st.bt / st.chi2t.  Warp-collective.
+//   chi2 = sum_finite y^2 + sum_{channels inside a window} m (m - 2 y)      (exactly sum (y - m)^2: m == 0 elsewhere)
 template <int NC>
-__device__ __forceinline__ void warp_eval(const DeviceProblem& pr, FitShared<NC>& w, const float* spec, int lane,
-                                          float y2a, float y2b, unsigned& n_gauss, unsigned& n_chunks) {
+__device__ __forceinline__ void warp_eval(const DeviceProblem& pr, const FitTables& tb, FitSlot<4 * NC>& sl,
+                                          FitWarpScratch<NC>& w, int lane) {
     constexpr int P = 4 * NC;
     constexpr int NH = P * (P + 1) / 2;
     constexpr int NACC = NH + P + 1;
+    constexpr int RR = FitWarpScratch<NC>::RED_ROWS;
     const int nhf = pr.nhf;
-    // 1. fp64 set-up spread over lanes: line positions/widths, Planck terms
-    for (int idx = lane; idx < NC * nhf; idx += 32) {
-        const int c = idx / nhf, k = idx - c * nhf;
-        LineCoef lc;
-        float icf, hwf;
-        line_coef(pr, &w.st.pt[4 * c], k, lc, icf, hwf);
-        w.lines[c][k] = lc;
-        w.ic[c][k] = icf;
-        w.hw[c][k] = hwf;
-    }
-    if (lane < NC) {
-        CompCoef cc;
-        comp_coefs(pr, &w.st.pt[4 * lane], cc);
-        w.cc[lane] = cc;
+    // 1. fp64 line set-up, one line per lane
+    if (lane < nhf) {
+        const double c1 = tb.c1mrho[lane], rho = tb.rho[lane], kdv = tb.kdv[lane];
+        const float lw = tb.lw[lane];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            LineCoef lc;
+            float lo, hi;
+            line_coef(c1, rho, kdv, lw, pr.v0, pr.inv_dv, sl.st.pt[4 * c], sl.inv_sigma[c], lc, lo, hi);
+            w.lines[c][lane] = lc;
+            w.wlo[c][lane] = lo;
+            w.whi[c][lane] = hi;
+        }
     }
     __syncwarp();
-    // 2. which hyperfines touch chunk `lane` and chunk `lane + 32`  (lines are sorted by centre)
+    // 2. which hyperfines touch chunk `lane` and chunk `lane + 32` (whole groups of neighbouring lines; sorted)
     const int nchunks = (pr.nchan + 31) >> 5;
+    const int ngroups = pr.ngroups;
     unsigned packed[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -115,12 +129,13 @@ __device__ __forceinline__ void warp_eval(const DeviceProblem& pr, FitShared<NC>
         unsigned pk = 0;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            int klo = 0, khi = 0;
-            for (int k = 0; k < nhf; ++k) {
-                const float icv = w.ic[c][k], hwv = w.hw[c][k];
-                klo += (icv + hwv < lo_edge) ? 1 : 0;
-                khi += (icv - hwv <= hi_edge) ? 1 : 0;
+            int glo = 0, ghi = 0;
+            for (int g = 0; g < ngroups; ++g) {
+                const int first = tb.gstart[g], last = tb.gstart[g + 1] - 1;
+                glo += (w.whi[c][last] < lo_edge) ? 1 : 0;
+                ghi += (w.wlo[c][first] <= hi_edge) ? 1 : 0;
             }
+            int klo = tb.gstart[glo], khi = tb.gstart[ghi];
             if (ch >= nchunks) klo = khi = 0;
             pk |= ((unsigned)klo | ((unsigned)khi << 8)) << (16 * c);
         }
@@ -128,12 +143,14 @@ __device__ __forceinline__ void warp_eval(const DeviceProblem& pr, FitShared<NC>
     }
     CompCoef cc[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) cc[c] = w.cc[c];
+    for (int c = 0; c < NC; ++c) cc[c] = sl.cc[c];
     const float ic0 = (float)pr.ic0;
+    const float* __restrict__ spec = sl.spec;
 
     float acc[NACC];
 #pragma unroll
     for (int e = 0; e < NACC; ++e) acc[e] = 0.f;
+    unsigned n_gauss = 0, n_chunks = 0;
 
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -144,16 +161,20 @@ __device__ __forceinline__ void warp_eval(const DeviceProblem& pr, FitShared<NC>
             mine = mine || ((f & 0xffu) < ((f >> 8) & 0xffu));
         }
         unsigned act = __ballot_sync(FULL, mine);
-        // chunks no hyperfine touches: model == 0 exactly, Jacobian == 0 -> chi2 += sum(y^2) (precomputed)
-        if (!mine) acc[NACC - 1] += (h == 0) ? y2a : y2b;
+        int jn = act ? (__ffs(act) - 1) : 0;
+        float ynext = act ? __ldg(spec + (((jn + 32 * h) << 5) + lane)) : 0.f;
         while (act) {
-            const int j = __ffs(act) - 1;
+            const int j = jn;
+            const float y = ynext;
             act &= act - 1;
+            if (act) {   // prefetch the next active chunk of the row (L2-resident)
+                jn = __ffs(act) - 1;
+                ynext = __ldg(spec + (((jn + 32 * h) << 5) + lane));
+            }
             const unsigned pk = __shfl_sync(FULL, packed[h], j);
             const int i = ((j + 32 * h) << 5) + lane;
-            const float y = spec[i];
             const float fi = (float)i;
-            float G[NC], A[NC], B[NC];
+            float Gs[NC], As[NC], Bs[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const unsigned f = pk >> (16 * c);
@@ -168,16 +189,17 @@ __device__ __forceinline__ void warp_eval(const DeviceProblem& pr, FitShared<NC>
                     lc.lw = q.w;
                     gauss_accum(fi, lc, g, a, b);
                 }
-                G[c] = g;
-                A[c] = a;
-                B[c] = b;
+                Gs[c] = g;
+                As[c] = a;
+                Bs[c] = b;
                 n_gauss += (khi > klo) ? (unsigned)(khi - klo) : 0u;
             }
             n_chunks += 1;
             float m, J[P];
-            rt_channel<NC>(G, A, B, fi - ic0, cc, m, J);
+            rt_channel<NC>(Gs, As, Bs, fi - ic0, cc, m, J);
             const bool valid = (y == y);   // NaN channels (and the NaN padding) carry no weight
             const float r = valid ? (y - m) : 0.f;
+            const float dchi = valid ? m * (m - 2.f * y) : 0.f;
 #pragma unroll
             for (int u = 0; u < P; ++u) J[u] = valid ? J[u] : 0.f;
             int q = 0;
@@ -191,28 +213,81 @@ __device__ __forceinline__ void warp_eval(const DeviceProblem& pr, FitShared<NC>
             }
 #pragma unroll
             for (int u = 0; u < P; ++u) acc[NH + u] = fmaf(J[u], r, acc[NH + u]);
-            acc[NACC - 1] = fmaf(r, r, acc[NACC - 1]);
+            acc[NACC - 1] += dchi;
         }
     }
-    // 3. cross-lane reduction in fp64 through shared memory
+    // 3. cross-lane reduction in fp64 through shared memory, RR accumulators per pass
 #pragma unroll
-    for (int e = 0; e < NACC; ++e) w.red[e][lane] = acc[e];
-    __syncwarp();
-    for (int e = lane; e < NACC; e += 32) {
-        double s = 0.0;
-#pragma unroll 8
-        for (int m = 0; m < 32; ++m) s += (double)w.red[e][m];
-        if (e < NH)
-            w.st.Ht[e] = s;
-        else if (e < NH + P)
-            w.st.bt[e - NH] = s;
-        else
-            w.st.chi2t = s;
+    for (int base = 0; base < NACC; base += RR) {
+#pragma unroll
+        for (int e = 0; e < RR; ++e)
+            if (base + e < NACC) w.red[e][lane] = acc[base + e];
+        __syncwarp();
+        const int e = base + lane;
+        if (lane < RR && e < NACC) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int m = 0; m < 32; m += 4) {
+                s0 += (double)w.red[lane][m];
+                s1 += (double)w.red[lane][m + 1];
+                s2 += (double)w.red[lane][m + 2];
+                s3 += (double)w.red[lane][m + 3];
+            }
+            const double s = (s0 + s1) + (s2 + s3);
+            if (e < NH)
+                sl.st.Ht[e] = s;
+            else if (e < NH + P)
+                sl.st.bt[e - NH] = s;
+            else
+                sl.st.chi2t = sl.sumsq + s;
+        }
+        __syncwarp();
     }
-    __syncwarp();
+    if (lane == 0) {
+        sl.n_gauss += n_gauss;
+        sl.n_chunks += n_chunks;
+    }
 }
 
+// Solver-lane helper: coefficients of the trial point the next evaluation will use.
 template <int NC>
+__device__ __forceinline__ void prepare_trial(const DeviceProblem& pr, FitSlot<4 * NC>& sl) {
+#pragma unroll 1
+    for (int c = 0; c < NC; ++c) {
+        CompCoef cc;
+        comp_coefs(pr.T0c, pr.dT0, pr.Jbg0, pr.Jbg1, &sl.st.pt[4 * c], cc);
+        sl.cc[c] = cc;
+        sl.inv_sigma[c] = 1.0 / sl.st.pt[4 * c + 1];
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void write_result(const FitSlot<P>& sl, const LMConfig& cf, bool fitted,
+                                             double* __restrict__ params, double* __restrict__ perr,
+                                             double* __restrict__ chi2, double* __restrict__ err_used,
+                                             int* __restrict__ status, unsigned* __restrict__ counts) {
+    const long long pix = sl.pix;
+    const bool good = fitted && sl.st.status > 0;
+    const double err2 = sl.err * sl.err;
+    double pe[P];
+    if (good) lm_errors<P>(sl.st, cf, err2, pe);
+#pragma unroll 1
+    for (int j = 0; j < P; ++j) {
+        params[pix * P + j] = good ? sl.st.p[j] : 0.0;
+        perr[pix * P + j] = good ? pe[j] : 0.0;
+    }
+    chi2[pix] = good ? lm_reported_chi2<P>(sl.st) / err2 : 0.0;
+    err_used[pix] = sl.err;
+    status[pix] = fitted ? sl.st.status : 0;
+    if (counts) {
+        counts[4 * pix + 0] = fitted ? (unsigned)sl.st.nevals : 0u;
+        counts[4 * pix + 1] = fitted ? (unsigned)sl.st.nrej : 0u;
+        counts[4 * pix + 2] = fitted ? sl.n_gauss : 0u;
+        counts[4 * pix + 3] = fitted ? sl.n_chunks : 0u;
+    }
+}
+
+template <int NC, int G>
 __global__ void __launch_bounds__(FIT_WARPS * 32, 4)
     fit_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
                const double* __restrict__ guesses, const double* __restrict__ err_in, double* __restrict__ params,
@@ -221,113 +296,111 @@ __global__ void __launch_bounds__(FIT_WARPS * 32, 4)
                const long long* __restrict__ row_index) {
     constexpr int P = 4 * NC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ FitTables tb;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = fit_shared_fixed_bytes<NC>() + (size_t)stride * sizeof(float);
-    FitShared<NC>& w = *reinterpret_cast<FitShared<NC>*>(smem_raw + warp * per_warp);
-    float* spec = reinterpret_cast<float*>(smem_raw + warp * per_warp + fit_shared_fixed_bytes<NC>());
+    if (threadIdx.x < MAXHF_FIT) {
+        const int k = threadIdx.x;
+        tb.rho[k] = pr.rho[k];
+        tb.c1mrho[k] = pr.c1mrho[k];
+        tb.kdv[k] = pr.kdv[k];
+        tb.lw[k] = pr.lw[k];
+    }
+    if (threadIdx.x <= MAXHF_FIT) tb.gstart[threadIdx.x] = pr.gstart[threadIdx.x];
+    if (threadIdx.x < 8) {
+        tb.lo[threadIdx.x] = pr.lo[threadIdx.x];
+        tb.hi[threadIdx.x] = pr.hi[threadIdx.x];
+    }
+    __syncthreads();
+    unsigned char* wbase = smem_raw + (size_t)warp * fit_warp_bytes<NC, G>();
+    FitWarpScratch<NC>& w = *reinterpret_cast<FitWarpScratch<NC>*>(wbase + G * slot_stride<P>());
+    auto slot = [&](int s) -> FitSlot<P>& { return *reinterpret_cast<FitSlot<P>*>(wbase + (size_t)s * slot_stride<P>()); };
+    const LMConfig cf{tb.lo, tb.hi, pr.ftol, pr.max_iter};
     const int nchan = pr.nchan;
 
+    bool live = false;        // this lane's slot holds a pixel being fitted
+    bool dry = (lane >= G);   // the queue has nothing more for this lane
     for (;;) {
-        unsigned long long pix = 0;
-        if (lane == 0) pix = atomicAdd(queue, 1ULL);
-        pix = __shfl_sync(FULL, pix, 0);
-        if (pix >= (unsigned long long)pr.npix) break;
-
-        // ---- stage the spectrum: coalesced, vectorised, streaming (read once)
-        const unsigned long long row = row_index ? (unsigned long long)row_index[pix] : pix;
-        const float4* src = reinterpret_cast<const float4*>(spectra + row * stride);
-        for (int i = lane; i < (int)(stride >> 2); i += 32) reinterpret_cast<float4*>(spec)[i] = __ldcs(src + i);
+        // ---- refill: every lane with an empty slot takes the next pixel
+        long long pix = -1;
+        if (!live && !dry) {
+            pix = (long long)atomicAdd(queue, 1ULL);
+            if (pix >= pr.npix) {
+                pix = -1;
+                dry = true;
+            }
+        }
+        unsigned fresh = __ballot_sync(FULL, pix >= 0);
+        while (fresh) {
+            const int s = __ffs(fresh) - 1;
+            fresh &= fresh - 1;
+            const long long px = __shfl_sync(FULL, pix, s);
+            // ---- prologue (warp-cooperative, coalesced, one pass): weights err = population std of the finite
+            //      channels (Cube.fiteach), sum y^2, peak for signal_cut
+            const long long row = row_index ? row_index[px] : px;
+            const float* sp = spectra + row * stride;
+            double s1 = 0.0, sq = 0.0, ymax = -INFINITY;
+            int n = 0;
+#pragma unroll 4
+            for (int i = lane; i < nchan; i += 32) {
+                const float y = __ldg(sp + i);
+                if (y == y) {
+                    const double yd = (double)y;
+                    s1 += yd;
+                    sq = fma(yd, yd, sq);
+                    ++n;
+                    ymax = fmax(ymax, yd);
+                }
+            }
+            s1 = warp_sum(s1);
+            sq = warp_sum(sq);
+            n = warp_sum_i(n);
+            ymax = warp_max(ymax);
+            if (lane == s) {
+                FitSlot<P>& sl = slot(s);
+                const double mean = (n > 0) ? s1 / n : 0.0;
+                const double var = (n > 0) ? fmax(sq / n - mean * mean, 0.0) : NAN;
+                double err = sqrt(var);
+                if (pr.weight_mode == 1 && err_in != nullptr) err = err_in[px];
+                sl.pix = px;
+                sl.spec = sp;
+                sl.err = err;
+                sl.sumsq = sq;
+                sl.n_gauss = 0;
+                sl.n_chunks = 0;
+                bool go = (err > 0.0) && !isinf(err);
+                if (go && pr.signal_cut > 0.0 && !(ymax / err >= pr.signal_cut)) go = false;
+                const bool ok = go && lm_init<P>(sl.st, guesses + px * P, cf);
+                if (ok) {
+                    prepare_trial<NC>(pr, sl);
+                    live = true;
+                } else {   // not fitted: zeros, like pyspeckit's blank parcube
+                    write_result<P>(sl, cf, false, params, perr, chi2, err_used, status, counts);
+                }
+            }
+        }
         __syncwarp();
-
-        // ---- weights: err = population std of the finite channels (Cube.fiteach), peak for signal_cut
-        double s1 = 0.0, ymax = -INFINITY;
-        int n = 0;
-        for (int i = lane; i < nchan; i += 32) {
-            const float y = spec[i];
-            if (y == y) {
-                s1 += (double)y;
-                ++n;
-                ymax = fmax(ymax, (double)y);
-            }
+        unsigned alive = __ballot_sync(FULL, live);
+        if (!alive) {
+            if (__ballot_sync(FULL, !dry) == 0) break;   // nothing in flight and the queue is exhausted
+            continue;
         }
-        s1 = warp_sum(s1);
-        n = warp_sum_i(n);
-        ymax = warp_max(ymax);
-        const double mean = (n > 0) ? s1 / n : 0.0;
-        double s2 = 0.0;
-        for (int i = lane; i < nchan; i += 32) {
-            const float y = spec[i];
-            if (y == y) {
-                const double d = (double)y - mean;
-                s2 += d * d;
-            }
+        // ---- one evaluation per live slot
+        while (alive) {
+            const int s = __ffs(alive) - 1;
+            alive &= alive - 1;
+            warp_eval<NC>(pr, tb, slot(s), w, lane);
         }
-        s2 = warp_sum(s2);
-        double err = (n > 0) ? sqrt(s2 / n) : NAN;
-        if (pr.weight_mode == 1 && err_in != nullptr) err = err_in[pix];
-
-        // ---- sum(y^2) per 32-channel chunk (skewed reads: conflict-free), chunk = lane and lane + 32
-        float y2a = 0.f, y2b = 0.f;
-        {
-            const int nchunks = (nchan + 31) >> 5;
-            if (lane < nchunks) {
-                for (int m = 0; m < 32; ++m) {
-                    const float y = spec[(lane << 5) + ((m + lane) & 31)];
-                    if (y == y) y2a = fmaf(y, y, y2a);
-                }
-            }
-            if (lane + 32 < nchunks) {
-                for (int m = 0; m < 32; ++m) {
-                    const float y = spec[((lane + 32) << 5) + ((m + lane) & 31)];
-                    if (y == y) y2b = fmaf(y, y, y2b);
-                }
-            }
-        }
-
-        bool go = (err > 0.0) && !isinf(err);
-        if (go && pr.signal_cut > 0.0 && !(ymax / err >= pr.signal_cut)) go = false;
-        int ok = 0;
-        if (lane == 0 && go) ok = lm_init<P>(w.st, guesses + pix * P, pr.lo, pr.hi, pr.max_iter, pr.ftol) ? 1 : 0;
-        ok = __shfl_sync(FULL, ok, 0);
-        unsigned n_gauss = 0, n_chunks = 0;
-        int st_final = 0;
-        if (ok) {
-            __syncwarp();
-            warp_eval<NC>(pr, w, spec, lane, y2a, y2b, n_gauss, n_chunks);
-            int done = 0;
-            if (lane == 0) done = lm_adopt_first<P>(w.st);
-            done = __shfl_sync(FULL, done, 0);
-            while (!done) {
-                if (lane == 0) done = dev_lm_propose<P>(&w.st);
-                done = __shfl_sync(FULL, done, 0);
-                if (done) break;
-                __syncwarp();
-                warp_eval<NC>(pr, w, spec, lane, y2a, y2b, n_gauss, n_chunks);
-                if (lane == 0) done = dev_lm_update<P>(&w.st);
-                done = __shfl_sync(FULL, done, 0);
-            }
-            __syncwarp();
-            st_final = w.st.status;
-        }
-        // ---- results (zeros on failure, like pyspeckit's blank parcube)
-        if (lane == 0) {
-            double pe[P];
-            const bool good = ok && st_final > 0;
-            const double err2 = err * err;
-            if (good) dev_lm_errors<P>(&w.st, err2, pe);
-#pragma unroll
-            for (int j = 0; j < P; ++j) {
-                params[pix * P + j] = good ? w.st.p[j] : 0.0;
-                perr[pix * P + j] = good ? pe[j] : 0.0;
-            }
-            chi2[pix] = good ? lm_reported_chi2<P>(w.st) / err2 : 0.0;
-            err_used[pix] = err;
-            status[pix] = ok ? st_final : 0;
-            if (counts) {
-                counts[4 * pix + 0] = ok ? (unsigned)w.st.nevals : 0u;
-                counts[4 * pix + 1] = ok ? (unsigned)w.st.nrej : 0u;
-                counts[4 * pix + 2] = n_gauss;
-                counts[4 * pix + 3] = n_chunks;
+        __syncwarp();
+        // ---- SIMT solver step: lane s owns slot s
+        if (live) {
+            FitSlot<P>& sl = slot(lane);
+            int done = (sl.st.nevals == 0) ? lm_adopt_first<P>(sl.st) : lm_update<P>(sl.st, cf);
+            if (!done) done = lm_propose<P>(sl.st, cf);
+            if (done) {
+                write_result<P>(sl, cf, true, params, perr, chi2, err_used, status, counts);
+                live = false;
+            } else {
+                prepare_trial<NC>(pr, sl);
             }
         }
         __syncwarp();
@@ -825,25 +898,54 @@ static int fail(b200fit_ctx* ctx, int code, const char* what, cudaError_t ce = c
         if (ce_ != cudaSuccess) return fail(ctx, B200FIT_E_CUDA, #call, ce_); \
     } while (0)
 
+template <int NC, int G>
+static int launch_fit_g(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_spectra, int64_t stride,
+                        const double* d_guesses, const double* d_err, double* d_params, double* d_perr, double* d_chi2,
+                        double* d_err_used, int32_t* d_status, uint32_t* d_counts, void* d_workspace,
+                        const int64_t* d_row_index, cudaStream_t stream) {
+    const size_t smem = FIT_WARPS * fit_warp_bytes<NC, G>();
+    CK(cudaFuncSetAttribute(fit_kernel<NC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel<NC, G>, FIT_WARPS * 32, smem));
+    if (per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit kernel does not fit on an SM");
+    long long blocks = (long long)ctx->num_sms * per_sm;   // persistent: a whole number of CTAs per SM
+    const long long need = (pr.npix + (long long)FIT_WARPS * G - 1) / ((long long)FIT_WARPS * G);
+    if (blocks > need) blocks = need;
+    CK(cudaMemsetAsync(d_workspace, 0, sizeof(unsigned long long), stream));
+    fit_kernel<NC, G><<<(unsigned)blocks, FIT_WARPS * 32, smem, stream>>>(
+        pr, d_spectra, (long long)stride, d_guesses, d_err, d_params, d_perr, d_chi2, d_err_used, d_status, d_counts,
+        (unsigned long long*)d_workspace, (const long long*)d_row_index);
+    CK(cudaGetLastError());
+    return B200FIT_OK;
+}
+
+// pixels in flight per warp (solver SIMT width); B200FIT_GROUP overrides for tuning experiments
+static int fit_group_size() {
+    static int g = -1;
+    if (g < 0) {
+        const char* e = getenv("B200FIT_GROUP");
+        g = e ? atoi(e) : 8;
+        if (g != 4 && g != 8 && g != 16) g = 8;
+    }
+    return g;
+}
+
 template <int NC>
 static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_spectra, int64_t stride,
                       const double* d_guesses, const double* d_err, double* d_params, double* d_perr, double* d_chi2,
                       double* d_err_used, int32_t* d_status, uint32_t* d_counts, void* d_workspace,
                       const int64_t* d_row_index, cudaStream_t stream) {
-    const size_t smem = FIT_WARPS * (fit_shared_fixed_bytes<NC>() + (size_t)stride * sizeof(float));
-    CK(cudaFuncSetAttribute(fit_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel<NC>, FIT_WARPS * 32, smem));
-    if (per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit kernel does not fit on an SM");
-    long long blocks = (long long)ctx->num_sms * per_sm;   // persistent: a whole number of CTAs per SM
-    const long long need = (pr.npix + FIT_WARPS - 1) / FIT_WARPS;
-    if (blocks > need) blocks = need;
-    CK(cudaMemsetAsync(d_workspace, 0, sizeof(unsigned long long), stream));
-    fit_kernel<NC><<<(unsigned)blocks, FIT_WARPS * 32, smem, stream>>>(
-        pr, d_spectra, (long long)stride, d_guesses, d_err, d_params, d_perr, d_chi2, d_err_used, d_status, d_counts,
-        (unsigned long long*)d_workspace, (const long long*)d_row_index);
-    CK(cudaGetLastError());
-    return B200FIT_OK;
+    switch (fit_group_size()) {
+        case 4:
+            return launch_fit_g<NC, 4>(ctx, pr, d_spectra, stride, d_guesses, d_err, d_params, d_perr, d_chi2,
+                                       d_err_used, d_status, d_counts, d_workspace, d_row_index, stream);
+        case 16:
+            return launch_fit_g<NC, 16>(ctx, pr, d_spectra, stride, d_guesses, d_err, d_params, d_perr, d_chi2,
+                                        d_err_used, d_status, d_counts, d_workspace, d_row_index, stream);
+        default:
+            return launch_fit_g<NC, 8>(ctx, pr, d_spectra, stride, d_guesses, d_err, d_params, d_perr, d_chi2,
+                                       d_err_used, d_status, d_counts, d_workspace, d_row_index, stream);
+    }
 }
 
 extern "C" {

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Profiling workload: a row slab of BASELINE configs[1] (NH3 256x256x800) through the C ABI on one GPU:
+1-comp fit, 2-comp fit, AICc selection.  Used under ncu (launch list + --set full of fit_kernel<2>).
+usage: python profiles/profile_fit.py [nrows] [reps]"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mufasa_b200 import _abi, synth                      # noqa: E402
+from mufasa_b200.engine import get_engine                 # noqa: E402
+from mufasa_b200.spec_models.meta_model import MetaModel  # noqa: E402
+
+nrows = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+cfg = int(os.environ.get("PROFILE_CFG", "2"))
+eng = get_engine(0)
+dev = eng.device
+fittype, ny, nx, nchan, dv = synth.CONFIGS[cfg]
+
+
+def gpu_modelcube(parcube, v, ft):
+    P, ry, rx = parcube.shape
+    prob = _abi.make_problem(ft, P // 4, len(v), ry * rx, v[0], v[1] - v[0], [-1e30] * P, [1e30] * P)
+    par = torch.from_numpy(np.ascontiguousarray(parcube.reshape(P, ry * rx).T)).to(dev)
+    m = eng.model(prob, par)[:, :len(v)]
+    return m.cpu().numpy().T.reshape(len(v), ry, rx)
+
+
+y0 = (ny - nrows) // 2
+syn = synth.make_cube(cfg, gpu_modelcube, rows=(y0, y0 + nrows))
+v = syn["v"]
+npix = nrows * nx
+mm = MetaModel(fittype, 1)
+cube_dev = torch.from_numpy(syn["cube"].reshape(nchan, npix)).to(dev)
+rows = eng.gather(cube_dev)
+probs, gs = {}, {}
+for nc in (1, 2):
+    lo = [-3.5, mm.sigmin, mm.Texmin, mm.taumin] * nc
+    hi = [4.5, mm.sigmax, mm.Texmax, mm.taumax] * nc
+    g = synth.clamp_guesses(syn["guess%d" % nc], lo, hi, eps=mm.eps)
+    gs[nc] = torch.from_numpy(np.ascontiguousarray(g.reshape(4 * nc, npix).T)).to(dev)
+    probs[nc] = _abi.make_problem(fittype, nc, nchan, npix, v[0], dv, lo, hi)
+for r in range(reps):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    o1 = eng.fit(probs[1], rows, gs[1])
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    o2 = eng.fit(probs[2], rows, gs[2])
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    a = eng.aicc_global(probs[1], rows, o1["params"], o2["params"])
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    st = o2["status"].cpu().numpy()
+    cn = o2["counts"].cpu().numpy().astype(np.float64)
+    print("rep %d npix %d: fit1 %.2f ms  fit2 %.2f ms  aicc %.2f ms | 2c: conv %.3f maxiter %.3f mean evals %.1f "
+          "(median %.0f, p90 %.0f, max %.0f) | ncomp hist %s" % (
+              r, npix, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, np.isin(st, [1, 2, 3, 4]).mean(),
+              (st == 5).mean(), cn[:, 0].mean(), np.median(cn[:, 0]), np.percentile(cn[:, 0], 90), cn[:, 0].max(),
+              np.bincount(a["ncomp"].cpu().numpy().astype(int), minlength=3).tolist()), flush=True)
+    hist = np.bincount(st.clip(-1, 8) + 1, minlength=10)
+    print("status hist (-1..8):", hist.tolist(), flush=True)

@@ -22,30 +22,22 @@ struct Eval {
 
     const DeviceProblem& pr;
     const float* spec;
-    std::vector<float> chunkY2;
+    double sumsq = 0.0;
     int nchunks;
     uint64_t n_gauss = 0, n_chunks = 0;
 
-    Eval(const DeviceProblem& p, const float* s) : pr(p), spec(s) {
-        nchunks = (pr.nchan + 31) / 32;
-        chunkY2.assign(nchunks, 0.f);
-        for (int j = 0; j < nchunks; ++j) {
-            float acc = 0.f;
-            for (int m = 0; m < 32; ++m) {
-                const int i = 32 * j + m;
-                if (i < pr.nchan && spec[i] == spec[i]) acc = fmaf(spec[i], spec[i], acc);
-            }
-            chunkY2[j] = acc;
-        }
-    }
+    Eval(const DeviceProblem& p, const float* s, double sq) : pr(p), spec(s), sumsq(sq) { nchunks = (pr.nchan + 31) / 32; }
 
     void run(const double* p, double* H, double* b, double& chi2) {
         CompCoef cc[NC];
         LineCoef lc[NC][MAXHF_FIT];
-        float ic[NC][MAXHF_FIT], hw[NC][MAXHF_FIT];
+        float wlo[NC][MAXHF_FIT], whi[NC][MAXHF_FIT];
         for (int c = 0; c < NC; ++c) {
-            comp_coefs(pr, p + 4 * c, cc[c]);
-            for (int k = 0; k < pr.nhf; ++k) line_coef(pr, p + 4 * c, k, lc[c][k], ic[c][k], hw[c][k]);
+            comp_coefs(pr.T0c, pr.dT0, pr.Jbg0, pr.Jbg1, p + 4 * c, cc[c]);
+            const double inv_sigma = 1.0 / p[4 * c + 1];
+            for (int k = 0; k < pr.nhf; ++k)
+                line_coef(pr.c1mrho[k], pr.rho[k], pr.kdv[k], pr.lw[k], pr.v0, pr.inv_dv, p[4 * c], inv_sigma, lc[c][k],
+                          wlo[c][k], whi[c][k]);
         }
         std::vector<float> acc(32 * NACC, 0.f);
         for (int j = 0; j < nchunks; ++j) {
@@ -53,18 +45,17 @@ struct Eval {
             bool active = false;
             const float lo_edge = 32.f * j, hi_edge = 32.f * j + 31.f;
             for (int c = 0; c < NC; ++c) {
-                klo[c] = 0;
-                khi[c] = 0;
-                for (int k = 0; k < pr.nhf; ++k) {
-                    klo[c] += (ic[c][k] + hw[c][k] < lo_edge) ? 1 : 0;
-                    khi[c] += (ic[c][k] - hw[c][k] <= hi_edge) ? 1 : 0;
+                int glo = 0, ghi = 0;
+                for (int g = 0; g < pr.ngroups; ++g) {
+                    const int first = pr.gstart[g], last = pr.gstart[g + 1] - 1;
+                    glo += (whi[c][last] < lo_edge) ? 1 : 0;
+                    ghi += (wlo[c][first] <= hi_edge) ? 1 : 0;
                 }
+                klo[c] = pr.gstart[glo];
+                khi[c] = pr.gstart[ghi];
                 if (klo[c] < khi[c]) active = true;
             }
-            if (!active) {
-                acc[(j & 31) * NACC + NACC - 1] += chunkY2[j];
-                continue;
-            }
+            if (!active) continue;
             n_chunks++;
             for (int lane = 0; lane < 32; ++lane) {
                 const int i = 32 * j + lane;
@@ -85,22 +76,41 @@ struct Eval {
                 for (int u = 0; u < P; ++u)
                     for (int v = u; v < P; ++v) a[q] = fmaf(J[u], J[v], a[q]), ++q;
                 for (int u = 0; u < P; ++u) a[NH + u] = fmaf(J[u], r, a[NH + u]);
-                a[NACC - 1] = fmaf(r, r, a[NACC - 1]);
+                a[NACC - 1] += m * (m - 2.f * y);
             }
             for (int c = 0; c < NC; ++c) n_gauss += (uint64_t)(khi[c] > klo[c] ? khi[c] - klo[c] : 0);
         }
         for (int e = 0; e < NACC; ++e) {
-            double s = 0.0;
-            for (int lane = 0; lane < 32; ++lane) s += (double)acc[lane * NACC + e];
+            double s[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int lane = 0; lane < 32; ++lane) s[lane & 3] += (double)acc[lane * NACC + e];
+            const double t = (s[0] + s[1]) + (s[2] + s[3]);
             if (e < NH)
-                H[e] = s;
+                H[e] = t;
             else if (e < NH + P)
-                b[e - NH] = s;
+                b[e - NH] = t;
             else
-                chi2 = s;
+                chi2 = sumsq + t;
         }
     }
 };
+
+// weights as the kernel's prologue computes them: one pass, fp64
+static double spectrum_stats(const DeviceProblem& pr, const float* spec, double& sumsq, double& ymax) {
+    double sum = 0.0;
+    sumsq = 0.0;
+    ymax = -INFINITY;
+    int n = 0;
+    for (int i = 0; i < pr.nchan; ++i)
+        if (spec[i] == spec[i]) {
+            sum += spec[i];
+            sumsq += (double)spec[i] * (double)spec[i];
+            ++n;
+            ymax = fmax(ymax, (double)spec[i]);
+        }
+    if (n == 0) return NAN;
+    const double mean = sum / n;
+    return sqrt(fmax(sumsq / n - mean * mean, 0.0));
+}
 
 template <int NC>
 void fit_pixel(const DeviceProblem& pr, const float* spec, const double* guess, const double* err_in, double* params,
@@ -110,38 +120,24 @@ void fit_pixel(const DeviceProblem& pr, const float* spec, const double* guess, 
     *chi2_out = 0.0;
     *status = 0;
     if (counts) counts[0] = counts[1] = counts[2] = counts[3] = 0;
-    // weights (Cube.fiteach: std of the finite channels) + peak for signal_cut
-    double sum = 0.0, ymax = -INFINITY;
-    int n = 0;
-    for (int i = 0; i < pr.nchan; ++i)
-        if (spec[i] == spec[i]) {
-            sum += spec[i];
-            ++n;
-            ymax = fmax(ymax, (double)spec[i]);
-        }
-    double err = NAN;
-    if (n > 0) {
-        const double mean = sum / n;
-        double ss = 0.0;
-        for (int i = 0; i < pr.nchan; ++i)
-            if (spec[i] == spec[i]) ss += ((double)spec[i] - mean) * ((double)spec[i] - mean);
-        err = sqrt(ss / n);
-    }
+    double sumsq, ymax;
+    double err = spectrum_stats(pr, spec, sumsq, ymax);
     if (pr.weight_mode == 1 && err_in) err = *err_in;
     *err_used = err;
     if (!(err > 0.0) || std::isinf(err)) return;
     if (pr.signal_cut > 0.0 && !(ymax / err >= pr.signal_cut)) return;
 
+    const LMConfig cf{pr.lo, pr.hi, pr.ftol, pr.max_iter};
     LMState<P> s;
-    if (!lm_init<P>(s, guess, pr.lo, pr.hi, pr.max_iter, pr.ftol)) return;
-    Eval<NC> ev(pr, spec);
+    if (!lm_init<P>(s, guess, cf)) return;
+    Eval<NC> ev(pr, spec, sumsq);
     ev.run(s.pt, s.Ht, s.bt, s.chi2t);
     int done = lm_adopt_first<P>(s);
     while (!done) {
-        done = lm_propose<P>(s);
+        done = lm_propose<P>(s, cf);
         if (done) break;
         ev.run(s.pt, s.Ht, s.bt, s.chi2t);
-        done = lm_update<P>(s);
+        done = lm_update<P>(s, cf);
     }
     *status = s.status;
     if (counts) {
@@ -153,7 +149,7 @@ void fit_pixel(const DeviceProblem& pr, const float* spec, const double* guess, 
     if (s.status > 0) {
         const double err2 = err * err;
         for (int j = 0; j < P; ++j) params[j] = s.p[j];
-        lm_errors<P>(s, err2, perr);
+        lm_errors<P>(s, cf, err2, perr);
         *chi2_out = lm_reported_chi2<P>(s) / err2;
     }
 }
@@ -185,11 +181,13 @@ extern "C" int emul_eval(const b200fit_problem* prob, const float* spec, const d
     DeviceProblem pr;
     const int rc = make_device_problem(*prob, pr);
     if (rc) return rc;
+    double sumsq, ymax;
+    spectrum_stats(pr, spec, sumsq, ymax);
     if (pr.ncomp == 1) {
-        Eval<1> ev(pr, spec);
+        Eval<1> ev(pr, spec, sumsq);
         ev.run(p, H, b, *chi2);
     } else {
-        Eval<2> ev(pr, spec);
+        Eval<2> ev(pr, spec, sumsq);
         ev.run(p, H, b, *chi2);
     }
     return 0;
@@ -202,18 +200,21 @@ extern "C" int emul_trace2(const b200fit_problem* prob, const float* spec, const
     const int rc = make_device_problem(*prob, pr);
     if (rc) return rc;
     constexpr int P = 8;
+    const LMConfig cf{pr.lo, pr.hi, pr.ftol, pr.max_iter};
     LMState<P> s;
-    if (!lm_init<P>(s, guess, pr.lo, pr.hi, pr.max_iter, pr.ftol)) return -1;
-    Eval<2> ev(pr, spec);
+    if (!lm_init<P>(s, guess, cf)) return -1;
+    double sumsq, ymax;
+    spectrum_stats(pr, spec, sumsq, ymax);
+    Eval<2> ev(pr, spec, sumsq);
     ev.run(s.pt, s.Ht, s.bt, s.chi2t);
     int done = lm_adopt_first<P>(s);
     while (!done) {
-        done = lm_propose<P>(s);
+        done = lm_propose<P>(s, cf);
         if (done) break;
         ev.run(s.pt, s.Ht, s.bt, s.chi2t);
         const double c0 = s.chi2;
         const int it0 = s.iters;
-        done = lm_update<P>(s);
+        done = lm_update<P>(s, cf);
         fprintf(stderr, "ev %3d it %3d %s chi2 %.9f -> %.9f act %.3e par %.3e delta %.3e alpha %.3g pnorm %.3e peg %02x pt:", s.nevals,
                 s.iters, s.iters > it0 ? "ACC" : "rej", c0, s.chi2t, 1 - s.chi2t / c0, s.par, s.delta, s.alpha, s.pnorm, s.peg);
         for (int j = 0; j < P; ++j) fprintf(stderr, " %.6g", s.pt[j]);
