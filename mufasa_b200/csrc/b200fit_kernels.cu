@@ -28,7 +28,6 @@
 namespace b200fit {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int FIT_WARPS = 4;   // warps per block of the fit kernel
 
 // ---------------------------------------------------------------------------------------------------------
 // warp helpers
@@ -49,36 +48,38 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// fit_kernel<NC, G>: persistent warps; every warp keeps a GROUP of G pixels in flight ("slots").
-//   round := { refill empty slots from the atomic pixel queue (warp-cooperative prologue: weights, sum y^2);
-//              for each live slot: ONE warp-cooperative evaluation at its trial point (lanes = channels);
-//              SIMT solver step: lane s advances the LM state machine of slot s }.
-// The solver is branchy fp64 scalar code; running it on one lane per pixel with G pixels per warp amortises
-// its issue slots G-fold (v1 ran it on lane 0 only: 63 % of all executed instructions, profiles/r1a_*).
-// Slots finish independently (iteration counts differ by >10x) and are refilled at once, so a slow pixel never
-// holds the other G-1 slots back.  Spectra are NOT staged in shared memory: an evaluation touches only the
-// 32-channel chunks inside a hyperfine window (~half of the row) and the in-flight rows (148 SMs x 16 warps x G
-// x 3.2 KB ~ 60 MB) stay L2-resident (126 MB), so shared memory is spent on solver state instead.
+// The fit: a ROUND LOOP of two small, uniform kernels over a compacted list of the pixels still iterating.
+//   fit_prologue_kernel  warp per pixel, once: weights (std of the finite channels), sum y^2, LM initialisation,
+//                        active list 0
+//   fit_eval_kernel      warp per ACTIVE pixel: fp32 model + analytic Jacobian over the hyperfine windows,
+//                        J^T J / J^T r / chi2 (fp32 per lane, fp64 across lanes) at the pixel's trial point
+//   fit_solve_kernel     THREAD per active pixel: one step of the LM state machine (fp64 Cholesky trust-region
+//                        solve, mpfit limits); finished pixels write their results, the rest join the next list
+// Why not one fused persistent kernel (rounds 1a-1c, profiles/): the solver is ~5k instructions of branchy fp64
+// scalar code per step.  Fused, it ran on 1 (v1) or ~4 (v2, pixel groups) lanes of a warp, and evaluation +
+// solver code together (107-263 KB) thrashed the 32 KB instruction cache -- >50 % of all stall samples were
+// "no instruction".  Split, every warp of a kernel runs the same few KB of code, the solver runs 32 pixels per
+// warp, pixels that converge early free their lanes at once (iteration counts differ by >10x), and the state
+// that crosses kernels (~1.1 KB per pixel and round) is noise next to the arithmetic: the path is compute bound.
 template <int P>
-struct alignas(8) FitSlot {
+struct alignas(8) PixState {
     LMState<P> st;
-    CompCoef cc[P / 4];          // coefficients of the trial point st.pt (filled by the slot's solver lane)
+    CompCoef cc[P / 4];          // coefficients of the trial point st.pt (filled by the solver)
     double inv_sigma[P / 4];
     double err, sumsq;           // weight (std of the finite channels); sum of y^2 over the finite channels
-    long long pix;
-    const float* spec;
-    unsigned n_gauss, n_chunks;
+    unsigned n_gauss, n_chunks;  // roofline accounting
 };
 
-// slot stride in bytes: == 8 (mod 128), so that lanes s = 0..15 touching the same field of their own slot hit
-// distinct 8-byte bank pairs
-template <int P>
-__host__ __device__ constexpr size_t slot_stride() {
-    return (sizeof(FitSlot<P>) + 119) / 128 * 128 + 8;
-}
+struct FitQueues {               // head of the workspace
+    unsigned int count[2];       // sizes of the ping-pong active lists
+    unsigned int pad[62];
+};
+
+constexpr int EVAL_WARPS = 4;    // warps per block, evaluation / prologue kernels
+constexpr int SOLVE_THREADS = 64;
 
 template <int NC>
-struct FitWarpScratch {
+struct alignas(16) EvalScratch {
     static constexpr int P = 4 * NC;
     static constexpr int NH = P * (P + 1) / 2;
     static constexpr int NACC = NH + P + 1;
@@ -88,216 +89,7 @@ struct FitWarpScratch {
     float red[RED_ROWS][33];                     // cross-lane reduction scratch (+1 pad: conflict-free both ways)
 };
 
-template <int NC, int G>
-__host__ __device__ constexpr size_t fit_warp_bytes() {
-    return (G * slot_stride<4 * NC>() + sizeof(FitWarpScratch<NC>) + 15) / 16 * 16;
-}
-
-// One evaluation of slot `sl` at its trial point st.pt: fills st.Ht / st.bt / st.chi2t.  Warp-collective.
-//   chi2 = sum_finite y^2 + sum_{channels inside a window} m (m - 2 y)      (exactly sum (y - m)^2: m == 0 elsewhere)
-template <int NC>
-__device__ __forceinline__ void warp_eval(const DeviceProblem& pr, const FitTables& tb, FitSlot<4 * NC>& sl,
-                                          FitWarpScratch<NC>& w, int lane) {
-    constexpr int P = 4 * NC;
-    constexpr int NH = P * (P + 1) / 2;
-    constexpr int NACC = NH + P + 1;
-    constexpr int RR = FitWarpScratch<NC>::RED_ROWS;
-    const int nhf = pr.nhf;
-    // 1. fp64 line set-up, one line per lane
-    if (lane < nhf) {
-        const double c1 = tb.c1mrho[lane], rho = tb.rho[lane], kdv = tb.kdv[lane];
-        const float lw = tb.lw[lane];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            LineCoef lc;
-            float lo, hi;
-            line_coef(c1, rho, kdv, lw, pr.v0, pr.inv_dv, sl.st.pt[4 * c], sl.inv_sigma[c], lc, lo, hi);
-            w.lines[c][lane] = lc;
-            w.wlo[c][lane] = lo;
-            w.whi[c][lane] = hi;
-        }
-    }
-    __syncwarp();
-    // 2. which hyperfines touch chunk `lane` and chunk `lane + 32` (whole groups of neighbouring lines; sorted)
-    const int nchunks = (pr.nchan + 31) >> 5;
-    const int ngroups = pr.ngroups;
-    unsigned packed[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int ch = lane + 32 * h;
-        const float lo_edge = 32.f * ch, hi_edge = 32.f * ch + 31.f;
-        unsigned pk = 0;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            int glo = 0, ghi = 0;
-            for (int g = 0; g < ngroups; ++g) {
-                const int first = tb.gstart[g], last = tb.gstart[g + 1] - 1;
-                glo += (w.whi[c][last] < lo_edge) ? 1 : 0;
-                ghi += (w.wlo[c][first] <= hi_edge) ? 1 : 0;
-            }
-            int klo = tb.gstart[glo], khi = tb.gstart[ghi];
-            if (ch >= nchunks) klo = khi = 0;
-            pk |= ((unsigned)klo | ((unsigned)khi << 8)) << (16 * c);
-        }
-        packed[h] = pk;
-    }
-    CompCoef cc[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) cc[c] = sl.cc[c];
-    const float ic0 = (float)pr.ic0;
-    const float* __restrict__ spec = sl.spec;
-
-    float acc[NACC];
-#pragma unroll
-    for (int e = 0; e < NACC; ++e) acc[e] = 0.f;
-    unsigned n_gauss = 0, n_chunks = 0;
-
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        bool mine = false;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const unsigned f = packed[h] >> (16 * c);
-            mine = mine || ((f & 0xffu) < ((f >> 8) & 0xffu));
-        }
-        unsigned act = __ballot_sync(FULL, mine);
-        int jn = act ? (__ffs(act) - 1) : 0;
-        float ynext = act ? __ldg(spec + (((jn + 32 * h) << 5) + lane)) : 0.f;
-        while (act) {
-            const int j = jn;
-            const float y = ynext;
-            act &= act - 1;
-            if (act) {   // prefetch the next active chunk of the row (L2-resident)
-                jn = __ffs(act) - 1;
-                ynext = __ldg(spec + (((jn + 32 * h) << 5) + lane));
-            }
-            const unsigned pk = __shfl_sync(FULL, packed[h], j);
-            const int i = ((j + 32 * h) << 5) + lane;
-            const float fi = (float)i;
-            float Gs[NC], As[NC], Bs[NC];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const unsigned f = pk >> (16 * c);
-                const int klo = f & 0xffu, khi = (f >> 8) & 0xffu;
-                float g = 0.f, a = 0.f, b = 0.f;
-                for (int k = klo; k < khi; ++k) {
-                    const float4 q = *reinterpret_cast<const float4*>(&w.lines[c][k]);
-                    LineCoef lc;
-                    lc.nf = q.x;
-                    lc.b = q.y;
-                    lc.a = q.z;
-                    lc.lw = q.w;
-                    gauss_accum(fi, lc, g, a, b);
-                }
-                Gs[c] = g;
-                As[c] = a;
-                Bs[c] = b;
-                n_gauss += (khi > klo) ? (unsigned)(khi - klo) : 0u;
-            }
-            n_chunks += 1;
-            float m, J[P];
-            rt_channel<NC>(Gs, As, Bs, fi - ic0, cc, m, J);
-            const bool valid = (y == y);   // NaN channels (and the NaN padding) carry no weight
-            const float r = valid ? (y - m) : 0.f;
-            const float dchi = valid ? m * (m - 2.f * y) : 0.f;
-#pragma unroll
-            for (int u = 0; u < P; ++u) J[u] = valid ? J[u] : 0.f;
-            int q = 0;
-#pragma unroll
-            for (int u = 0; u < P; ++u) {
-#pragma unroll
-                for (int v = u; v < P; ++v) {
-                    acc[q] = fmaf(J[u], J[v], acc[q]);
-                    ++q;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < P; ++u) acc[NH + u] = fmaf(J[u], r, acc[NH + u]);
-            acc[NACC - 1] += dchi;
-        }
-    }
-    // 3. cross-lane reduction in fp64 through shared memory, RR accumulators per pass
-#pragma unroll
-    for (int base = 0; base < NACC; base += RR) {
-#pragma unroll
-        for (int e = 0; e < RR; ++e)
-            if (base + e < NACC) w.red[e][lane] = acc[base + e];
-        __syncwarp();
-        const int e = base + lane;
-        if (lane < RR && e < NACC) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-            for (int m = 0; m < 32; m += 4) {
-                s0 += (double)w.red[lane][m];
-                s1 += (double)w.red[lane][m + 1];
-                s2 += (double)w.red[lane][m + 2];
-                s3 += (double)w.red[lane][m + 3];
-            }
-            const double s = (s0 + s1) + (s2 + s3);
-            if (e < NH)
-                sl.st.Ht[e] = s;
-            else if (e < NH + P)
-                sl.st.bt[e - NH] = s;
-            else
-                sl.st.chi2t = sl.sumsq + s;
-        }
-        __syncwarp();
-    }
-    if (lane == 0) {
-        sl.n_gauss += n_gauss;
-        sl.n_chunks += n_chunks;
-    }
-}
-
-// Solver-lane helper: coefficients of the trial point the next evaluation will use.
-template <int NC>
-__device__ __forceinline__ void prepare_trial(const DeviceProblem& pr, FitSlot<4 * NC>& sl) {
-#pragma unroll 1
-    for (int c = 0; c < NC; ++c) {
-        CompCoef cc;
-        comp_coefs(pr.T0c, pr.dT0, pr.Jbg0, pr.Jbg1, &sl.st.pt[4 * c], cc);
-        sl.cc[c] = cc;
-        sl.inv_sigma[c] = 1.0 / sl.st.pt[4 * c + 1];
-    }
-}
-
-template <int P>
-__device__ __forceinline__ void write_result(const FitSlot<P>& sl, const LMConfig& cf, bool fitted,
-                                             double* __restrict__ params, double* __restrict__ perr,
-                                             double* __restrict__ chi2, double* __restrict__ err_used,
-                                             int* __restrict__ status, unsigned* __restrict__ counts) {
-    const long long pix = sl.pix;
-    const bool good = fitted && sl.st.status > 0;
-    const double err2 = sl.err * sl.err;
-    double pe[P];
-    if (good) lm_errors<P>(sl.st, cf, err2, pe);
-#pragma unroll 1
-    for (int j = 0; j < P; ++j) {
-        params[pix * P + j] = good ? sl.st.p[j] : 0.0;
-        perr[pix * P + j] = good ? pe[j] : 0.0;
-    }
-    chi2[pix] = good ? lm_reported_chi2<P>(sl.st) / err2 : 0.0;
-    err_used[pix] = sl.err;
-    status[pix] = fitted ? sl.st.status : 0;
-    if (counts) {
-        counts[4 * pix + 0] = fitted ? (unsigned)sl.st.nevals : 0u;
-        counts[4 * pix + 1] = fitted ? (unsigned)sl.st.nrej : 0u;
-        counts[4 * pix + 2] = fitted ? sl.n_gauss : 0u;
-        counts[4 * pix + 3] = fitted ? sl.n_chunks : 0u;
-    }
-}
-
-template <int NC, int G>
-__global__ void __launch_bounds__(FIT_WARPS * 32, 4)
-    fit_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
-               const double* __restrict__ guesses, const double* __restrict__ err_in, double* __restrict__ params,
-               double* __restrict__ perr, double* __restrict__ chi2, double* __restrict__ err_used,
-               int* __restrict__ status, unsigned* __restrict__ counts, unsigned long long* __restrict__ queue,
-               const long long* __restrict__ row_index) {
-    constexpr int P = 4 * NC;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ FitTables tb;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void load_fit_tables(const DeviceProblem& pr, FitTables& tb) {
     if (threadIdx.x < MAXHF_FIT) {
         const int k = threadIdx.x;
         tb.rho[k] = pr.rho[k];
@@ -311,97 +103,342 @@ __global__ void __launch_bounds__(FIT_WARPS * 32, 4)
         tb.hi[threadIdx.x] = pr.hi[threadIdx.x];
     }
     __syncthreads();
-    unsigned char* wbase = smem_raw + (size_t)warp * fit_warp_bytes<NC, G>();
-    FitWarpScratch<NC>& w = *reinterpret_cast<FitWarpScratch<NC>*>(wbase + G * slot_stride<P>());
-    auto slot = [&](int s) -> FitSlot<P>& { return *reinterpret_cast<FitSlot<P>*>(wbase + (size_t)s * slot_stride<P>()); };
-    const LMConfig cf{tb.lo, tb.hi, pr.ftol, pr.max_iter};
-    const int nchan = pr.nchan;
+}
 
-    bool live = false;        // this lane's slot holds a pixel being fitted
-    bool dry = (lane >= G);   // the queue has nothing more for this lane
-    for (;;) {
-        // ---- refill: every lane with an empty slot takes the next pixel
-        long long pix = -1;
-        if (!live && !dry) {
-            pix = (long long)atomicAdd(queue, 1ULL);
-            if (pix >= pr.npix) {
-                pix = -1;
-                dry = true;
-            }
-        }
-        unsigned fresh = __ballot_sync(FULL, pix >= 0);
-        while (fresh) {
-            const int s = __ffs(fresh) - 1;
-            fresh &= fresh - 1;
-            const long long px = __shfl_sync(FULL, pix, s);
-            // ---- prologue (warp-cooperative, coalesced, one pass): weights err = population std of the finite
-            //      channels (Cube.fiteach), sum y^2, peak for signal_cut
-            const long long row = row_index ? row_index[px] : px;
-            const float* sp = spectra + row * stride;
-            double s1 = 0.0, sq = 0.0, ymax = -INFINITY;
-            int n = 0;
+// Coefficients of the trial point the next evaluation will use.
+template <int NC>
+__device__ __forceinline__ void prepare_trial(const DeviceProblem& pr, PixState<4 * NC>& ps) {
+#pragma unroll 1
+    for (int c = 0; c < NC; ++c) {
+        CompCoef cc;
+        comp_coefs(pr.T0c, pr.dT0, pr.Jbg0, pr.Jbg1, &ps.st.pt[4 * c], cc);
+        ps.cc[c] = cc;
+        ps.inv_sigma[c] = 1.0 / ps.st.pt[4 * c + 1];
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void write_result(const PixState<P>& ps, long long pix, const LMConfig& cf, bool fitted,
+                                             double* __restrict__ params, double* __restrict__ perr,
+                                             double* __restrict__ chi2, double* __restrict__ err_used,
+                                             int* __restrict__ status, unsigned* __restrict__ counts) {
+    const bool good = fitted && ps.st.status > 0;
+    const double err2 = ps.err * ps.err;
+    double pe[P];
+    if (good) lm_errors<P>(ps.st, cf, err2, pe);
+#pragma unroll 1
+    for (int j = 0; j < P; ++j) {
+        params[pix * P + j] = good ? ps.st.p[j] : 0.0;
+        perr[pix * P + j] = good ? pe[j] : 0.0;
+    }
+    chi2[pix] = good ? lm_reported_chi2<P>(ps.st) / err2 : 0.0;
+    err_used[pix] = ps.err;
+    status[pix] = fitted ? ps.st.status : 0;
+    if (counts) {
+        counts[4 * pix + 0] = fitted ? (unsigned)ps.st.nevals : 0u;
+        counts[4 * pix + 1] = fitted ? (unsigned)ps.st.nrej : 0u;
+        counts[4 * pix + 2] = fitted ? ps.n_gauss : 0u;
+        counts[4 * pix + 3] = fitted ? ps.n_chunks : 0u;
+    }
+}
+
+// ---- prologue: warp per pixel -------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(EVAL_WARPS * 32)
+    fit_prologue_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
+                        const long long* __restrict__ row_index, const double* __restrict__ guesses,
+                        const double* __restrict__ err_in, PixState<4 * NC>* __restrict__ states,
+                        unsigned* __restrict__ list0, FitQueues* __restrict__ fq, double* __restrict__ params,
+                        double* __restrict__ perr, double* __restrict__ chi2, double* __restrict__ err_used,
+                        int* __restrict__ status, unsigned* __restrict__ counts) {
+    constexpr int P = 4 * NC;
+    __shared__ FitTables tb;
+    load_fit_tables(pr, tb);
+    const LMConfig cf{tb.lo, tb.hi, pr.ftol, pr.max_iter};
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * EVAL_WARPS + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * EVAL_WARPS;
+    const int nchan = pr.nchan;
+    for (long long px = warp0; px < pr.npix; px += nwarps) {
+        // weights err = population std of the finite channels (Cube.fiteach), sum y^2, peak for signal_cut:
+        // one coalesced pass, fp64 accumulators
+        const long long row = row_index ? row_index[px] : px;
+        const float* sp = spectra + row * stride;
+        double s1 = 0.0, sq = 0.0, ymax = -INFINITY;
+        int n = 0;
 #pragma unroll 4
-            for (int i = lane; i < nchan; i += 32) {
-                const float y = __ldg(sp + i);
-                if (y == y) {
-                    const double yd = (double)y;
-                    s1 += yd;
-                    sq = fma(yd, yd, sq);
-                    ++n;
-                    ymax = fmax(ymax, yd);
-                }
-            }
-            s1 = warp_sum(s1);
-            sq = warp_sum(sq);
-            n = warp_sum_i(n);
-            ymax = warp_max(ymax);
-            if (lane == s) {
-                FitSlot<P>& sl = slot(s);
-                const double mean = (n > 0) ? s1 / n : 0.0;
-                const double var = (n > 0) ? fmax(sq / n - mean * mean, 0.0) : NAN;
-                double err = sqrt(var);
-                if (pr.weight_mode == 1 && err_in != nullptr) err = err_in[px];
-                sl.pix = px;
-                sl.spec = sp;
-                sl.err = err;
-                sl.sumsq = sq;
-                sl.n_gauss = 0;
-                sl.n_chunks = 0;
-                bool go = (err > 0.0) && !isinf(err);
-                if (go && pr.signal_cut > 0.0 && !(ymax / err >= pr.signal_cut)) go = false;
-                const bool ok = go && lm_init<P>(sl.st, guesses + px * P, cf);
-                if (ok) {
-                    prepare_trial<NC>(pr, sl);
-                    live = true;
-                } else {   // not fitted: zeros, like pyspeckit's blank parcube
-                    write_result<P>(sl, cf, false, params, perr, chi2, err_used, status, counts);
-                }
+        for (int i = lane; i < nchan; i += 32) {
+            const float y = __ldg(sp + i);
+            if (y == y) {
+                const double yd = (double)y;
+                s1 += yd;
+                sq = fma(yd, yd, sq);
+                ++n;
+                ymax = fmax(ymax, yd);
             }
         }
-        __syncwarp();
-        unsigned alive = __ballot_sync(FULL, live);
-        if (!alive) {
-            if (__ballot_sync(FULL, !dry) == 0) break;   // nothing in flight and the queue is exhausted
-            continue;
+        s1 = warp_sum(s1);
+        sq = warp_sum(sq);
+        n = warp_sum_i(n);
+        ymax = warp_max(ymax);
+        if (lane == 0) {
+            PixState<P>& ps = states[px];
+            const double mean = (n > 0) ? s1 / n : 0.0;
+            const double var = (n > 0) ? fmax(sq / n - mean * mean, 0.0) : NAN;
+            double err = sqrt(var);
+            if (pr.weight_mode == 1 && err_in != nullptr) err = err_in[px];
+            ps.err = err;
+            ps.sumsq = sq;
+            ps.n_gauss = 0;
+            ps.n_chunks = 0;
+            bool go = (err > 0.0) && !isinf(err);
+            if (go && pr.signal_cut > 0.0 && !(ymax / err >= pr.signal_cut)) go = false;
+            const bool ok = go && lm_init<P>(ps.st, guesses + px * P, cf);
+            if (ok) {
+                prepare_trial<NC>(pr, ps);
+                list0[atomicAdd(&fq->count[0], 1u)] = (unsigned)px;
+            } else {   // not fitted: zeros, like pyspeckit's blank parcube
+                write_result<P>(ps, px, cf, false, params, perr, chi2, err_used, status, counts);
+            }
         }
-        // ---- one evaluation per live slot
-        while (alive) {
-            const int s = __ffs(alive) - 1;
-            alive &= alive - 1;
-            warp_eval<NC>(pr, tb, slot(s), w, lane);
+    }
+}
+
+// ---- evaluation: warp per active pixel -----------------------------------------------------------------------
+//   chi2 = sum_finite y^2 + sum_{channels inside a window} m (m - 2 y)      (exactly sum (y - m)^2: m == 0 elsewhere)
+template <int NC>
+__global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
+    fit_eval_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
+                    const long long* __restrict__ row_index, PixState<4 * NC>* __restrict__ states,
+                    const unsigned* __restrict__ list, FitQueues* __restrict__ fq, int cur) {
+    constexpr int P = 4 * NC;
+    constexpr int NH = P * (P + 1) / 2;
+    constexpr int NACC = NH + P + 1;
+    constexpr int RR = EvalScratch<NC>::RED_ROWS;
+    __shared__ FitTables tb;
+    __shared__ EvalScratch<NC> scratch[EVAL_WARPS];
+    load_fit_tables(pr, tb);
+    const int lane = threadIdx.x & 31;
+    EvalScratch<NC>& w = scratch[threadIdx.x >> 5];
+    const unsigned count = fq->count[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) fq->count[cur ^ 1] = 0;   // the list this round's solver appends to
+    const unsigned warp0 = blockIdx.x * EVAL_WARPS + (threadIdx.x >> 5);
+    const unsigned nwarps = gridDim.x * EVAL_WARPS;
+    const int nhf = pr.nhf;
+    const int nchunks = (pr.nchan + 31) >> 5;
+    const int ngroups = pr.ngroups;
+    const float ic0 = (float)pr.ic0;
+
+    for (unsigned idx = warp0; idx < count; idx += nwarps) {
+        const long long px = list[idx];
+        PixState<P>& ps = states[px];
+        const long long row = row_index ? row_index[px] : px;
+        const float* __restrict__ spec = spectra + row * stride;
+        // 1. fp64 line set-up, one line per lane
+        if (lane < nhf) {
+            const double c1 = tb.c1mrho[lane], rho = tb.rho[lane], kdv = tb.kdv[lane];
+            const float lw = tb.lw[lane];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                LineCoef lc;
+                float lo, hi;
+                line_coef(c1, rho, kdv, lw, pr.v0, pr.inv_dv, ps.st.pt[4 * c], ps.inv_sigma[c], lc, lo, hi);
+                w.lines[c][lane] = lc;
+                w.wlo[c][lane] = lo;
+                w.whi[c][lane] = hi;
+            }
+        }
+        CompCoef cc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) cc[c] = ps.cc[c];
+        __syncwarp();
+        // 2. which hyperfines touch chunk `lane` and chunk `lane + 32` (whole groups of neighbouring lines; sorted)
+        unsigned packed[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ch = lane + 32 * h;
+            const float lo_edge = 32.f * ch, hi_edge = 32.f * ch + 31.f;
+            unsigned pk = 0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                int glo = 0, ghi = 0;
+                for (int g = 0; g < ngroups; ++g) {
+                    const int first = tb.gstart[g], last = tb.gstart[g + 1] - 1;
+                    glo += (w.whi[c][last] < lo_edge) ? 1 : 0;
+                    ghi += (w.wlo[c][first] <= hi_edge) ? 1 : 0;
+                }
+                int klo = tb.gstart[glo], khi = tb.gstart[ghi];
+                if (ch >= nchunks) klo = khi = 0;
+                pk |= ((unsigned)klo | ((unsigned)khi << 8)) << (16 * c);
+            }
+            packed[h] = pk;
+        }
+
+        float acc[NACC];
+#pragma unroll
+        for (int e = 0; e < NACC; ++e) acc[e] = 0.f;
+        unsigned n_gauss = 0, n_chunks = 0;
+
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const unsigned mypk = h ? packed[1] : packed[0];
+            bool mine = false;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const unsigned f = mypk >> (16 * c);
+                mine = mine || ((f & 0xffu) < ((f >> 8) & 0xffu));
+            }
+            unsigned act = __ballot_sync(FULL, mine);
+            int jn = act ? (__ffs(act) - 1) : 0;
+            float ynext = act ? __ldg(spec + (((jn + 32 * h) << 5) + lane)) : 0.f;
+            while (act) {
+                const int j = jn;
+                const float y = ynext;
+                act &= act - 1;
+                if (act) {   // prefetch the next active chunk of the row
+                    jn = __ffs(act) - 1;
+                    ynext = __ldg(spec + (((jn + 32 * h) << 5) + lane));
+                }
+                const unsigned pk = __shfl_sync(FULL, mypk, j);
+                const int i = ((j + 32 * h) << 5) + lane;
+                const float fi = (float)i;
+                float Gs[NC], As[NC], Bs[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const unsigned f = pk >> (16 * c);
+                    const int klo = f & 0xffu, khi = (f >> 8) & 0xffu;
+                    float g = 0.f, a = 0.f, b = 0.f;
+                    for (int k = klo; k < khi; ++k) {
+                        const float4 q = *reinterpret_cast<const float4*>(&w.lines[c][k]);
+                        LineCoef lc;
+                        lc.nf = q.x;
+                        lc.b = q.y;
+                        lc.a = q.z;
+                        lc.lw = q.w;
+                        gauss_accum(fi, lc, g, a, b);
+                    }
+                    Gs[c] = g;
+                    As[c] = a;
+                    Bs[c] = b;
+                    n_gauss += (khi > klo) ? (unsigned)(khi - klo) : 0u;
+                }
+                n_chunks += 1;
+                float m, J[P];
+                rt_channel<NC>(Gs, As, Bs, fi - ic0, cc, m, J);
+                const bool valid = (y == y);   // NaN channels (and the NaN padding) carry no weight
+                const float r = valid ? (y - m) : 0.f;
+                const float dchi = valid ? m * (m - 2.f * y) : 0.f;
+#pragma unroll
+                for (int u = 0; u < P; ++u) J[u] = valid ? J[u] : 0.f;
+                int q = 0;
+#pragma unroll
+                for (int u = 0; u < P; ++u) {
+#pragma unroll
+                    for (int v = u; v < P; ++v) {
+                        acc[q] = fmaf(J[u], J[v], acc[q]);
+                        ++q;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < P; ++u) acc[NH + u] = fmaf(J[u], r, acc[NH + u]);
+                acc[NACC - 1] += dchi;
+            }
+        }
+        // 3. cross-lane reduction in fp64 through shared memory, RR accumulators per pass
+#pragma unroll
+        for (int base = 0; base < NACC; base += RR) {
+#pragma unroll
+            for (int e = 0; e < RR; ++e)
+                if (base + e < NACC) w.red[e][lane] = acc[base + e];
+            __syncwarp();
+            const int e = base + lane;
+            if (lane < RR && e < NACC) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int m = 0; m < 32; m += 4) {
+                    s0 += (double)w.red[lane][m];
+                    s1 += (double)w.red[lane][m + 1];
+                    s2 += (double)w.red[lane][m + 2];
+                    s3 += (double)w.red[lane][m + 3];
+                }
+                const double s = (s0 + s1) + (s2 + s3);
+                if (e < NH)
+                    ps.st.Ht[e] = s;
+                else if (e < NH + P)
+                    ps.st.bt[e - NH] = s;
+                else
+                    ps.st.chi2t = ps.sumsq + s;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            ps.n_gauss += n_gauss;
+            ps.n_chunks += n_chunks;
+        }
+    }
+}
+
+// ---- solver: thread per active pixel -------------------------------------------------------------------------
+// The state machine is a long chain of dependent fp64 operations on ~1 KB of per-pixel state: run out of global
+// memory it is bound by load latency (~100 us per step, round 1d).  Each warp therefore stages the states of its
+// 32 pixels in shared memory with coalesced copies, steps them there, and copies them back.
+// Shared-memory stride == 8 (mod 128) bytes: the 32 lanes touching the same fp64 field of their own state hit
+// 32 distinct 8-byte bank pairs.
+template <int P>
+__host__ __device__ constexpr size_t solve_stride() {
+    return (sizeof(PixState<P>) + 119) / 128 * 128 + 8;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(SOLVE_THREADS)
+    fit_solve_kernel(const DeviceProblem pr, PixState<4 * NC>* __restrict__ states, const unsigned* __restrict__ list,
+                     unsigned* __restrict__ next_list, FitQueues* __restrict__ fq, int cur,
+                     double* __restrict__ params, double* __restrict__ perr, double* __restrict__ chi2,
+                     double* __restrict__ err_used, int* __restrict__ status, unsigned* __restrict__ counts) {
+    constexpr int P = 4 * NC;
+    constexpr int NV = sizeof(PixState<P>) / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ FitTables tb;
+    load_fit_tables(pr, tb);
+    const LMConfig cf{tb.lo, tb.hi, pr.ftol, pr.max_iter};
+    const unsigned count = fq->count[cur];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wsm = smem_raw + (size_t)warp * 32 * solve_stride<P>();
+    PixState<P>& ps = *reinterpret_cast<PixState<P>*>(wsm + (size_t)lane * solve_stride<P>());
+    for (unsigned base = blockIdx.x * SOLVE_THREADS + warp * 32; base < count; base += gridDim.x * SOLVE_THREADS) {
+        const unsigned idx = base + lane;
+        const unsigned px = (idx < count) ? list[idx] : 0xffffffffu;
+        // stage in: one state per step, the warp's lanes stride over its 8-byte words
+#pragma unroll 1
+        for (int t = 0; t < 32; ++t) {
+            const unsigned pt = __shfl_sync(FULL, px, t);
+            if (pt == 0xffffffffu) break;
+            const uint2* __restrict__ g = reinterpret_cast<const uint2*>(states + pt);
+            uint2* s = reinterpret_cast<uint2*>(wsm + (size_t)t * solve_stride<P>());
+            for (int k = lane; k < NV; k += 32) s[k] = g[k];
         }
         __syncwarp();
-        // ---- SIMT solver step: lane s owns slot s
-        if (live) {
-            FitSlot<P>& sl = slot(lane);
-            int done = (sl.st.nevals == 0) ? lm_adopt_first<P>(sl.st) : lm_update<P>(sl.st, cf);
-            if (!done) done = lm_propose<P>(sl.st, cf);
+        bool keep = false;
+        if (px != 0xffffffffu) {
+            int done = (ps.st.nevals == 0) ? lm_adopt_first<P>(ps.st) : lm_update<P>(ps.st, cf);
+            if (!done) done = lm_propose<P>(ps.st, cf);
             if (done) {
-                write_result<P>(sl, cf, true, params, perr, chi2, err_used, status, counts);
-                live = false;
+                write_result<P>(ps, (long long)px, cf, true, params, perr, chi2, err_used, status, counts);
             } else {
-                prepare_trial<NC>(pr, sl);
+                prepare_trial<NC>(pr, ps);
+                next_list[atomicAdd(&fq->count[cur ^ 1], 1u)] = px;
+                keep = true;
             }
+        }
+        __syncwarp();
+        // stage out the states that go on
+#pragma unroll 1
+        for (int t = 0; t < 32; ++t) {
+            const unsigned pt = __shfl_sync(FULL, keep ? px : 0xffffffffu, t);
+            if (pt == 0xffffffffu) continue;
+            uint2* __restrict__ g = reinterpret_cast<uint2*>(states + pt);
+            const uint2* s = reinterpret_cast<const uint2*>(wsm + (size_t)t * solve_stride<P>());
+            for (int k = lane; k < NV; k += 32) g[k] = s[k];
         }
         __syncwarp();
     }
@@ -879,6 +916,8 @@ struct b200fit_ctx {
     int device;
     int num_sms;
     std::string err;
+    cudaEvent_t check_ev[4];
+    volatile unsigned* h_count;   // pinned, 4 slots: active-pixel counts read back by the fit's round loop
 };
 
 static int fail(b200fit_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess) {
@@ -898,54 +937,80 @@ static int fail(b200fit_ctx* ctx, int code, const char* what, cudaError_t ce = c
         if (ce_ != cudaSuccess) return fail(ctx, B200FIT_E_CUDA, #call, ce_); \
     } while (0)
 
-template <int NC, int G>
-static int launch_fit_g(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_spectra, int64_t stride,
-                        const double* d_guesses, const double* d_err, double* d_params, double* d_perr, double* d_chi2,
-                        double* d_err_used, int32_t* d_status, uint32_t* d_counts, void* d_workspace,
-                        const int64_t* d_row_index, cudaStream_t stream) {
-    const size_t smem = FIT_WARPS * fit_warp_bytes<NC, G>();
-    CK(cudaFuncSetAttribute(fit_kernel<NC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel<NC, G>, FIT_WARPS * 32, smem));
-    if (per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit kernel does not fit on an SM");
-    long long blocks = (long long)ctx->num_sms * per_sm;   // persistent: a whole number of CTAs per SM
-    const long long need = (pr.npix + (long long)FIT_WARPS * G - 1) / ((long long)FIT_WARPS * G);
-    if (blocks > need) blocks = need;
-    CK(cudaMemsetAsync(d_workspace, 0, sizeof(unsigned long long), stream));
-    fit_kernel<NC, G><<<(unsigned)blocks, FIT_WARPS * 32, smem, stream>>>(
-        pr, d_spectra, (long long)stride, d_guesses, d_err, d_params, d_perr, d_chi2, d_err_used, d_status, d_counts,
-        (unsigned long long*)d_workspace, (const long long*)d_row_index);
-    CK(cudaGetLastError());
-    return B200FIT_OK;
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <int NC>
+static size_t fit_workspace_bytes(long long npix) {
+    return sizeof(FitQueues) + 2 * align_up((size_t)npix * sizeof(unsigned), 256) +
+           (size_t)npix * sizeof(PixState<4 * NC>) + 256;
 }
 
-// pixels in flight per warp (solver SIMT width); B200FIT_GROUP overrides for tuning experiments
-static int fit_group_size() {
-    static int g = -1;
-    if (g < 0) {
-        const char* e = getenv("B200FIT_GROUP");
-        g = e ? atoi(e) : 8;
-        if (g != 4 && g != 8 && g != 16) g = 8;
-    }
-    return g;
-}
-
+// Round loop.  Every pixel finishes within 2*max_iter + 3 rounds (lm_update caps evaluations); the host checks
+// the active count every CHECK rounds through a pinned counter, two checks behind the launches, so the GPU never
+// idles waiting for the host and at most 2*CHECK empty rounds are launched after the last pixel converged.
 template <int NC>
 static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_spectra, int64_t stride,
                       const double* d_guesses, const double* d_err, double* d_params, double* d_perr, double* d_chi2,
                       double* d_err_used, int32_t* d_status, uint32_t* d_counts, void* d_workspace,
                       const int64_t* d_row_index, cudaStream_t stream) {
-    switch (fit_group_size()) {
-        case 4:
-            return launch_fit_g<NC, 4>(ctx, pr, d_spectra, stride, d_guesses, d_err, d_params, d_perr, d_chi2,
-                                       d_err_used, d_status, d_counts, d_workspace, d_row_index, stream);
-        case 16:
-            return launch_fit_g<NC, 16>(ctx, pr, d_spectra, stride, d_guesses, d_err, d_params, d_perr, d_chi2,
-                                        d_err_used, d_status, d_counts, d_workspace, d_row_index, stream);
-        default:
-            return launch_fit_g<NC, 8>(ctx, pr, d_spectra, stride, d_guesses, d_err, d_params, d_perr, d_chi2,
-                                       d_err_used, d_status, d_counts, d_workspace, d_row_index, stream);
+    constexpr int P = 4 * NC;
+    unsigned char* ws = (unsigned char*)d_workspace;
+    FitQueues* fq = (FitQueues*)ws;
+    const size_t list_bytes = align_up((size_t)pr.npix * sizeof(unsigned), 256);
+    unsigned* lists[2] = {(unsigned*)(ws + sizeof(FitQueues)), (unsigned*)(ws + sizeof(FitQueues) + list_bytes)};
+    PixState<P>* states = (PixState<P>*)(ws + sizeof(FitQueues) + 2 * list_bytes);
+    if (pr.npix >= (1LL << 32)) return fail(ctx, B200FIT_E_ARG, "fit: npix must be < 2^32 per call");
+
+    CK(cudaMemsetAsync(fq, 0, sizeof(FitQueues), stream));
+    const long long pwarps = (pr.npix + EVAL_WARPS - 1) / EVAL_WARPS;
+    const long long cap = (long long)ctx->num_sms * 16;
+    const unsigned pgrid = (unsigned)(pwarps < cap ? pwarps : cap);
+    fit_prologue_kernel<NC><<<pgrid, EVAL_WARPS * 32, 0, stream>>>(
+        pr, d_spectra, (long long)stride, (const long long*)d_row_index, d_guesses, d_err, states, lists[0], fq, d_params,
+        d_perr, d_chi2, d_err_used, d_status, d_counts);
+    CK(cudaGetLastError());
+
+    int eval_per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC>, EVAL_WARPS * 32, 0));
+    if (eval_per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit_eval_kernel does not fit on an SM");
+    long long egrid = (long long)ctx->num_sms * eval_per_sm;        // a whole number of CTAs per SM
+    if (egrid > pwarps) egrid = pwarps;
+    const size_t solve_smem = (size_t)SOLVE_THREADS * solve_stride<P>();
+    CK(cudaFuncSetAttribute(fit_solve_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    int solve_per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solve_per_sm, fit_solve_kernel<NC>, SOLVE_THREADS, solve_smem));
+    if (solve_per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit_solve_kernel does not fit on an SM");
+    const long long sblocks = (pr.npix + SOLVE_THREADS - 1) / SOLVE_THREADS;
+    long long sgrid = (long long)ctx->num_sms * solve_per_sm;
+    if (sgrid > sblocks) sgrid = sblocks;
+
+    const int max_rounds = 2 * pr.max_iter + 3;
+    constexpr int CHECK = 8, RING = 4;
+    int nchecks = 0;
+    bool finished = false;
+    for (int r = 0; r < max_rounds && !finished; ++r) {
+        const int cur = r & 1;
+        fit_eval_kernel<NC><<<(unsigned)egrid, EVAL_WARPS * 32, 0, stream>>>(
+            pr, d_spectra, (long long)stride, (const long long*)d_row_index, states, lists[cur], fq, cur);
+        fit_solve_kernel<NC><<<(unsigned)sgrid, SOLVE_THREADS, solve_smem, stream>>>(
+            pr, states, lists[cur], lists[cur ^ 1], fq, cur, d_params, d_perr, d_chi2, d_err_used, d_status, d_counts);
+        if ((r + 1) % CHECK == 0) {
+            const int slot = nchecks % RING;
+            if (nchecks >= RING - 2) {   // wait for the check issued (RING - 2) checks ago
+                const int old = (nchecks - (RING - 2)) % RING;
+                CK(cudaEventSynchronize(ctx->check_ev[old]));
+                if (ctx->h_count[old] == 0) finished = true;
+            }
+            if (!finished) {
+                CK(cudaMemcpyAsync((void*)&ctx->h_count[slot], &fq->count[cur ^ 1], sizeof(unsigned), cudaMemcpyDeviceToHost,
+                                   stream));
+                CK(cudaEventRecord(ctx->check_ev[slot], stream));
+                ++nchecks;
+            }
+        }
     }
+    CK(cudaGetLastError());
+    return B200FIT_OK;
 }
 
 extern "C" {
@@ -968,19 +1033,38 @@ int b200fit_create(b200fit_ctx** out, int device) {
         return B200FIT_E_CUDA;
     }
     ctx->num_sms = prop.multiProcessorCount;
+    ctx->h_count = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMallocHost((void**)&ctx->h_count, 4 * sizeof(unsigned)) != cudaSuccess) {
+        delete ctx;
+        return B200FIT_E_CUDA;
+    }
+    for (int i = 0; i < 4; ++i) {
+        if (cudaEventCreateWithFlags(&ctx->check_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return B200FIT_E_CUDA;
+        }
+    }
     *out = ctx;
     return B200FIT_OK;
 }
 
-void b200fit_destroy(b200fit_ctx* ctx) { delete ctx; }
+void b200fit_destroy(b200fit_ctx* ctx) {
+    if (!ctx) return;
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->check_ev[i]);
+    if (ctx->h_count) cudaFreeHost((void*)ctx->h_count);
+    delete ctx;
+}
 
 const char* b200fit_last_error(const b200fit_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int b200fit_num_sms(const b200fit_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
 
 size_t b200fit_workspace_bytes(const b200fit_problem* prob) {
-    (void)prob;
-    return 256;   // work-queue counter (+ padding)
+    // queues + two active lists + the per-pixel LM state that crosses the round loop's kernels
+    if (!prob || prob->npix < 0) return 0;
+    const size_t a = fit_workspace_bytes<1>(prob->npix), b = fit_workspace_bytes<2>(prob->npix);
+    const size_t fit = (prob->ncomp == 1) ? a : b;
+    return fit < 256 ? 256 : fit;
 }
 
 int b200fit_gather_spectra(b200fit_ctx* ctx, const float* d_cube, int32_t nchan, int64_t nplane,

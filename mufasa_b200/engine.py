@@ -32,7 +32,7 @@ class Engine(object):
             raise B200FitError("b200fit_create failed (%d)" % rc)
         self.ctx = ctx
         self.num_sms = self.lib.b200fit_num_sms(self.ctx)
-        self._ws = torch.zeros(256, dtype=torch.uint8, device=self.device)
+        self._ws = torch.zeros(4096, dtype=torch.uint8, device=self.device)
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -53,6 +53,14 @@ class Engine(object):
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def workspace(self, prob):
+        """Device scratch of b200fit_workspace_bytes(prob) bytes (grown on demand, reused across calls)."""
+        need = int(self.lib.b200fit_workspace_bytes(C.byref(prob)))
+        if self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
 
     @staticmethod
     def nchan_stride(nchan):
@@ -95,7 +103,8 @@ class Engine(object):
         rc = self.lib.b200fit_fit(self.ctx, C.byref(prob), _ptr(spectra), spectra.shape[1], _ptr(row_index),
                                   _ptr(guesses), _ptr(err),
                                   _ptr(out["params"]), _ptr(out["perr"]), _ptr(out["chi2"]), _ptr(out["err_used"]),
-                                  _ptr(out["status"]), _ptr(out["counts"]), _ptr(self._ws), self._stream())
+                                  _ptr(out["status"]), _ptr(out["counts"]), _ptr(self.workspace(prob)),
+                                  self._stream())
         self._check(rc, "b200fit_fit")
         return out
 
