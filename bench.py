@@ -10,7 +10,7 @@ workload : BASELINE.json configs[1] -- synthetic NH3(1,1) cube 256 x 256 x 800 c
 value    : (spectra of all ranks) / (max-over-ranks device time per step), cube rows already resident in HBM.
 e2e      : the same job through the public host API (mufasa_b200.UltraCube) starting from HOST (pinned) buffers:
            H2D of the cube and guesses, all kernels, D2H of parameter / error / lnk / ncomp maps, host bookkeeping.
-roofline : dominant kernel = fit_kernel<2> (2-component LM fit).  The path is compute bound: the
+roofline : dominant kernel = fit_eval_kernel<2> (model + Jacobian + normal equations of the 2-component fit).  The path is compute bound: the
            fraction reported is algorithmic pipe work / time / pipe peak for the binding pipe (FP32 FMA, XU ex2,
            FP64), with the HBM figure alongside.
 cpu_baseline / --impl reference: the CPU oracle (numpy restatement of the reference's pyspeckit/mpfit path; the
@@ -49,57 +49,66 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md).  NVML is polled from a thread
+    (nvidia_ml_py); a polling `nvidia-smi -lms` process takes the driver lock for milliseconds per query and slows a
+    launch-latency-bound loop like this one by ~30 %, so it is only the fallback."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
-        self.index = index
-        self.proc = None
-        self.lines = []
+    def __init__(self, index, period=0.05):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.thread, self.stop_flag, self.nvml, self.smax = None, False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nvml = None
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((sm, pw))
+                for name, bit in self.BAD.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nvml is None:
+            return self._smi_once()
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.smax, reasons=["no samples"])
+        sm = [x[0] for x in self.samples]
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=self.smax, power_w_max=float(max(x[1] for x in self.samples)),
+                    samples=len(sm), reasons=sorted(self.reasons), how="NVML polled every %d ms" % int(self.period * 1e3))
+
+    def _smi_once(self):
         try:
-            self.proc.wait(timeout=5)
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            f = [float(x) for x in out.strip().split(",")]
+            return dict(sm_mhz=f[0], sm_max_mhz=f[1], reasons=[], how="one nvidia-smi query after the timed region")
         except Exception:
-            self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                smax.append(float(f[1]))
-                power.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), power_w_max=float(max(power)),
-                    samples=len(sm), reasons=sorted(reasons))
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml and nvidia-smi unavailable"])
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -308,13 +317,14 @@ def run_b200(args):
         dev_step()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clock_sampler:
         sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_fit1 = t_fit2 = t_aicc = 0.0
+    launches0 = eng.launch_count()
     start.record()
     per = []
     for _ in range(args.steps):
@@ -323,6 +333,7 @@ def run_b200(args):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     stop.record()
     torch.cuda.synchronize()
+    launches_timed = eng.launch_count() - launches0
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -337,36 +348,60 @@ def run_b200(args):
     ms_per_step = float(tt.item()) / args.steps
     value = npix * world / (ms_per_step * 1e-3)
 
-    # ---------------- roofline of the dominant kernel (fit_kernel<2>) on rank 0 -------------------------------
+    # ---------------- roofline of the dominant kernel (fit_eval_kernel<2>) on rank 0 ---------------------------
+    # One extra, untimed-for-`value` step with CUDA events recorded by the library around every kernel of the fit
+    # (b200fit_set_profiling: events on the launching stream).
     peaks = measured_peaks()
+    eng.set_profiling(True)
+    eng.fit(prob1, rows, lims[1][2], out=out1)
+    prof1 = eng.get_profile()
+    eng.fit(prob2, rows, lims[2][2], out=out2)
+    prof2 = eng.get_profile()
+    eng.set_profiling(False)
     cnt = out2["counts"].to(torch.float64)
     evals = float(cnt[:, 0].sum().item())                 # fused model + Jacobian evaluations, summed over pixels
     exec_gauss = float(cnt[:, 2].sum().item()) * 32.0      # gaussians actually evaluated (windowed)
+    exec_chan = float(cnt[:, 3].sum().item()) * 32.0       # channels actually visited (active 32-channel chunks)
     H, C, P = 18, 2, 8
     sfu = evals * nchan * C * (H + 2)                      # SFU_J = N*C*(H+2)
     f32 = evals * nchan * C * (12 * H + 30)                # F32_J = N*C*(12H+30)
     f64 = evals * nchan * (P * (P + 1) + 2 * P + 2)        # F64_J = N*(P(P+1)+2P+2)
-    t2 = t_fit2 * 1e-3 / args.steps                        # seconds per launch
+    sfu_exec = exec_gauss + exec_chan * C                  # ex2 actually issued: gaussians + e^-tau per component
+    launches_eval = max(1, prof2["rounds"])
+    t_eval = prof2["eval_ms"] * 1e-3                       # sum over the launches of one fit
     clk = peaks["sm_max_mhz"] * 1e6
     nsm = eng.num_sms
     pk = {"fp32": nsm * 128 * 2 * clk, "xu": nsm * 16 * clk, "fp64": nsm * 64 * 2 * clk}
-    ach = {"fp32": f32 / t2, "xu": sfu / t2, "fp64": f64 / t2}
+    ach = {"fp32": f32 / t_eval, "xu": sfu / t_eval, "fp64": f64 / t_eval}
     frac = {k: ach[k] / pk[k] for k in pk}
     bound = max(frac, key=lambda k: frac[k])
     hbm_bytes = npix * (nchan * 4 + P * 8 + (2 * P + 2) * 8 + 4 + 16)
-    roofline = {"bound": bound, "kernel": "fit_kernel<2>", "achieved": ach[bound] / 1e12, "peak": pk[bound] / 1e12,
-                "unit": "TFLOP/s" if bound != "xu" else "Top/s", "frac": frac[bound], "traffic": None,
+    t2 = t_fit2 * 1e-3 / args.steps                        # seconds per 2c fit inside the timed steps
+    roofline = {"bound": bound, "kernel": "fit_eval_kernel<2>", "achieved": ach[bound] / 1e12,
+                "peak": pk[bound] / 1e12, "unit": "TFLOP/s" if bound != "xu" else "Top/s", "frac": frac[bound],
+                "traffic": None,
+                "definition": "ALGORITHMIC work (SURVEY 8d per-evaluation figures x evaluations counted by the kernel) "
+                              "/ summed CUDA-event duration of the kernel's launches in one 2c fit; the kernel skips "
+                              "gaussians beyond 6.2 sigma (exactly 0 in fp32), see frac_executed",
+                "frac_executed": {"xu": sfu_exec / t_eval / pk["xu"]},
                 "pipes": {k: {"achieved_T": ach[k] / 1e12, "peak_T": pk[k] / 1e12, "frac": frac[k]} for k in pk},
                 "peak_source": "derived: %d SMs x lanes x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json, %s)" % (
                     nsm, peaks["sm_max_mhz"], peaks["source"]),
                 "hbm": {"achieved": hbm_bytes / t2 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": hbm_bytes / t2 / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"]},
-                "algorithmic_per_launch": {"evaluations": evals, "xu_ops": sfu, "fp32_flop": f32, "fp64_flop": f64,
-                                           "executed_gaussians": exec_gauss,
-                                           "algorithmic_gaussians": evals * nchan * C * H},
-                "launch_ms": t2 * 1e3,
+                "per_launch": {"launches": launches_eval, "avg_ms": prof2["eval_ms"] / launches_eval,
+                               "xu_ops": sfu / launches_eval, "fp32_flop": f32 / launches_eval,
+                               "fp64_flop": f64 / launches_eval},
+                "algorithmic_per_fit": {"evaluations": evals, "xu_ops": sfu, "fp32_flop": f32, "fp64_flop": f64,
+                                        "executed_gaussians": exec_gauss, "algorithmic_gaussians": evals * nchan * C * H},
+                "fit_2c_ms": {"prologue": prof2["prologue_ms"], "eval": prof2["eval_ms"], "solve": prof2["solve_ms"],
+                              "rounds": prof2["rounds"]},
+                "fit_1c_ms": {"prologue": prof1["prologue_ms"], "eval": prof1["eval_ms"], "solve": prof1["solve_ms"],
+                              "rounds": prof1["rounds"]},
                 "share_of_step": {"fit_1c": t_fit1 / total_ms, "fit_2c": t_fit2 / total_ms,
-                                  "aicc": t_aicc / total_ms}}
+                                  "aicc": t_aicc / total_ms,
+                                  "fit_eval_kernel<2>": prof2["eval_ms"] / ms_per_step,
+                                  "fit_solve_kernel<2>": prof2["solve_ms"] / ms_per_step}}
 
     line = None
     if rank == 0:
@@ -378,10 +413,10 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": float(e2e_t.item()) * 1e3,
                         "api": "UltraCube.fit_cube(1, simpfit) + fit_cube(2, simpfit) + get_best_2c_parcube()"},
-                "gpu_launches": 7 * args.steps,
+                "gpu_launches": int(launches_timed),
                 "fit2c_only": {"value": npix / t2, "unit": UNIT, "ms": t2 * 1e3},
                 "roofline": roofline, "clocks": clocks,
-                "fit_stats": {"converged_2c": float(np.isin(st2, [1, 2, 3, 4]).mean()),
+                "fit_stats": {"converged_2c": float(np.isin(st2, [1, 2, 3, 4, 6]).mean()),
                               "maxiter_2c": float((st2 == 5).mean()),
                               "mean_evals_2c": evals / npix,
                               "mean_evals_1c": float(out1["counts"][:, 0].to(torch.float64).mean().item())}}
@@ -410,6 +445,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostics only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200FIT_ABI_VERSION 2
+#define B200FIT_ABI_VERSION 3
 
 enum {
     B200FIT_OK = 0,
@@ -52,6 +52,15 @@ void b200fit_destroy(b200fit_ctx* ctx);
 const char* b200fit_last_error(const b200fit_ctx* ctx);
 int b200fit_abi_version(void);
 int b200fit_num_sms(const b200fit_ctx* ctx);
+
+/* Measurement hooks (no reference analogue; bench.py's roofline and launch accounting).
+ *   b200fit_launch_count: kernels launched by this context since creation.
+ *   b200fit_set_profiling(on): record CUDA events around the kernels of b200fit_fit on the launching stream.
+ *   b200fit_get_profile: waits for the last profiled fit and returns out[4] = {prologue ms, sum of evaluation-kernel
+ *   ms, sum of solver-kernel ms, rounds launched}. */
+uint64_t b200fit_launch_count(const b200fit_ctx* ctx);
+int b200fit_set_profiling(b200fit_ctx* ctx, int32_t on);
+int b200fit_get_profile(b200fit_ctx* ctx, double* out);
 
 /* Description of one fit call == the arguments MUFASA hands to pcube.fiteach (multi_v_fit.py:374-383) plus the
  * spectral axis pyspeckit takes from pcube.xarr. */
@@ -93,11 +102,16 @@ int b200fit_gather_spectra(b200fit_ctx* ctx, const float* d_cube, int32_t nchan,
  *   d_perr    [npix][P] fp64   0 for pegged parameters       (errcube = mpfit perror)
  *   d_chi2    [npix] fp64      sum(((y-M)/err)^2) at the solution (mpfit fnorm)
  *   d_err_used[npix] fp64      the weight actually used
- *   d_status  [npix] int32     1,2,3,4 converged (MINPACK meaning), 5 = max_iter, 0 = not fitted / bad guess,
- *                              -16 = non-finite; has_fit = status > 0
+ *   d_status  [npix] int32     1,2,3,4 converged (MINPACK meaning), 6 = converged to the precision of the fp32
+ *                              model evaluation (MINPACK info 6, "ftol too small"), 5 = max_iter, 7 = xtol too small,
+ *                              0 = not fitted / bad guess, -16 = non-finite; has_fit = status > 0
  *   d_counts  [npix][4] uint32 {evaluations, rejected steps, executed gaussian-lane evals / 32, active chunks}
  *                              (roofline accounting); may be NULL
- *   d_workspace: b200fit_workspace_bytes() bytes of device scratch */
+ *   d_workspace: b200fit_workspace_bytes(prob) bytes of device scratch (two active lists + ~0.6 / 1.1 KB of LM state
+ *              per pixel for ncomp 1 / 2)
+ * The fit is a loop of rounds {evaluation kernel over the active pixels; solver kernel}; the call polls the
+ * active count through a pinned counter and returns once every pixel finished (kernels may still be draining on
+ * ``stream``: results are ordered after them on that stream). */
 int b200fit_fit(b200fit_ctx* ctx, const b200fit_problem* prob,
                 const float* d_spectra, int64_t nchan_stride, const int64_t* d_row_index,
                 const double* d_guesses, const double* d_err,

@@ -4,11 +4,11 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libb200fit.so")
+LIB_PATH = os.environ.get("B200FIT_LIB", os.path.join(HERE, "csrc", "libb200fit.so"))   # override: A/B experiments
 
 MODEL_IDS = {"nh3_multi_v": 0, "n2hp_multi_v": 1}
 MAX_NCHAN = 2048
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Problem(C.Structure):
@@ -49,6 +49,9 @@ SIGNATURES = {
     "b200fit_last_error": (C.c_char_p, [_vp]),
     "b200fit_abi_version": (C.c_int, []),
     "b200fit_num_sms": (C.c_int, [_vp]),
+    "b200fit_launch_count": (C.c_uint64, [_vp]),
+    "b200fit_set_profiling": (C.c_int, [_vp, _i32]),
+    "b200fit_get_profile": (C.c_int, [_vp, _vp]),
     "b200fit_nchan_stride": (_i64, [_i32]),
     "b200fit_workspace_bytes": (_sz, [_PP]),
     "b200fit_gather_spectra": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
@@ -71,11 +74,14 @@ def load():
         raise B200FitError("libb200fit.so is not built (%s); run __graft_entry__.build() -- there is no CPU fallback"
                            % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
+    experiment = "B200FIT_LIB" in os.environ          # A/B runs against an older build: tolerate missing hooks
     for name, (res, args) in SIGNATURES.items():
+        if experiment and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.b200fit_abi_version() != ABI_VERSION:
+    if lib.b200fit_abi_version() != ABI_VERSION and not experiment:
         raise B200FitError("ABI version mismatch")
     _lib = lib
     return lib

@@ -25,7 +25,7 @@
 #else
 #define B2_HD inline
 #define B2_NOINL inline
-#define B2_ROLL _Pragma("unroll 1")
+#define B2_ROLL
 #endif
 
 namespace b200fit {
@@ -217,6 +217,13 @@ constexpr double LM_NOISE_REL = 5e-7;     // relative evaluation noise of a chi2
 constexpr double LM_MACHEP = 2.220446049250313e-16;
 constexpr double LM_DWARF = 2.2250738585072014e-308;
 constexpr double LM_XTOL = 1e-10, LM_GTOL = 1e-10, LM_FACTOR = 100.0;
+// MINPACK's termination test 6 ("ftol is too small: no further reduction in the sum of squares is possible") fires
+// when both the actual and the predicted relative reduction are below the machine precision of the function.
+// Here the function is chi2 of an fp32 model: its precision is ~1e-7, not 2e-16.  Without this test a pixel whose
+// chi2 has stalled at that level keeps taking noise-driven steps along any flat valley until maxiter (200), where
+// mpfit -- evaluating in fp64 -- stopped with status 1 long before.  3e-8 is the largest floor that leaves the parity
+// statistics against the oracle unchanged; status 6 counts as converged, as in MINPACK.
+constexpr double LM_FTOL_NOISE = 3e-8;
 
 // Per-call solver constants (limits live in shared memory in the kernel).
 struct LMConfig {
@@ -594,9 +601,7 @@ B2_HD int lm_update(LMState<P>& s, const LMConfig& cf) {
     }
     int st = 0;
     if (fabs(actred) <= cf.ftol && prered <= cf.ftol && 0.5 * ratio <= 1.0) st = 1;
-#ifdef LM_FTOL_FLOOR
-    else if (fabs(actred) <= LM_FTOL_FLOOR && prered <= LM_FTOL_FLOOR && 0.5 * ratio <= 1.0) st = 6;
-#endif
+    else if (fabs(actred) <= LM_FTOL_NOISE && prered <= LM_FTOL_NOISE && 0.5 * ratio <= 1.0) st = 6;
     if (s.delta <= LM_XTOL * s.xnorm) st = (st == 1) ? 3 : 2;
     if (st != 0) {
         s.status = st;

@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "b200fit_host.h"
 
@@ -379,16 +380,9 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
 }
 
 // ---- solver: thread per active pixel -------------------------------------------------------------------------
-// The state machine is a long chain of dependent fp64 operations on ~1 KB of per-pixel state: run out of global
-// memory it is bound by load latency (~100 us per step, round 1d).  Each warp therefore stages the states of its
-// 32 pixels in shared memory with coalesced copies, steps them there, and copies them back.
-// Shared-memory stride == 8 (mod 128) bytes: the 32 lanes touching the same fp64 field of their own state hit
-// 32 distinct 8-byte bank pairs.
-template <int P>
-__host__ __device__ constexpr size_t solve_stride() {
-    return (sizeof(PixState<P>) + 119) / 128 * 128 + 8;
-}
-
+// The state is stepped in place in global memory (L1/L2-cached).  Staging the 32 states of a warp through shared
+// memory was measured 2x SLOWER (round 1g: 63 vs 30 ms summed over a 2c fit): the copy loops serialise ~10 dependent
+// global round trips per state while the solver itself touches each field only once or twice.
 template <int NC>
 __global__ void __launch_bounds__(SOLVE_THREADS)
     fit_solve_kernel(const DeviceProblem pr, PixState<4 * NC>* __restrict__ states, const unsigned* __restrict__ list,
@@ -396,51 +390,21 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
                      double* __restrict__ params, double* __restrict__ perr, double* __restrict__ chi2,
                      double* __restrict__ err_used, int* __restrict__ status, unsigned* __restrict__ counts) {
     constexpr int P = 4 * NC;
-    constexpr int NV = sizeof(PixState<P>) / 8;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ FitTables tb;
     load_fit_tables(pr, tb);
     const LMConfig cf{tb.lo, tb.hi, pr.ftol, pr.max_iter};
     const unsigned count = fq->count[cur];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* wsm = smem_raw + (size_t)warp * 32 * solve_stride<P>();
-    PixState<P>& ps = *reinterpret_cast<PixState<P>*>(wsm + (size_t)lane * solve_stride<P>());
-    for (unsigned base = blockIdx.x * SOLVE_THREADS + warp * 32; base < count; base += gridDim.x * SOLVE_THREADS) {
-        const unsigned idx = base + lane;
-        const unsigned px = (idx < count) ? list[idx] : 0xffffffffu;
-        // stage in: one state per step, the warp's lanes stride over its 8-byte words
-#pragma unroll 1
-        for (int t = 0; t < 32; ++t) {
-            const unsigned pt = __shfl_sync(FULL, px, t);
-            if (pt == 0xffffffffu) break;
-            const uint2* __restrict__ g = reinterpret_cast<const uint2*>(states + pt);
-            uint2* s = reinterpret_cast<uint2*>(wsm + (size_t)t * solve_stride<P>());
-            for (int k = lane; k < NV; k += 32) s[k] = g[k];
+    for (unsigned idx = blockIdx.x * SOLVE_THREADS + threadIdx.x; idx < count; idx += gridDim.x * SOLVE_THREADS) {
+        const unsigned px = list[idx];
+        PixState<P>& ps = states[px];
+        int done = (ps.st.nevals == 0) ? lm_adopt_first<P>(ps.st) : lm_update<P>(ps.st, cf);
+        if (!done) done = lm_propose<P>(ps.st, cf);
+        if (done) {
+            write_result<P>(ps, (long long)px, cf, true, params, perr, chi2, err_used, status, counts);
+        } else {
+            prepare_trial<NC>(pr, ps);
+            next_list[atomicAdd(&fq->count[cur ^ 1], 1u)] = px;
         }
-        __syncwarp();
-        bool keep = false;
-        if (px != 0xffffffffu) {
-            int done = (ps.st.nevals == 0) ? lm_adopt_first<P>(ps.st) : lm_update<P>(ps.st, cf);
-            if (!done) done = lm_propose<P>(ps.st, cf);
-            if (done) {
-                write_result<P>(ps, (long long)px, cf, true, params, perr, chi2, err_used, status, counts);
-            } else {
-                prepare_trial<NC>(pr, ps);
-                next_list[atomicAdd(&fq->count[cur ^ 1], 1u)] = px;
-                keep = true;
-            }
-        }
-        __syncwarp();
-        // stage out the states that go on
-#pragma unroll 1
-        for (int t = 0; t < 32; ++t) {
-            const unsigned pt = __shfl_sync(FULL, keep ? px : 0xffffffffu, t);
-            if (pt == 0xffffffffu) continue;
-            uint2* __restrict__ g = reinterpret_cast<uint2*>(states + pt);
-            const uint2* s = reinterpret_cast<const uint2*>(wsm + (size_t)t * solve_stride<P>());
-            for (int k = lane; k < NV; k += 32) g[k] = s[k];
-        }
-        __syncwarp();
     }
 }
 
@@ -918,6 +882,22 @@ struct b200fit_ctx {
     std::string err;
     cudaEvent_t check_ev[4];
     volatile unsigned* h_count;   // pinned, 4 slots: active-pixel counts read back by the fit's round loop
+    unsigned long long launches = 0;          // kernels launched by this context (all entry points)
+    int profiling = 0;                        // record CUDA events around the fit's kernels
+    std::vector<cudaEvent_t> prof_ev;         // event pool (grown on demand)
+    size_t prof_used = 0;
+    int prof_rounds = 0;
+
+    cudaEvent_t next_event(cudaStream_t stream) {
+        if (prof_used == prof_ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            prof_ev.push_back(e);
+        }
+        cudaEvent_t e = prof_ev[prof_used++];
+        cudaEventRecord(e, stream);
+        return e;
+    }
 };
 
 static int fail(b200fit_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess) {
@@ -962,6 +942,12 @@ static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_
     if (pr.npix >= (1LL << 32)) return fail(ctx, B200FIT_E_ARG, "fit: npix must be < 2^32 per call");
 
     CK(cudaMemsetAsync(fq, 0, sizeof(FitQueues), stream));
+    const bool prof = ctx->profiling != 0;
+    if (prof) {
+        ctx->prof_used = 0;
+        ctx->prof_rounds = 0;
+        ctx->next_event(stream);   // [0] before the prologue
+    }
     const long long pwarps = (pr.npix + EVAL_WARPS - 1) / EVAL_WARPS;
     const long long cap = (long long)ctx->num_sms * 16;
     const unsigned pgrid = (unsigned)(pwarps < cap ? pwarps : cap);
@@ -969,19 +955,16 @@ static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_
         pr, d_spectra, (long long)stride, (const long long*)d_row_index, d_guesses, d_err, states, lists[0], fq, d_params,
         d_perr, d_chi2, d_err_used, d_status, d_counts);
     CK(cudaGetLastError());
+    ctx->launches += 1;
+    if (prof) ctx->next_event(stream);   // [1] after the prologue
 
     int eval_per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC>, EVAL_WARPS * 32, 0));
     if (eval_per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit_eval_kernel does not fit on an SM");
     long long egrid = (long long)ctx->num_sms * eval_per_sm;        // a whole number of CTAs per SM
     if (egrid > pwarps) egrid = pwarps;
-    const size_t solve_smem = (size_t)SOLVE_THREADS * solve_stride<P>();
-    CK(cudaFuncSetAttribute(fit_solve_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
-    int solve_per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solve_per_sm, fit_solve_kernel<NC>, SOLVE_THREADS, solve_smem));
-    if (solve_per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit_solve_kernel does not fit on an SM");
     const long long sblocks = (pr.npix + SOLVE_THREADS - 1) / SOLVE_THREADS;
-    long long sgrid = (long long)ctx->num_sms * solve_per_sm;
+    long long sgrid = (long long)ctx->num_sms * 8;
     if (sgrid > sblocks) sgrid = sblocks;
 
     const int max_rounds = 2 * pr.max_iter + 3;
@@ -992,8 +975,14 @@ static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_
         const int cur = r & 1;
         fit_eval_kernel<NC><<<(unsigned)egrid, EVAL_WARPS * 32, 0, stream>>>(
             pr, d_spectra, (long long)stride, (const long long*)d_row_index, states, lists[cur], fq, cur);
-        fit_solve_kernel<NC><<<(unsigned)sgrid, SOLVE_THREADS, solve_smem, stream>>>(
+        if (prof) ctx->next_event(stream);   // [2 + 2r] after the evaluation of round r
+        fit_solve_kernel<NC><<<(unsigned)sgrid, SOLVE_THREADS, 0, stream>>>(
             pr, states, lists[cur], lists[cur ^ 1], fq, cur, d_params, d_perr, d_chi2, d_err_used, d_status, d_counts);
+        ctx->launches += 2;
+        if (prof) {
+            ctx->next_event(stream);         // [3 + 2r] after the solver step of round r
+            ctx->prof_rounds = r + 1;
+        }
         if ((r + 1) % CHECK == 0) {
             const int slot = nchecks % RING;
             if (nchecks >= RING - 2) {   // wait for the check issued (RING - 2) checks ago
@@ -1051,6 +1040,7 @@ int b200fit_create(b200fit_ctx** out, int device) {
 void b200fit_destroy(b200fit_ctx* ctx) {
     if (!ctx) return;
     for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->check_ev[i]);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->h_count) cudaFreeHost((void*)ctx->h_count);
     delete ctx;
 }
@@ -1058,6 +1048,36 @@ void b200fit_destroy(b200fit_ctx* ctx) {
 const char* b200fit_last_error(const b200fit_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int b200fit_num_sms(const b200fit_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+
+uint64_t b200fit_launch_count(const b200fit_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b200fit_set_profiling(b200fit_ctx* ctx, int32_t on) {
+    if (!ctx) return B200FIT_E_ARG;
+    ctx->profiling = on ? 1 : 0;
+    ctx->prof_used = 0;
+    ctx->prof_rounds = 0;
+    return B200FIT_OK;
+}
+
+int b200fit_get_profile(b200fit_ctx* ctx, double* out) {
+    if (!ctx || !out) return B200FIT_E_ARG;
+    for (int i = 0; i < 4; ++i) out[i] = 0.0;
+    const int rounds = ctx->prof_rounds;
+    if (ctx->prof_used < (size_t)(2 + 2 * rounds) || ctx->prof_used < 2) return B200FIT_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->prof_ev[1 + 2 * rounds]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->prof_ev[0], ctx->prof_ev[1]));
+    out[0] = ms;
+    for (int r = 0; r < rounds; ++r) {
+        CK(cudaEventElapsedTime(&ms, ctx->prof_ev[1 + 2 * r], ctx->prof_ev[2 + 2 * r]));
+        out[1] += ms;
+        CK(cudaEventElapsedTime(&ms, ctx->prof_ev[2 + 2 * r], ctx->prof_ev[3 + 2 * r]));
+        out[2] += ms;
+    }
+    out[3] = rounds;
+    return B200FIT_OK;
+}
 
 size_t b200fit_workspace_bytes(const b200fit_problem* prob) {
     // queues + two active lists + the per-pixel LM state that crosses the round loop's kernels
@@ -1077,6 +1097,7 @@ int b200fit_gather_spectra(b200fit_ctx* ctx, const float* d_cube, int32_t nchan,
     gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_cube, nchan, nplane, (const long long*)d_pix_index, npix,
                                                           flip, d_spectra, nchan_stride);
     CK(cudaGetLastError());
+    ctx->launches += 1;
     return B200FIT_OK;
 }
 
@@ -1118,6 +1139,7 @@ int b200fit_model(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d
     model_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, 0, (cudaStream_t)stream>>>(pr, d_params, d_model,
                                                                                                  nchan_stride);
     CK(cudaGetLastError());
+    ctx->launches += 1;
     return B200FIT_OK;
 }
 
@@ -1133,9 +1155,11 @@ int b200fit_mask_argmax(b200fit_ctx* ctx, const int32_t* d_mask_counts, int64_t 
         if (blocks > (long long)ctx->num_sms * 8) blocks = (long long)ctx->num_sms * 8;
         mask_argmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_mask_counts, npix, index_offset, key);
         CK(cudaGetLastError());
+        ctx->launches += 1;
     }
     mask_argmax_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(key, (long long*)d_best);
     CK(cudaGetLastError());
+    ctx->launches += 1;
     return B200FIT_OK;
 }
 
@@ -1151,6 +1175,7 @@ int b200fit_mask_bits(b200fit_ctx* ctx, const b200fit_problem* prob, const doubl
     mask_bits_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pr, d_params1, d_params2, model_f32, (const long long*)d_best,
                                                         pix, d_bits);
     CK(cudaGetLastError());
+    ctx->launches += 1;
     return B200FIT_OK;
 }
 
@@ -1177,6 +1202,7 @@ int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_s
         pr, d_spectra, nchan_stride, (const long long*)d_row_index, d_params1, d_params2, d_fill_bits, only_empty,
         expand, model_f32, t10, t20, t21, d_rss, d_nsamp, d_lnk, d_ncomp, d_mask_counts);
     CK(cudaGetLastError());
+    ctx->launches += 1;
     return B200FIT_OK;
 }
 
@@ -1200,6 +1226,7 @@ int b200fit_resid_stats(b200fit_ctx* ctx, const b200fit_problem* prob, const flo
         pr, d_spectra, nchan_stride, (const long long*)d_row_index, d_params, expand, model_f32, npow2, d_rms,
         d_chisq_red);
     CK(cudaGetLastError());
+    ctx->launches += 1;
     return B200FIT_OK;
 }
 

@@ -66,6 +66,19 @@ class Engine(object):
     def nchan_stride(nchan):
         return (int(nchan) + 31) // 32 * 32
 
+    # -- measurement hooks ---------------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.b200fit_launch_count(self.ctx))
+
+    def set_profiling(self, on):
+        self._check(self.lib.b200fit_set_profiling(self.ctx, 1 if on else 0), "b200fit_set_profiling")
+
+    def get_profile(self):
+        """dict(prologue_ms, eval_ms, solve_ms, rounds) of the last profiled fit."""
+        out = (C.c_double * 4)()
+        self._check(self.lib.b200fit_get_profile(self.ctx, C.cast(out, C.c_void_p)), "b200fit_get_profile")
+        return dict(prologue_ms=out[0], eval_ms=out[1], solve_ms=out[2], rounds=int(out[3]))
+
     # -- kernels -------------------------------------------------------------------------------------------
     def gather(self, cube_dev, pix_index_dev=None, flip=False, out=None):
         """[nchan, nplane] fp32 (FITS order, flattened plane) -> [npix, stride] pixel-major rows."""

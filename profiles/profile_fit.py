@@ -40,11 +40,14 @@ cube_dev = torch.from_numpy(syn["cube"].reshape(nchan, npix)).to(dev)
 rows = eng.gather(cube_dev)
 probs, gs = {}, {}
 for nc in (1, 2):
-    lo = [-3.5, mm.sigmin, mm.Texmin, mm.taumin] * nc
-    hi = [4.5, mm.sigmax, mm.Texmax, mm.taumax] * nc
+    vlo, vhi = (-3.5, 4.5) if os.environ.get("PROFILE_VLIM", "narrow") == "narrow" else (-11.0, 11.0)
+    lo = [vlo, mm.sigmin, mm.Texmin, mm.taumin] * nc
+    hi = [vhi, mm.sigmax, mm.Texmax, mm.taumax] * nc
     g = synth.clamp_guesses(syn["guess%d" % nc], lo, hi, eps=mm.eps)
     gs[nc] = torch.from_numpy(np.ascontiguousarray(g.reshape(4 * nc, npix).T)).to(dev)
     probs[nc] = _abi.make_problem(fittype, nc, nchan, npix, v[0], dv, lo, hi)
+if os.environ.get("PROFILE_EVENTS", "0") == "1":
+    eng.set_profiling(True)
 for r in range(reps):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -54,6 +57,8 @@ for r in range(reps):
     o2 = eng.fit(probs[2], rows, gs[2])
     torch.cuda.synchronize()
     t2 = time.perf_counter()
+    if os.environ.get("PROFILE_EVENTS", "0") == "1":
+        print("   2c profile:", eng.get_profile(), flush=True)
     a = eng.aicc_global(probs[1], rows, o1["params"], o2["params"])
     torch.cuda.synchronize()
     t3 = time.perf_counter()
@@ -61,7 +66,7 @@ for r in range(reps):
     cn = o2["counts"].cpu().numpy().astype(np.float64)
     print("rep %d npix %d: fit1 %.2f ms  fit2 %.2f ms  aicc %.2f ms | 2c: conv %.3f maxiter %.3f mean evals %.1f "
           "(median %.0f, p90 %.0f, max %.0f) | ncomp hist %s" % (
-              r, npix, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, np.isin(st, [1, 2, 3, 4]).mean(),
+              r, npix, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, np.isin(st, [1, 2, 3, 4, 6]).mean(),
               (st == 5).mean(), cn[:, 0].mean(), np.median(cn[:, 0]), np.percentile(cn[:, 0], 90), cn[:, 0].max(),
               np.bincount(a["ncomp"].cpu().numpy().astype(int), minlength=3).tolist()), flush=True)
     hist = np.bincount(st.clip(-1, 8) + 1, minlength=10)

