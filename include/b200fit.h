@@ -100,7 +100,7 @@ int b200fit_gather_spectra(b200fit_ctx* ctx, const float* d_cube, int32_t nchan,
  *   d_err     [npix] fp64 or NULL (weight_mode 0)
  *   d_params  [npix][P] fp64   zeros on failure              (parcube)
  *   d_perr    [npix][P] fp64   0 for pegged parameters       (errcube = mpfit perror)
- *   d_chi2    [npix] fp64      sum(((y-M)/err)^2) at the solution (mpfit fnorm)
+ *   d_chi2    [npix] fp64      sum(((y-M)/err)^2) at the returned parameters
  *   d_err_used[npix] fp64      the weight actually used
  *   d_status  [npix] int32     1,2,3,4 converged (MINPACK meaning), 6 = converged to the precision of the fp32
  *                              model evaluation (MINPACK info 6, "ftol too small"), 5 = max_iter, 7 = xtol too small,

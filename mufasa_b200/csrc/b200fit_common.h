@@ -618,11 +618,12 @@ B2_HD int lm_update(LMState<P>& s, const LMConfig& cf) {
     return LM_CONTINUE;
 }
 
-// chi2 as mpfit reports it: fnorm = max(fnorm(final point), fnorm1(last trial))**2 -- the last trial may be a
-// rejected step (mpfit.py termination block).
+// chi2 AT THE RETURNED PARAMETERS.  (mpfit's own fnorm is max(fnorm(final), fnorm1(last trial))**2 -- the chi2 of a
+// rejected step when the fit ends on one.  MUFASA never reads it: pyspeckit stores no per-pixel chi2 and
+// UltraCube.get_chisq / get_rss re-evaluate the model at parcube, UltraCube.py:1384-1565.)
 template <int P>
 B2_HD double lm_reported_chi2(const LMState<P>& s) {
-    return (s.chi2_last > s.chi2) ? s.chi2_last : s.chi2;
+    return s.chi2;
 }
 
 // Parameter errors: sqrt(diag(err^2 (H_FF)^-1)), zero for pegged parameters (mpfit calc_covar on the

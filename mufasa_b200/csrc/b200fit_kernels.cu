@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "b200fit_host.h"
+#include "b200fit_lanes.cuh"
 
 namespace b200fit {
 
@@ -379,10 +380,11 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
     }
 }
 
-// ---- solver: thread per active pixel -------------------------------------------------------------------------
-// The state is stepped in place in global memory (L1/L2-cached).  Staging the 32 states of a warp through shared
-// memory was measured 2x SLOWER (round 1g: 63 vs 30 ms summed over a 2c fit): the copy loops serialise ~10 dependent
-// global round trips per state while the solver itself touches each field only once or twice.
+// ---- solver: P lanes per active pixel (b200fit_lanes.cuh) ------------------------------------------------------
+// The state is stepped in registers: each lane loads its parameter's entries and its row of J^T J straight from
+// the per-pixel state in global memory (L2-resident), and writes back only what changed.  History of this kernel
+// (profiles/): thread per pixel on global state 30 ms per 2c fit, the same staged through shared memory 63 ms
+// (copy loops serialise global round trips), both bound by the ~20k-instruction dependent chain of one serial step.
 template <int NC>
 __global__ void __launch_bounds__(SOLVE_THREADS)
     fit_solve_kernel(const DeviceProblem pr, PixState<4 * NC>* __restrict__ states, const unsigned* __restrict__ list,
@@ -390,20 +392,60 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
                      double* __restrict__ params, double* __restrict__ perr, double* __restrict__ chi2,
                      double* __restrict__ err_used, int* __restrict__ status, unsigned* __restrict__ counts) {
     constexpr int P = 4 * NC;
+    constexpr unsigned GROUPS = SOLVE_THREADS / P;   // pixels per block and pass
     __shared__ FitTables tb;
     load_fit_tables(pr, tb);
     const LMConfig cf{tb.lo, tb.hi, pr.ftol, pr.max_iter};
+    const LaneGroup<P> g;
     const unsigned count = fq->count[cur];
-    for (unsigned idx = blockIdx.x * SOLVE_THREADS + threadIdx.x; idx < count; idx += gridDim.x * SOLVE_THREADS) {
+    for (unsigned idx = blockIdx.x * GROUPS + threadIdx.x / P; idx < count; idx += gridDim.x * GROUPS) {
         const unsigned px = list[idx];
         PixState<P>& ps = states[px];
-        int done = (ps.st.nevals == 0) ? lm_adopt_first<P>(ps.st) : lm_update<P>(ps.st, cf);
-        if (!done) done = lm_propose<P>(ps.st, cf);
-        if (done) {
-            write_result<P>(ps, (long long)px, cf, true, params, perr, chi2, err_used, status, counts);
+        LaneState<P> s;
+        lane_load<P>(g, ps.st, cf, s);
+        bool accepted = false;
+        int done;
+        if (s.nevals == 0) {
+            done = lane_adopt_first<P>(s);
+            accepted = !done;
         } else {
-            prepare_trial<NC>(pr, ps);
-            next_list[atomicAdd(&fq->count[cur ^ 1], 1u)] = px;
+            done = lane_update<P>(g, s, cf, accepted);
+        }
+        if (!done) done = lane_propose<P>(g, s);
+        if (done) {
+            // results (zeros on failure, like pyspeckit's blank parcube)
+            const bool good = s.status > 0;
+            const double err = ps.err, err2 = err * err;
+            const double pe = good ? lane_error<P>(g, s, err2) : 0.0;
+            params[(size_t)px * P + g.gl] = good ? s.p : 0.0;
+            perr[(size_t)px * P + g.gl] = pe;
+            if (g.gl == 0) {
+                chi2[px] = good ? s.chi2 / err2 : 0.0;   // at the returned parameters (lm_reported_chi2)
+                err_used[px] = err;
+                status[px] = s.status;
+                if (counts) {
+                    counts[4 * (size_t)px + 0] = (unsigned)s.nevals;
+                    counts[4 * (size_t)px + 1] = (unsigned)s.nrej;
+                    counts[4 * (size_t)px + 2] = ps.n_gauss;
+                    counts[4 * (size_t)px + 3] = ps.n_chunks;
+                }
+            }
+        } else {
+            lane_store<P>(g, ps.st, s, accepted);
+            // coefficients of the next trial point (every lane computes, lane 0 stores: same issue cost in SIMT)
+#pragma unroll 1
+            for (int c = 0; c < NC; ++c) {
+                double p4[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) p4[k] = g.bcast(s.pt, 4 * c + k);
+                CompCoef cc;
+                comp_coefs(pr.T0c, pr.dT0, pr.Jbg0, pr.Jbg1, p4, cc);
+                if (g.gl == 0) {
+                    ps.cc[c] = cc;
+                    ps.inv_sigma[c] = 1.0 / p4[1];
+                }
+            }
+            if (g.gl == 0) next_list[atomicAdd(&fq->count[cur ^ 1], 1u)] = px;
         }
     }
 }
@@ -963,8 +1005,9 @@ static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_
     if (eval_per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit_eval_kernel does not fit on an SM");
     long long egrid = (long long)ctx->num_sms * eval_per_sm;        // a whole number of CTAs per SM
     if (egrid > pwarps) egrid = pwarps;
-    const long long sblocks = (pr.npix + SOLVE_THREADS - 1) / SOLVE_THREADS;
-    long long sgrid = (long long)ctx->num_sms * 8;
+    const long long sgroups = SOLVE_THREADS / P;                     // pixels per solver block and pass
+    const long long sblocks = (pr.npix + sgroups - 1) / sgroups;
+    long long sgrid = (long long)ctx->num_sms * 32;
     if (sgrid > sblocks) sgrid = sblocks;
 
     const int max_rounds = 2 * pr.max_iter + 3;

@@ -49,7 +49,11 @@ def fit_spectrum(y, xghz, guess, minpars, maxpars, fittype, maxiter=200):
         return zero
     if res.status <= 0 or res.perror is None:
         return (np.zeros(npar), np.zeros(npar), 0.0, int(res.status), res.nfev, float(err_val))
-    return res.params, res.perror, float(res.fnorm), int(res.status), res.nfev, float(err_val)
+    # chi2 AT THE RETURNED PARAMETERS.  mpfit's own ``fnorm`` is max(fnorm(final), fnorm1(last trial))**2, i.e. the
+    # chi2 of a REJECTED step whenever the fit ends on one; MUFASA never reads it (pyspeckit stores no per-pixel
+    # chi2; UltraCube.get_chisq / get_rss re-evaluate the model at parcube), so parity is defined on this value.
+    chi2 = float(np.sum(deviates(res.params) ** 2))
+    return res.params, res.perror, chi2, int(res.status), res.nfev, float(err_val)
 
 
 _G = {}
