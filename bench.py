@@ -247,8 +247,7 @@ def run_b200(args):
     # ---------------- end-to-end arm: the public API from host buffers ----------------------------------------
     def e2e_step():
         uc = UltraCube(cube=spec, fittype=fittype, device=local)
-        uc.fit_cube(ncomp=1, simpfit=True, guesses=syn["guess1"].copy())
-        uc.fit_cube(ncomp=2, simpfit=True, guesses=syn["guess2"].copy())
+        uc.fit_cube(ncomp=[1, 2], simpfit=True, guesses={1: syn["guess1"].copy(), 2: syn["guess2"].copy()})
         res = uc.get_best_2c_parcube()
         return uc, res
 
@@ -300,11 +299,12 @@ def run_b200(args):
     def dev_step(timers=None):
         if timers is not None:
             ev[0].record()
-        eng.fit(prob1, rows, lims[1][2], out=out1)
+        # the 1- and the 2-component fit in flight together (b200fit_fit_batch): same results as two calls, the
+        # latency-bound late rounds of one overlap the other
+        eng.fit_batch([dict(prob=prob1, spectra=rows, guesses=lims[1][2], out=out1),
+                       dict(prob=prob2, spectra=rows, guesses=lims[2][2], out=out2)])
         if timers is not None:
             ev[1].record()
-        eng.fit(prob2, rows, lims[2][2], out=out2)
-        if timers is not None:
             ev[2].record()
         eng.aicc_pass(prob1, rows, out1["params"], out2["params"], aout)
         best = eng.mask_argmax(aout["mask_counts"])
@@ -376,7 +376,7 @@ def run_b200(args):
     frac = {k: ach[k] / pk[k] for k in pk}
     bound = max(frac, key=lambda k: frac[k])
     hbm_bytes = npix * (nchan * 4 + P * 8 + (2 * P + 2) * 8 + 4 + 16)
-    t2 = t_fit2 * 1e-3 / args.steps                        # seconds per 2c fit inside the timed steps
+    t2 = (prof2["prologue_ms"] + prof2["eval_ms"] + prof2["solve_ms"]) * 1e-3   # seconds per 2c fit run on its own
     roofline = {"bound": bound, "kernel": "fit_eval_kernel<2>", "achieved": ach[bound] / 1e12,
                 "peak": pk[bound] / 1e12, "unit": "TFLOP/s" if bound != "xu" else "Top/s", "frac": frac[bound],
                 "traffic": None,
@@ -398,8 +398,7 @@ def run_b200(args):
                               "rounds": prof2["rounds"]},
                 "fit_1c_ms": {"prologue": prof1["prologue_ms"], "eval": prof1["eval_ms"], "solve": prof1["solve_ms"],
                               "rounds": prof1["rounds"]},
-                "share_of_step": {"fit_1c": t_fit1 / total_ms, "fit_2c": t_fit2 / total_ms,
-                                  "aicc": t_aicc / total_ms,
+                "share_of_step": {"fits_1c_and_2c_batched": t_fit1 / total_ms, "aicc": t_aicc / total_ms,
                                   "fit_eval_kernel<2>": prof2["eval_ms"] / ms_per_step,
                                   "fit_solve_kernel<2>": prof2["solve_ms"] / ms_per_step}}
 
@@ -412,7 +411,7 @@ def run_b200(args):
                 "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": float(e2e_t.item()) * 1e3,
-                        "api": "UltraCube.fit_cube(1, simpfit) + fit_cube(2, simpfit) + get_best_2c_parcube()"},
+                        "api": "UltraCube.fit_cube([1, 2], simpfit) + get_best_2c_parcube()"},
                 "gpu_launches": int(launches_timed),
                 "fit2c_only": {"value": npix / t2, "unit": UNIT, "ms": t2 * 1e3},
                 "roofline": roofline, "clocks": clocks,

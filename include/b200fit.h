@@ -119,6 +119,28 @@ int b200fit_fit(b200fit_ctx* ctx, const b200fit_problem* prob,
                 int32_t* d_status, uint32_t* d_counts,
                 void* d_workspace, void* stream);
 
+/* Several fits in flight at once (typically the 1- and the 2-component fit of the same spectra, which
+ * UltraCube.fit_cube loops over, UltraCube.py:312-320): the rounds of the jobs are interleaved on internal streams, so
+ * the latency-bound late rounds of one fit overlap the other's work.  Results are identical to separate b200fit_fit
+ * calls.  Each job needs its own workspace and output buffers; ``stream`` orders the whole batch (fork / join). */
+#define B200FIT_MAX_BATCH 4
+typedef struct {
+    const b200fit_problem* prob;
+    const float* d_spectra;
+    int64_t nchan_stride;
+    const int64_t* d_row_index;
+    const double* d_guesses;
+    const double* d_err;
+    double* d_params;
+    double* d_perr;
+    double* d_chi2;
+    double* d_err_used;
+    int32_t* d_status;
+    uint32_t* d_counts;
+    void* d_workspace;
+} b200fit_fit_args;
+int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* jobs, int32_t njobs, void* stream);
+
 /* Model evaluation: replaces pcube.get_modelcube() (one multi_v_spectrum call per pixel,
  * HyperfineModel.py:22-109), in fp64 with the reference's frequency-space operation order.
  *   d_params [npix][P]; all-zero or non-finite rows produce NaN rows (pyspeckit convention)

@@ -74,22 +74,37 @@ class UltraCube(object):
             self._ref_pcube = p
         return p
 
-    def fit_cube(self, ncomp, simpfit=False, **kwargs):
-        """UltraCube.py:272-326."""
+    def fit_cube(self, ncomp, simpfit=False, concurrent=True, **kwargs):
+        """UltraCube.py:272-326.  With several ``ncomp`` the reference fits them one after the other; here the host
+        drivers still run in that order, but the GPU fits are launched together (``concurrent``; Engine.fit_batch)
+        so the slow tail of one fit overlaps the other.  Results are identical to sequential fits."""
         if 'multicore' not in kwargs:
             kwargs['multicore'] = self.n_cores
         if 'snr_min' not in kwargs:
             kwargs['snr_min'] = self.snr_min
         if not isinstance(ncomp, Iterable):
             ncomp = [ncomp]
+        ncomp = list(ncomp)
+        batch = [] if (concurrent and len(ncomp) > 1) else None
         for nc in ncomp:
             if self.pcubes:
                 _, pcube_ref = next(iter(self.pcubes.items()))
                 self.pcubes[str(nc)] = self.load_pcube(pcube_ref=pcube_ref)
             else:
                 self.pcubes[str(nc)] = self.load_pcube()
+            self.pcubes[str(nc)]._deferred = batch
+            kw = dict(kwargs)
+            if isinstance(kw.get('guesses'), dict):          # per-ncomp guesses for a batched call
+                kw['guesses'] = kw['guesses'].get(nc)
             self.pcubes[str(nc)] = fit_cube(self.cube, self.pcubes[str(nc)], fittype=self.fittype, simpfit=simpfit,
-                                            ncomp=nc, **kwargs)
+                                            ncomp=nc, **kw)
+            self.pcubes[str(nc)]._deferred = None
+        if batch:
+            eng = batch[0]["pcube"].engine
+            outs = eng.fit_batch(batch)
+            for job, out in zip(batch, outs):
+                job["pcube"].finish_fit(job, out)
+        for nc in ncomp:
             p = self.pcubes[str(nc)]
             if p.has_fit.sum() > 0 and p.parcube is not None:
                 self._include_fit_in_mask(nc)

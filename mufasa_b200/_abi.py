@@ -35,6 +35,17 @@ def make_problem(fittype, ncomp, nchan, npix, v0, dv, lo, hi, nu_ref_ghz=0.0, ma
     return p
 
 
+class FitArgs(C.Structure):
+    """struct b200fit_fit_args"""
+    _fields_ = [("prob", C.POINTER(Problem)), ("d_spectra", C.c_void_p), ("nchan_stride", C.c_int64),
+                ("d_row_index", C.c_void_p), ("d_guesses", C.c_void_p), ("d_err", C.c_void_p),
+                ("d_params", C.c_void_p), ("d_perr", C.c_void_p), ("d_chi2", C.c_void_p), ("d_err_used", C.c_void_p),
+                ("d_status", C.c_void_p), ("d_counts", C.c_void_p), ("d_workspace", C.c_void_p)]
+
+
+MAX_BATCH = 4
+
+
 class B200FitError(RuntimeError):
     pass
 
@@ -56,6 +67,7 @@ SIGNATURES = {
     "b200fit_workspace_bytes": (_sz, [_PP]),
     "b200fit_gather_spectra": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "b200fit_fit": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200fit_fit_batch": (C.c_int, [_vp, C.POINTER(FitArgs), _i32, _vp]),
     "b200fit_model": (C.c_int, [_vp, _PP, _vp, _vp, _i64, _vp]),
     "b200fit_aicc": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp]),

@@ -922,8 +922,10 @@ struct b200fit_ctx {
     int device;
     int num_sms;
     std::string err;
-    cudaEvent_t check_ev[4];
-    volatile unsigned* h_count;   // pinned, 4 slots: active-pixel counts read back by the fit's round loop
+    cudaEvent_t check_ev[B200FIT_MAX_BATCH * 4];
+    volatile unsigned* h_count;   // pinned, 4 slots per job: active-pixel counts read back by the fit's round loop
+    cudaStream_t job_stream[B200FIT_MAX_BATCH];
+    cudaEvent_t fork_ev, join_ev[B200FIT_MAX_BATCH];
     unsigned long long launches = 0;          // kernels launched by this context (all entry points)
     int profiling = 0;                        // record CUDA events around the fit's kernels
     std::vector<cudaEvent_t> prof_ev;         // event pool (grown on demand)
@@ -970,22 +972,44 @@ static size_t fit_workspace_bytes(long long npix) {
 // Round loop.  Every pixel finishes within 2*max_iter + 3 rounds (lm_update caps evaluations); the host checks
 // the active count every CHECK rounds through a pinned counter, two checks behind the launches, so the GPU never
 // idles waiting for the host and at most 2*CHECK empty rounds are launched after the last pixel converged.
-template <int NC>
-static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_spectra, int64_t stride,
-                      const double* d_guesses, const double* d_err, double* d_params, double* d_perr, double* d_chi2,
-                      double* d_err_used, int32_t* d_status, uint32_t* d_counts, void* d_workspace,
-                      const int64_t* d_row_index, cudaStream_t stream) {
-    constexpr int P = 4 * NC;
-    unsigned char* ws = (unsigned char*)d_workspace;
-    FitQueues* fq = (FitQueues*)ws;
-    const size_t list_bytes = align_up((size_t)pr.npix * sizeof(unsigned), 256);
-    unsigned* lists[2] = {(unsigned*)(ws + sizeof(FitQueues)), (unsigned*)(ws + sizeof(FitQueues) + list_bytes)};
-    PixState<P>* states = (PixState<P>*)(ws + sizeof(FitQueues) + 2 * list_bytes);
-    if (pr.npix >= (1LL << 32)) return fail(ctx, B200FIT_E_ARG, "fit: npix must be < 2^32 per call");
+// A FitJob is one fit in flight; b200fit_fit_batch interleaves the rounds of several jobs on separate streams so
+// that the latency-bound late rounds of one fit (few slowly converging pixels left) overlap another fit's work.
+struct FitJob {
+    int nc = 0;
+    DeviceProblem pr;
+    const float* d_spectra = nullptr;
+    long long stride = 0;
+    const long long* d_row_index = nullptr;
+    const double* d_guesses = nullptr;
+    const double* d_err = nullptr;
+    double *d_params = nullptr, *d_perr = nullptr, *d_chi2 = nullptr, *d_err_used = nullptr;
+    int* d_status = nullptr;
+    unsigned* d_counts = nullptr;
+    FitQueues* fq = nullptr;
+    unsigned* lists[2] = {nullptr, nullptr};
+    void* states = nullptr;
+    cudaStream_t stream = nullptr;
+    unsigned egrid = 0, sgrid = 0;
+    int r = 0, max_rounds = 0, nchecks = 0, slot0 = 0;
+    bool finished = false, prof = false;
+};
 
-    CK(cudaMemsetAsync(fq, 0, sizeof(FitQueues), stream));
-    const bool prof = ctx->profiling != 0;
-    if (prof) {
+constexpr int FIT_CHECK = 8, FIT_RING = 4;
+
+template <int NC>
+static int job_begin(b200fit_ctx* ctx, FitJob& jb, void* d_workspace) {
+    constexpr int P = 4 * NC;
+    const DeviceProblem& pr = jb.pr;
+    unsigned char* ws = (unsigned char*)d_workspace;
+    jb.fq = (FitQueues*)ws;
+    const size_t list_bytes = align_up((size_t)pr.npix * sizeof(unsigned), 256);
+    jb.lists[0] = (unsigned*)(ws + sizeof(FitQueues));
+    jb.lists[1] = (unsigned*)(ws + sizeof(FitQueues) + list_bytes);
+    jb.states = ws + sizeof(FitQueues) + 2 * list_bytes;
+    if (pr.npix >= (1LL << 32)) return fail(ctx, B200FIT_E_ARG, "fit: npix must be < 2^32 per call");
+    cudaStream_t stream = jb.stream;
+    CK(cudaMemsetAsync(jb.fq, 0, sizeof(FitQueues), stream));
+    if (jb.prof) {
         ctx->prof_used = 0;
         ctx->prof_rounds = 0;
         ctx->next_event(stream);   // [0] before the prologue
@@ -994,11 +1018,11 @@ static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_
     const long long cap = (long long)ctx->num_sms * 16;
     const unsigned pgrid = (unsigned)(pwarps < cap ? pwarps : cap);
     fit_prologue_kernel<NC><<<pgrid, EVAL_WARPS * 32, 0, stream>>>(
-        pr, d_spectra, (long long)stride, (const long long*)d_row_index, d_guesses, d_err, states, lists[0], fq, d_params,
-        d_perr, d_chi2, d_err_used, d_status, d_counts);
+        pr, jb.d_spectra, jb.stride, jb.d_row_index, jb.d_guesses, jb.d_err, (PixState<P>*)jb.states, jb.lists[0], jb.fq,
+        jb.d_params, jb.d_perr, jb.d_chi2, jb.d_err_used, jb.d_status, jb.d_counts);
     CK(cudaGetLastError());
     ctx->launches += 1;
-    if (prof) ctx->next_event(stream);   // [1] after the prologue
+    if (jb.prof) ctx->next_event(stream);   // [1] after the prologue
 
     int eval_per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC>, EVAL_WARPS * 32, 0));
@@ -1009,39 +1033,47 @@ static int launch_fit(b200fit_ctx* ctx, const DeviceProblem& pr, const float* d_
     const long long sblocks = (pr.npix + sgroups - 1) / sgroups;
     long long sgrid = (long long)ctx->num_sms * 32;
     if (sgrid > sblocks) sgrid = sblocks;
+    jb.egrid = (unsigned)egrid;
+    jb.sgrid = (unsigned)sgrid;
+    jb.max_rounds = 2 * pr.max_iter + 3;
+    jb.r = 0;
+    jb.nchecks = 0;
+    jb.finished = false;
+    return B200FIT_OK;
+}
 
-    const int max_rounds = 2 * pr.max_iter + 3;
-    constexpr int CHECK = 8, RING = 4;
-    int nchecks = 0;
-    bool finished = false;
-    for (int r = 0; r < max_rounds && !finished; ++r) {
-        const int cur = r & 1;
-        fit_eval_kernel<NC><<<(unsigned)egrid, EVAL_WARPS * 32, 0, stream>>>(
-            pr, d_spectra, (long long)stride, (const long long*)d_row_index, states, lists[cur], fq, cur);
-        if (prof) ctx->next_event(stream);   // [2 + 2r] after the evaluation of round r
-        fit_solve_kernel<NC><<<(unsigned)sgrid, SOLVE_THREADS, 0, stream>>>(
-            pr, states, lists[cur], lists[cur ^ 1], fq, cur, d_params, d_perr, d_chi2, d_err_used, d_status, d_counts);
-        ctx->launches += 2;
-        if (prof) {
-            ctx->next_event(stream);         // [3 + 2r] after the solver step of round r
-            ctx->prof_rounds = r + 1;
+template <int NC>
+static int job_round(b200fit_ctx* ctx, FitJob& jb) {
+    constexpr int P = 4 * NC;
+    cudaStream_t stream = jb.stream;
+    const int r = jb.r, cur = r & 1;
+    fit_eval_kernel<NC><<<jb.egrid, EVAL_WARPS * 32, 0, stream>>>(jb.pr, jb.d_spectra, jb.stride, jb.d_row_index,
+                                                                  (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
+    if (jb.prof) ctx->next_event(stream);   // [2 + 2r] after the evaluation of round r
+    fit_solve_kernel<NC><<<jb.sgrid, SOLVE_THREADS, 0, stream>>>(jb.pr, (PixState<P>*)jb.states, jb.lists[cur],
+                                                                 jb.lists[cur ^ 1], jb.fq, cur, jb.d_params, jb.d_perr,
+                                                                 jb.d_chi2, jb.d_err_used, jb.d_status, jb.d_counts);
+    ctx->launches += 2;
+    if (jb.prof) {
+        ctx->next_event(stream);            // [3 + 2r] after the solver step of round r
+        ctx->prof_rounds = r + 1;
+    }
+    jb.r = r + 1;
+    if ((r + 1) % FIT_CHECK == 0) {
+        const int slot = jb.slot0 + jb.nchecks % FIT_RING;
+        if (jb.nchecks >= FIT_RING - 2) {   // wait for the check issued (FIT_RING - 2) checks ago
+            const int old = jb.slot0 + (jb.nchecks - (FIT_RING - 2)) % FIT_RING;
+            CK(cudaEventSynchronize(ctx->check_ev[old]));
+            if (ctx->h_count[old] == 0) jb.finished = true;
         }
-        if ((r + 1) % CHECK == 0) {
-            const int slot = nchecks % RING;
-            if (nchecks >= RING - 2) {   // wait for the check issued (RING - 2) checks ago
-                const int old = (nchecks - (RING - 2)) % RING;
-                CK(cudaEventSynchronize(ctx->check_ev[old]));
-                if (ctx->h_count[old] == 0) finished = true;
-            }
-            if (!finished) {
-                CK(cudaMemcpyAsync((void*)&ctx->h_count[slot], &fq->count[cur ^ 1], sizeof(unsigned), cudaMemcpyDeviceToHost,
-                                   stream));
-                CK(cudaEventRecord(ctx->check_ev[slot], stream));
-                ++nchecks;
-            }
+        if (!jb.finished) {
+            CK(cudaMemcpyAsync((void*)&ctx->h_count[slot], &jb.fq->count[cur ^ 1], sizeof(unsigned),
+                               cudaMemcpyDeviceToHost, stream));
+            CK(cudaEventRecord(ctx->check_ev[slot], stream));
+            ++jb.nchecks;
         }
     }
-    CK(cudaGetLastError());
+    if (jb.r >= jb.max_rounds) jb.finished = true;
     return B200FIT_OK;
 }
 
@@ -1066,15 +1098,21 @@ int b200fit_create(b200fit_ctx** out, int device) {
     }
     ctx->num_sms = prop.multiProcessorCount;
     ctx->h_count = nullptr;
-    if (cudaSetDevice(device) != cudaSuccess || cudaMallocHost((void**)&ctx->h_count, 4 * sizeof(unsigned)) != cudaSuccess) {
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_count, B200FIT_MAX_BATCH * 4 * sizeof(unsigned)) != cudaSuccess) {
         delete ctx;
         return B200FIT_E_CUDA;
     }
-    for (int i = 0; i < 4; ++i) {
-        if (cudaEventCreateWithFlags(&ctx->check_ev[i], cudaEventDisableTiming) != cudaSuccess) {
-            delete ctx;
-            return B200FIT_E_CUDA;
-        }
+    bool okc = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < B200FIT_MAX_BATCH * 4; ++i)
+        okc = okc && cudaEventCreateWithFlags(&ctx->check_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < B200FIT_MAX_BATCH; ++i) {
+        okc = okc && cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming) == cudaSuccess;
+        okc = okc && cudaStreamCreateWithFlags(&ctx->job_stream[i], cudaStreamNonBlocking) == cudaSuccess;
+    }
+    if (!okc) {
+        delete ctx;
+        return B200FIT_E_CUDA;
     }
     *out = ctx;
     return B200FIT_OK;
@@ -1082,7 +1120,12 @@ int b200fit_create(b200fit_ctx** out, int device) {
 
 void b200fit_destroy(b200fit_ctx* ctx) {
     if (!ctx) return;
-    for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->check_ev[i]);
+    for (int i = 0; i < B200FIT_MAX_BATCH * 4; ++i) cudaEventDestroy(ctx->check_ev[i]);
+    for (int i = 0; i < B200FIT_MAX_BATCH; ++i) {
+        cudaEventDestroy(ctx->join_ev[i]);
+        cudaStreamDestroy(ctx->job_stream[i]);
+    }
+    cudaEventDestroy(ctx->fork_ev);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->h_count) cudaFreeHost((void*)ctx->h_count);
     delete ctx;
@@ -1144,24 +1187,91 @@ int b200fit_gather_spectra(b200fit_ctx* ctx, const float* d_cube, int32_t nchan,
     return B200FIT_OK;
 }
 
+int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* args, int32_t njobs, void* stream_) {
+    if (!ctx || !args) return fail(ctx, B200FIT_E_ARG, "fit: null context/arguments");
+    if (njobs < 0 || njobs > B200FIT_MAX_BATCH) return fail(ctx, B200FIT_E_ARG, "fit: njobs must be in [0, B200FIT_MAX_BATCH]");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FitJob jobs[B200FIT_MAX_BATCH];
+    int live = 0;
+    for (int j = 0; j < njobs; ++j) {
+        const b200fit_fit_args& a = args[j];
+        if (!a.prob) return fail(ctx, B200FIT_E_ARG, "fit: null problem");
+        FitJob& jb = jobs[live];
+        const int rc = make_device_problem(*a.prob, jb.pr);
+        if (rc) return fail(ctx, rc, "fit: invalid problem description");
+        if (jb.pr.npix == 0) continue;
+        if (!a.d_spectra || !a.d_guesses || !a.d_params || !a.d_perr || !a.d_chi2 || !a.d_err_used || !a.d_status ||
+            !a.d_workspace)
+            return fail(ctx, B200FIT_E_ARG, "fit: null device pointer");
+        if (a.nchan_stride < jb.pr.nchan || (a.nchan_stride & 31)) return fail(ctx, B200FIT_E_ARG, "fit: bad nchan_stride");
+        if (jb.pr.weight_mode == 1 && !a.d_err) return fail(ctx, B200FIT_E_ARG, "fit: weight_mode 1 needs d_err");
+        jb.nc = jb.pr.ncomp;
+        jb.d_spectra = a.d_spectra;
+        jb.stride = a.nchan_stride;
+        jb.d_row_index = (const long long*)a.d_row_index;
+        jb.d_guesses = a.d_guesses;
+        jb.d_err = a.d_err;
+        jb.d_params = a.d_params;
+        jb.d_perr = a.d_perr;
+        jb.d_chi2 = a.d_chi2;
+        jb.d_err_used = a.d_err_used;
+        jb.d_status = a.d_status;
+        jb.d_counts = a.d_counts;
+        jb.slot0 = live * FIT_RING;
+        jb.states = a.d_workspace;   // resolved in job_begin
+        ++live;
+    }
+    if (live == 0) return B200FIT_OK;
+    CK(cudaSetDevice(ctx->device));
+    const bool forked = live > 1;
+    if (forked) CK(cudaEventRecord(ctx->fork_ev, stream));
+    for (int j = 0; j < live; ++j) {
+        FitJob& jb = jobs[j];
+        jb.stream = forked ? ctx->job_stream[j] : stream;
+        jb.prof = ctx->profiling != 0 && j == 0 && !forked;
+        if (forked) CK(cudaStreamWaitEvent(jb.stream, ctx->fork_ev, 0));
+        void* ws = jb.states;
+        const int rc = (jb.nc == 1) ? job_begin<1>(ctx, jb, ws) : job_begin<2>(ctx, jb, ws);
+        if (rc) return rc;
+    }
+    for (bool any = true; any;) {
+        any = false;
+        for (int j = 0; j < live; ++j) {
+            FitJob& jb = jobs[j];
+            if (jb.finished) continue;
+            const int rc = (jb.nc == 1) ? job_round<1>(ctx, jb) : job_round<2>(ctx, jb);
+            if (rc) return rc;
+            any = true;
+        }
+    }
+    if (forked) {
+        for (int j = 0; j < live; ++j) {
+            CK(cudaEventRecord(ctx->join_ev[j], jobs[j].stream));
+            CK(cudaStreamWaitEvent(stream, ctx->join_ev[j], 0));
+        }
+    }
+    CK(cudaGetLastError());
+    return B200FIT_OK;
+}
+
 int b200fit_fit(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_spectra, int64_t nchan_stride,
                 const int64_t* d_row_index, const double* d_guesses, const double* d_err, double* d_params, double* d_perr, double* d_chi2,
                 double* d_err_used, int32_t* d_status, uint32_t* d_counts, void* d_workspace, void* stream) {
-    if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "fit: null context/problem");
-    DeviceProblem pr;
-    const int rc = make_device_problem(*prob, pr);
-    if (rc) return fail(ctx, rc, "fit: invalid problem description");
-    if (pr.npix == 0) return B200FIT_OK;
-    if (!d_spectra || !d_guesses || !d_params || !d_perr || !d_chi2 || !d_err_used || !d_status || !d_workspace)
-        return fail(ctx, B200FIT_E_ARG, "fit: null device pointer");
-    if (nchan_stride < pr.nchan || (nchan_stride & 31)) return fail(ctx, B200FIT_E_ARG, "fit: bad nchan_stride");
-    if (pr.weight_mode == 1 && !d_err) return fail(ctx, B200FIT_E_ARG, "fit: weight_mode 1 needs d_err");
-    CK(cudaSetDevice(ctx->device));
-    if (pr.ncomp == 1)
-        return launch_fit<1>(ctx, pr, d_spectra, nchan_stride, d_guesses, d_err, d_params, d_perr, d_chi2, d_err_used,
-                             d_status, d_counts, d_workspace, d_row_index, (cudaStream_t)stream);
-    return launch_fit<2>(ctx, pr, d_spectra, nchan_stride, d_guesses, d_err, d_params, d_perr, d_chi2, d_err_used,
-                         d_status, d_counts, d_workspace, d_row_index, (cudaStream_t)stream);
+    b200fit_fit_args a;
+    a.prob = prob;
+    a.d_spectra = d_spectra;
+    a.nchan_stride = nchan_stride;
+    a.d_row_index = d_row_index;
+    a.d_guesses = d_guesses;
+    a.d_err = d_err;
+    a.d_params = d_params;
+    a.d_perr = d_perr;
+    a.d_chi2 = d_chi2;
+    a.d_err_used = d_err_used;
+    a.d_status = d_status;
+    a.d_counts = d_counts;
+    a.d_workspace = d_workspace;
+    return b200fit_fit_batch(ctx, &a, 1, stream);
 }
 
 static long long aux_blocks(const b200fit_ctx* ctx, long long npix) {

@@ -121,6 +121,57 @@ class Engine(object):
         self._check(rc, "b200fit_fit")
         return out
 
+    def alloc_fit_out(self, prob, want_counts=True):
+        npix, P = int(prob.npix), 4 * int(prob.ncomp)
+        dev = self.device
+        return dict(params=torch.empty((npix, P), dtype=torch.float64, device=dev),
+                    perr=torch.empty((npix, P), dtype=torch.float64, device=dev),
+                    chi2=torch.empty(npix, dtype=torch.float64, device=dev),
+                    err_used=torch.empty(npix, dtype=torch.float64, device=dev),
+                    status=torch.empty(npix, dtype=torch.int32, device=dev),
+                    counts=torch.empty((npix, 4), dtype=torch.int32, device=dev) if want_counts else None)
+
+    def fit_batch(self, jobs):
+        """Several fits in flight at once (b200fit_fit_batch): ``jobs`` = list of dicts with keys prob, spectra,
+        guesses and optionally err, row_index, out.  Typically the 1- and 2-component fits of the same rows: the
+        latency-bound late rounds of one overlap the other's work.  Returns the list of result dicts."""
+        n = len(jobs)
+        if n > _abi.MAX_BATCH:
+            raise B200FitError("at most %d fits per batch" % _abi.MAX_BATCH)
+        if not hasattr(self, "_ws_batch"):
+            self._ws_batch = [None] * _abi.MAX_BATCH
+        arr = (_abi.FitArgs * max(n, 1))()
+        outs, keep = [], []
+        for j, job in enumerate(jobs):
+            prob, spectra, guesses = job["prob"], job["spectra"], job["guesses"]
+            npix, P = int(prob.npix), 4 * int(prob.ncomp)
+            assert spectra.dtype == torch.float32 and spectra.is_contiguous()
+            assert guesses.dtype == torch.float64 and guesses.is_contiguous() and tuple(guesses.shape) == (npix, P)
+            row_index = job.get("row_index")
+            assert row_index is not None or spectra.shape[0] == npix
+            out = job.get("out") or self.alloc_fit_out(prob)
+            need = int(self.lib.b200fit_workspace_bytes(C.byref(prob)))
+            ws = self._ws_batch[j]
+            if ws is None or ws.numel() < need:
+                self._ws_batch[j] = None
+                ws = self._ws_batch[j] = torch.empty(need, dtype=torch.uint8, device=self.device)
+            a = arr[j]
+            a.prob = C.pointer(prob)
+            a.d_spectra, a.nchan_stride = spectra.data_ptr(), spectra.shape[1]
+            a.d_row_index = row_index.data_ptr() if row_index is not None else None
+            a.d_guesses = guesses.data_ptr()
+            a.d_err = job["err"].data_ptr() if job.get("err") is not None else None
+            a.d_params, a.d_perr = out["params"].data_ptr(), out["perr"].data_ptr()
+            a.d_chi2, a.d_err_used = out["chi2"].data_ptr(), out["err_used"].data_ptr()
+            a.d_status = out["status"].data_ptr()
+            a.d_counts = out["counts"].data_ptr() if out.get("counts") is not None else None
+            a.d_workspace = ws.data_ptr()
+            outs.append(out)
+            keep.append((prob, spectra, guesses, row_index))
+        rc = self.lib.b200fit_fit_batch(self.ctx, arr, n, self._stream())
+        self._check(rc, "b200fit_fit_batch")
+        return outs
+
     def model(self, prob, params, stride=None):
         """fp64 model rows [npix, stride] (NaN rows where params are all-zero / non-finite)."""
         npix = int(prob.npix)

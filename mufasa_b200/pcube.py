@@ -93,6 +93,7 @@ class PCube(object):
         self.npars = None
         self._device = device
         self._dev = {}            # device-resident state, shared between PCubes of one data cube
+        self._deferred = None     # list collecting fit jobs when UltraCube batches several fits (see fiteach)
         self.timing = {}
 
     # ---------------------------------------------------------------------------------------------------
@@ -218,7 +219,20 @@ class PCube(object):
         gsel = np.ascontiguousarray(guesses.reshape(P, ny * nx)[:, pix].T)
         g_dev = torch.from_numpy(gsel).to(dev, non_blocking=True)
         idx_dev = None if npix == ny * nx else torch.from_numpy(pix.astype(np.int64)).to(dev, non_blocking=True)
+        job = dict(prob=prob, spectra=rows, guesses=g_dev, row_index=idx_dev, pcube=self, pix=pix)
+        if self._deferred is not None:
+            # UltraCube.fit_cube over several ncomp: the fits are launched together (Engine.fit_batch) so that the
+            # latency-bound late rounds of one overlap the other; results are filled in by finish_fit()
+            self._deferred.append(job)
+            return
         out = eng.fit(prob, rows, g_dev, row_index=idx_dev)
+        self.finish_fit(job, out)
+
+    def finish_fit(self, job, out):
+        """Copy the results of a (possibly batched) fit back into parcube / errcube / has_fit ..."""
+        pix = job["pix"]
+        P = self.npars
+        ny, nx = self.has_fit.shape
         packed = torch.cat([out["params"], out["perr"], out["chi2"][:, None], out["err_used"][:, None],
                             out["status"].to(torch.float64)[:, None],
                             out["counts"][:, 0].to(torch.float64)[:, None]], dim=1).cpu().numpy()

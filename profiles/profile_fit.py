@@ -69,5 +69,15 @@ for r in range(reps):
               r, npix, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, np.isin(st, [1, 2, 3, 4, 6]).mean(),
               (st == 5).mean(), cn[:, 0].mean(), np.median(cn[:, 0]), np.percentile(cn[:, 0], 90), cn[:, 0].max(),
               np.bincount(a["ncomp"].cpu().numpy().astype(int), minlength=3).tolist()), flush=True)
+    if os.environ.get("PROFILE_BATCH", "0") == "1":
+        torch.cuda.synchronize()
+        tb0 = time.perf_counter()
+        ob = eng.fit_batch([dict(prob=probs[1], spectra=rows, guesses=gs[1]),
+                            dict(prob=probs[2], spectra=rows, guesses=gs[2])])
+        torch.cuda.synchronize()
+        tb1 = time.perf_counter()
+        same = all(bool(torch.equal(ob[0][k], o1[k])) and bool(torch.equal(ob[1][k], o2[k]))
+                   for k in ("params", "perr", "chi2", "status"))
+        print("   batch(1c || 2c): %.2f ms   identical to the separate fits: %s" % ((tb1 - tb0) * 1e3, same), flush=True)
     hist = np.bincount(st.clip(-1, 8) + 1, minlength=10)
     print("status hist (-1..8):", hist.tolist(), flush=True)
