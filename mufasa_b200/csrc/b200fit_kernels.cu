@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
                     const unsigned f = pk >> (16 * c);
                     const int klo = f & 0xffu, khi = (f >> 8) & 0xffu;
                     float g = 0.f, a = 0.f, b = 0.f;
+#pragma unroll 4
                     for (int k = klo; k < khi; ++k) {
                         const float4 q = *reinterpret_cast<const float4*>(&w.lines[c][k]);
                         LineCoef lc;
@@ -327,23 +328,21 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
                 n_chunks += 1;
                 float m, J[P];
                 rt_channel<NC>(Gs, As, Bs, fi - ic0, cc, m, J);
-                const bool valid = (y == y);   // NaN channels (and the NaN padding) carry no weight
-                const float r = valid ? (y - m) : 0.f;
-                const float dchi = valid ? m * (m - 2.f * y) : 0.f;
+                if (y == y) {   // NaN channels (and the NaN padding) carry no weight
+                    const float r = y - m;
+                    int q = 0;
 #pragma unroll
-                for (int u = 0; u < P; ++u) J[u] = valid ? J[u] : 0.f;
-                int q = 0;
+                    for (int u = 0; u < P; ++u) {
 #pragma unroll
-                for (int u = 0; u < P; ++u) {
-#pragma unroll
-                    for (int v = u; v < P; ++v) {
-                        acc[q] = fmaf(J[u], J[v], acc[q]);
-                        ++q;
+                        for (int v = u; v < P; ++v) {
+                            acc[q] = fmaf(J[u], J[v], acc[q]);
+                            ++q;
+                        }
                     }
-                }
 #pragma unroll
-                for (int u = 0; u < P; ++u) acc[NH + u] = fmaf(J[u], r, acc[NH + u]);
-                acc[NACC - 1] += dchi;
+                    for (int u = 0; u < P; ++u) acc[NH + u] = fmaf(J[u], r, acc[NH + u]);
+                    acc[NACC - 1] = fmaf(m, m - 2.f * y, acc[NACC - 1]);
+                }
             }
         }
         // 3. cross-lane reduction in fp64 through shared memory, RR accumulators per pass
@@ -456,6 +455,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
 // Hyperfine terms below exp(-90) relative are skipped: they cannot change the rounded sum.
 struct CompF64 {
     double tex, tau, nuoff[MAXHF_FULL], inv2w2[MAXHF_FULL], tw[MAXHF_FULL];
+    double acut[MAXHF_FULL];   // |x + nuoff - line| beyond which the term is below exp(-90): skipped without the divide
 };
 
 __device__ __forceinline__ void comp_setup_f64(const DeviceProblem& pr, const double* p4, CompF64& c) {
@@ -468,12 +468,21 @@ __device__ __forceinline__ void comp_setup_f64(const DeviceProblem& pr, const do
         c.nuoff[k] = __dmul_rn(__ddiv_rn(vel, CKMS), line);
         c.inv2w2[k] = __dmul_rn(2.0, __dmul_rn(nuwidth, nuwidth));   // 2.0 * nuwidth**2 (the divisor)
         c.tw[k] = __dmul_rn(c.tau, pr.wts_full[k]);
+        c.acut[k] = sqrt(90.0 * c.inv2w2[k]) * (1.0 + 1e-9);   // generous: the exact arg > -90 test still follows
     }
 }
 
 __device__ __forceinline__ double xarr_ghz(const DeviceProblem& pr, int i) {
     const double v = __dadd_rn(pr.v0, __dmul_rn(pr.dv, (double)i));
     return __ddiv_rn(__dmul_rn(__dmul_rn(pr.nu_ref_ghz, 1e9), __dsub_rn(1.0, __ddiv_rn(v, CKMS))), 1e9);
+}
+
+// exp(x) as numpy evaluates it.  glibc's exp is within ~0.51 ulp, i.e. practically correctly rounded; CUDA's is
+// within 1 ulp.  The difference matters in exactly one place: exp(-tau) for tau ~ 1e-16 decides whether
+// 1 - exp(-tau) is 0 or 1.1e-16, i.e. whether a channel at the edge of a hyperfine window belongs to the AICc sample
+// mask ``model > 0``.  For tiny |x| the correctly rounded result is fma(x, 1 + x/2, 1).
+__device__ __forceinline__ double exp_np(double x) {
+    return (fabs(x) < 9.5367431640625e-07) ? fma(x, fma(x, 0.5, 1.0), 1.0) : exp(x);
 }
 
 __device__ __forceinline__ double t_antenna(double T0, double T) {
@@ -491,10 +500,11 @@ __device__ __forceinline__ double model_f64(const DeviceProblem& pr, const CompF
         double tauprof = 0.0;
         for (int k = 0; k < pr.nfull; ++k) {
             const double a = __dsub_rn(__dadd_rn(x, cp.nuoff[k]), pr.lines_full[k]);
+            if (fabs(a) > cp.acut[k]) continue;
             const double arg = __ddiv_rn(-__dmul_rn(a, a), cp.inv2w2[k]);
             if (arg > -90.0) tauprof = __dadd_rn(tauprof, __dmul_rn(cp.tw[k], exp(arg)));
         }
-        const double e = exp(-tauprof);
+        const double e = exp_np(-tauprof);
         const double jt = t_antenna(T0, cp.tex);
         bg = __dadd_rn(__dmul_rn(jt, __dsub_rn(1.0, e)), __dmul_rn(bg, e));
     }
