@@ -208,6 +208,7 @@ class PCube(object):
         self._modelcube = None
         self.fittype, self.npars = fittype, P
         self.last_minpars, self.last_maxpars = list(minpars), list(maxpars)
+        self.last_guesses, self.last_maskmap = guesses, ok
         if npix == 0:
             return
 

@@ -1,0 +1,108 @@
+"""End-to-end GPU tests through the reference-facing API (UltraCube / cubefit_gen / cubefit_simp), BASELINE configs
+[0] and [1] at reduced size, plus size-independent properties at larger sizes."""
+import numpy as np
+import pytest
+
+import _tiles as T
+from mufasa_b200 import synth
+from mufasa_b200.cube import SpecCube
+from oracle import fiteach as F
+from oracle import model as M
+
+pytestmark = pytest.mark.gpu
+
+
+def _ucube(syn):
+    from mufasa_b200.UltraCube import UltraCube
+    return UltraCube(cube=SpecCube(syn["cube"], syn["v"]), fittype=syn["fittype"], device=0)
+
+
+def test_config0_fit_cube_moment_guesses():
+    """configs[0]: NH3 1-component fit via UltraCube.fit_cube -> cubefit_gen (moment guesses, tautex_renorm, clamps,
+    snr mask) on a 24 x 24 x 500 cut of the 64 x 64 x 500 cube; oracle = mpfit restatement on the SAME guesses,
+    limits and mask the driver handed to fiteach."""
+    syn = synth.make_cube(1, T.oracle_modelcube, shape=(24, 24, 500))
+    uc = _ucube(syn)
+    uc.fit_cube(ncomp=1, snr_min=3.0)
+    p = uc.pcubes["1"]
+    assert p.has_fit.sum() > 0.6 * p.has_fit.size                     # border trimmed / low S/N pixels are masked
+    g = np.where(p.last_maskmap[None], p.last_guesses, np.nan)
+    o = F.fiteach(syn["cube"], syn["v"], g, p.last_minpars, p.last_maxpars, syn["fittype"], multicore=8)
+    assert np.array_equal(p.has_fit, o["has_fit"])
+    npix = p.has_fit.size
+    c = T.criteria(p.parcube.reshape(4, npix).T, p.chi2map.ravel(), p.statusmap.ravel(), o, 4,
+                   perr=p.errcube.reshape(4, npix).T)
+    sel = c["both"]
+    assert sel.sum() > 0.95 * p.has_fit.sum()
+    assert (c["par_ok"] & c["chi2_ok"])[sel].mean() > 0.99
+    # parameter errors agree with mpfit's covariance
+    with np.errstate(all="ignore"):
+        re = np.abs(p.errcube - o["errcube"]) / o["errcube"]
+    assert np.nanmedian(re[:, sel.reshape(p.has_fit.shape)]) < 1e-3
+    # truth recovery (sanity, not parity): velocities within 5 sigma
+    m = p.has_fit
+    dz = np.abs(p.parcube[0][m] - syn["truth1"][0][m]) / p.errcube[0][m]
+    assert np.median(dz) < 2.0
+
+
+def test_config1_model_selection_end_to_end():
+    """configs[1] at reduced size: 1c + 2c fits (batched) + AICc selection through UltraCube; the ncomp map recovers
+    the known truth map (0 in the noise border, 2 inside the disc, 1 elsewhere) for the bulk of the pixels."""
+    syn = synth.make_cube(2, T.oracle_modelcube, rows=(96, 104), shape=(200, 64, 800))
+    uc = _ucube(syn)
+    uc.fit_cube(ncomp=[1, 2], simpfit=True, guesses={1: syn["guess1"].copy(), 2: syn["guess2"].copy()})
+    parcube, errcube, lnk10, lnk20, lnk21 = uc.get_best_2c_parcube()
+    nmap = uc.ncomp_map
+    truth = syn["ncomp_true"]
+    assert nmap.shape == truth.shape
+    assert (nmap == truth).mean() > 0.85
+    assert (nmap[truth == 0] == 0).mean() > 0.95          # pure noise is not called a detection
+    # selection logic is self-consistent with the likelihood maps
+    with np.errstate(invalid="ignore"):
+        two = (lnk21 > 5) & (lnk20 > 5)
+        one = ~two & (uc.get_AICc_likelihood(1, 0) > 5)
+    assert np.array_equal(nmap == 2, two & (uc.get_AICc_likelihood(1, 0) > 5))
+    assert np.array_equal(nmap == 1, one)
+    assert np.all(np.isnan(parcube[4:, nmap < 2])) and np.all(np.isnan(parcube[:, nmap == 0]))
+    # batched fits == separate fits, bit for bit
+    uc2 = _ucube(syn)
+    uc2.fit_cube(ncomp=1, simpfit=True, guesses=syn["guess1"].copy())
+    uc2.fit_cube(ncomp=2, simpfit=True, guesses=syn["guess2"].copy())
+    for k in ("1", "2"):
+        assert np.array_equal(uc.pcubes[k].parcube, uc2.pcubes[k].parcube)
+        assert np.array_equal(uc.pcubes[k].errcube, uc2.pcubes[k].errcube)
+
+
+def test_partition_invariance_and_idempotence():
+    """Size-independent properties: per-pixel results do not depend on how the cube is partitioned or
+    ordered (row slabs == whole cube, bit for bit), and refitting from the solution returns the solution."""
+    import torch
+    from mufasa_b200 import _abi
+    from mufasa_b200.engine import get_engine
+    eng = get_engine(0)
+    tile = T.sample_tile(2, nrows=6, xstep=4)
+    lo, hi = T.limits_vectors(tile["fittype"], 2)
+    g = synth.clamp_guesses(tile["guess2"], lo, hi)
+    spec, gg = T.pixel_major(tile, g)
+    npix = spec.shape[0]
+    prob = lambda n: _abi.make_problem(tile["fittype"], 2, tile["nchan"], n, tile["v"][0], tile["dv"], lo, hi)
+    d_spec, d_g = torch.from_numpy(spec).cuda(), torch.from_numpy(gg).cuda()
+    whole = {k: v.clone() for k, v in eng.fit(prob(npix), d_spec, d_g).items()}
+    half = npix // 2
+    a = {k: v.clone() for k, v in eng.fit(prob(half), d_spec[:half].contiguous(), d_g[:half].contiguous()).items()}
+    b = {k: v.clone() for k, v in eng.fit(prob(npix - half), d_spec[half:].contiguous(), d_g[half:].contiguous()).items()}
+    for k in ("params", "perr", "chi2", "status"):
+        assert torch.equal(whole[k], torch.cat([a[k], b[k]]))
+    # a permuted pixel order through row_index gives the same per-pixel answers
+    perm = torch.randperm(npix, generator=torch.Generator().manual_seed(3)).cuda()
+    pm = eng.fit(prob(npix), d_spec, d_g[perm].contiguous(), row_index=perm.to(torch.int64))
+    assert torch.equal(pm["params"], whole["params"][perm]) and torch.equal(pm["status"], whole["status"][perm])
+    # idempotence: start from the converged solution -> stays there (within the evaluation noise), few evaluations
+    conv = torch.isin(whole["status"], torch.tensor([1, 2, 3, 4, 6], device="cuda", dtype=torch.int32))
+    again = eng.fit(prob(npix), d_spec, whole["params"].clone())
+    dz = (again["params"] - whole["params"]).abs() / torch.where(whole["perr"] > 0, whole["perr"],
+                                                                   torch.full_like(whole["perr"], float("inf")))
+    sel = conv & (again["status"] > 0)
+    assert sel.float().mean() > 0.8
+    assert float(dz.max(dim=1).values[sel].median()) < 1e-3
+    assert float(again["counts"][:, 0][sel].float().median()) <= 4
