@@ -71,6 +71,8 @@ struct DeviceProblem {
     int nfull;                     // reference-table entries (original order) for the fp64 model kernels
     int ngroups;                   // groups of neighbouring hyperfines (windowing granularity of the fit kernel)
     int gstart[MAXHF_FIT + 1];     // group g = lines [gstart[g], gstart[g+1])
+    int ngroups_full;              // the same for the reference-order table (contiguous runs of neighbouring lines)
+    int gstart_full[MAXHF_FULL + 1];
     long long npix;
     double v0, dv, inv_dv;         // ascending velocity axis
     double ftol, signal_cut;

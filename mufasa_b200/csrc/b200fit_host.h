@@ -50,6 +50,11 @@ inline int make_device_problem(const b200fit_problem& in, DeviceProblem& out) {
         out.lines_full[k] = (1 - lt->voff_full[k] / CKMS) * lt->nu0_hz / 1e9;
         out.wts_full[k] = lt->wts_full[k] / wsum;
     }
+    // contiguous runs of neighbouring lines in the reference-order table (window tests of the fp64 model kernels)
+    out.ngroups_full = 0;
+    for (int k = 0; k < lt->nfull; ++k)
+        if (k == 0 || std::fabs(lt->voff_full[k] - lt->voff_full[k - 1]) > 3.0) out.gstart_full[out.ngroups_full++] = k;
+    for (int g = out.ngroups_full; g <= MAXHF_FULL; ++g) out.gstart_full[g] = lt->nfull;
     // distinct hyperfines, ascending velocity offset; equal offsets merged (exact: identical gaussians)
     std::vector<std::pair<double, double>> v;
     for (int k = 0; k < lt->nfull; ++k) {

@@ -70,6 +70,7 @@ struct alignas(8) PixState {
     double inv_sigma[P / 4];
     double err, sumsq;           // weight (std of the finite channels); sum of y^2 over the finite channels
     unsigned n_gauss, n_chunks;  // roofline accounting
+    int fitted, pad_;            // 1 once the LM state is initialised (0: bad guess / no weight -> zeros, status 0)
 };
 
 struct FitQueues {               // head of the workspace
@@ -193,10 +194,12 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32)
             ps.sumsq = sq;
             ps.n_gauss = 0;
             ps.n_chunks = 0;
+            ps.fitted = 0;
             bool go = (err > 0.0) && !isinf(err);
             if (go && pr.signal_cut > 0.0 && !(ymax / err >= pr.signal_cut)) go = false;
             const bool ok = go && lm_init<P>(ps.st, guesses + px * P, cf);
             if (ok) {
+                ps.fitted = 1;
                 prepare_trial<NC>(pr, ps);
                 list0[atomicAdd(&fq->count[0], 1u)] = (unsigned)px;
             } else {   // not fitted: zeros, like pyspeckit's blank parcube
@@ -412,23 +415,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
         }
         if (!done) done = lane_propose<P>(g, s);
         if (done) {
-            // results (zeros on failure, like pyspeckit's blank parcube)
-            const bool good = s.status > 0;
-            const double err = ps.err, err2 = err * err;
-            const double pe = good ? lane_error<P>(g, s, err2) : 0.0;
-            params[(size_t)px * P + g.gl] = good ? s.p : 0.0;
-            perr[(size_t)px * P + g.gl] = pe;
-            if (g.gl == 0) {
-                chi2[px] = good ? s.chi2 / err2 : 0.0;   // at the returned parameters (lm_reported_chi2)
-                err_used[px] = err;
-                status[px] = s.status;
-                if (counts) {
-                    counts[4 * (size_t)px + 0] = (unsigned)s.nevals;
-                    counts[4 * (size_t)px + 1] = (unsigned)s.nrej;
-                    counts[4 * (size_t)px + 2] = ps.n_gauss;
-                    counts[4 * (size_t)px + 3] = ps.n_chunks;
-                }
-            }
+            lane_store<P>(g, ps.st, s, accepted);   // results are written by fit_finalize_kernel
         } else {
             lane_store<P>(g, ps.st, s, accepted);
             // coefficients of the next trial point (every lane computes, lane 0 stores: same issue cost in SIMT)
@@ -449,6 +436,46 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
     }
 }
 
+// ---- results: P lanes per pixel, once, after the last round -----------------------------------------------------
+// Parameter errors sqrt(diag(err^2 (H_FF)^-1)) (0 for pegged parameters, mpfit calc_covar on the column-zeroed
+// Jacobian) and the result rows.  Kept out of the solver kernel so that its code -- one more factorisation and
+// eight more triangular solves -- does not sit in the instruction stream of every round.
+template <int NC>
+__global__ void __launch_bounds__(SOLVE_THREADS)
+    fit_finalize_kernel(const DeviceProblem pr, const PixState<4 * NC>* __restrict__ states,
+                        double* __restrict__ params, double* __restrict__ perr, double* __restrict__ chi2,
+                        double* __restrict__ err_used, int* __restrict__ status, unsigned* __restrict__ counts) {
+    constexpr int P = 4 * NC;
+    constexpr unsigned GROUPS = SOLVE_THREADS / P;
+    __shared__ FitTables tb;
+    load_fit_tables(pr, tb);
+    const LMConfig cf{tb.lo, tb.hi, pr.ftol, pr.max_iter};
+    const LaneGroup<P> g;
+    for (long long px = (long long)blockIdx.x * GROUPS + threadIdx.x / P; px < pr.npix;
+         px += (long long)gridDim.x * GROUPS) {
+        const PixState<P>& ps = states[px];
+        if (!ps.fitted) continue;            // zeros were written by the prologue
+        LaneState<P> s;
+        lane_load<P>(g, ps.st, cf, s);
+        const bool good = s.status > 0;
+        const double err = ps.err, err2 = err * err;
+        const double pe = good ? lane_error<P>(g, s, err2) : 0.0;
+        params[(size_t)px * P + g.gl] = good ? s.p : 0.0;
+        perr[(size_t)px * P + g.gl] = pe;
+        if (g.gl == 0) {
+            chi2[px] = good ? s.chi2 / err2 : 0.0;   // at the returned parameters (lm_reported_chi2)
+            err_used[px] = err;
+            status[px] = s.status;
+            if (counts) {
+                counts[4 * (size_t)px + 0] = (unsigned)s.nevals;
+                counts[4 * (size_t)px + 1] = (unsigned)s.nrej;
+                counts[4 * (size_t)px + 2] = ps.n_gauss;
+                counts[4 * (size_t)px + 3] = ps.n_chunks;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // fp64 model in the reference's operation order (HyperfineModel.py:41-58, 91-107; BaseModel.py:191-192).
 // Explicit _rn intrinsics keep nvcc from contracting mul+add into FMA, so the arithmetic is the numpy sequence.
@@ -456,20 +483,43 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
 struct CompF64 {
     double tex, tau, nuoff[MAXHF_FULL], inv2w2[MAXHF_FULL], tw[MAXHF_FULL];
     double acut[MAXHF_FULL];   // |x + nuoff - line| beyond which the term is below exp(-90): skipped without the divide
+    int clo[MAXHF_FULL], chi[MAXHF_FULL];   // per line group: channels outside [clo, chi] are beyond every acut (+2 margin)
 };
 
-__device__ __forceinline__ void comp_setup_f64(const DeviceProblem& pr, const double* p4, CompF64& c) {
-    const double vel = p4[0], width = p4[1];
-    c.tex = p4[2];
-    c.tau = p4[3];
-    for (int k = 0; k < pr.nfull; ++k) {
+// Warp-cooperative set-up of one component: lane k prepares line k (the divisions and the square root are the
+// expensive part), then lane g derives the channel range of line group g.  Call with all 32 lanes.
+__device__ __forceinline__ void comp_setup_f64(const DeviceProblem& pr, const double* p4, CompF64& c, int lane) {
+    const double vel = p4[0], width = p4[1], tau = p4[3];
+    if (lane == 0) {
+        c.tex = p4[2];
+        c.tau = tau;
+    }
+    if (lane < pr.nfull) {
+        const int k = lane;
         const double line = pr.lines_full[k];
         const double nuwidth = fabs(__dmul_rn(__ddiv_rn(width, CKMS), line));
         c.nuoff[k] = __dmul_rn(__ddiv_rn(vel, CKMS), line);
-        c.inv2w2[k] = __dmul_rn(2.0, __dmul_rn(nuwidth, nuwidth));   // 2.0 * nuwidth**2 (the divisor)
-        c.tw[k] = __dmul_rn(c.tau, pr.wts_full[k]);
-        c.acut[k] = sqrt(90.0 * c.inv2w2[k]) * (1.0 + 1e-9);   // generous: the exact arg > -90 test still follows
+        const double d = __dmul_rn(2.0, __dmul_rn(nuwidth, nuwidth));   // 2.0 * nuwidth**2 (the divisor)
+        c.inv2w2[k] = d;
+        c.tw[k] = __dmul_rn(tau, pr.wts_full[k]);
+        c.acut[k] = sqrt(90.0 * d) * (1.0 + 1e-9);   // generous: the exact arg > -90 test still follows
     }
+    __syncwarp();
+    // channel range of every line group (integer pre-test; x decreases with the channel index)
+    if (lane < pr.ngroups_full) {
+        const int g = lane;
+        double xmin = INFINITY, xmax = -INFINITY;
+        for (int k = pr.gstart_full[g]; k < pr.gstart_full[g + 1]; ++k) {
+            const double ctr = pr.lines_full[k] - c.nuoff[k];
+            xmin = fmin(xmin, ctr - c.acut[k]);
+            xmax = fmax(xmax, ctr + c.acut[k]);
+        }
+        const double ilo = ((1.0 - xmax / pr.nu_ref_ghz) * CKMS - pr.v0) / pr.dv;
+        const double ihi = ((1.0 - xmin / pr.nu_ref_ghz) * CKMS - pr.v0) / pr.dv;
+        c.clo[g] = (int)fmax(fmin(floor(ilo) - 2.0, 1e9), -1e9);
+        c.chi[g] = (int)fmax(fmin(ceil(ihi) + 2.0, 1e9), -1e9);
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ double xarr_ghz(const DeviceProblem& pr, int i) {
@@ -489,26 +539,65 @@ __device__ __forceinline__ double t_antenna(double T0, double T) {
     return __ddiv_rn(T0, __dsub_rn(exp(__ddiv_rn(T0, T)), 1.0));
 }
 
-// model of NC components at channel i; comps in shared/local memory
-__device__ __forceinline__ double model_f64(const DeviceProblem& pr, const CompF64* comps, int ncomp, int i) {
-    const double x = xarr_ghz(pr, i);
-    const double T0 = __ddiv_rn(__dmul_rn(__dmul_rn(H_CGS, x), 1e9), KB_CGS);
-    const double bg0 = t_antenna(T0, TCMB);
-    double bg = bg0;
-    for (int c = 0; c < ncomp; ++c) {
-        const CompF64& cp = comps[c];
-        double tauprof = 0.0;
-        for (int k = 0; k < pr.nfull; ++k) {
+// optical depth profile of one component at frequency x (HyperfineModel.py:99-103); terms below exp(-90) of their
+// peak are skipped (they cannot change the rounded sum: exp(-90) = 8e-40)
+__device__ __forceinline__ double tauprof_f64(const DeviceProblem& pr, const CompF64& cp, double x, int i) {
+    double tauprof = 0.0;
+    for (int g = 0; g < pr.ngroups_full; ++g) {
+        if (i < cp.clo[g] || i > cp.chi[g]) continue;   // integer pre-test: the whole group is out of reach
+        for (int k = pr.gstart_full[g]; k < pr.gstart_full[g + 1]; ++k) {
             const double a = __dsub_rn(__dadd_rn(x, cp.nuoff[k]), pr.lines_full[k]);
             if (fabs(a) > cp.acut[k]) continue;
             const double arg = __ddiv_rn(-__dmul_rn(a, a), cp.inv2w2[k]);
             if (arg > -90.0) tauprof = __dadd_rn(tauprof, __dmul_rn(cp.tw[k], exp(arg)));
         }
-        const double e = exp_np(-tauprof);
-        const double jt = t_antenna(T0, cp.tex);
-        bg = __dadd_rn(__dmul_rn(jt, __dsub_rn(1.0, e)), __dmul_rn(bg, e));
     }
+    return tauprof;
+}
+
+// One radiative-transfer slab in the reference's operation order.  tau == 0 leaves the background untouched
+// bit for bit (jt * (1 - 1) + bg * 1 == bg), so the Planck terms are not evaluated for it.
+__device__ __forceinline__ double slab_f64(double bg, double T0, double tex, double tauprof) {
+    if (tauprof == 0.0) return bg;
+    const double e = exp_np(-tauprof);
+    const double jt = t_antenna(T0, tex);
+    return __dadd_rn(__dmul_rn(jt, __dsub_rn(1.0, e)), __dmul_rn(bg, e));
+}
+
+__device__ __forceinline__ double planck_T0(double x) {
+    return __ddiv_rn(__dmul_rn(__dmul_rn(H_CGS, x), 1e9), KB_CGS);
+}
+
+// model of ``ncomp`` (<= 2) components at channel i; comps in shared/local memory.  A channel outside every
+// hyperfine window is exactly 0 (bg0 - bg0) and costs only the window tests.
+__device__ __forceinline__ double model_f64(const DeviceProblem& pr, const CompF64* comps, int ncomp, int i) {
+    const double x = xarr_ghz(pr, i);
+    const double t0 = tauprof_f64(pr, comps[0], x, i);
+    const double t1 = (ncomp > 1) ? tauprof_f64(pr, comps[1], x, i) : 0.0;
+    if (t0 == 0.0 && t1 == 0.0) return 0.0;
+    const double T0 = planck_T0(x);
+    const double bg0 = t_antenna(T0, TCMB);
+    double bg = slab_f64(bg0, T0, comps[0].tex, t0);
+    if (ncomp > 1) bg = slab_f64(bg, T0, comps[1].tex, t1);
     return __dsub_rn(bg, bg0);
+}
+
+// the 1-component model (comps[0]) and the 2-component model (comps[1], comps[2]) of one pixel at channel i,
+// sharing the frequency axis and the Planck terms (AICc pass)
+__device__ __forceinline__ void model_pair_f64(const DeviceProblem& pr, const CompF64* comps, bool v1, bool v2, int i,
+                                               double& m1, double& m2) {
+    const double x = xarr_ghz(pr, i);
+    const double ta = v1 ? tauprof_f64(pr, comps[0], x, i) : 0.0;
+    const double tb = v2 ? tauprof_f64(pr, comps[1], x, i) : 0.0;
+    const double tc = v2 ? tauprof_f64(pr, comps[2], x, i) : 0.0;
+    m1 = 0.0;
+    m2 = 0.0;
+    if (ta == 0.0 && tb == 0.0 && tc == 0.0) return;
+    const double T0 = planck_T0(x);
+    const double bg0 = t_antenna(T0, TCMB);
+    if (ta != 0.0) m1 = __dsub_rn(slab_f64(bg0, T0, comps[0].tex, ta), bg0);
+    if (tb != 0.0 || tc != 0.0)
+        m2 = __dsub_rn(slab_f64(slab_f64(bg0, T0, comps[1].tex, tb), T0, comps[2].tex, tc), bg0);
 }
 
 __device__ __forceinline__ bool params_valid(const double* p, int P) {
@@ -537,8 +626,8 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
          pix += (long long)gridDim.x * AUX_WARPS) {
         const double* p = params + pix * P;
         const bool valid = params_valid(p, P);
-        if (valid && lane < pr.ncomp) comp_setup_f64(pr, p + 4 * lane, sh[warp].comps[lane]);
-        __syncwarp();
+        if (valid)
+            for (int c = 0; c < pr.ncomp; ++c) comp_setup_f64(pr, p + 4 * c, sh[warp].comps[c], lane);
         for (int i = lane; i < (int)stride; i += 32) {
             double m = NAN;
             if (valid && i < pr.nchan) m = model_f64(pr, sh[warp].comps, pr.ncomp, i);
@@ -582,9 +671,11 @@ __device__ __forceinline__ void dilate_bits(unsigned* bits, int nchan, int expan
 
 __device__ __forceinline__ void setup_pixel_models(const DeviceProblem& pr, AuxShared& sh, const double* p1,
                                                    const double* p2, bool v1, bool v2, int lane) {
-    if (v1 && lane == 0) comp_setup_f64(pr, p1, sh.comps[0]);
-    if (v2 && lane >= 1 && lane <= 2) comp_setup_f64(pr, p2 + 4 * (lane - 1), sh.comps[lane]);
-    __syncwarp();
+    if (v1) comp_setup_f64(pr, p1, sh.comps[0], lane);
+    if (v2) {
+        comp_setup_f64(pr, p2, sh.comps[1], lane);
+        comp_setup_f64(pr, p2 + 4, sh.comps[2], lane);
+    }
 }
 
 // Un-dilated union mask (model1 > 0) | (model2 > 0) of ONE pixel, written as a bit set: the spectral mask the
@@ -609,8 +700,8 @@ __global__ void __launch_bounds__(32)
         const int i = (wd << 5) + lane;
         bool on = false;
         if (wd < nwords && i < pr.nchan) {
-            double m1 = v1 ? model_f64(pr, &sh.comps[0], 1, i) : 0.0;
-            double m2 = v2 ? model_f64(pr, &sh.comps[1], 2, i) : 0.0;
+            double m1, m2;
+            model_pair_f64(pr, sh.comps, v1, v2, i, m1, m2);
             on = model_f32 ? (((float)m1 > 0.f) || ((float)m2 > 0.f)) : ((m1 > 0.0) || (m2 > 0.0));
         }
         const unsigned b = __ballot_sync(FULL, on);
@@ -672,8 +763,8 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
             const int i = (wd << 5) + lane;
             bool on = false;
             if (i < pr.nchan) {
-                double m1 = v1 ? model_f64(pr, &sh[warp].comps[0], 1, i) : 0.0;
-                double m2 = v2 ? model_f64(pr, &sh[warp].comps[1], 2, i) : 0.0;
+                double m1, m2;
+                model_pair_f64(pr, sh[warp].comps, v1, v2, i, m1, m2);
                 if (model_f32) {
                     m1s[i] = (float)m1;
                     m2s[i] = (float)m2;
@@ -803,8 +894,7 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
             }
             continue;
         }
-        if (lane < pr.ncomp) comp_setup_f64(pr, p + 4 * lane, sh[warp].comps[lane]);
-        __syncwarp();
+        for (int c = 0; c < pr.ncomp; ++c) comp_setup_f64(pr, p + 4 * c, sh[warp].comps[c], lane);
         const long long row = row_index ? row_index[pix] : pix;
         const float* y = spectra + row * stride;
         for (int wd = 0; wd < nwords; ++wd) {
@@ -1253,6 +1343,22 @@ int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* args, int32_t nj
             if (rc) return rc;
             any = true;
         }
+    }
+    for (int j = 0; j < live; ++j) {   // parameter errors + result rows, once per fit
+        FitJob& jb = jobs[j];
+        const long long groups = SOLVE_THREADS / (4 * jb.nc);
+        long long fgrid = (jb.pr.npix + groups - 1) / groups;
+        if (fgrid > (long long)ctx->num_sms * 32) fgrid = (long long)ctx->num_sms * 32;
+        if (jb.nc == 1)
+            fit_finalize_kernel<1><<<(unsigned)fgrid, SOLVE_THREADS, 0, jb.stream>>>(
+                jb.pr, (const PixState<4>*)jb.states, jb.d_params, jb.d_perr, jb.d_chi2, jb.d_err_used, jb.d_status,
+                jb.d_counts);
+        else
+            fit_finalize_kernel<2><<<(unsigned)fgrid, SOLVE_THREADS, 0, jb.stream>>>(
+                jb.pr, (const PixState<8>*)jb.states, jb.d_params, jb.d_perr, jb.d_chi2, jb.d_err_used, jb.d_status,
+                jb.d_counts);
+        CK(cudaGetLastError());
+        ctx->launches += 1;
     }
     if (forked) {
         for (int j = 0; j < live; ++j) {

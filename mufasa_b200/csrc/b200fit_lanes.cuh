@@ -164,8 +164,8 @@ __device__ __forceinline__ bool lane_chol(const LaneGroup<P>& g, const double (&
             ok = false;
             d = (d0 > 0.0) ? d0 : 1.0;
         }
-        const double s = sqrt(d);
-        const double inv = 1.0 / s;
+        const double inv = rsqrt(d);             // 1 / L_jj  (rsqrt + one multiply instead of sqrt + divide)
+        const double s = d * inv;
         const double l = (i > j) ? a[j] * inv : ((i == j) ? s : 0.0);   // L_ij
         lrow[j] = l;
         if (i == j) linv = inv;
@@ -215,6 +215,8 @@ __device__ __forceinline__ double lane_newton_den(const LaneGroup<P>& g, const d
 }
 
 // MINPACK lmpar on the normal equations (see lm_par).  Returns this lane's step component; updates par.
+// One call site each for the factorisation, the two triangular solves and the Newton denominator: the kernel's
+// instruction footprint is what limits it at full occupancy (profiles/r1j: "no instruction" was the top stall).
 template <int P>
 __device__ __forceinline__ double lane_par(const LaneGroup<P>& g, const double (&H)[P], double dg, double rhs,
                                            unsigned fixed, double delta, double& par) {
@@ -226,18 +228,23 @@ __device__ __forceinline__ double lane_par(const LaneGroup<P>& g, const double (
         if (it > 0 && par == 0.0) par = fmax(LM_DWARF, 0.001 * paru);
         const bool spd = lane_chol<P>(g, H, dg, (it == 0) ? 0.0 : par, fixed, lrow, linv);
         const double temp = fp;
-        if (it > 0 || spd) {
+        const bool solved = (it > 0 || spd);
+        if (solved) {
             const double y = lane_fwd<P>(g, lrow, linv, rhs);
             x = lane_bwd<P>(g, lrow, linv, y);
             dxnorm = lane_dnorm<P>(g, dg, x);
             fp = dxnorm - delta;
         }
+        if (it == 0 && spd && fp <= 0.1 * delta) {
+            par = 0.0;
+            return x;
+        }
+        if (it > 0 && (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || it == 10)) break;
+        // Newton correction (fp / delta) / |L^-1 (D^2 x / |D x|)|^2
+        double corr = 0.0;
+        if (solved) corr = (fp / delta) / lane_newton_den<P>(g, lrow, linv, dg, x, dxnorm, fixedbit);
         if (it == 0) {
-            if (spd && fp <= 0.1 * delta) {
-                par = 0.0;
-                return x;
-            }
-            if (spd) parl = (fp / delta) / lane_newton_den<P>(g, lrow, linv, dg, x, dxnorm, fixedbit);
+            parl = corr;                       // 0 when H is not positive definite
             const double t = rhs / dg;
             const double gnorm = sqrt(g.sum(t * t));
             paru = gnorm / delta;
@@ -245,13 +252,11 @@ __device__ __forceinline__ double lane_par(const LaneGroup<P>& g, const double (
             par = fmax(par, parl);
             par = fmin(par, paru);
             if (par == 0.0) par = gnorm / dxnorm;
-            continue;
+        } else {
+            if (fp > 0.0) parl = fmax(parl, par);
+            if (fp < 0.0) paru = fmin(paru, par);
+            par = fmax(parl, par + corr);
         }
-        if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || it == 10) break;
-        const double parc = (fp / delta) / lane_newton_den<P>(g, lrow, linv, dg, x, dxnorm, fixedbit);
-        if (fp > 0.0) parl = fmax(parl, par);
-        if (fp < 0.0) paru = fmin(paru, par);
-        par = fmax(parl, par + parc);
     }
     return x;
 }

@@ -54,6 +54,8 @@ for r in range(reps):
     o1 = eng.fit(probs[1], rows, gs[1])
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    if os.environ.get("PROFILE_EVENTS", "0") == "1":
+        print("   1c profile:", eng.get_profile(), flush=True)
     o2 = eng.fit(probs[2], rows, gs[2])
     torch.cuda.synchronize()
     t2 = time.perf_counter()
@@ -79,5 +81,8 @@ for r in range(reps):
         same = all(bool(torch.equal(ob[0][k], o1[k])) and bool(torch.equal(ob[1][k], o2[k]))
                    for k in ("params", "perr", "chi2", "status"))
         print("   batch(1c || 2c): %.2f ms   identical to the separate fits: %s" % ((tb1 - tb0) * 1e3, same), flush=True)
+    if r == 0:
+        ne = cn[:, 0]
+        print("   active pixels at round r (2c):", {rr: int((ne > rr).sum()) for rr in (0, 5, 10, 20, 40, 80, 120, 160, 200, 240, 280, 320)}, flush=True)
     hist = np.bincount(st.clip(-1, 8) + 1, minlength=10)
     print("status hist (-1..8):", hist.tolist(), flush=True)
