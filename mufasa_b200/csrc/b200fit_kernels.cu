@@ -211,7 +211,24 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32)
 
 // ---- evaluation: warp per active pixel -----------------------------------------------------------------------
 //   chi2 = sum_finite y^2 + sum_{channels inside a window} m (m - 2 y)      (exactly sum (y - m)^2: m == 0 elsewhere)
-template <int NC>
+// Templated on the species so that the hyperfine GROUPS (runs of neighbouring lines that share one channel window)
+// are compile-time: per 32-channel chunk and component the warp tests NG group bits and runs fully unrolled
+// gaussian code for the groups that reach the chunk -- no loop control, no index arithmetic (the dynamic
+// ``for k in [klo, khi)`` loop of the previous version was 15 % of all executed instructions, profiles/r1k).
+template <int MODEL>
+struct LineGroups;
+template <>
+struct LineGroups<B200FIT_MODEL_NH3_11> {   // sorted by velocity offset: -19.5 (2) | -7.5 (3) | main (8) | +7.5 (3) | +19.6 (2)
+    static constexpr int NG = 5;
+    __host__ __device__ static constexpr int start(int g) { return g == 0 ? 0 : g == 1 ? 2 : g == 2 ? 5 : g == 3 ? 13 : g == 4 ? 16 : 18; }
+};
+template <>
+struct LineGroups<B200FIT_MODEL_N2HP_10> {  // -8.0 (1) | -0.6 .. 1.0 (3) | 5.5 .. 6.9 (3)
+    static constexpr int NG = 3;
+    __host__ __device__ static constexpr int start(int g) { return g == 0 ? 0 : g == 1 ? 1 : g == 2 ? 4 : 7; }
+};
+
+template <int NC, int MODEL>
 __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
     fit_eval_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
                     const long long* __restrict__ row_index, PixState<4 * NC>* __restrict__ states,
@@ -220,6 +237,8 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
     constexpr int NH = P * (P + 1) / 2;
     constexpr int NACC = NH + P + 1;
     constexpr int RR = EvalScratch<NC>::RED_ROWS;
+    using LG = LineGroups<MODEL>;
+    constexpr int NG = LG::NG;
     __shared__ FitTables tb;
     __shared__ EvalScratch<NC> scratch[EVAL_WARPS];
     load_fit_tables(pr, tb);
@@ -231,7 +250,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
     const unsigned nwarps = gridDim.x * EVAL_WARPS;
     const int nhf = pr.nhf;
     const int nchunks = (pr.nchan + 31) >> 5;
-    const int ngroups = pr.ngroups;
+    const int nhalf = (nchunks > 32) ? 2 : 1;
     const float ic0 = (float)pr.ic0;
 
     for (unsigned idx = warp0; idx < count; idx += nwarps) {
@@ -257,24 +276,25 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
 #pragma unroll
         for (int c = 0; c < NC; ++c) cc[c] = ps.cc[c];
         __syncwarp();
-        // 2. which hyperfines touch chunk `lane` and chunk `lane + 32` (whole groups of neighbouring lines; sorted)
-        unsigned packed[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        // 2. which line groups reach chunk `lane` (and chunk `lane + 32`): bit 8c + g
+        unsigned packed[2] = {0u, 0u};
+        unsigned my_lines = 0;   // gaussians this lane's chunks will cost (roofline accounting)
+        for (int h = 0; h < nhalf; ++h) {
             const int ch = lane + 32 * h;
             const float lo_edge = 32.f * ch, hi_edge = 32.f * ch + 31.f;
             unsigned pk = 0;
+            if (ch < nchunks) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                int glo = 0, ghi = 0;
-                for (int g = 0; g < ngroups; ++g) {
-                    const int first = tb.gstart[g], last = tb.gstart[g + 1] - 1;
-                    glo += (w.whi[c][last] < lo_edge) ? 1 : 0;
-                    ghi += (w.wlo[c][first] <= hi_edge) ? 1 : 0;
+                for (int c = 0; c < NC; ++c) {
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        const bool on = (w.whi[c][LG::start(g + 1) - 1] >= lo_edge) && (w.wlo[c][LG::start(g)] <= hi_edge);
+                        if (on) {
+                            pk |= 1u << (8 * c + g);
+                            my_lines += LG::start(g + 1) - LG::start(g);
+                        }
+                    }
                 }
-                int klo = tb.gstart[glo], khi = tb.gstart[ghi];
-                if (ch >= nchunks) klo = khi = 0;
-                pk |= ((unsigned)klo | ((unsigned)khi << 8)) << (16 * c);
             }
             packed[h] = pk;
         }
@@ -282,18 +302,12 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
         float acc[NACC];
 #pragma unroll
         for (int e = 0; e < NACC; ++e) acc[e] = 0.f;
-        unsigned n_gauss = 0, n_chunks = 0;
+        unsigned n_chunks = 0;
 
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < nhalf; ++h) {
             const unsigned mypk = h ? packed[1] : packed[0];
-            bool mine = false;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const unsigned f = mypk >> (16 * c);
-                mine = mine || ((f & 0xffu) < ((f >> 8) & 0xffu));
-            }
-            unsigned act = __ballot_sync(FULL, mine);
+            unsigned act = __ballot_sync(FULL, mypk != 0u);
             int jn = act ? (__ffs(act) - 1) : 0;
             float ynext = act ? __ldg(spec + (((jn + 32 * h) << 5) + lane)) : 0.f;
             while (act) {
@@ -310,23 +324,25 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
                 float Gs[NC], As[NC], Bs[NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    const unsigned f = pk >> (16 * c);
-                    const int klo = f & 0xffu, khi = (f >> 8) & 0xffu;
                     float g = 0.f, a = 0.f, b = 0.f;
-#pragma unroll 4
-                    for (int k = klo; k < khi; ++k) {
-                        const float4 q = *reinterpret_cast<const float4*>(&w.lines[c][k]);
-                        LineCoef lc;
-                        lc.nf = q.x;
-                        lc.b = q.y;
-                        lc.a = q.z;
-                        lc.lw = q.w;
-                        gauss_accum(fi, lc, g, a, b);
+#pragma unroll
+                    for (int gi = 0; gi < NG; ++gi) {
+                        if (pk & (1u << (8 * c + gi))) {   // warp-uniform
+#pragma unroll
+                            for (int k = LG::start(gi); k < LG::start(gi + 1); ++k) {
+                                const float4 q = *reinterpret_cast<const float4*>(&w.lines[c][k]);
+                                LineCoef lc;
+                                lc.nf = q.x;
+                                lc.b = q.y;
+                                lc.a = q.z;
+                                lc.lw = q.w;
+                                gauss_accum(fi, lc, g, a, b);
+                            }
+                        }
                     }
                     Gs[c] = g;
                     As[c] = a;
                     Bs[c] = b;
-                    n_gauss += (khi > klo) ? (unsigned)(khi - klo) : 0u;
                 }
                 n_chunks += 1;
                 float m, J[P];
@@ -375,6 +391,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
             }
             __syncwarp();
         }
+        const unsigned n_gauss = (unsigned)warp_sum_i((int)my_lines);
         if (lane == 0) {
             ps.n_gauss += n_gauss;
             ps.n_chunks += n_chunks;
@@ -1075,7 +1092,7 @@ static size_t fit_workspace_bytes(long long npix) {
 // A FitJob is one fit in flight; b200fit_fit_batch interleaves the rounds of several jobs on separate streams so
 // that the latency-bound late rounds of one fit (few slowly converging pixels left) overlap another fit's work.
 struct FitJob {
-    int nc = 0;
+    int nc = 0, model_id = 0;
     DeviceProblem pr;
     const float* d_spectra = nullptr;
     long long stride = 0;
@@ -1124,8 +1141,27 @@ static int job_begin(b200fit_ctx* ctx, FitJob& jb, void* d_workspace) {
     ctx->launches += 1;
     if (jb.prof) ctx->next_event(stream);   // [1] after the prologue
 
+    // the evaluation kernel's hyperfine groups are compile-time: they must be the ones the host derived
+    {
+        bool same = true;
+        if (jb.model_id == B200FIT_MODEL_NH3_11) {
+            using LG = LineGroups<B200FIT_MODEL_NH3_11>;
+            same = pr.ngroups == LG::NG;
+            for (int g = 0; same && g <= LG::NG; ++g) same = pr.gstart[g] == LG::start(g);
+        } else {
+            using LG = LineGroups<B200FIT_MODEL_N2HP_10>;
+            same = pr.ngroups == LG::NG;
+            for (int g = 0; same && g <= LG::NG; ++g) same = pr.gstart[g] == LG::start(g);
+        }
+        if (!same) return fail(ctx, B200FIT_E_MODEL, "fit: hyperfine group table mismatch");
+    }
     int eval_per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC>, EVAL_WARPS * 32, 0));
+    if (jb.model_id == B200FIT_MODEL_NH3_11)
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC, B200FIT_MODEL_NH3_11>,
+                                                         EVAL_WARPS * 32, 0));
+    else
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10>,
+                                                         EVAL_WARPS * 32, 0));
     if (eval_per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit_eval_kernel does not fit on an SM");
     long long egrid = (long long)ctx->num_sms * eval_per_sm;        // a whole number of CTAs per SM
     if (egrid > pwarps) egrid = pwarps;
@@ -1147,8 +1183,12 @@ static int job_round(b200fit_ctx* ctx, FitJob& jb) {
     constexpr int P = 4 * NC;
     cudaStream_t stream = jb.stream;
     const int r = jb.r, cur = r & 1;
-    fit_eval_kernel<NC><<<jb.egrid, EVAL_WARPS * 32, 0, stream>>>(jb.pr, jb.d_spectra, jb.stride, jb.d_row_index,
-                                                                  (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
+    if (jb.model_id == B200FIT_MODEL_NH3_11)
+        fit_eval_kernel<NC, B200FIT_MODEL_NH3_11><<<jb.egrid, EVAL_WARPS * 32, 0, stream>>>(
+            jb.pr, jb.d_spectra, jb.stride, jb.d_row_index, (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
+    else
+        fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10><<<jb.egrid, EVAL_WARPS * 32, 0, stream>>>(
+            jb.pr, jb.d_spectra, jb.stride, jb.d_row_index, (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
     if (jb.prof) ctx->next_event(stream);   // [2 + 2r] after the evaluation of round r
     fit_solve_kernel<NC><<<jb.sgrid, SOLVE_THREADS, 0, stream>>>(jb.pr, (PixState<P>*)jb.states, jb.lists[cur],
                                                                  jb.lists[cur ^ 1], jb.fq, cur, jb.d_params, jb.d_perr,
@@ -1306,6 +1346,7 @@ int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* args, int32_t nj
         if (a.nchan_stride < jb.pr.nchan || (a.nchan_stride & 31)) return fail(ctx, B200FIT_E_ARG, "fit: bad nchan_stride");
         if (jb.pr.weight_mode == 1 && !a.d_err) return fail(ctx, B200FIT_E_ARG, "fit: weight_mode 1 needs d_err");
         jb.nc = jb.pr.ncomp;
+        jb.model_id = a.prob->model_id;
         jb.d_spectra = a.d_spectra;
         jb.stride = a.nchan_stride;
         jb.d_row_index = (const long long*)a.d_row_index;

@@ -144,14 +144,10 @@ def cubefit_simp(cube, pcube, ncomp, guesses, multicore=None, maskmap=None, fitt
     multicore = validate_n_cores(multicore)
 
     data = _cube_data(cube)
-    footprint_mask = pcube.footprint() if hasattr(pcube, "footprint") else np.any(np.isfinite(data), axis=0)
+    if hasattr(pcube, "rows_on_device"):
+        pcube.rows_on_device()          # start the (asynchronous) upload + layout pass; host logic below overlaps it
     planemask = np.any(np.isfinite(guesses), axis=0)
     peaksnr, planemask, kwargs = handle_snr(pcube, snr_min, planemask, **kwargs)
-
-    if maskmap is not None:
-        maskmap = maskmap & planemask & footprint_mask
-    else:
-        maskmap = planemask & footprint_mask
 
     v_peak_hwidth = 10
     v_guess = guesses[::4]
@@ -176,6 +172,13 @@ def cubefit_simp(cube, pcube, ncomp, guesses, multicore=None, maskmap=None, fitt
     impose_lim(guesses[1::4], sigmin, sigmax, eps)
     impose_lim(guesses[2::4], Texmin, Texmax, eps)
     impose_lim(guesses[3::4], taumin, taumax, eps)
+
+    # (the reference builds the footprint first, multi_v_fit.py:150; nothing above depends on it)
+    footprint_mask = pcube.footprint() if hasattr(pcube, "footprint") else np.any(np.isfinite(data), axis=0)
+    if maskmap is not None:
+        maskmap = maskmap & planemask & footprint_mask
+    else:
+        maskmap = planemask & footprint_mask
 
     kwargs['start_from_point'] = get_start_point(maskmap, weight=None)
     kwargs['multicore'] = multicore

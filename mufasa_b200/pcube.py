@@ -238,6 +238,8 @@ class PCube(object):
                             out["status"].to(torch.float64)[:, None],
                             out["counts"][:, 0].to(torch.float64)[:, None]], dim=1).cpu().numpy()
         flat = lambda a: a.reshape(a.shape[0], ny * nx) if a.ndim == 3 else a.reshape(ny * nx)
+        if pix.size == ny * nx:
+            pix = slice(None)           # every pixel fitted: plain copies instead of fancy-index scatters
         flat(self.parcube)[:, pix] = packed[:, :P].T
         flat(self.errcube)[:, pix] = packed[:, P:2 * P].T
         flat(self.chi2map)[pix] = packed[:, 2 * P]

@@ -43,5 +43,5 @@ for (f, l), a in agg.items():
 for f, b in sorted(byfile.items(), key=lambda kv: -kv[1][1]):
     print("  %-40s inst %5.1f%% samples %5.1f%% (no_inst %5.1f%%)" % (f, 100 * b[0] / tot_i, 100 * b[1] / tot_s, 100 * b[2] / tot_s))
 print("top lines by samples:")
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:topn]:
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1][int(__import__("os").environ.get("SORT_INST", "0") == "0")])[:topn]:
     print("  %-22s:%4d inst %5.1f%% samp %5.1f%% thr/inst %4.1f | %s" % (k[0], k[1], 100 * a[0] / tot_i, 100 * a[1] / tot_s, a[4] / max(a[0], 1), a[2].strip()))
