@@ -417,35 +417,35 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
     const LMConfig cf{tb.lo, tb.hi, pr.ftol, pr.max_iter};
     const LaneGroup<P> g;
     const unsigned count = fq->count[cur];
-    for (unsigned idx = blockIdx.x * GROUPS + threadIdx.x / P; idx < count; idx += gridDim.x * GROUPS) {
-        const unsigned px = list[idx];
+    const unsigned gsub = threadIdx.x / P;   // group of this lane within the block
+    // warp-uniform trip count: all groups of a warp loop together, the ones past the end carry ``valid = false``
+    for (unsigned idx0 = blockIdx.x * GROUPS; idx0 < count; idx0 += gridDim.x * GROUPS) {
+        const unsigned warp_first = idx0 + (gsub & ~((32u / P) - 1u));
+        if (warp_first >= count) continue;   // the whole warp is past the end (uniform)
+        const unsigned idx = idx0 + gsub;
+        const bool valid = idx < count;
+        const unsigned px = valid ? list[idx] : list[warp_first];
         PixState<P>& ps = states[px];
         LaneState<P> s;
         lane_load<P>(g, ps.st, cf, s);
         bool accepted = false;
-        int done;
-        if (s.nevals == 0) {
-            done = lane_adopt_first<P>(s);
-            accepted = !done;
-        } else {
-            done = lane_update<P>(g, s, cf, accepted);
-        }
-        if (!done) done = lane_propose<P>(g, s);
-        if (done) {
-            lane_store<P>(g, ps.st, s, accepted);   // results are written by fit_finalize_kernel
-        } else {
-            lane_store<P>(g, ps.st, s, accepted);
-            // coefficients of the next trial point (every lane computes, lane 0 stores: same issue cost in SIMT)
+        const int done = lane_step<P>(g, s, cf, valid, accepted);
+        // coefficients of the next trial point (every lane computes, lane 0 of a live group stores)
+        double p4[NC][4];
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p4[c][k] = g.bcast(s.pt, 4 * c + k);
+        if (!valid) continue;
+        lane_store<P>(g, ps.st, s, accepted);   // results are written by fit_finalize_kernel
+        if (!done) {
 #pragma unroll 1
             for (int c = 0; c < NC; ++c) {
-                double p4[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) p4[k] = g.bcast(s.pt, 4 * c + k);
                 CompCoef cc;
-                comp_coefs(pr.T0c, pr.dT0, pr.Jbg0, pr.Jbg1, p4, cc);
+                comp_coefs(pr.T0c, pr.dT0, pr.Jbg0, pr.Jbg1, p4[c], cc);
                 if (g.gl == 0) {
                     ps.cc[c] = cc;
-                    ps.inv_sigma[c] = 1.0 / p4[1];
+                    ps.inv_sigma[c] = 1.0 / p4[c][1];
                 }
             }
             if (g.gl == 0) next_list[atomicAdd(&fq->count[cur ^ 1], 1u)] = px;
@@ -468,15 +468,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
     load_fit_tables(pr, tb);
     const LMConfig cf{tb.lo, tb.hi, pr.ftol, pr.max_iter};
     const LaneGroup<P> g;
-    for (long long px = (long long)blockIdx.x * GROUPS + threadIdx.x / P; px < pr.npix;
-         px += (long long)gridDim.x * GROUPS) {
+    const long long npad = (pr.npix + (32 / P) - 1) / (32 / P) * (32 / P);   // whole warps loop together
+    for (long long px_ = (long long)blockIdx.x * GROUPS + threadIdx.x / P; px_ < npad;
+         px_ += (long long)gridDim.x * GROUPS) {
+        const bool inside = px_ < pr.npix;
+        const long long px = inside ? px_ : pr.npix - 1;
         const PixState<P>& ps = states[px];
-        if (!ps.fitted) continue;            // zeros were written by the prologue
         LaneState<P> s;
         lane_load<P>(g, ps.st, cf, s);
-        const bool good = s.status > 0;
+        const bool good = ps.fitted && s.status > 0;
         const double err = ps.err, err2 = err * err;
-        const double pe = good ? lane_error<P>(g, s, err2) : 0.0;
+        const double pe_all = lane_error<P>(g, s, err2);   // warp-uniform collectives
+        if (!ps.fitted || !inside) continue;   // zeros were written by the prologue
+        const double pe = good ? pe_all : 0.0;
         params[(size_t)px * P + g.gl] = good ? s.p : 0.0;
         perr[(size_t)px * P + g.gl] = pe;
         if (g.gl == 0) {

@@ -4,8 +4,12 @@
 // lm_update / lm_propose / lm_par / lm_errors -- that version stays the readable restatement and is what the
 // host emulation in tests/host_emul runs); here lane j of a P-lane group owns parameter j: p_j, the trial p_j,
 // its scaling, its gradient entry and ROW j of the symmetric J^T J.  Scalars (chi2, trust radius, lambda, ...)
-// are replicated, so all lanes of a group follow the same control flow; groups of one warp may diverge, every
-// shuffle therefore uses the group's own lane mask.  Each loop over parameters of the serial code becomes one
+// are replicated, so all lanes of a group compute the same scalars.  CONTROL FLOW IS WARP-UNIFORM: every collective
+// (shuffle, ballot) is executed by all 32 lanes with the constant full mask and segment width P, and a group whose
+// branch is not taken simply discards the result.  (The first version let the groups of a warp diverge and used
+// per-group masks: a non-constant mask makes nvcc wrap every shuffle in MATCH.ANY / WARPSYNC.COLLECTIVE /
+// reconvergence code -- ~20 % of the executed instructions, profiles/r1j -- and the divergent lmpar loop cost the
+// maximum trip count of the four groups anyway.)  Each loop over parameters of the serial code becomes one
 // step plus a log2(P)-deep shuffle reduction, the Cholesky factorisation is right-looking with one pivot
 // broadcast and P-1-j rank-1 broadcasts per column: the dependent-instruction chain of one LM step shrinks from
 // ~20k instructions (thread per pixel, rolled loops) to ~2.5k, which is what bounds the late rounds of a fit,
@@ -17,34 +21,36 @@ namespace b200fit {
 
 template <int P>
 struct LaneGroup {
-    unsigned mask;   // lanes of this group within the warp
+    static constexpr unsigned FULLMASK = 0xffffffffu;
+    static constexpr unsigned GMASK = (P == 32) ? 0xffffffffu : ((1u << P) - 1u);
     int gl;          // lane index inside the group = parameter index
-    int base;
+    int base;        // first lane of the group
     __device__ __forceinline__ LaneGroup() {
         const int lane = threadIdx.x & 31;
         gl = lane & (P - 1);
         base = lane & ~(P - 1);
-        mask = ((P == 32) ? 0xffffffffu : ((1u << P) - 1u)) << base;
     }
+    // all of these must be reached by all 32 lanes of the warp
     __device__ __forceinline__ double sum(double v) const {
 #pragma unroll
-        for (int o = P / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, P);
+        for (int o = P / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o, P);
         return v;
     }
     __device__ __forceinline__ double max(double v) const {
 #pragma unroll
-        for (int o = P / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o, P));
+        for (int o = P / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULLMASK, v, o, P));
         return v;
     }
     __device__ __forceinline__ double min(double v) const {
 #pragma unroll
-        for (int o = P / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(mask, v, o, P));
+        for (int o = P / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULLMASK, v, o, P));
         return v;
     }
-    __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(mask, v, src, P); }
+    __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(FULLMASK, v, src, P); }
     __device__ __forceinline__ unsigned ballot(bool pred) const {
-        return (__ballot_sync(mask, pred) >> base) & ((P == 32) ? 0xffffffffu : ((1u << P) - 1u));
+        return (__ballot_sync(FULLMASK, pred) >> base) & GMASK;
     }
+    __device__ __forceinline__ bool any_in_warp(bool pred) const { return __any_sync(FULLMASK, pred); }
 };
 
 // Registers of one lane.
@@ -215,38 +221,49 @@ __device__ __forceinline__ double lane_newton_den(const LaneGroup<P>& g, const d
 }
 
 // MINPACK lmpar on the normal equations (see lm_par).  Returns this lane's step component; updates par.
-// One call site each for the factorisation, the two triangular solves and the Newton denominator: the kernel's
-// instruction footprint is what limits it at full occupancy (profiles/r1j: "no instruction" was the top stall).
+// ``live``: this group wants a step (false for groups that are done or hold no pixel).  The iteration runs until
+// no group of the warp is live; a group that has found its lambda keeps executing the collectives and discards
+// the results.  One call site each for the factorisation, the triangular solves and the Newton denominator.
 template <int P>
 __device__ __forceinline__ double lane_par(const LaneGroup<P>& g, const double (&H)[P], double dg, double rhs,
-                                           unsigned fixed, double delta, double& par) {
+                                           unsigned fixed, double delta, double& par, bool live) {
     const bool fixedbit = (fixed >> g.gl) & 1u;
-    double lrow[P], linv, x = 0.0;
+    double lrow[P], linv, x = 0.0, xout = 0.0;
     double dxnorm = INFINITY, fp = INFINITY, parl = 0.0, paru = 0.0;
 #pragma unroll 1
-    for (int it = 0;; ++it) {
-        if (it > 0 && par == 0.0) par = fmax(LM_DWARF, 0.001 * paru);
+    for (int it = 0; it <= 10; ++it) {
+        if (!g.any_in_warp(live)) break;
+        if (live && it > 0 && par == 0.0) par = fmax(LM_DWARF, 0.001 * paru);
         const bool spd = lane_chol<P>(g, H, dg, (it == 0) ? 0.0 : par, fixed, lrow, linv);
         const double temp = fp;
         const bool solved = (it > 0 || spd);
+        const double y = lane_fwd<P>(g, lrow, linv, rhs);
+        const double xs = lane_bwd<P>(g, lrow, linv, y);
+        const double dxs = lane_dnorm<P>(g, dg, xs);
+        // Newton correction (fp / delta) / |L^-1 (D^2 x / |D x|)|^2
+        const double den = lane_newton_den<P>(g, lrow, linv, dg, xs, dxs, fixedbit);
+        const double t = rhs / dg;
+        const double gnorm = sqrt(g.sum(t * t));
+        if (!live) continue;
         if (solved) {
-            const double y = lane_fwd<P>(g, lrow, linv, rhs);
-            x = lane_bwd<P>(g, lrow, linv, y);
-            dxnorm = lane_dnorm<P>(g, dg, x);
+            x = xs;
+            dxnorm = dxs;
             fp = dxnorm - delta;
         }
         if (it == 0 && spd && fp <= 0.1 * delta) {
             par = 0.0;
-            return x;
+            xout = x;
+            live = false;
+            continue;
         }
-        if (it > 0 && (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || it == 10)) break;
-        // Newton correction (fp / delta) / |L^-1 (D^2 x / |D x|)|^2
-        double corr = 0.0;
-        if (solved) corr = (fp / delta) / lane_newton_den<P>(g, lrow, linv, dg, x, dxnorm, fixedbit);
+        if (it > 0 && (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || it == 10)) {
+            xout = x;
+            live = false;
+            continue;
+        }
+        const double corr = solved ? (fp / delta) / den : 0.0;
         if (it == 0) {
             parl = corr;                       // 0 when H is not positive definite
-            const double t = rhs / dg;
-            const double gnorm = sqrt(g.sum(t * t));
             paru = gnorm / delta;
             if (paru == 0.0) paru = LM_DWARF / fmin(delta, 0.1);
             par = fmax(par, parl);
@@ -258,7 +275,7 @@ __device__ __forceinline__ double lane_par(const LaneGroup<P>& g, const double (
             par = fmax(parl, par + corr);
         }
     }
-    return x;
+    return xout;
 }
 
 template <int P>
@@ -268,53 +285,132 @@ __device__ __forceinline__ unsigned lane_pegged(const LaneGroup<P>& g, const Lan
     return g.ballot(peg);
 }
 
+// One solver step of every group of the warp.  ``first_eval``: the group's state holds its very first evaluation
+// (adopt it); ``valid``: the group holds a pixel at all.  Returns LM_DONE / LM_CONTINUE per group; ``accepted`` tells
+// the caller whether p / b / H changed.  Warp-uniform: call with all 32 lanes.
 template <int P>
-__device__ __forceinline__ int lane_adopt_first(LaneState<P>& s) {
-    s.nevals = 1;
-    if (!(s.chi2t == s.chi2t) || isinf(s.chi2t)) {
-        s.status = -16;
-        return LM_DONE;
-    }
-    s.chi2 = s.chi2t;
-    s.chi2_last = s.chi2t;
-    s.b = s.bt;
-    s.hd = s.htd;
+__device__ __forceinline__ int lane_step(const LaneGroup<P>& g, LaneState<P>& s, const LMConfig& cf, bool valid,
+                                         bool& accepted) {
+    int done = valid ? LM_CONTINUE : LM_DONE;
+    accepted = false;
+    // ---- judge the trial evaluation (lm_adopt_first / lm_update) ------------------------------------------
+    const bool first_eval = (s.nevals == 0);
+    const double trap = g.sum((s.pt - s.p) * (s.b + s.bt));
+    const double xnorm_t = lane_dnorm<P>(g, s.diag, s.pt);   // |D p| should the trial point be accepted
+    if (valid) {
+        const bool finite = (s.chi2t == s.chi2t) && !isinf(s.chi2t);
+        if (first_eval) {
+            s.nevals = 1;
+            if (!finite) {
+                s.status = -16;
+                done = LM_DONE;
+            } else {
+                s.chi2 = s.chi2t;
+                s.chi2_last = s.chi2t;
+                s.b = s.bt;
+                s.hd = s.htd;
 #pragma unroll
-    for (int k = 0; k < P; ++k) s.H[k] = s.Ht[k];
-    return LM_CONTINUE;
-}
-
-template <int P>
-__device__ __forceinline__ int lane_propose(const LaneGroup<P>& g, LaneState<P>& s) {
-    if (s.fresh) {
-        s.peg = lane_pegged<P>(g, s);
-        const bool pegbit = (s.peg >> g.gl) & 1u;
+                for (int k = 0; k < P; ++k) s.H[k] = s.Ht[k];
+                accepted = true;
+            }
+        } else {
+            s.nevals += 1;
+            s.chi2_last = s.chi2t;
+            if (!finite) {
+                s.status = -16;
+                done = LM_DONE;
+            } else {
+                const double direct = s.chi2 - s.chi2t;
+                const double act_abs = (fabs(direct) > 40.0 * LM_NOISE_REL * s.chi2) ? direct : trap;
+                double actred = -1.0;
+                if (0.01 * s.chi2t < s.chi2) actred = act_abs / s.chi2;
+                const double temp1sq = s.alpha * s.alpha * s.sHs / s.chi2;
+                const double temp2sq = s.alpha * s.par * s.pnorm * s.pnorm / s.chi2;
+                const double prered = temp1sq + temp2sq / 0.5;
+                const double dirder = -(temp1sq + temp2sq);
+                double ratio = 0.0;
+                if (prered != 0.0) ratio = actred / prered;
+                if (ratio <= 0.25) {
+                    double temp = (actred >= 0.0) ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
+                    if (0.01 * s.chi2t >= s.chi2 || temp < 0.1) temp = 0.1;
+                    s.delta = temp * fmin(s.delta, s.pnorm / 0.1);
+                    s.par = s.par / temp;
+                } else if (s.par == 0.0 || ratio >= 0.75) {
+                    s.delta = s.pnorm / 0.5;
+                    s.par = 0.5 * s.par;
+                }
+                if (ratio >= 1e-4) {
+                    s.p = s.pt;
+                    s.b = s.bt;
+                    s.hd = s.htd;
+#pragma unroll
+                    for (int k = 0; k < P; ++k) s.H[k] = s.Ht[k];
+                    s.chi2 = s.chi2t;
+                    s.xnorm = xnorm_t;
+                    s.iters += 1;
+                    s.first = 0;
+                    s.fresh = 1;
+                    accepted = true;
+                } else {
+                    s.nrej += 1;
+                }
+                int st = 0;
+                if (fabs(actred) <= cf.ftol && prered <= cf.ftol && 0.5 * ratio <= 1.0) st = 1;
+                else if (fabs(actred) <= LM_FTOL_NOISE && prered <= LM_FTOL_NOISE && 0.5 * ratio <= 1.0) st = 6;
+                if (s.delta <= LM_XTOL * s.xnorm) st = (st == 1) ? 3 : 2;
+                if (st != 0) {
+                    s.status = st;
+                    done = LM_DONE;
+                } else if (s.iters >= cf.max_iter || s.nevals >= 2 * cf.max_iter + 2) {
+                    s.status = 5;
+                    done = LM_DONE;
+                } else if (s.delta <= LM_MACHEP * s.xnorm) {
+                    s.status = 7;
+                    done = LM_DONE;
+                }
+            }
+        }
+    }
+    // ---- propose the next trial point (lm_propose) ---------------------------------------------------------
+    // start of an outer iteration (fresh Jacobian): pegged set, scaling, gradient test -- computed by every group,
+    // applied by the groups that are at that point
+    const unsigned peg_new = lane_pegged<P>(g, s);
+    const bool fresh = (done == LM_CONTINUE) && s.fresh;
+    {
+        const bool pegbit = (peg_new >> g.gl) & 1u;
         const double fnorm = sqrt(s.chi2);
         const double cn = pegbit ? 0.0 : sqrt(s.hd > 0.0 ? s.hd : 0.0);
+        double diag_new = s.diag;
         if (s.first)
-            s.diag = (cn == 0.0) ? 1.0 : cn;
+            diag_new = (cn == 0.0) ? 1.0 : cn;
         else if (cn > s.diag)
-            s.diag = cn;
+            diag_new = cn;
         const double gn = (cn != 0.0 && fnorm != 0.0) ? fabs(s.b) / (cn * fnorm) : 0.0;
         const double gnorm = g.max(gn);
-        if (s.first) {
-            s.xnorm = lane_dnorm<P>(g, s.diag, s.p);
-            s.delta = LM_FACTOR * s.xnorm;
-            if (s.delta == 0.0) s.delta = LM_FACTOR;
+        const double xnorm0 = lane_dnorm<P>(g, diag_new, s.p);
+        if (fresh) {
+            s.peg = peg_new;
+            s.diag = diag_new;
+            if (s.first) {
+                s.xnorm = xnorm0;
+                s.delta = LM_FACTOR * s.xnorm;
+                if (s.delta == 0.0) s.delta = LM_FACTOR;
+            }
+            if (gnorm <= LM_GTOL) {
+                s.status = 4;
+                done = LM_DONE;
+            } else {
+                s.fresh = 0;
+            }
         }
-        if (gnorm <= LM_GTOL) {
-            s.status = 4;
-            return LM_DONE;
-        }
-        s.fresh = 0;
     }
+    const bool live = (done == LM_CONTINUE);
     const bool pegbit = (s.peg >> g.gl) & 1u;
     const bool fixedbit = pegbit || !(s.hd > 0.0);   // zero column: no information, leave untouched
     const unsigned fixed = g.ballot(fixedbit);
     const double rhs = fixedbit ? 0.0 : s.b;
     double par = s.par;
-    double dl = lane_par<P>(g, s.H, s.diag, rhs, fixed, s.delta, par);
-    s.par = par;
+    double dl = lane_par<P>(g, s.H, s.diag, rhs, fixed, s.delta, par, live);
     // mpfit: parameters sitting on a limit may only step into the box; the whole step is shortened so that no
     // other parameter crosses a limit
     if (fixedbit) dl = 0.0;
@@ -332,85 +428,24 @@ __device__ __forceinline__ int lane_propose(const LaneGroup<P>& g, LaneState<P>&
     const double l1 = s.lo * (1.0 + (s.lo >= 0 ? 1.0 : -1.0) * LM_MACHEP) + (s.lo == 0.0 ? LM_MACHEP : 0.0);
     if (pn >= u1) pn = s.hi;
     if (pn <= l1) pn = s.lo;
-    s.pt = pn;
-    s.alpha = alpha;
-    s.pnorm = lane_dnorm<P>(g, s.diag, dl);
-    if (s.first) s.delta = fmin(s.delta, s.pnorm);
+    const double pnorm = lane_dnorm<P>(g, s.diag, dl);
     // |J s|^2 (dl is zero for every fixed / pegged parameter)
     double row = 0.0;
 #pragma unroll
     for (int k = 0; k < P; ++k) row += s.H[k] * g.bcast(dl, k);
-    s.sHs = g.sum(dl * row);
-    return LM_CONTINUE;
+    const double sHs = g.sum(dl * row);
+    if (live) {
+        s.par = par;
+        s.pt = pn;
+        s.alpha = alpha;
+        s.pnorm = pnorm;
+        if (s.first) s.delta = fmin(s.delta, s.pnorm);
+        s.sHs = sHs;
+    }
+    return done;
 }
 
-// Returns LM_DONE when finished; ``accepted`` tells the caller whether p / b / H changed.
-template <int P>
-__device__ __forceinline__ int lane_update(const LaneGroup<P>& g, LaneState<P>& s, const LMConfig& cf,
-                                           bool& accepted) {
-    accepted = false;
-    s.nevals += 1;
-    s.chi2_last = s.chi2t;
-    const bool finite = (s.chi2t == s.chi2t) && !isinf(s.chi2t);
-    if (!finite) {
-        s.status = -16;
-        return LM_DONE;
-    }
-    const double direct = s.chi2 - s.chi2t;
-    const double trap = g.sum((s.pt - s.p) * (s.b + s.bt));
-    const double act_abs = (fabs(direct) > 40.0 * LM_NOISE_REL * s.chi2) ? direct : trap;
-    double actred = -1.0;
-    if (0.01 * s.chi2t < s.chi2) actred = act_abs / s.chi2;
-    const double temp1sq = s.alpha * s.alpha * s.sHs / s.chi2;
-    const double temp2sq = s.alpha * s.par * s.pnorm * s.pnorm / s.chi2;
-    const double prered = temp1sq + temp2sq / 0.5;
-    const double dirder = -(temp1sq + temp2sq);
-    double ratio = 0.0;
-    if (prered != 0.0) ratio = actred / prered;
-    if (ratio <= 0.25) {
-        double temp = (actred >= 0.0) ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
-        if (0.01 * s.chi2t >= s.chi2 || temp < 0.1) temp = 0.1;
-        s.delta = temp * fmin(s.delta, s.pnorm / 0.1);
-        s.par = s.par / temp;
-    } else if (s.par == 0.0 || ratio >= 0.75) {
-        s.delta = s.pnorm / 0.5;
-        s.par = 0.5 * s.par;
-    }
-    if (ratio >= 1e-4) {
-        s.p = s.pt;
-        s.b = s.bt;
-        s.hd = s.htd;
-#pragma unroll
-        for (int k = 0; k < P; ++k) s.H[k] = s.Ht[k];
-        s.chi2 = s.chi2t;
-        s.xnorm = lane_dnorm<P>(g, s.diag, s.p);
-        s.iters += 1;
-        s.first = 0;
-        s.fresh = 1;
-        accepted = true;
-    } else {
-        s.nrej += 1;
-    }
-    int st = 0;
-    if (fabs(actred) <= cf.ftol && prered <= cf.ftol && 0.5 * ratio <= 1.0) st = 1;
-    else if (fabs(actred) <= LM_FTOL_NOISE && prered <= LM_FTOL_NOISE && 0.5 * ratio <= 1.0) st = 6;
-    if (s.delta <= LM_XTOL * s.xnorm) st = (st == 1) ? 3 : 2;
-    if (st != 0) {
-        s.status = st;
-        return LM_DONE;
-    }
-    if (s.iters >= cf.max_iter || s.nevals >= 2 * cf.max_iter + 2) {
-        s.status = 5;
-        return LM_DONE;
-    }
-    if (s.delta <= LM_MACHEP * s.xnorm) {
-        s.status = 7;
-        return LM_DONE;
-    }
-    return LM_CONTINUE;
-}
-
-// Parameter error of this lane's parameter (see lm_errors).
+// Parameter error of this lane's parameter (see lm_errors).  Warp-uniform.
 template <int P>
 __device__ __forceinline__ double lane_error(const LaneGroup<P>& g, const LaneState<P>& s, double err2) {
     const unsigned peg = lane_pegged<P>(g, s);
