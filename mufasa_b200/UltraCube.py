@@ -179,20 +179,22 @@ class UltraCube(object):
         p2 = self._params_dev(2, eng)
         model_f32 = self.cube._data.dtype == np.float32
         out = eng.aicc_global(prob, rows, p1, p2, expand=expand, model_f32=model_f32, thr=thr)
-        rss = out["rss"].cpu().numpy().reshape(ny, nx, 3)
-        nsamp = out["nsamp"].cpu().numpy().reshape(ny, nx)
-        lnk = out["lnk"].cpu().numpy().reshape(ny, nx, 3)
+        # one field-major D2H copy: rss0..2, nsamp, lnk10/20/21, ncomp
+        packed = torch.cat([out["rss"], out["nsamp"][:, None], out["lnk"], out["ncomp"].to(torch.float64)[:, None]],
+                           dim=1).t().contiguous().cpu().numpy()
+        rss = packed[0:3].reshape(3, ny, nx)
+        nsamp = packed[3].reshape(ny, nx)
+        lnk = packed[4:7].reshape(3, ny, nx)
         with np.errstate(all="ignore"):
             for nc in (0, 1, 2):
-                self.rss_maps[str(nc)] = np.ascontiguousarray(rss[:, :, nc])
-                ns = np.where(np.isnan(rss[:, :, nc]), np.nan, nsamp)
+                self.rss_maps[str(nc)] = rss[nc].copy()
+                ns = np.where(np.isnan(rss[nc]), np.nan, nsamp)
                 self.NSamp_maps[str(nc)] = ns
                 p = 4 * nc
                 self.AICc_maps[str(nc)] = ns * np.log(self.rss_maps[str(nc)] / ns) + 2 * p + \
                     (2 * p * (p + 1)) / (ns - p - 1)
-        self.lnk_maps = {"_key": key, "10": np.ascontiguousarray(lnk[:, :, 0]),
-                         "20": np.ascontiguousarray(lnk[:, :, 1]), "21": np.ascontiguousarray(lnk[:, :, 2])}
-        self.ncomp_map = out["ncomp"].cpu().numpy().reshape(ny, nx)
+        self.lnk_maps = {"_key": key, "10": lnk[0].copy(), "20": lnk[1].copy(), "21": lnk[2].copy()}
+        self.ncomp_map = packed[7].astype(np.int8).reshape(ny, nx)
 
     def get_rss(self, ncomp, mask=None, planemask=None, update=True, expand=20):
         """Residual sum of squares over the dilated union model mask (UltraCube.py:432-451)."""

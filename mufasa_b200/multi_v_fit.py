@@ -58,7 +58,9 @@ def get_vstats(velocities, signal_mask=None):
     if signal_mask is not None:
         mask = np.logical_and(mask, signal_mask)
     m1_good = m1[mask]
-    return np.median(m1_good), np.percentile(m1_good, 99), np.percentile(m1_good, 1)
+    # one selection pass for the three order statistics (np.median == the 50th percentile with linear interpolation)
+    v_median, v_99p, v_1p = np.percentile(m1_good, [50, 99, 1])
+    return v_median, v_99p, v_1p
 
 
 def get_start_point(maskmap, weight=None, return_xy=True):

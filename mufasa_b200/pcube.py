@@ -234,19 +234,28 @@ class PCube(object):
         pix = job["pix"]
         P = self.npars
         ny, nx = self.has_fit.shape
-        packed = torch.cat([out["params"], out["perr"], out["chi2"][:, None], out["err_used"][:, None],
-                            out["status"].to(torch.float64)[:, None],
-                            out["counts"][:, 0].to(torch.float64)[:, None]], dim=1).cpu().numpy()
+        # one device-side transpose to field-major [2P + 4, npix], one D2H copy through a pinned buffer, then
+        # contiguous row copies into the maps
+        packed_d = torch.cat([out["params"], out["perr"], out["chi2"][:, None], out["err_used"][:, None],
+                              out["status"].to(torch.float64)[:, None],
+                              out["counts"][:, 0].to(torch.float64)[:, None]], dim=1).t().contiguous()
+        stages = self._dev.setdefault("d2h_stage", {})          # pinned staging buffers, one per result shape
+        stage = stages.get(tuple(packed_d.shape))
+        if stage is None:
+            stage = stages[tuple(packed_d.shape)] = torch.empty(packed_d.shape, dtype=torch.float64).pin_memory()
+        stage.copy_(packed_d, non_blocking=True)
+        torch.cuda.current_stream(packed_d.device).synchronize()
+        packed = stage.numpy()
         flat = lambda a: a.reshape(a.shape[0], ny * nx) if a.ndim == 3 else a.reshape(ny * nx)
         if pix.size == ny * nx:
             pix = slice(None)           # every pixel fitted: plain copies instead of fancy-index scatters
-        flat(self.parcube)[:, pix] = packed[:, :P].T
-        flat(self.errcube)[:, pix] = packed[:, P:2 * P].T
-        flat(self.chi2map)[pix] = packed[:, 2 * P]
-        flat(self.errmap_used)[pix] = packed[:, 2 * P + 1]
-        st = packed[:, 2 * P + 2].astype(np.int32)
+        flat(self.parcube)[:, pix] = packed[:P]
+        flat(self.errcube)[:, pix] = packed[P:2 * P]
+        flat(self.chi2map)[pix] = packed[2 * P]
+        flat(self.errmap_used)[pix] = packed[2 * P + 1]
+        st = packed[2 * P + 2].astype(np.int32)
         flat(self.statusmap)[pix] = st
-        flat(self.nevalmap)[pix] = packed[:, 2 * P + 3].astype(np.int32)
+        flat(self.nevalmap)[pix] = packed[2 * P + 3].astype(np.int32)
         flat(self.has_fit)[pix] = st > 0
         if not self.has_fit.any():
             # pyspeckit: "The first fitted pixel did not yield a fit" -> AssertionError, which cubefit_gen turns

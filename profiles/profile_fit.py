@@ -81,6 +81,23 @@ for r in range(reps):
         same = all(bool(torch.equal(ob[0][k], o1[k])) and bool(torch.equal(ob[1][k], o2[k]))
                    for k in ("params", "perr", "chi2", "status"))
         print("   batch(1c || 2c): %.2f ms   identical to the separate fits: %s" % ((tb1 - tb0) * 1e3, same), flush=True)
+    if os.environ.get("PROFILE_BATCH", "0") == "2":
+        half = npix // 2
+        jobs = []
+        for nc in (1, 2):
+            for (a, b) in ((0, half), (half, npix)):
+                pj = _abi.make_problem(fittype, nc, nchan, b - a, v[0], dv, [float(x) for x in probs[nc].lo[:4 * nc]],
+                                       [float(x) for x in probs[nc].hi[:4 * nc]])
+                jobs.append(dict(prob=pj, spectra=rows[a:b], guesses=gs[nc][a:b].contiguous()))
+        for _ in range(2):
+            torch.cuda.synchronize()
+            tb0 = time.perf_counter()
+            ob = eng.fit_batch(jobs)
+            torch.cuda.synchronize()
+            tb1 = time.perf_counter()
+        same = bool(torch.equal(torch.cat([ob[2]["params"], ob[3]["params"]]), o2["params"])) and \
+            bool(torch.equal(torch.cat([ob[0]["params"], ob[1]["params"]]), o1["params"]))
+        print("   batch of 4 (1c, 2c) x (two pixel halves): %.2f ms   identical: %s" % ((tb1 - tb0) * 1e3, same), flush=True)
     if r == 0:
         ne = cn[:, 0]
         print("   active pixels at round r (2c):", {rr: int((ne > rr).sum()) for rr in (0, 5, 10, 20, 40, 80, 120, 160, 200, 240, 280, 320)}, flush=True)
