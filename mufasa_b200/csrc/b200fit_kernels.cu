@@ -229,7 +229,7 @@ struct LineGroups<B200FIT_MODEL_N2HP_10> {  // -8.0 (1) | -0.6 .. 1.0 (3) | 5.5 
 };
 
 template <int NC, int MODEL>
-__global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
+__global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)   // measured: 96 regs help 1c, hurt 2c
     fit_eval_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
                     const long long* __restrict__ row_index, PixState<4 * NC>* __restrict__ states,
                     const unsigned* __restrict__ list, FitQueues* __restrict__ fq, int cur) {
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4)
 // (profiles/): thread per pixel on global state 30 ms per 2c fit, the same staged through shared memory 63 ms
 // (copy loops serialise global round trips), both bound by the ~20k-instruction dependent chain of one serial step.
 template <int NC>
-__global__ void __launch_bounds__(SOLVE_THREADS)
+__global__ void __launch_bounds__(SOLVE_THREADS, 8)   // 128 regs (a few spills) beat 168 / 202: latency bound
     fit_solve_kernel(const DeviceProblem pr, PixState<4 * NC>* __restrict__ states, const unsigned* __restrict__ list,
                      unsigned* __restrict__ next_list, FitQueues* __restrict__ fq, int cur,
                      double* __restrict__ params, double* __restrict__ perr, double* __restrict__ chi2,
