@@ -236,20 +236,22 @@ class UltraCube(object):
         self._run_aicc(thr=(lnk10_thres, lnk20_thres, lnk21_thres))
         lnk10, lnk20, lnk21 = (self.get_AICc_likelihood(1, 0), self.get_AICc_likelihood(2, 0),
                                self.get_AICc_likelihood(2, 1))
-        parcube = copy(self.pcubes['2'].parcube)
-        errcube = copy(self.pcubes['2'].errcube)
-        mask = self.ncomp_map == 2
-        if include_1c:
-            parcube[:4, ~mask] = self.pcubes['1'].parcube[:4, ~mask]
-            errcube[:4, ~mask] = self.pcubes['1'].errcube[:4, ~mask]
-            parcube[4:8, ~mask] = np.nan
-            errcube[4:8, ~mask] = np.nan
-        else:
-            parcube[:, ~mask] = np.nan
-            errcube[:, ~mask] = np.nan
-        mask = self.ncomp_map >= 1
-        parcube[:, ~mask] = np.nan
-        errcube[:, ~mask] = np.nan
+        # same selection as the reference's masked assignments (UltraCube.py:1350-1367), as in-place masked copies
+        # (np.copyto(where=...): one pass per statement, no temporaries)
+        not_two = (self.ncomp_map != 2)[None]
+        none = (self.ncomp_map < 1)[None]
+        out = []
+        for c2, c1 in ((self.pcubes['2'].parcube, self.pcubes['1'].parcube),
+                       (self.pcubes['2'].errcube, self.pcubes['1'].errcube)):
+            c = c2.copy()
+            if include_1c:
+                np.copyto(c[:4], c1[:4], where=not_two)
+                np.copyto(c[4:], np.nan, where=not_two)
+            else:
+                np.copyto(c, np.nan, where=not_two)
+            np.copyto(c, np.nan, where=none)
+            out.append(c)
+        parcube, errcube = out
         if return_lnks:
             lnk10[~self.has_fit(ncomp=1)] = np.nan
             m2 = self.has_fit(ncomp=2)
