@@ -188,6 +188,17 @@ int b200fit_resid_stats(b200fit_ctx* ctx, const b200fit_problem* prob,
                         const double* d_params, int32_t expand, int32_t model_f32,
                         double* d_rms, double* d_chisq_red, void* stream);
 
+/* Robust noise and peak per pixel -- the step right before the fit in cubefit_gen / cubefit_simp:
+ * replaces signals.get_rms_robust (mufasa/signals.py:48-121: mad_std, then refine_rms with the sigma_cut signal mask
+ * dilated by ``expand`` channels), the per-pixel half of signals.get_snr (:24-45) and multi_v_fit.snr_estimate's
+ * errmap = mad_std(cube, axis=0) (:677-702).  fp64, bit-identical to numpy on a float64 copy of the spectrum.
+ *   d_planemask [npix] uint8 or NULL: pixels excluded by trim_cube_edge (signals.py:199-226) -> NaN
+ *   d_rms0 [npix] = 1.4826 nanmedian|y - nanmedian y|  (first pass);  d_rms [npix] = the refined value;
+ *   d_peak [npix] = max over the included channels (peak S/N = d_peak / d_rms) */
+int b200fit_rms_snr(b200fit_ctx* ctx, int32_t nchan, int64_t npix, const float* d_spectra, int64_t nchan_stride,
+                    const int64_t* d_row_index, const unsigned char* d_planemask, double sigma_cut, int32_t expand,
+                    double* d_rms0, double* d_rms, double* d_peak, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

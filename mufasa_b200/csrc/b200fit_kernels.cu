@@ -1004,6 +1004,112 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Robust noise + peak per pixel: signals.get_rms_robust (mufasa/signals.py:48-121) and the per-pixel half of get_snr
+// (:24-45) / multi_v_fit.snr_estimate (:677-702), one warp per pixel, fp64 like numpy on a float64 copy:
+//   rms0 = 1.4826... * nanmedian(|y - nanmedian(y)|)            over the included (finite, planemask) channels
+//   sig  = dilate(y > sigma_cut * rms0, expand along the spectral axis)                       (refine_rms :94-121)
+//   rms  = the same MAD over included & ~sig channels;   peak = max over the included channels
+// Medians by bitonic sort in shared memory (npow2 >= nchan keys, +inf padding).
+constexpr double MAD_TO_STD = 1.482602218505602;
+
+__device__ __forceinline__ void warp_bitonic_sort(double* key, int npow2, int lane) {
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (npow2 >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+                const int l = i | j;
+                const bool up = ((i & k) == 0);
+                const double a = key[i], b = key[l];
+                if ((a > b) == up) {
+                    key[i] = b;
+                    key[l] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__device__ __forceinline__ double sorted_median(const double* key, int n) {   // numpy: mean of the two middle values
+    if (n <= 0) return NAN;
+    return (n & 1) ? key[n >> 1] : 0.5 * (key[(n >> 1) - 1] + key[n >> 1]);
+}
+
+// MAD-based sigma of the channels flagged in ``inc`` (bit set); warp-collective, result on every lane
+__device__ __forceinline__ double warp_mad_std(const float* __restrict__ y, const unsigned* inc, int nchan, int npow2,
+                                               double* key, int lane) {
+    int n = 0;
+    for (int i = lane; i < npow2; i += 32) {
+        const bool on = (i < nchan) && ((inc[i >> 5] >> (i & 31)) & 1u);
+        key[i] = on ? (double)y[i] : INFINITY;
+        n += on ? 1 : 0;
+    }
+    n = warp_sum_i(n);
+    __syncwarp();
+    warp_bitonic_sort(key, npow2, lane);
+    const double med = sorted_median(key, n);
+    __syncwarp();
+    for (int i = lane; i < npow2; i += 32) {
+        const bool on = (i < nchan) && ((inc[i >> 5] >> (i & 31)) & 1u);
+        key[i] = on ? fabs((double)y[i] - med) : INFINITY;
+    }
+    __syncwarp();
+    warp_bitonic_sort(key, npow2, lane);
+    const double mad = sorted_median(key, n);
+    __syncwarp();
+    return MAD_TO_STD * mad;
+}
+
+__global__ void __launch_bounds__(AUX_WARPS * 32)
+    rms_robust_kernel(int nchan, long long npix, const float* __restrict__ spectra, long long stride,
+                      const long long* __restrict__ row_index, const unsigned char* __restrict__ planemask,
+                      double sigma_cut, int expand, int npow2, double* __restrict__ rms0_out,
+                      double* __restrict__ rms_out, double* __restrict__ peak_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned inc[AUX_WARPS][MASK_WORDS];
+    __shared__ unsigned sig[AUX_WARPS][MASK_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* key = reinterpret_cast<double*>(smem_raw) + (size_t)warp * npow2;
+    const int nwords = (nchan + 31) >> 5;
+    for (long long pix = (long long)blockIdx.x * AUX_WARPS + warp; pix < npix; pix += (long long)gridDim.x * AUX_WARPS) {
+        const long long row = row_index ? row_index[pix] : pix;
+        const float* y = spectra + row * stride;
+        const bool plane = planemask ? (planemask[pix] != 0) : true;
+        double peak = -INFINITY;
+        for (int wd = 0; wd < nwords; ++wd) {
+            const int i = (wd << 5) + lane;
+            const float v = (i < nchan) ? y[i] : NAN;
+            const bool on = plane && (v - v == 0.f);                 // finite
+            if (on) peak = fmax(peak, (double)v);
+            const unsigned b = __ballot_sync(FULL, on);
+            if (lane == 0) inc[warp][wd] = b;
+        }
+        peak = warp_max(peak);
+        __syncwarp();
+        const double rms0 = warp_mad_std(y, inc[warp], nchan, npow2, key, lane);
+        // signal mask on the RAW data (LazyComparisonMask cube > rms * sigma_cut), dilated along the spectral axis
+        const double thr = sigma_cut * rms0;
+        for (int wd = 0; wd < nwords; ++wd) {
+            const int i = (wd << 5) + lane;
+            const bool on = (i < nchan) && ((double)y[i] > thr);    // NaN compares false
+            const unsigned b = __ballot_sync(FULL, on);
+            if (lane == 0) sig[warp][wd] = b;
+        }
+        __syncwarp();
+        dilate_bits(sig[warp], nchan, expand, lane);
+        for (int wd = lane; wd < nwords; wd += 32) sig[warp][wd] = inc[warp][wd] & ~sig[warp][wd];
+        __syncwarp();
+        const double rms = warp_mad_std(y, sig[warp], nchan, npow2, key, lane);
+        if (lane == 0) {
+            rms0_out[pix] = rms0;
+            rms_out[pix] = rms;
+            peak_out[pix] = (peak == -INFINITY) ? NAN : peak;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Cube layout: [nchan][nplane] (FITS) -> rows [npix][stride], compacted by pix_index, NaN padded, optional flip.
 __global__ void __launch_bounds__(256)
     gather_kernel(const float* __restrict__ cube, int nchan, long long nplane, const long long* __restrict__ pix_index,
@@ -1515,6 +1621,28 @@ int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_s
     aicc_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, smem, (cudaStream_t)stream>>>(
         pr, d_spectra, nchan_stride, (const long long*)d_row_index, d_params1, d_params2, d_fill_bits, only_empty,
         expand, model_f32, t10, t20, t21, d_rss, d_nsamp, d_lnk, d_ncomp, d_mask_counts);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    return B200FIT_OK;
+}
+
+int b200fit_rms_snr(b200fit_ctx* ctx, int32_t nchan, int64_t npix, const float* d_spectra, int64_t nchan_stride,
+                    const int64_t* d_row_index, const unsigned char* d_planemask, double sigma_cut, int32_t expand,
+                    double* d_rms0, double* d_rms, double* d_peak, void* stream) {
+    if (!ctx) return B200FIT_E_ARG;
+    if (npix == 0) return B200FIT_OK;
+    if (!d_spectra || !d_rms0 || !d_rms || !d_peak || nchan < 1 || nchan > B200FIT_MAX_NCHAN || nchan_stride < nchan ||
+        npix < 0)
+        return fail(ctx, B200FIT_E_ARG, "rms_snr: bad argument");
+    if (expand < 0 || expand > 64) return fail(ctx, B200FIT_E_ARG, "rms_snr: expand must be in [0, 64]");
+    CK(cudaSetDevice(ctx->device));
+    int npow2 = 64;
+    while (npow2 < nchan) npow2 <<= 1;
+    const size_t smem = (size_t)AUX_WARPS * npow2 * sizeof(double);
+    CK(cudaFuncSetAttribute(rms_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rms_robust_kernel<<<(unsigned)aux_blocks(ctx, npix), AUX_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        nchan, npix, d_spectra, nchan_stride, (const long long*)d_row_index, d_planemask, sigma_cut, expand, npow2,
+        d_rms0, d_rms, d_peak);
     CK(cudaGetLastError());
     ctx->launches += 1;
     return B200FIT_OK;

@@ -232,6 +232,19 @@ class Engine(object):
         out["fill_bits"] = bits
         return out
 
+    def rms_snr(self, nchan, spectra, planemask=None, sigma_cut=2.5, expand=20, row_index=None):
+        """signals.get_rms_robust + the peak for get_snr / snr_estimate, per pixel on the GPU.  Returns device
+        tensors rms0 (plain mad_std), rms (refined), peak (max over the included channels)."""
+        npix = int(spectra.shape[0]) if row_index is None else int(row_index.numel())
+        out = {k: torch.empty(npix, dtype=torch.float64, device=self.device) for k in ("rms0", "rms", "peak")}
+        if planemask is not None:
+            assert planemask.dtype == torch.uint8 and planemask.numel() == npix and planemask.is_contiguous()
+        rc = self.lib.b200fit_rms_snr(self.ctx, int(nchan), npix, _ptr(spectra), spectra.shape[1], _ptr(row_index),
+                                      _ptr(planemask), float(sigma_cut), int(expand), _ptr(out["rms0"]),
+                                      _ptr(out["rms"]), _ptr(out["peak"]), self._stream())
+        self._check(rc, "b200fit_rms_snr")
+        return out
+
     def resid_stats(self, prob, spectra, params, expand=20, model_f32=True, row_index=None):
         npix = int(prob.npix)
         out = dict(rms=torch.empty(npix, dtype=torch.float64, device=self.device),

@@ -87,12 +87,19 @@ def snr_estimate(pcube, errmap, smooth=True):
     Gaussian2DKernel(1)."""
     from . import signals
     cube = pcube.cube if hasattr(pcube, 'cube') else pcube
+    peak = None
     if errmap is None:
-        errmap = signals.mad_std(cube, axis=0)
+        if hasattr(pcube, "rms_robust"):     # per-pixel MAD + peak on the GPU (b200fit_rms_snr), same values
+            r = pcube.rms_robust()
+            errmap, peak = r["rms0"], r["peak"]
+        else:
+            errmap = signals.mad_std(cube, axis=0)
     err_med = np.nanmedian(errmap)
     err_mask = errmap < err_med * 3.0
     with np.errstate(all="ignore"):
-        peaksnr = np.nanmax(cube, axis=0) / errmap      # == nanmax(cube / errmap) for errmap > 0
+        if peak is None:
+            peak = np.nanmax(cube, axis=0)
+        peaksnr = peak / errmap      # == nanmax(cube / errmap) for errmap > 0
     if smooth:
         peaksnr = signals.convolve_gauss2d(peaksnr, 1.0)
     return peaksnr, None, errmap, err_mask
@@ -218,10 +225,19 @@ def cubefit_gen(cube, pcube, ncomp=2, paraname=None, modname=None, chisqname=Non
     linewidth_sigma = False
     trim = 3
     include = signals.trim_cube_edge(cube, trim=trim)        # bool [nchan, ny, nx] (the masked cube of the reference)
+    # robust rms + peak per pixel on the GPU (b200fit_rms_snr; same values as signals.get_rms_robust / get_snr)
+    gpu_noise = None
+    if hasattr(pcube, "rms_robust"):
+        gpu_noise = pcube.rms_robust(planemask=np.any(include, axis=0), sigma_cut=2.5, expand=20)
     m0, m1, m2, rms = signals.get_moments(cube, include=include, window_hwidth=mod_info.window_hwidth,
                                           linewidth_sigma=linewidth_sigma,
-                                          central_win_hwidth=mod_info.central_win_hwidth, return_rms=True)
-    peaksnr = signals.get_snr(cube, rms=rms, include=include)
+                                          central_win_hwidth=mod_info.central_win_hwidth, return_rms=True,
+                                          rms=None if gpu_noise is None else gpu_noise["rms"])
+    if gpu_noise is None:
+        peaksnr = signals.get_snr(cube, rms=rms, include=include)
+    else:
+        with np.errstate(all="ignore"):
+            peaksnr = gpu_noise["peak"] / rms
 
     vmax = np.nanmax(m1) + sigmax / 2
     vmin = np.nanmin(m1) - sigmax / 2

@@ -128,6 +128,26 @@ class PCube(object):
             self._dev["footprint"] = fp.cpu().numpy().reshape(self.cube.shape[1:])
         return self._dev["footprint"]
 
+    def rms_robust(self, planemask=None, sigma_cut=2.5, expand=20):
+        """signals.get_rms_robust / the peak for get_snr, per pixel on the GPU (b200fit_rms_snr).  ``planemask``
+        [ny, nx] bool = pixels kept by trim_cube_edge (None: all).  Returns dict of [ny, nx] float64 maps: rms0
+        (= mad_std(cube, axis=0)), rms (refined), peak.  Cached per (planemask, sigma_cut, expand)."""
+        ny, nx = self.cube.shape[1:]
+        key = ("rms", None if planemask is None else np.asarray(planemask, bool).tobytes(), float(sigma_cut), int(expand))
+        cache = self._dev.setdefault("rms_cache", {})
+        if key not in cache:
+            eng = self.engine
+            rows = self.rows_on_device()
+            pm = None
+            if planemask is not None:
+                pm = torch.from_numpy(np.ascontiguousarray(planemask, dtype=np.uint8).ravel()).to(eng.device)
+            out = eng.rms_snr(self.cube.shape[0], rows, planemask=pm, sigma_cut=sigma_cut, expand=expand)
+            packed = torch.stack([out["rms0"], out["rms"], out["peak"]]).cpu().numpy()
+            cache.clear()
+            cache[key] = dict(rms0=packed[0].reshape(ny, nx), rms=packed[1].reshape(ny, nx),
+                              peak=packed[2].reshape(ny, nx))
+        return cache[key]
+
     def share_device(self, other):
         """Use the device-resident rows of another PCube built on the same data cube."""
         if other.cube is not self.cube and other.cube.shape != self.cube.shape:

@@ -157,7 +157,7 @@ def moments(data, include, v):
 
 
 def get_moments(cube, window_hwidth=5, linewidth_sigma=True, trim=3, return_rms=False, central_win_hwidth=None,
-                include=None):
+                include=None, rms=None):
     """signals.py:329-396 on (data, include).  ``include`` = mask of an already trimmed cube (cubefit_gen trims first
     and passes trim=None)."""
     snr_cut = 3
@@ -166,7 +166,8 @@ def get_moments(cube, window_hwidth=5, linewidth_sigma=True, trim=3, return_rms=
     v = _vaxis(cube)
     if include is None:
         include = trim_cube_edge(cube, trim=trim) if trim is not None else np.isfinite(data)
-    rms = get_rms_robust(cube, sigma_cut=noise_mask_cut, include=include)
+    if rms is None:      # ``rms``: the same map computed per pixel on the GPU (PCube.rms_robust)
+        rms = get_rms_robust(cube, sigma_cut=noise_mask_cut, include=include)
     v_peak = v_estimate(data, include, v, rms, snr_cut=snr_cut)
     if central_win_hwidth is not None:
         v_mode = estimate_mode(v_peak, bins=25)

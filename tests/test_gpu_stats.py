@@ -163,3 +163,35 @@ def test_resid_stats(engine, fitted_tile):
         # bit-level agreement where the dilated masks agree; a mask-edge channel (see test_aicc_selection) moves
         # N by 1-2 of ~400 elsewhere
         assert np.median(rel) < 1e-9 and rel.max() < 2e-2
+
+
+def test_rms_snr_matches_numpy_signals(engine):
+    """b200fit_rms_snr vs the numpy mirror of signals.get_rms_robust / get_snr / mad_std: bit-identical (fp64
+    medians of the same values), including NaN channels, a fully masked pixel and a planemask."""
+    import torch
+    from mufasa_b200 import signals
+    tile = T.sample_tile(2, nrows=2, xstep=16)
+    cube = tile["cube"].copy()
+    cube[100:130, 0, 3] = np.nan
+    cube[:, 1, 5] = np.nan
+    nchan, ny, nx = cube.shape
+    planemask = np.ones((ny, nx), bool)
+    planemask[0, :2] = False
+    include = np.isfinite(cube) & planemask[None]
+    with np.errstate(all="ignore"):
+        rms0_ref = signals.mad_std(cube, axis=0)                                   # snr_estimate's errmap
+        rms_ref = signals.get_rms_robust(cube, sigma_cut=2.5, expand=20, include=include)
+        snr_ref = signals.get_snr(cube, rms=rms_ref, include=include)
+    t = dict(tile)
+    t["cube"] = cube
+    spec, _ = T.pixel_major(t, tile["guess1"])
+    d_spec = torch.from_numpy(spec).cuda()
+    a = engine.rms_snr(nchan, d_spec)
+    b = engine.rms_snr(nchan, d_spec, planemask=torch.from_numpy(planemask.astype(np.uint8).ravel()).cuda())
+    assert np.array_equal(a["rms0"].cpu().numpy().reshape(ny, nx), rms0_ref, equal_nan=True)
+    rms = b["rms"].cpu().numpy().reshape(ny, nx)
+    assert np.array_equal(rms, rms_ref, equal_nan=True)
+    with np.errstate(all="ignore"):
+        snr = b["peak"].cpu().numpy().reshape(ny, nx) / rms
+    assert np.array_equal(snr, snr_ref, equal_nan=True)
+    assert np.isnan(rms[1, 5]) and np.all(np.isnan(rms[0, :2])) and np.isfinite(rms[0, 3])
