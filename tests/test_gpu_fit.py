@@ -119,3 +119,57 @@ def test_edge_cases(engine):
     out0 = engine.fit(prob0, torch.empty((0, spec.shape[1]), dtype=torch.float32, device="cuda"),
                       torch.empty((0, 4), dtype=torch.float64, device="cuda"))
     assert out0["params"].shape[0] == 0
+
+
+def test_odd_sizes_weights_and_iteration_cap(engine):
+    """Pixel counts that do not fill a warp of solver groups, caller-supplied weights (weight_mode 1) and a small
+    max_iter: per-pixel results must not depend on the batch they are fitted in."""
+    import torch
+    tile = T.sample_tile(2, nrows=2, xstep=8)
+    for ncomp in (1, 2):
+        lo, hi = T.limits_vectors(tile["fittype"], ncomp)
+        g = synth.clamp_guesses(tile["guess%d" % ncomp], lo, hi)
+        spec, gg = T.pixel_major(tile, g)
+        d_spec, d_g = torch.from_numpy(spec).cuda(), torch.from_numpy(gg).cuda()
+        full = engine.fit(_abi.make_problem(tile["fittype"], ncomp, tile["nchan"], spec.shape[0], tile["v"][0],
+                                            tile["dv"], lo, hi), d_spec, d_g)
+        full = {k: v.clone() for k, v in full.items()}
+        for n in (1, 3, 5, 37):
+            sub = engine.fit(_abi.make_problem(tile["fittype"], ncomp, tile["nchan"], n, tile["v"][0], tile["dv"], lo,
+                                               hi), d_spec[:n].contiguous(), d_g[:n].contiguous())
+            for k in ("params", "perr", "chi2", "status"):
+                assert torch.equal(sub[k], full[k][:n]), (ncomp, n, k)
+        # weight_mode 1: err given by the caller; 2x the weights used before -> same parameters, errors x2, chi2 / 4
+        prob_w = _abi.make_problem(tile["fittype"], ncomp, tile["nchan"], spec.shape[0], tile["v"][0], tile["dv"], lo,
+                                   hi, weight_mode=1)
+        w = engine.fit(prob_w, d_spec, d_g, err=(2.0 * full["err_used"]).contiguous())
+        ok = full["status"] > 0
+        assert torch.equal(w["status"], full["status"])
+        assert torch.equal(w["params"][ok], full["params"][ok])
+        assert torch.allclose(w["perr"][ok], 2.0 * full["perr"][ok], rtol=1e-12, atol=0)
+        assert torch.allclose(w["chi2"][ok], full["chi2"][ok] / 4.0, rtol=1e-12, atol=0)
+        # iteration cap: at most max_iter accepted steps, flagged 5 where it bites, still a valid fit (has_fit)
+        prob_c = _abi.make_problem(tile["fittype"], ncomp, tile["nchan"], spec.shape[0], tile["v"][0], tile["dv"], lo,
+                                   hi, max_iter=3)
+        c = engine.fit(prob_c, d_spec, d_g)
+        st = c["status"].cpu().numpy()
+        assert np.all(st > 0) and (st == 5).any()
+        assert int(c["counts"][:, 0].max()) <= 2 * 3 + 2
+
+
+def test_descending_velocity_axis():
+    """A cube stored with descending velocity (common in FITS) gives the same fit as its ascending twin."""
+    from mufasa_b200.cube import SpecCube
+    from mufasa_b200.UltraCube import UltraCube
+    syn = synth.make_cube(2, T.oracle_modelcube, rows=(100, 102), shape=(200, 24, 800))
+    res = []
+    for flip in (False, True):
+        cube, v = (syn["cube"][::-1].copy(), syn["v"][::-1].copy()) if flip else (syn["cube"], syn["v"])
+        uc = UltraCube(cube=SpecCube(cube, v), fittype=syn["fittype"], device=0)
+        uc.fit_cube(ncomp=1, simpfit=True, guesses=syn["guess1"].copy())
+        res.append(uc.pcubes["1"])
+    assert np.array_equal(res[0].has_fit, res[1].has_fit)
+    assert np.array_equal(res[0].parcube, res[1].parcube)
+    assert np.array_equal(res[0].errcube, res[1].errcube)
+    m0, m1 = res[0].get_modelcube(), res[1].get_modelcube()
+    assert np.array_equal(m0, m1[::-1], equal_nan=True)
