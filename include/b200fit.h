@@ -199,6 +199,31 @@ int b200fit_rms_snr(b200fit_ctx* ctx, int32_t nchan, int64_t npix, const float* 
                     const int64_t* d_row_index, const unsigned char* d_planemask, double sigma_cut, int32_t expand,
                     double* d_rms0, double* d_rms, double* d_peak, void* stream);
 
+/* Moment / signal-mask pre-pass of cubefit_gen (signals.get_moments, mufasa/signals.py:329-396) as primitives on
+ * BIT CUBES: bits[ny*nx][nchan_stride/32] uint32, bit b of word w <-> channel 32 w + b, pixels in row-major plane
+ * order (NOT compacted: the morphology needs the neighbours).  Composition: mufasa_b200/prepass.py.
+ *   b200fit_signal_bits     bits = (y > snr_cut * rms[pix])                                  (signals.py:264, :316)
+ *   b200fit_bits_morph      op 0: binary_erosion with ball(2) (v_estimate :266); 1 / 2: erosion / dilation with the
+ *                           6-connected cross (binary_opening, get_v_mask :322); 3: dilation with disk(3) in the plane
+ *                           (:386).  Erosion sees True outside the cube, dilation False.  d_in != d_out.
+ *   b200fit_bits_window     out = in & (vc - hwidth < V_i < vc + hwidth); vc per pixel (d_vcenter) or vcenter_all
+ *   b200fit_v_at_peak       velocity of the first maximum over the channels set in d_bits_a (& d_bits_b, optional),
+ *                           finite and in the planemask; NaN without one                    (get_v_at_peak :229-248)
+ *   b200fit_masked_moments  moment0/1/2 of spectral_cube over the set, finite, planemask channels       (:388-391) */
+int b200fit_signal_bits(b200fit_ctx* ctx, int32_t nchan, int64_t npix, const float* d_spectra, int64_t nchan_stride,
+                        const double* d_rms, double snr_cut, uint32_t* d_bits, void* stream);
+int b200fit_bits_morph(b200fit_ctx* ctx, int32_t op, int32_t nchan, int32_t ny, int32_t nx, int64_t nchan_stride,
+                       const uint32_t* d_in, uint32_t* d_out, void* stream);
+int b200fit_bits_window(b200fit_ctx* ctx, int32_t nchan, int64_t npix, int64_t nchan_stride, double v0, double dv,
+                        const uint32_t* d_in, const double* d_vcenter, double vcenter_all, double hwidth,
+                        uint32_t* d_out, void* stream);
+int b200fit_v_at_peak(b200fit_ctx* ctx, int32_t nchan, int64_t npix, const float* d_spectra, int64_t nchan_stride,
+                      const uint32_t* d_bits_a, const uint32_t* d_bits_b, const unsigned char* d_planemask, double v0,
+                      double dv, double* d_vpeak, void* stream);
+int b200fit_masked_moments(b200fit_ctx* ctx, int32_t nchan, int64_t npix, const float* d_spectra, int64_t nchan_stride,
+                           const uint32_t* d_bits, const unsigned char* d_planemask, double v0, double dv, double* d_m0,
+                           double* d_m1, double* d_m2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

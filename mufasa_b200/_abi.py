@@ -74,6 +74,13 @@ SIGNATURES = {
     "b200fit_mask_argmax": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "b200fit_mask_bits": (C.c_int, [_vp, _PP, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "b200fit_rms_snr": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, C.c_double, _i32, _vp, _vp, _vp, _vp]),
+    "b200fit_signal_bits": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, C.c_double, _vp, _vp]),
+    "b200fit_bits_morph": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp]),
+    "b200fit_bits_window": (C.c_int, [_vp, _i32, _i64, _i64, C.c_double, C.c_double, _vp, _vp, C.c_double, C.c_double,
+                                      _vp, _vp]),
+    "b200fit_v_at_peak": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp]),
+    "b200fit_masked_moments": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp,
+                                         _vp]),
     "b200fit_resid_stats": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
 }
 

@@ -1,0 +1,52 @@
+// b200fit_ctx.h -- the per-device context behind the opaque b200fit_ctx handle, shared by the library's .cu files.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200fit.h"
+
+struct b200fit_ctx {
+    int device;
+    int num_sms;
+    std::string err;
+    cudaEvent_t check_ev[B200FIT_MAX_BATCH * 4];
+    volatile unsigned* h_count;   // pinned, 4 slots per job: active-pixel counts read back by the fit's round loop
+    cudaStream_t job_stream[B200FIT_MAX_BATCH];
+    cudaEvent_t fork_ev, join_ev[B200FIT_MAX_BATCH];
+    unsigned long long launches = 0;          // kernels launched by this context (all entry points)
+    int profiling = 0;                        // record CUDA events around the fit's kernels
+    std::vector<cudaEvent_t> prof_ev;         // event pool (grown on demand)
+    size_t prof_used = 0;
+    int prof_rounds = 0;
+
+    cudaEvent_t next_event(cudaStream_t stream) {
+        if (prof_used == prof_ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            prof_ev.push_back(e);
+        }
+        cudaEvent_t e = prof_ev[prof_used++];
+        cudaEventRecord(e, stream);
+        return e;
+    }
+};
+
+static inline int fail(b200fit_ctx* ctx, int code, const char* what, cudaError_t ce = cudaSuccess) {
+    if (ctx) {
+        ctx->err = what;
+        if (ce != cudaSuccess) {
+            ctx->err += ": ";
+            ctx->err += cudaGetErrorString(ce);
+        }
+    }
+    return code;
+}
+
+#define CK(call)                                                    \
+    do {                                                            \
+        cudaError_t ce_ = (call);                                   \
+        if (ce_ != cudaSuccess) return fail(ctx, B200FIT_E_CUDA, #call, ce_); \
+    } while (0)
+
