@@ -206,8 +206,11 @@ def cubefit_simp(cube, pcube, ncomp, guesses, multicore=None, maskmap=None, fitt
 
 def cubefit_gen(cube, pcube, ncomp=2, paraname=None, modname=None, chisqname=None, guesses=None, errmap11name=None,
                 multicore=None, mask_function=None, snr_min=0.0, momedgetrim=True, saveguess=False,
-                fittype='nh3_multi_v', **kwargs):
+                fittype='nh3_multi_v', gpu_prepass=True, **kwargs):
     """multi_v_fit.py:211-417: moment maps -> guesses -> tautex_renorm -> clamps -> masks -> fiteach.
+
+    ``gpu_prepass=False`` runs the moment / rms / S/N pre-pass with the numpy mirror (mufasa_b200/signals.py)
+    instead of the GPU kernels (mufasa_b200/prepass.py); the two agree (tests/test_gpu_pipeline.py).
 
     ``paraname`` / ``modname`` / ``chisqname`` (FITS writers) are outside the fit path and not supported here."""
     from . import signals
@@ -224,25 +227,29 @@ def cubefit_gen(cube, pcube, ncomp=2, paraname=None, modname=None, chisqname=Non
 
     linewidth_sigma = False
     trim = 3
-    include = signals.trim_cube_edge(cube, trim=trim)        # bool [nchan, ny, nx] (the masked cube of the reference)
-    # robust rms + peak per pixel on the GPU (b200fit_rms_snr; same values as signals.get_rms_robust / get_snr)
-    gpu_noise = None
-    if hasattr(pcube, "rms_robust"):
-        gpu_noise = pcube.rms_robust(planemask=np.any(include, axis=0), sigma_cut=2.5, expand=20)
-    m0, m1, m2, rms = signals.get_moments(cube, include=include, window_hwidth=mod_info.window_hwidth,
-                                          linewidth_sigma=linewidth_sigma,
-                                          central_win_hwidth=mod_info.central_win_hwidth, return_rms=True,
-                                          rms=None if gpu_noise is None else gpu_noise["rms"])
-    if gpu_noise is None:
-        peaksnr = signals.get_snr(cube, rms=rms, include=include)
-    else:
+    if gpu_prepass and hasattr(pcube, "rows_on_device"):
+        # the whole pre-pass on the GPU (mufasa_b200/prepass.py): the include-mask of the trimmed cube is
+        # isfinite(cube) & cube_plane, so only the 2-D footprint is trimmed on the host (signals.trim_cube_edge)
+        from . import prepass
+        cube_plane = pcube.footprint().copy()
+        if np.sum(cube_plane) > 1000:
+            cube_plane = signals.trim_edge(cube_plane, trim=trim)
+        m0, m1, m2, rms = prepass.get_moments(pcube, cube_plane, window_hwidth=mod_info.window_hwidth,
+                                              linewidth_sigma=linewidth_sigma,
+                                              central_win_hwidth=mod_info.central_win_hwidth, return_rms=True)
         with np.errstate(all="ignore"):
-            peaksnr = gpu_noise["peak"] / rms
+            peaksnr = pcube._dev["prepass_peak"] / rms
+    else:
+        include = signals.trim_cube_edge(cube, trim=trim)    # bool [nchan, ny, nx] (the masked cube of the reference)
+        m0, m1, m2, rms = signals.get_moments(cube, include=include, window_hwidth=mod_info.window_hwidth,
+                                              linewidth_sigma=linewidth_sigma,
+                                              central_win_hwidth=mod_info.central_win_hwidth, return_rms=True)
+        peaksnr = signals.get_snr(cube, rms=rms, include=include)
+        cube_plane = np.any(include, axis=0)
 
     vmax = np.nanmax(m1) + sigmax / 2
     vmin = np.nanmin(m1) - sigmax / 2
 
-    cube_plane = np.any(include, axis=0)
     if 'planemask' in kwargs:
         planemask = kwargs.pop('planemask') & cube_plane
     else:

@@ -106,3 +106,31 @@ def test_partition_invariance_and_idempotence():
     assert sel.float().mean() > 0.8
     assert float(dz.max(dim=1).values[sel].median()) < 1e-3
     assert float(again["counts"][:, 0][sel].float().median()) <= 4
+
+
+def test_cubefit_gen_gpu_prepass_equals_numpy_prepass():
+    """cubefit_gen with the GPU pre-pass (moments, rms, peak S/N, masks) hands fiteach the same guesses, limits and
+    mask as with the numpy mirror of mufasa/signals.py."""
+    from mufasa_b200 import multi_v_fit as mvf
+    from mufasa_b200.pcube import PCube
+    syn = synth.make_cube(1, T.oracle_modelcube, shape=(40, 44, 500))      # > 1000 pixels: the edge gets trimmed
+    spec = SpecCube(syn["cube"], syn["v"])
+
+    captured = {}
+
+    def grab(tag):
+        def fiteach(self, **kw):
+            captured[tag] = kw
+        return fiteach
+
+    for tag in ("gpu", "host"):
+        p = PCube(syn["cube"], syn["v"], device=0)
+        p.fiteach = grab(tag).__get__(p)
+        mvf.cubefit_gen(spec, p, ncomp=2, snr_min=3.0, fittype=syn["fittype"], gpu_prepass=(tag == "gpu"))
+    a, b = captured["gpu"], captured["host"]
+    assert np.array_equal(a["maskmap"], b["maskmap"])
+    assert a["maskmap"].sum() > 500
+    assert np.allclose(a["minpars"], b["minpars"], rtol=1e-12) and np.allclose(a["maxpars"], b["maxpars"], rtol=1e-12)
+    m = a["maskmap"]
+    assert np.allclose(a["guesses"][:, m], b["guesses"][:, m], rtol=1e-9, atol=1e-12)
+    assert a["start_from_point"] == b["start_from_point"]
