@@ -62,6 +62,16 @@ class Engine(object):
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def pinned_stage(self, shape, dtype=torch.float64):
+        """Pinned host staging buffer for D2H copies, cached per shape (page-locking costs ~10 ms per call)."""
+        cache = self.__dict__.setdefault("_pinned", {})
+        key = (tuple(shape), dtype)
+        if key not in cache:
+            if len(cache) > 16:
+                cache.clear()
+            cache[key] = torch.empty(shape, dtype=dtype).pin_memory()
+        return cache[key]
+
     @staticmethod
     def nchan_stride(nchan):
         return (int(nchan) + 31) // 32 * 32

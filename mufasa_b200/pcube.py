@@ -259,10 +259,7 @@ class PCube(object):
         packed_d = torch.cat([out["params"], out["perr"], out["chi2"][:, None], out["err_used"][:, None],
                               out["status"].to(torch.float64)[:, None],
                               out["counts"][:, 0].to(torch.float64)[:, None]], dim=1).t().contiguous()
-        stages = self._dev.setdefault("d2h_stage", {})          # pinned staging buffers, one per result shape
-        stage = stages.get(tuple(packed_d.shape))
-        if stage is None:
-            stage = stages[tuple(packed_d.shape)] = torch.empty(packed_d.shape, dtype=torch.float64).pin_memory()
+        stage = self.engine.pinned_stage(tuple(packed_d.shape))   # pinned staging buffers live with the engine
         stage.copy_(packed_d, non_blocking=True)
         torch.cuda.current_stream(packed_d.device).synchronize()
         packed = stage.numpy()
