@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)   // measu
                     float g = 0.f, a = 0.f, b = 0.f;
 #pragma unroll
                     for (int gi = 0; gi < NG; ++gi) {
-                        if (pk & (1u << (8 * c + gi))) {   // warp-uniform
+                        if (__any_sync(FULL, (pk >> (8 * c + gi)) & 1u)) {   // pk is warp-uniform; the vote tells nvcc so
 #pragma unroll
                             for (int k = LG::start(gi); k < LG::start(gi + 1); ++k) {
                                 const float4 q = *reinterpret_cast<const float4*>(&w.lines[c][k]);
