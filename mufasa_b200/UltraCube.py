@@ -110,6 +110,25 @@ class UltraCube(object):
                 self._include_fit_in_mask(nc)
             self._invalidate_stats()
 
+    # ---- on-disk contract ------------------------------------------------------------------
+    def save_fit(self, savename, ncomp, header_note=None):
+        """UltraCube.py:371-376 -> save_fit :805-826 -> multi_v_fit.save_pcube."""
+        p = self.pcubes.get(str(ncomp))
+        if p is not None and p.parcube is not None:
+            mvf.save_pcube(p, savename, ncomp, header_note=header_note)
+        else:
+            logger.warning("no fit was performed and thus no file will be saved")
+
+    def load_model_fit(self, filename, ncomp, calc_model=True, multicore=None):
+        """UltraCube.py:379-387 -> load_model_fit :829-858: resume from a saved ``{root}_{n}vcomp.fits``."""
+        p = self.load_pcube(pcube_ref=self._ref_pcube)
+        mvf.register_pcube(p, MetaModel(fittype=self.fittype, ncomp=ncomp))
+        p.load_model_fit(filename, npars=4 * ncomp, fittype=self.fittype)
+        self.pcubes[str(ncomp)] = p
+        if calc_model and p.has_fit.any():
+            self._include_fit_in_mask(ncomp)
+        self._invalidate_stats()
+
     def _invalidate_stats(self):
         for d in (self.rss_maps, self.NSamp_maps, self.AICc_maps, self.lnk_maps, self.residual_cubes, self.rms_maps,
                   self.rchisq_maps):

@@ -329,9 +329,68 @@ def cubefit_gen(cube, pcube, ncomp=2, paraname=None, modname=None, chisqname=Non
     except (ValueError, AssertionError) as e:
         logger.warning("The starting fit position is somehow not among the valid: " + str(e))
         retry_fit(pcube, kwargs, start_point, peaksnr=peaksnr)
-    if paraname is not None or modname is not None or chisqname is not None:
-        raise NotImplementedError("FITS writers are outside the fit path (SURVEY.md 8f #2)")
+    if paraname is not None:
+        save_pcube(pcube, paraname, ncomp=ncomp)
+    if modname is not None or chisqname is not None:
+        raise NotImplementedError("model-cube / legacy chi-square writers are not part of the fit path")
     return pcube
+
+
+def make_header(ndim, ref_header):
+    """multi_v_fit.py:481-520: a fresh header carrying the WCS / beam cards of ``ref_header`` (dict-like of
+    keyword -> value | (value, comment), or None)."""
+    from datetime import datetime
+    from .utils import fits_io
+    hdr = fits_io.Header()
+    hdr.set('DATE', datetime.now().strftime('%Y-%m-%dT%H:%M:%S'), "Written by mufasa_b200")
+    if ndim == 3:
+        keylist = ['OBJECT', 'BMAJ', 'BMIN', 'BPA', 'WCSAXES', 'CRPIX1', 'CRPIX2', 'CRPIX3', 'CDELT1', 'CDELT2',
+                   'CDELT3', 'CUNIT1', 'CUNIT2', 'CUNIT3', 'CTYPE1', 'CTYPE2', 'CTYPE3', 'CRVAL1', 'CRVAL2', 'CRVAL3',
+                   'LONPOLE', 'LATPOLE', 'WCSNAME', 'MJDREF', 'RADESYS', 'EQUINOX', 'SPECSYS']
+    else:
+        keylist = ['OBJECT', 'BMAJ', 'BMIN', 'BPA', 'WCSAXES', 'CRPIX1', 'CRPIX2', 'CDELT1', 'CDELT2', 'CUNIT1',
+                   'CUNIT2', 'CTYPE1', 'CTYPE2', 'CRVAL1', 'CRVAL2', 'LONPOLE', 'LATPOLE', 'WCSNAME', 'MJDREF',
+                   'RADESYS', 'EQUINOX', 'SPECSYS']
+    if ref_header is not None:
+        for key in keylist:
+            if key in ref_header:
+                v = ref_header[key]
+                val, com = v if isinstance(v, tuple) else (v, None)
+                hdr.set(key, val, com)
+    if 'WCSAXES' in hdr and hdr.value('WCSAXES') != ndim:
+        hdr.set('WCSAXES', ndim, 'Number of coordinate axes')
+    hdr.history.append("=" * 50)
+    hdr.history.append("Written by mufasa_b200 on {}".format(datetime.now().strftime('%Y-%m-%d %H:%M:%S')))
+    hdr.comments.append("=" * 50)
+    hdr.comments.append("MUFASA citation: Chen et al. (2020), DOI: 10.3847/1538-4357/ab7378")
+    return hdr
+
+
+def save_pcube(pcube, savename, ncomp, npara=4, header_note=None):
+    """multi_v_fit.py:523-582: ``concatenate([parcube, errcube])`` as one FITS image with the PLANEi cards that name
+    the planes -- the file ``Region.load_fits`` / ``load_model_fit`` read back."""
+    from .utils import fits_io
+    hdr = make_header(ndim=3, ref_header=getattr(pcube, 'header', None))
+    if header_note is None:
+        header_note = 'Parameter maps derived from {}-comp model fits'.format(ncomp)
+    hdr.set('NOTES', header_note)
+    hdr.set('CDELT3', 1, '[unitless] Coordinate increment at reference point')
+    hdr.set('CTYPE3', 'FITPAR', 'fitted parameters')
+    hdr.set('CRVAL3', 0, '[unitless] Coordinate value at reference point')
+    hdr.set('CRPIX3', 1, '[unitless] Pixel coordinate of reference point')
+    hdr.set('CUNIT3', 'None', '[unitless] Units of coordinate increment and value')
+    names = (('VELOCITY', '[km/s] vlsr'), ('SIGMA', '[km/s] velocity dispersion'),
+             ('TEX', '[K] excitation temperature'), ('TAU', '[unitless] peak optical depth'))
+    for err in (False, True):
+        for i in range(ncomp):
+            for k, (nm, com) in enumerate(names):
+                plane = ((ncomp if err else 0) + i) * npara + k
+                label = ('e' if err else '') + nm + ('' if ncomp == 1 else '_{}'.format(i + 1))
+                note = ('estimated error of ' if err else '') + com + ('' if ncomp == 1 else
+                                                                       ' of component {}'.format(i + 1))
+                hdr.set('PLANE{}'.format(plane), label, note)
+    fits_io.write(savename, np.concatenate([pcube.parcube, pcube.errcube]), hdr)
+    logger.debug("{} saved.".format(savename))
 
 
 def match_pcube_mask(pcube, maskmap):

@@ -280,6 +280,23 @@ class PCube(object):
             raise AssertionError("No pixel yielded a fit. Please check the guesses, limits and mask.")
 
     # ---------------------------------------------------------------------------------------------------
+    def load_model_fit(self, fitsfilename, npars, fittype=None, **kwargs):
+        """pyspeckit ``Cube.load_model_fit`` for MUFASA's products (UltraCube.py:829-858): planes [0, npars) are the
+        parameters, [npars, 2 npars) their errors (multi_v_fit.save_pcube)."""
+        from .utils import fits_io
+        data, hdr = fits_io.read(fitsfilename)
+        if data.ndim != 3 or data.shape[0] < 2 * npars or data.shape[1:] != self.cube.shape[1:]:
+            raise ValueError("{}: expected [>= {}, {}, {}] planes".format(fitsfilename, 2 * npars, *self.cube.shape[1:]))
+        self.parcube = np.array(data[:npars], dtype=np.float64)
+        self.errcube = np.array(data[npars:2 * npars], dtype=np.float64)
+        with np.errstate(invalid="ignore"):
+            self.has_fit = np.any(self.parcube != 0, axis=0) & np.all(np.isfinite(self.parcube), axis=0)
+        self.npars = npars
+        self.fittype = FITTYPE_ALIASES.get(fittype, fittype) if fittype is not None else self.fittype
+        self._modelcube = None
+        self.fit_header = hdr
+        return self
+
     def get_modelcube(self, update=False, multicore=1, mask=None):
         """Model cube from parcube (pyspeckit get_modelcube: NaN where there is no fit), dtype of the data cube,
         cached in ``_modelcube``; callers may mutate the returned array (master_fitter.py:2516-2520)."""

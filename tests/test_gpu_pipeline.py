@@ -134,3 +134,24 @@ def test_cubefit_gen_gpu_prepass_equals_numpy_prepass():
     m = a["maskmap"]
     assert np.allclose(a["guesses"][:, m], b["guesses"][:, m], rtol=1e-9, atol=1e-12)
     assert a["start_from_point"] == b["start_from_point"]
+
+
+def test_save_and_resume_from_fits(tmp_path):
+    """Fit, save {root}_{n}vcomp.fits, resume in a fresh UltraCube from the files: identical likelihood maps and
+    ncomp map (the on-disk contract of MUFASA's multi-stage pipeline, master_fitter.py:1700-1718)."""
+    syn = synth.make_cube(2, T.oracle_modelcube, rows=(100, 104), shape=(200, 32, 800))
+    uc = _ucube(syn)
+    uc.fit_cube(ncomp=[1, 2], simpfit=True, guesses={1: syn["guess1"].copy(), 2: syn["guess2"].copy()})
+    ref = uc.get_best_2c_parcube()
+    files = {}
+    for nc in (1, 2):
+        files[nc] = str(tmp_path / ("syn_%dvcomp.fits" % nc))
+        uc.save_fit(files[nc], nc)
+    uc2 = _ucube(syn)
+    for nc in (1, 2):
+        uc2.load_model_fit(files[nc], nc)
+        assert np.array_equal(uc2.pcubes[str(nc)].parcube, uc.pcubes[str(nc)].parcube)
+    got = uc2.get_best_2c_parcube()
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(uc.ncomp_map, uc2.ncomp_map)
