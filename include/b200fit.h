@@ -168,6 +168,21 @@ int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob,
                  double* d_rss, double* d_nsamp, double* d_lnk, signed char* d_ncomp, int32_t* d_mask_counts,
                  void* stream);
 
+/* The same comparison for any pair of fits A (ncomp_a components, d_params1 [npix][4 ncomp_a]) and B (ncomp_b,
+ * d_params2 [npix][4 ncomp_b]) of the same spectra -- e.g. a NEW fit against the OLD one with the same number of
+ * components, expand = 0, which is what replace_bad_pix decides on (master_fitter.py:1449 ->
+ * calc_AICc_likelihood(ucube_new, nc, nc, ucube_B=old), UltraCube.py:1120-1216).  Outputs: d_rss [npix][3] = rss of
+ * the zero model, A, B over the union mask; d_lnk [npix][3] = lnk(A, 0), lnk(B, 0), lnk(B, A); d_ncomp = ncomp_b where
+ * lnk(B, A) > thr[2] and lnk(B, 0) > thr[1], else ncomp_a, and 0 where lnk(A, 0) <= thr[0]. */
+int b200fit_aicc_pair(b200fit_ctx* ctx, const b200fit_problem* prob, int32_t ncomp_a, int32_t ncomp_b,
+                      const float* d_spectra, int64_t nchan_stride, const int64_t* d_row_index,
+                      const double* d_params1, const double* d_params2, const uint32_t* d_fill_bits,
+                      int32_t only_empty, int32_t expand, int32_t model_f32, const double* thr, double* d_rss,
+                      double* d_nsamp, double* d_lnk, signed char* d_ncomp, int32_t* d_mask_counts, void* stream);
+int b200fit_mask_bits_pair(b200fit_ctx* ctx, const b200fit_problem* prob, int32_t ncomp_a, int32_t ncomp_b,
+                           const double* d_params1, const double* d_params2, int32_t model_f32, const int64_t* d_best,
+                           int64_t pix, uint32_t* d_bits, void* stream);
+
 /* d_best[2] (int64, device) = {largest mask count, index_offset + lowest pixel index holding it} -- the argmax the
  * reference takes with np.where(nsamp_map == nanmax(nsamp_map)) (UltraCube.py:1428-1429).  index_offset lets
  * each rank of a partitioned cube report global pixel indices. */

@@ -29,7 +29,7 @@ logger = logging.getLogger(__name__)
 
 class UltraCube(object):
     def __init__(self, cubefile=None, cube=None, fittype=None, snr_min=None, rmsfile=None, cnv_factor=2,
-                 n_cores=True, device=None):
+                 n_cores=True, device=None, share_device_with=None):
         self.pcubes = {}
         self.residual_cubes = {}
         self.rms_maps = {}
@@ -61,6 +61,11 @@ class UltraCube(object):
         if rmsfile is not None:
             self.rmsfile = rmsfile
         self._ref_pcube = None
+        if share_device_with is not None:
+            # a second UltraCube on the SAME data (replace_bad_pix builds one per refit, master_fitter.py:1437):
+            # reuse the rows already resident on the GPU instead of uploading the cube again
+            other = share_device_with._ref_pcube or share_device_with.load_pcube()
+            self._ref_pcube = self.load_pcube(pcube_ref=other)
 
     # ---- pcube handling ---------------------------------------------------------------------------------
     def load_pcube(self, pcube_ref=None):
@@ -233,8 +238,11 @@ class UltraCube(object):
 
     def get_AICc_likelihood(self, ncomp1, ncomp2, **kwargs):
         """ln(L_A / L_B) = (AICc_B - AICc_A) / 2  (calc_AICc_likelihood, UltraCube.py:1120-1216)."""
-        if kwargs.get("ucube_B") is not None or kwargs.get("planemask") is not None:
-            raise NotImplementedError("two-cube comparison belongs to the refit loop (SURVEY.md 8f #3)")
+        if kwargs.get("ucube_B") is not None:
+            return calc_AICc_likelihood(self, ncomp1, ncomp2, ucube_B=kwargs["ucube_B"],
+                                        expand=kwargs.get("expand", 0), planemask=kwargs.get("planemask"))
+        if kwargs.get("planemask") is not None:
+            raise NotImplementedError("planemask updates of cached maps are not supported")
         self._run_aicc()
         return -1.0 * (self.AICc_maps[str(ncomp1)] - self.AICc_maps[str(ncomp2)]) / 2.0
 
@@ -316,6 +324,37 @@ def fit_cube(cube, pcube, fittype, simpfit=False, **kwargs):
     if simpfit:
         return mvf.cubefit_simp(cube, pcube, fittype=fittype, **kwargs)
     return mvf.cubefit_gen(cube, pcube, fittype=fittype, **kwargs)
+
+
+def calc_AICc_likelihood(ucube, ncomp_A, ncomp_B, ucube_B=None, multicore=True, expand=0, planemask=None):
+    """UltraCube.py:1120-1216.  With ``ucube_B``: model A of ``ucube`` against model B of ``ucube_B`` (both on the
+    same data) over their COMMON mask (model_A > 0) | (model_B > 0), dilated by ``expand`` (default 0), AICc values
+    computed fresh and not stored -- the comparison replace_bad_pix makes between a new and an old fit
+    (master_fitter.py:1449).  One b200fit_aicc_pair pass."""
+    if ucube_B is None:
+        lnk = ucube.get_AICc_likelihood(ncomp_A, ncomp_B)
+        return lnk if planemask is None else lnk[planemask]
+    if ncomp_A not in (1, 2) or ncomp_B not in (1, 2):
+        raise NotImplementedError("the CUDA path compares 1- and 2-component models")
+    ref = ucube._ref_pcube if ucube._ref_pcube is not None else ucube.load_pcube()
+    eng = ref.engine
+    ny, nx = ucube.cube.shape[1:]
+    rows = ref.rows_on_device()
+    prob = ref._problem(ucube.fittype, 1, ny * nx, [-1e30] * 4, [1e30] * 4)
+    pA = ucube._params_dev(ncomp_A, eng)
+    pB = ucube_B._params_dev(ncomp_B, eng)
+    out = eng.aicc_global(prob, rows, pA, pB, expand=expand, model_f32=ucube.cube._data.dtype == np.float32,
+                          ncomp_pair=(ncomp_A, ncomp_B))
+    packed = torch.cat([out["rss"], out["nsamp"][:, None]], dim=1).t().contiguous().cpu().numpy()
+    with np.errstate(all="ignore"):
+        aicc = []
+        for k, nc in ((1, ncomp_A), (2, ncomp_B)):
+            rss = packed[k].reshape(ny, nx)
+            ns = np.where(np.isnan(rss), np.nan, packed[3].reshape(ny, nx))
+            p = 4 * nc
+            aicc.append(ns * np.log(rss / ns) + 2 * p + (2 * p * (p + 1)) / (ns - p - 1))
+        lnk = -1.0 * (aicc[0] - aicc[1]) / 2.0
+    return lnk if planemask is None else lnk[planemask]
 
 
 def get_residual(cube, model):

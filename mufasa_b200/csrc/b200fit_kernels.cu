@@ -603,22 +603,25 @@ __device__ __forceinline__ double model_f64(const DeviceProblem& pr, const CompF
     return __dsub_rn(bg, bg0);
 }
 
-// the 1-component model (comps[0]) and the 2-component model (comps[1], comps[2]) of one pixel at channel i,
-// sharing the frequency axis and the Planck terms (AICc pass)
-__device__ __forceinline__ void model_pair_f64(const DeviceProblem& pr, const CompF64* comps, bool v1, bool v2, int i,
-                                               double& m1, double& m2) {
+// model A (comps[0 .. nA)) and model B (comps[2 .. 2 + nB)) of one pixel at channel i, sharing the frequency axis and
+// the Planck terms.  A = the 1-component fit, B = the 2-component fit in get_all_lnk_maps; A = a new fit, B = the
+// old fit with the same number of components in replace_bad_pix (master_fitter.py:1449).
+__device__ __forceinline__ void model_pair_f64(const DeviceProblem& pr, const CompF64* comps, bool vA, bool vB, int nA,
+                                               int nB, int i, double& mA, double& mB) {
     const double x = xarr_ghz(pr, i);
-    const double ta = v1 ? tauprof_f64(pr, comps[0], x, i) : 0.0;
-    const double tb = v2 ? tauprof_f64(pr, comps[1], x, i) : 0.0;
-    const double tc = v2 ? tauprof_f64(pr, comps[2], x, i) : 0.0;
-    m1 = 0.0;
-    m2 = 0.0;
-    if (ta == 0.0 && tb == 0.0 && tc == 0.0) return;
+    const double a0 = vA ? tauprof_f64(pr, comps[0], x, i) : 0.0;
+    const double a1 = (vA && nA > 1) ? tauprof_f64(pr, comps[1], x, i) : 0.0;
+    const double b0 = vB ? tauprof_f64(pr, comps[2], x, i) : 0.0;
+    const double b1 = (vB && nB > 1) ? tauprof_f64(pr, comps[3], x, i) : 0.0;
+    mA = 0.0;
+    mB = 0.0;
+    if (a0 == 0.0 && a1 == 0.0 && b0 == 0.0 && b1 == 0.0) return;
     const double T0 = planck_T0(x);
     const double bg0 = t_antenna(T0, TCMB);
-    if (ta != 0.0) m1 = __dsub_rn(slab_f64(bg0, T0, comps[0].tex, ta), bg0);
-    if (tb != 0.0 || tc != 0.0)
-        m2 = __dsub_rn(slab_f64(slab_f64(bg0, T0, comps[1].tex, tb), T0, comps[2].tex, tc), bg0);
+    if (a0 != 0.0 || a1 != 0.0)
+        mA = __dsub_rn(slab_f64(slab_f64(bg0, T0, comps[0].tex, a0), T0, comps[1].tex, a1), bg0);
+    if (b0 != 0.0 || b1 != 0.0)
+        mB = __dsub_rn(slab_f64(slab_f64(bg0, T0, comps[2].tex, b0), T0, comps[3].tex, b1), bg0);
 }
 
 __device__ __forceinline__ bool params_valid(const double* p, int P) {
@@ -633,7 +636,7 @@ __device__ __forceinline__ bool params_valid(const double* p, int P) {
 constexpr int AUX_WARPS = 4;
 
 struct AuxShared {
-    CompF64 comps[3];   // [0] = 1-comp fit, [1..2] = 2-comp fit
+    CompF64 comps[4];   // model A in [0, nA), model B in [2, 2 + nB)   (nA, nB in {1, 2})
 };
 
 // get_modelcube: one warp per pixel
@@ -690,20 +693,19 @@ __device__ __forceinline__ void dilate_bits(unsigned* bits, int nchan, int expan
     __syncwarp();
 }
 
-__device__ __forceinline__ void setup_pixel_models(const DeviceProblem& pr, AuxShared& sh, const double* p1,
-                                                   const double* p2, bool v1, bool v2, int lane) {
-    if (v1) comp_setup_f64(pr, p1, sh.comps[0], lane);
-    if (v2) {
-        comp_setup_f64(pr, p2, sh.comps[1], lane);
-        comp_setup_f64(pr, p2 + 4, sh.comps[2], lane);
-    }
+__device__ __forceinline__ void setup_pixel_models(const DeviceProblem& pr, AuxShared& sh, const double* pA,
+                                                   const double* pB, bool vA, bool vB, int nA, int nB, int lane) {
+    if (vA)
+        for (int c = 0; c < nA; ++c) comp_setup_f64(pr, pA + 4 * c, sh.comps[c], lane);
+    if (vB)
+        for (int c = 0; c < nB; ++c) comp_setup_f64(pr, pB + 4 * c, sh.comps[2 + c], lane);
 }
 
 // Un-dilated union mask (model1 > 0) | (model2 > 0) of ONE pixel, written as a bit set: the spectral mask the
 // include_nosamp rule copies into pixels without samples (UltraCube.py:1423-1438).
 __global__ void __launch_bounds__(32)
-    mask_bits_kernel(const DeviceProblem pr, const double* __restrict__ params1, const double* __restrict__ params2,
-                     int model_f32, const long long* __restrict__ best /* {count, pix} or null */, long long pix_arg,
+    mask_bits_kernel(const DeviceProblem pr, int nA, int nB, const double* __restrict__ params1,
+                     const double* __restrict__ params2, int model_f32, const long long* __restrict__ best /* {count, pix} or null */, long long pix_arg,
                      unsigned* __restrict__ bits_out) {
     __shared__ AuxShared sh;
     const int lane = threadIdx.x;
@@ -714,15 +716,15 @@ __global__ void __launch_bounds__(32)
         for (int wd = lane; wd < MASK_WORDS; wd += 32) bits_out[wd] = 0u;
         return;
     }
-    const bool v1 = params1 && params_valid(params1 + pix * 4, 4);
-    const bool v2 = params2 && params_valid(params2 + pix * 8, 8);
-    setup_pixel_models(pr, sh, params1 + pix * 4, params2 + pix * 8, v1, v2, lane);
+    const bool v1 = params1 && params_valid(params1 + pix * 4 * nA, 4 * nA);
+    const bool v2 = params2 && params_valid(params2 + pix * 4 * nB, 4 * nB);
+    setup_pixel_models(pr, sh, params1 + pix * 4 * nA, params2 + pix * 4 * nB, v1, v2, nA, nB, lane);
     for (int wd = 0; wd < MASK_WORDS; ++wd) {
         const int i = (wd << 5) + lane;
         bool on = false;
         if (wd < nwords && i < pr.nchan) {
             double m1, m2;
-            model_pair_f64(pr, sh.comps, v1, v2, i, m1, m2);
+            model_pair_f64(pr, sh.comps, v1, v2, nA, nB, i, m1, m2);
             on = model_f32 ? (((float)m1 > 0.f) || ((float)m2 > 0.f)) : ((m1 > 0.0) || (m2 > 0.0));
         }
         const unsigned b = __ballot_sync(FULL, on);
@@ -758,7 +760,7 @@ __global__ void mask_argmax_finish_kernel(const unsigned long long* __restrict__
 //   pass 2 (only_empty = 1): only the pixels with mask_counts[pix] == 0, with fill_bits (the global include_nosamp
 //                            mask, known only after pass 1 has seen every pixel of every rank).
 __global__ void __launch_bounds__(AUX_WARPS * 32)
-    aicc_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
+    aicc_kernel(const DeviceProblem pr, int nA, int nB, const float* __restrict__ spectra, long long stride,
                 const long long* __restrict__ row_index, const double* __restrict__ params1,
                 const double* __restrict__ params2, const unsigned* __restrict__ fill_bits, int only_empty, int expand,
                 int model_f32, double thr10, double thr20, double thr21, double* __restrict__ rss_out,
@@ -776,16 +778,16 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
     for (long long pix = (long long)blockIdx.x * AUX_WARPS + warp; pix < pr.npix;
          pix += (long long)gridDim.x * AUX_WARPS) {
         if (only_empty && mask_counts[pix] != 0) continue;
-        const bool v1 = params_valid(params1 + pix * 4, 4);
-        const bool v2 = params_valid(params2 + pix * 8, 8);
-        setup_pixel_models(pr, sh[warp], params1 + pix * 4, params2 + pix * 8, v1, v2, lane);
+        const bool v1 = params_valid(params1 + pix * 4 * nA, 4 * nA);
+        const bool v2 = params_valid(params2 + pix * 4 * nB, 4 * nB);
+        setup_pixel_models(pr, sh[warp], params1 + pix * 4 * nA, params2 + pix * 4 * nB, v1, v2, nA, nB, lane);
         // models (kept in smem) + union mask
         for (int wd = 0; wd < nwords; ++wd) {
             const int i = (wd << 5) + lane;
             bool on = false;
             if (i < pr.nchan) {
                 double m1, m2;
-                model_pair_f64(pr, sh[warp].comps, v1, v2, i, m1, m2);
+                model_pair_f64(pr, sh[warp].comps, v1, v2, nA, nB, i, m1, m2);
                 if (model_f32) {
                     m1s[i] = (float)m1;
                     m2s[i] = (float)m2;
@@ -861,7 +863,7 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
                 }
                 if (rr <= 0.0) rr = NAN;
                 rs[k] = rr;
-                const double p = 4.0 * k;
+                const double p = (k == 0) ? 0.0 : ((k == 1) ? 4.0 * nA : 4.0 * nB);
                 // aic.AIC / AICc (aic.py:136-181)
                 aic[k] = nn * log(rr / nn) + 2.0 * p + (2.0 * p * (p + 1.0)) / (nn - p - 1.0);
                 rss_out[pix * 3 + k] = rr;
@@ -870,7 +872,7 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
             double l10 = -1.0 * (aic[1] - aic[0]) / 2.0;
             double l20 = -1.0 * (aic[2] - aic[0]) / 2.0;
             double l21 = -1.0 * (aic[2] - aic[1]) / 2.0;
-            signed char nc = ((l21 > thr21) && (l20 > thr20)) ? 2 : 1;
+            signed char nc = ((l21 > thr21) && (l20 > thr20)) ? (signed char)nB : (signed char)nA;
             if (!(l10 > thr10)) nc = 0;
             // lnk maps are NaN where the corresponding fit does not exist (UltraCube.py:1369-1377)
             if (!v1) l10 = NAN;
@@ -1542,28 +1544,36 @@ int b200fit_mask_argmax(b200fit_ctx* ctx, const int32_t* d_mask_counts, int64_t 
     return B200FIT_OK;
 }
 
-int b200fit_mask_bits(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d_params1,
-                      const double* d_params2, int32_t model_f32, const int64_t* d_best, int64_t pix,
-                      uint32_t* d_bits, void* stream) {
+int b200fit_mask_bits_pair(b200fit_ctx* ctx, const b200fit_problem* prob, int32_t ncomp_a, int32_t ncomp_b,
+                           const double* d_params1, const double* d_params2, int32_t model_f32, const int64_t* d_best,
+                           int64_t pix, uint32_t* d_bits, void* stream) {
     if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "mask_bits: null context/problem");
+    if (ncomp_a < 1 || ncomp_a > 2 || ncomp_b < 1 || ncomp_b > 2) return fail(ctx, B200FIT_E_ARG, "mask_bits: ncomp must be 1 or 2");
     DeviceProblem pr;
     const int rc = make_device_problem(*prob, pr);
     if (rc) return fail(ctx, rc, "mask_bits: invalid problem description");
     if (!d_bits || (!d_params1 && !d_params2)) return fail(ctx, B200FIT_E_ARG, "mask_bits: bad argument");
     CK(cudaSetDevice(ctx->device));
-    mask_bits_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pr, d_params1, d_params2, model_f32, (const long long*)d_best,
-                                                        pix, d_bits);
+    mask_bits_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pr, ncomp_a, ncomp_b, d_params1, d_params2, model_f32,
+                                                        (const long long*)d_best, pix, d_bits);
     CK(cudaGetLastError());
     ctx->launches += 1;
     return B200FIT_OK;
 }
 
-int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_spectra, int64_t nchan_stride,
-                 const int64_t* d_row_index, const double* d_params1, const double* d_params2,
-                 const uint32_t* d_fill_bits, int32_t only_empty, int32_t expand, int32_t model_f32, const double* thr,
-                 double* d_rss, double* d_nsamp, double* d_lnk, signed char* d_ncomp, int32_t* d_mask_counts,
-                 void* stream) {
+int b200fit_mask_bits(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d_params1,
+                      const double* d_params2, int32_t model_f32, const int64_t* d_best, int64_t pix,
+                      uint32_t* d_bits, void* stream) {
+    return b200fit_mask_bits_pair(ctx, prob, 1, 2, d_params1, d_params2, model_f32, d_best, pix, d_bits, stream);
+}
+
+int b200fit_aicc_pair(b200fit_ctx* ctx, const b200fit_problem* prob, int32_t ncomp_a, int32_t ncomp_b,
+                      const float* d_spectra, int64_t nchan_stride, const int64_t* d_row_index,
+                      const double* d_params1, const double* d_params2, const uint32_t* d_fill_bits,
+                      int32_t only_empty, int32_t expand, int32_t model_f32, const double* thr, double* d_rss,
+                      double* d_nsamp, double* d_lnk, signed char* d_ncomp, int32_t* d_mask_counts, void* stream) {
     if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "aicc: null context/problem");
+    if (ncomp_a < 1 || ncomp_a > 2 || ncomp_b < 1 || ncomp_b > 2) return fail(ctx, B200FIT_E_ARG, "aicc: ncomp must be 1 or 2");
     DeviceProblem pr;
     const int rc = make_device_problem(*prob, pr);
     if (rc) return fail(ctx, rc, "aicc: invalid problem description");
@@ -1578,11 +1588,20 @@ int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_s
     const size_t smem = (size_t)AUX_WARPS * 2 * nchan_stride * (model_f32 ? sizeof(float) : sizeof(double));
     CK(cudaFuncSetAttribute(aicc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     aicc_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        pr, d_spectra, nchan_stride, (const long long*)d_row_index, d_params1, d_params2, d_fill_bits, only_empty,
-        expand, model_f32, t10, t20, t21, d_rss, d_nsamp, d_lnk, d_ncomp, d_mask_counts);
+        pr, ncomp_a, ncomp_b, d_spectra, nchan_stride, (const long long*)d_row_index, d_params1, d_params2, d_fill_bits,
+        only_empty, expand, model_f32, t10, t20, t21, d_rss, d_nsamp, d_lnk, d_ncomp, d_mask_counts);
     CK(cudaGetLastError());
     ctx->launches += 1;
     return B200FIT_OK;
+}
+
+int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_spectra, int64_t nchan_stride,
+                 const int64_t* d_row_index, const double* d_params1, const double* d_params2,
+                 const uint32_t* d_fill_bits, int32_t only_empty, int32_t expand, int32_t model_f32, const double* thr,
+                 double* d_rss, double* d_nsamp, double* d_lnk, signed char* d_ncomp, int32_t* d_mask_counts,
+                 void* stream) {
+    return b200fit_aicc_pair(ctx, prob, 1, 2, d_spectra, nchan_stride, d_row_index, d_params1, d_params2, d_fill_bits,
+                             only_empty, expand, model_f32, thr, d_rss, d_nsamp, d_lnk, d_ncomp, d_mask_counts, stream);
 }
 
 int b200fit_rms_snr(b200fit_ctx* ctx, int32_t nchan, int64_t npix, const float* d_spectra, int64_t nchan_stride,

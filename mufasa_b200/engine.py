@@ -201,9 +201,10 @@ class Engine(object):
                     mask_counts=torch.empty(npix, dtype=torch.int32, device=dev))
 
     def aicc_pass(self, prob, spectra, params1, params2, out, fill_bits=None, only_empty=False, expand=20,
-                  model_f32=True, thr=(5.0, 5.0, 5.0), row_index=None):
+                  model_f32=True, thr=(5.0, 5.0, 5.0), row_index=None, ncomp_pair=(1, 2)):
         thr_arr = (C.c_double * 3)(*[float(t) for t in thr])
-        rc = self.lib.b200fit_aicc(self.ctx, C.byref(prob), _ptr(spectra), spectra.shape[1], _ptr(row_index),
+        rc = self.lib.b200fit_aicc_pair(self.ctx, C.byref(prob), int(ncomp_pair[0]), int(ncomp_pair[1]),
+                                   _ptr(spectra), spectra.shape[1], _ptr(row_index),
                                    _ptr(params1), _ptr(params2), _ptr(fill_bits), 1 if only_empty else 0, int(expand),
                                    1 if model_f32 else 0, C.cast(thr_arr, C.c_void_p), _ptr(out["rss"]),
                                    _ptr(out["nsamp"]), _ptr(out["lnk"]), _ptr(out["ncomp"]), _ptr(out["mask_counts"]),
@@ -219,26 +220,27 @@ class Engine(object):
         self._check(rc, "b200fit_mask_argmax")
         return best
 
-    def mask_bits(self, prob, params1, params2, best=None, pix=-1, model_f32=True):
+    def mask_bits(self, prob, params1, params2, best=None, pix=-1, model_f32=True, ncomp_pair=(1, 2)):
         """device uint32[64] bit set of the un-dilated union model mask of one pixel."""
         bits = torch.empty(64, dtype=torch.int32, device=self.device)
-        rc = self.lib.b200fit_mask_bits(self.ctx, C.byref(prob), _ptr(params1), _ptr(params2), 1 if model_f32 else 0,
+        rc = self.lib.b200fit_mask_bits_pair(self.ctx, C.byref(prob), int(ncomp_pair[0]), int(ncomp_pair[1]),
+                                        _ptr(params1), _ptr(params2), 1 if model_f32 else 0,
                                         _ptr(best), int(pix), _ptr(bits), self._stream())
         self._check(rc, "b200fit_mask_bits")
         return bits
 
     def aicc_global(self, prob, spectra, params1, params2, expand=20, model_f32=True, thr=(5.0, 5.0, 5.0),
-                    row_index=None):
+                    row_index=None, ncomp_pair=(1, 2)):
         """lnk10/lnk20/lnk21, rss, N and the integer ncomp map of every pixel of ONE device's pixel set, with the
         include_nosamp rule applied over that set (single-GPU composition; dist.py composes it across ranks).
         No host synchronisation between the passes."""
         out = self.aicc_alloc(int(prob.npix))
         self.aicc_pass(prob, spectra, params1, params2, out, expand=expand, model_f32=model_f32, thr=thr,
-                       row_index=row_index)
+                       row_index=row_index, ncomp_pair=ncomp_pair)
         best = self.mask_argmax(out["mask_counts"])
-        bits = self.mask_bits(prob, params1, params2, best=best, model_f32=model_f32)
+        bits = self.mask_bits(prob, params1, params2, best=best, model_f32=model_f32, ncomp_pair=ncomp_pair)
         self.aicc_pass(prob, spectra, params1, params2, out, fill_bits=bits, only_empty=True, expand=expand,
-                       model_f32=model_f32, thr=thr, row_index=row_index)
+                       model_f32=model_f32, thr=thr, row_index=row_index, ncomp_pair=ncomp_pair)
         out["fill_bits"] = bits
         return out
 

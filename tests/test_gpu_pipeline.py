@@ -155,3 +155,34 @@ def test_save_and_resume_from_fits(tmp_path):
     for a, b in zip(ref, got):
         assert np.array_equal(a, b, equal_nan=True)
     assert np.array_equal(uc.ncomp_map, uc2.ncomp_map)
+
+
+def test_replace_bad_pix_refit_loop():
+    """master_fitter.replace_bad_pix (:1403-1464): pixels fitted from deliberately bad guesses are refitted from
+    their best neighbour's parameters and replaced where the new fit is the likelier one."""
+    from mufasa_b200 import master_fitter as mf
+    syn = synth.make_cube(2, T.oracle_modelcube, rows=(100, 108), shape=(200, 48, 800))
+    g = syn["guess1"].copy()
+    bad = np.zeros(g.shape[1:], bool)
+    bad[2:6, 10:30:3] = True
+    g[0][bad] += 6.0                              # 6 km/s off: the main group locks onto a satellite or noise
+    uc = _ucube(syn)
+    uc.fit_cube(ncomp=1, simpfit=True, guesses=g)
+    p = uc.pcubes["1"]
+    truth_v = syn["truth1"][0]
+    off_before = np.abs(p.parcube[0] - truth_v)
+    assert (off_before[bad] > 1.0).mean() > 0.5                  # the bad guesses did produce bad fits
+    chi2_before = p.chi2map.copy()
+    # reference recipe: a quality map ranks the neighbours (here the 1-vs-0 likelihood), best neighbour -> guesses
+    lnk10 = uc.get_AICc_likelihood(1, 0)
+    refit_mask = bad & p.has_fit
+    guesses, refit_mask = mf.get_refit_guesses(uc, refit_mask, ncomp=1, method='best_neighbour', refmap=lnk10)
+    good = mf.replace_bad_pix(uc, refit_mask, snr_min=0.0, guesses=guesses, ncomp=1, return_good_mask=True)
+    assert good.shape == bad.shape and good.sum() >= 0.5 * (off_before[bad] > 1.0).sum()
+    off_after = np.abs(p.parcube[0] - truth_v)
+    assert np.all(off_after[good] < 0.3)                         # the replaced pixels now sit on the truth
+    assert np.array_equal(p.parcube[:, ~good], uc.pcubes["1"].parcube[:, ~good])
+    # untouched pixels are untouched; statistics are rebuilt from the patched parameter cube
+    lnk10_new = uc.get_AICc_likelihood(1, 0)
+    assert np.all(lnk10_new[good] > lnk10[good])
+    assert np.array_equal(lnk10_new[~good & ~bad], lnk10[~good & ~bad], equal_nan=True)

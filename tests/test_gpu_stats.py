@@ -195,3 +195,45 @@ def test_rms_snr_matches_numpy_signals(engine):
         snr = b["peak"].cpu().numpy().reshape(ny, nx) / rms
     assert np.array_equal(snr, snr_ref, equal_nan=True)
     assert np.isnan(rms[1, 5]) and np.all(np.isnan(rms[0, :2])) and np.isfinite(rms[0, 3])
+
+
+def test_aicc_pair_new_vs_old_fit(engine, fitted_tile):
+    """calc_AICc_likelihood(ucube_new, nc, nc, ucube_B=old) (UltraCube.py:1120-1216, expand = 0): two 2-component
+    fits of the same spectra compared over their common mask -- b200fit_aicc_pair vs the oracle's get_rss / AICc."""
+    t = fitted_tile
+    cube = t["cube"]
+    nchan, ny, nx = cube.shape
+    npix = ny * nx
+    pB = t["p2"]                                  # "old" fit
+    pA = pB.copy()                                # "new" fit: perturbed parameters, a few pixels without a fit
+    rng = np.random.default_rng(11)
+    pA[0] += 0.05 * rng.normal(size=(ny, nx))
+    pA[3] *= 1.0 + 0.1 * rng.normal(size=(ny, nx))
+    pA[:, 1, 2] = 0.0
+    mA = M.modelcube(t["v"], pA, t["fittype"], dtype=np.float32)
+    mB = M.modelcube(t["v"], pB, t["fittype"], dtype=np.float32)
+    with np.errstate(all="ignore"):
+        mask = np.logical_or(mA > 0, mB > 0)
+        rssA, nA = ST.rss_maps(cube, mA.copy(), mask.copy(), expand=0)
+        rssB, nB = ST.rss_maps(cube, mB.copy(), mask.copy(), expand=0)
+        ref = ST.likelihood(ST.AICc(rssA, 8, nA), ST.AICc(rssB, 8, nB))
+    spec, _ = T.pixel_major(t, t["p1"])
+    out = engine.aicc_global(_prob(t, 1, npix), _dev(spec), _dev(pA.reshape(8, -1).T), _dev(pB.reshape(8, -1).T),
+                             expand=0, model_f32=True, ncomp_pair=(2, 2))
+    rss = out["rss"].cpu().numpy().reshape(ny, nx, 3)
+    ns = out["nsamp"].cpu().numpy().reshape(ny, nx)
+    with np.errstate(all="ignore"):
+        nsA = np.where(np.isnan(rss[:, :, 1]), np.nan, ns)
+        nsB = np.where(np.isnan(rss[:, :, 2]), np.nan, ns)
+        got = ST.likelihood(ST.AICc(rss[:, :, 1], 8, nsA), ST.AICc(rss[:, :, 2], 8, nsB))
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    same_n = np.isfinite(ref) & (nsA == nA)
+    assert same_n.sum() > 0.5 * np.isfinite(ref).sum()
+    assert np.max(np.abs(got[same_n] - ref[same_n])) < 1e-4 * np.maximum(1.0, np.abs(ref[same_n])).max()
+    # the decision replace_bad_pix takes (lnk > 0) agrees wherever it is not marginal
+    dec = np.isfinite(ref) & (np.abs(ref) > 0.05)
+    assert np.array_equal(got[dec] > 0, ref[dec] > 0)
+    # kernel's own lnk(B, A) = -lnk(A, B)
+    lnkBA = out["lnk"].cpu().numpy().reshape(ny, nx, 3)[:, :, 2]
+    ok = np.isfinite(lnkBA) & np.isfinite(got)
+    assert np.allclose(lnkBA[ok], -got[ok], rtol=1e-10, atol=1e-10)
