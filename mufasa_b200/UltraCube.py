@@ -61,6 +61,7 @@ class UltraCube(object):
         if rmsfile is not None:
             self.rmsfile = rmsfile
         self._ref_pcube = None
+        self.dist = None                  # (process group, global index of this slab's first pixel) when partitioned
         if share_device_with is not None:
             # a second UltraCube on the SAME data (replace_bad_pix builds one per refit, master_fitter.py:1437):
             # reuse the rows already resident on the GPU instead of uploading the cube again
@@ -202,7 +203,12 @@ class UltraCube(object):
         p1 = self._params_dev(1, eng)
         p2 = self._params_dev(2, eng)
         model_f32 = self.cube._data.dtype == np.float32
-        out = eng.aicc_global(prob, rows, p1, p2, expand=expand, model_f32=model_f32, thr=thr)
+        if self.dist is None:
+            out = eng.aicc_global(prob, rows, p1, p2, expand=expand, model_f32=model_f32, thr=thr)
+        else:       # row slab of a partitioned cube: the include_nosamp fill mask is global (dist.py)
+            from . import dist as D
+            out = D.aicc_distributed(eng, prob, rows, p1, p2, first_pixel=self.dist[1], expand=expand,
+                                     model_f32=model_f32, thr=thr, group=self.dist[0])
         # one field-major D2H copy: rss0..2, nsamp, lnk10/20/21, ncomp
         packed = torch.cat([out["rss"], out["nsamp"][:, None], out["lnk"], out["ncomp"].to(torch.float64)[:, None]],
                            dim=1).t().contiguous().cpu().numpy()

@@ -94,3 +94,63 @@ def aicc_distributed(engine, prob, rows, params1, params2, first_pixel, expand=2
     out["fill_bits"] = bits
     out["fill_from"] = (count, index, owner)
     return out
+
+
+def fit_and_select(cube, v_kms, fittype, guesses1, guesses2, device=None, group=None, gather=True):
+    """The model-selection job (1c fit + 2c fit + AICc 0/1/2 selection; UltraCube.fit_cube([1, 2]) +
+    get_best_2c_parcube) on a cube partitioned by row slabs over the ranks of ``group``.
+
+    ``cube`` [nchan, ny, nx], ``guesses1`` [4, ny, nx], ``guesses2`` [8, ny, nx]: the WHOLE arrays on every rank
+    (each rank touches only its slab; a loader that reads slabs directly can pass views of a larger virtual array).
+    Global couplings are resolved before partitioning: cubefit_simp's velocity window comes from the statistics of
+    the whole guess map, the include_nosamp fill mask from ``aicc_distributed``.  Per-pixel results are identical
+    to a single-GPU run.  Returns dict(parcube1, errcube1, parcube2, errcube2, best_parcube, best_errcube, lnk10,
+    lnk20, lnk21, ncomp) of [.., ny, nx] numpy arrays on rank 0 (None elsewhere) when ``gather``, else the slab's."""
+    import numpy as np
+    from . import multi_v_fit as mvf
+    from .cube import SpecCube
+    from .UltraCube import UltraCube
+    world, rank = _world(group)
+    nchan, ny, nx = cube.shape
+    y0, y1 = partition_rows(ny, world, rank)
+    dev = torch.cuda.current_device() if device is None else device
+    slab = np.ascontiguousarray(cube[:, y0:y1, :])
+    uc = UltraCube(cube=SpecCube(slab, v_kms), fittype=fittype, device=dev)
+    uc.dist = (group, y0 * nx)
+    g = {1: np.array(guesses1[:, y0:y1, :], dtype=np.float64), 2: np.array(guesses2[:, y0:y1, :], dtype=np.float64)}
+    vstats = {}
+    for nc, full in ((1, guesses1), (2, guesses2)):      # global statistics of the velocity guesses (cubefit_simp)
+        vg = np.array(full[::4], dtype=np.float64)
+        vg[vg == 0] = np.nan
+        vstats[nc] = mvf.get_vstats(vg)
+    for nc in (1, 2):
+        uc.pcubes.pop(str(nc), None)
+    # the two fits in flight together; each driver gets the global velocity statistics of its own guess map
+    batch = []
+    for nc in (1, 2):
+        p = uc.load_pcube(pcube_ref=uc._ref_pcube)
+        p._deferred = batch
+        uc.pcubes[str(nc)] = mvf.cubefit_simp(uc.cube, p, ncomp=nc, guesses=g[nc], fittype=fittype,
+                                              vstats=vstats[nc])
+        p._deferred = None
+    if batch:
+        outs = batch[0]["pcube"].engine.fit_batch(batch)
+        for job, out in zip(batch, outs):
+            job["pcube"].finish_fit(job, out)
+    for nc in (1, 2):
+        uc._include_fit_in_mask(nc)
+    best_par, best_err, lnk10, lnk20, lnk21 = uc.get_best_2c_parcube()
+    local = dict(parcube1=uc.pcubes["1"].parcube, errcube1=uc.pcubes["1"].errcube, parcube2=uc.pcubes["2"].parcube,
+                 errcube2=uc.pcubes["2"].errcube, best_parcube=best_par, best_errcube=best_err,
+                 lnk10=lnk10[None], lnk20=lnk20[None], lnk21=lnk21[None],
+                 ncomp=uc.ncomp_map.astype(np.float64)[None])
+    if not gather or world == 1:
+        return {k: (v[0] if k.startswith("lnk") or k == "ncomp" else v) for k, v in local.items()}
+    out = {}
+    device_t = torch.device("cuda", dev) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    for k, v in local.items():
+        t = gather_maps(torch.from_numpy(np.ascontiguousarray(v)).to(device_t), ny, group=group, dst=0)
+        if rank == 0:
+            a = t.cpu().numpy()
+            out[k] = a[0] if k.startswith("lnk") or k == "ncomp" else a
+    return out if rank == 0 else None

@@ -161,7 +161,9 @@ def cubefit_simp(cube, pcube, ncomp, guesses, multicore=None, maskmap=None, fitt
     v_peak_hwidth = 10
     v_guess = guesses[::4]
     v_guess[v_guess == 0] = np.nan
-    v_median, v_99p, v_1p = get_vstats(v_guess)
+    # (median, 99th, 1st percentile) of the velocity guesses: a GLOBAL quantity -- a partitioned run passes the
+    # statistics of the whole map (mufasa_b200/dist.py), SURVEY.md 7.5
+    v_median, v_99p, v_1p = kwargs.pop('vstats', None) or get_vstats(v_guess)
     vmax = v_median + v_peak_hwidth
     vmin = v_median - v_peak_hwidth
     if v_99p + sigmax > vmax:

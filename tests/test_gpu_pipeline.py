@@ -186,3 +186,18 @@ def test_replace_bad_pix_refit_loop():
     lnk10_new = uc.get_AICc_likelihood(1, 0)
     assert np.all(lnk10_new[good] > lnk10[good])
     assert np.array_equal(lnk10_new[~good & ~bad], lnk10[~good & ~bad], equal_nan=True)
+
+
+def test_dist_fit_and_select_single_rank_matches_ultracube():
+    """dist.fit_and_select (the partitioned job; here world size 1) == UltraCube.fit_cube([1, 2]) +
+    get_best_2c_parcube.  The 2-GPU run is checked bit for bit by profiles/dist_check.py under torchrun."""
+    from mufasa_b200 import dist as D
+    syn = synth.make_cube(2, T.oracle_modelcube, rows=(100, 104), shape=(200, 32, 800))
+    res = D.fit_and_select(syn["cube"], syn["v"], syn["fittype"], syn["guess1"].copy(), syn["guess2"].copy(), device=0)
+    uc = _ucube(syn)
+    uc.fit_cube(ncomp=[1, 2], simpfit=True, guesses={1: syn["guess1"].copy(), 2: syn["guess2"].copy()})
+    par, err, l10, l20, l21 = uc.get_best_2c_parcube()
+    assert np.array_equal(res["parcube2"], uc.pcubes["2"].parcube)
+    assert np.array_equal(res["best_parcube"], par, equal_nan=True)
+    assert np.array_equal(res["lnk21"], l21, equal_nan=True)
+    assert np.array_equal(res["ncomp"].astype(np.int8), uc.ncomp_map)
