@@ -49,8 +49,9 @@ class UltraCube(object):
         self.fittype = fittype
         self.meta_model = None
         self.device = device
-        if cubefile is not None:
-            raise NotImplementedError("FITS I/O is outside the fit path (SURVEY.md 8f #2): pass cube=SpecCube(...)")
+        self.cubefile = cubefile
+        if cubefile is not None and cube is None:
+            cube = SpecCube.read(cubefile)
         if not isinstance(cube, SpecCube):
             raise TypeError("cube must be a mufasa_b200.cube.SpecCube")
         self.cube = cube
@@ -79,6 +80,15 @@ class UltraCube(object):
         if self._ref_pcube is None:
             self._ref_pcube = p
         return p
+
+    def convolve_cube(self, savename=None, factor=None, edgetrim_width=5):
+        """Smooth the cube to ``factor`` x its beam and regrid it onto ``factor`` x larger pixels (UltraCube.py:218-
+        249 -> convolve_tools.convolve_sky_byfactor); the result is kept in ``self.cube_cnv``."""
+        from . import convolve_tools as cnvtool
+        if factor is None:
+            factor = self.cnv_factor
+        self.cube_cnv = cnvtool.convolve_sky_byfactor(self.cube, factor, savename, edgetrim_width=edgetrim_width,
+                                                      device=self.device)
 
     def fit_cube(self, ncomp, simpfit=False, concurrent=True, **kwargs):
         """UltraCube.py:272-326.  With several ``ncomp`` the reference fits them one after the other; here the host

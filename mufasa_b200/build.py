@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libb200fit.so")
-SOURCES = ["b200fit_kernels.cu", "b200fit_prepass.cu"]
+SOURCES = ["b200fit_kernels.cu", "b200fit_prepass.cu", "b200fit_convolve.cu"]
 HEADERS = ["b200fit_common.h", "b200fit_host.h", "b200fit_lanes.cuh", "b200fit_ctx.h", os.path.join("..", "..", "include", "b200fit.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

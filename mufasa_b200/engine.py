@@ -267,6 +267,35 @@ class Engine(object):
         self._check(rc, "b200fit_resid_stats")
         return out
 
+    def convolve_planes(self, cube_dev, kx=None, ky=None, k2=None, include=None, out=None):
+        """Spatial convolution of every channel plane (b200fit_convolve_planes).  cube_dev [nchan, ny, nx] fp32;
+        separable kernel ``kx``, ``ky`` [K] or general ``k2`` [K, K] (fp32 device tensors); ``include`` [ny, nx]
+        uint8 or None.  Returns the convolved cube (device)."""
+        assert cube_dev.dtype == torch.float32 and cube_dev.is_contiguous() and cube_dev.dim() == 3
+        nchan, ny, nx = (int(v) for v in cube_dev.shape)
+        if out is None:
+            out = torch.empty_like(cube_dev)
+        kern = k2 if k2 is not None else kx
+        ksize = int(kern.shape[0])
+        for t in (kx, ky, k2):
+            assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda)
+        if include is not None:
+            assert include.dtype == torch.uint8 and include.is_contiguous() and include.numel() == ny * nx
+        rc = self.lib.b200fit_convolve_planes(self.ctx, _ptr(cube_dev), nchan, ny, nx, _ptr(include), ksize, _ptr(kx),
+                                              _ptr(ky), _ptr(k2), _ptr(out), self._stream())
+        self._check(rc, "b200fit_convolve_planes")
+        return out
+
+    def resample_bilinear(self, cube_dev, out_ny, out_nx, ay, by, ax, bx):
+        """Bilinear regrid of every plane: output pixel (oy, ox) samples input (ay oy + by, ax ox + bx)."""
+        assert cube_dev.dtype == torch.float32 and cube_dev.is_contiguous() and cube_dev.dim() == 3
+        nchan, ny, nx = (int(v) for v in cube_dev.shape)
+        out = torch.empty((nchan, int(out_ny), int(out_nx)), dtype=torch.float32, device=self.device)
+        rc = self.lib.b200fit_resample_bilinear(self.ctx, _ptr(cube_dev), nchan, ny, nx, _ptr(out), int(out_ny),
+                                                int(out_nx), float(ay), float(by), float(ax), float(bx), self._stream())
+        self._check(rc, "b200fit_resample_bilinear")
+        return out
+
 
 _engines = {}
 

@@ -52,6 +52,24 @@ def binary_opening(mask, footprint=None):
     return binary_dilation(binary_erosion(mask, footprint), footprint)
 
 
+def remove_small_objects(mask, min_size=64):
+    """skimage.morphology.remove_small_objects on a boolean map: drop 4-connected components smaller than min_size."""
+    mask = np.asarray(mask, bool)
+    lab, n = nd.label(mask)
+    if n == 0:
+        return mask.copy()
+    sizes = np.bincount(lab.ravel())
+    small = sizes < min_size
+    small[0] = False
+    return mask & ~small[lab]
+
+
+def remove_small_holes(mask, area_threshold=64):
+    """skimage.morphology.remove_small_holes: fill 4-connected background components smaller than the threshold."""
+    mask = np.asarray(mask, bool)
+    return ~remove_small_objects(~mask, area_threshold)
+
+
 def mad_std(data, axis=0, include=None):
     """1.4826 * median(|x - median(x)|) over finite (and included) samples."""
     d = np.asarray(data, dtype=np.float64)

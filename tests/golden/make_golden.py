@@ -215,6 +215,33 @@ def make_guess():
     np.savez_compressed(os.path.join(HERE, "guess_golden.npz"), **out)
 
 
+def make_cnv():
+    """Pure-numpy pieces of the convolved-cube stage: component sorting / swapping (guess_refine.py:36-110),
+    refine_2c_guess (:395-416), downsample_header (utils/fits_utils.py:11-60)."""
+    from mufasa.utils import fits_utils as fu
+    rng = np.random.default_rng(11)
+    data = rng.uniform(0.1, 9.0, (16, 6, 7))
+    data[:, 0, 0] = np.nan
+    data[8, 1, 1] = np.nan
+    out = dict(data=data)
+    swapmask = rng.uniform(size=(6, 7)) > 0.5
+    out["swapmask"] = swapmask
+    out["swapped"] = gr.mask_swap_2comp(data.copy(), swapmask)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for m in ("error_v", "Tpeak", "tautex", "tau", "chen2020"):
+            out["sort_" + m] = gr.quick_2comp_sort(data.copy(), filtsize=2, method=m)
+        out["refine_2c"] = gr.refine_2c_guess(data[:8].copy(), f_sigv=0.5)
+    rows = []
+    for crpix, cdelt, factor in ((50.0, 0.1, 2), (128.5, -0.002444, 2), (1.0, 0.01, 3), (33.25, -1.5e-3, 2.5)):
+        h = {"CRPIX1": crpix, "CDELT1": cdelt, "CRPIX2": crpix + 3, "CDELT2": -cdelt}
+        h1 = fu.downsample_header(h, factor=factor, axis=1)
+        h2 = fu.downsample_header(h1, factor=factor, axis=2)
+        rows.append([crpix, cdelt, factor, h2["CRPIX1"], h2["CDELT1"], h2["CRPIX2"], h2["CDELT2"]])
+    out["downsample_header"] = np.array(rows)
+    np.savez_compressed(os.path.join(HERE, "cnv_golden.npz"), **out)
+
+
 def make_meta():
     out = {}
     for ft in ("nh3_multi_v", "n2hp_multi_v"):
@@ -238,6 +265,7 @@ if __name__ == "__main__":
     make_aic()
     make_stats()
     make_guess()
+    make_cnv()
     make_meta()
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith((".npz", ".json")):
