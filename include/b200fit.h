@@ -248,13 +248,15 @@ int b200fit_masked_moments(b200fit_ctx* ctx, int32_t nchan, int64_t npix, const 
  *                             voxel itself is NaN or its pixel excluded (d_include [ny*nx] uint8, NULL = all
  *                             included: the output keeps the input's mask) or nothing finite lies under the kernel.  ksize odd, <= 65.  Kernel: separable (d_kx, d_ky [ksize], d_k2 NULL:
  *                             K(dy,dx) = ky[dy] kx[dx], a circular beam) or general (d_k2 [ksize*ksize] row-major,
- *                             d_kx = d_ky = NULL).  The kernel need not be normalised.  d_out != d_cube.
+ *                             d_kx = d_ky = NULL).  The kernel need not be normalised; kernel_sum = the sum of its
+ *                             K*K weights (sum(kx) * sum(ky)), the normalisation of a fully finite neighbourhood.
+ *                             d_out != d_cube.
  *   b200fit_resample_bilinear out(c, oy, ox) = bilinear interpolation of plane c at (y, x) = (ay oy + by, ax ox + bx)
  *                             (0-based pixel centres); edge replicated within half a pixel of the image, NaN beyond
  *                             and wherever one of the four neighbours is NaN. */
 int b200fit_convolve_planes(b200fit_ctx* ctx, const float* d_cube, int32_t nchan, int32_t ny, int32_t nx,
                             const unsigned char* d_include, int32_t ksize, const float* d_kx, const float* d_ky,
-                            const float* d_k2, float* d_out, void* stream);
+                            const float* d_k2, double kernel_sum, float* d_out, void* stream);
 int b200fit_resample_bilinear(b200fit_ctx* ctx, const float* d_in, int32_t nchan, int32_t ny, int32_t nx, float* d_out,
                               int32_t out_ny, int32_t out_nx, double ay, double by, double ax, double bx, void* stream);
 

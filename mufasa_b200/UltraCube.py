@@ -13,6 +13,7 @@ while every per-pixel computation is a kernel of libb200fit.so.  Differences tha
 """
 import gc
 import logging
+import os
 from collections.abc import Iterable
 from copy import copy
 
@@ -335,6 +336,47 @@ class UltraCube(object):
 
 
 # ======================================================================================================================
+class UCubePlus(UltraCube):
+    """UltraCube with the file bookkeeping of a run (UltraCube.py:642-773): parameter maps live in
+    ``{paraDir}/{paraNameRoot}_{n}vcomp.fits``."""
+
+    def __init__(self, cubefile, cube=None, fittype=None, paraNameRoot=None, paraDir=None, **kwargs):
+        super().__init__(cubefile, cube, fittype=fittype, **kwargs)
+        self.cubeDir = os.path.dirname(cubefile)
+        if paraNameRoot is None:
+            self.paraNameRoot = "{}_paramaps".format(os.path.splitext(os.path.basename(cubefile))[0])
+        else:
+            self.paraNameRoot = paraNameRoot
+        self.paraDir = "{}/para_maps".format(self.cubeDir) if paraDir is None else paraDir
+        if not os.path.exists(self.paraDir):
+            os.makedirs(self.paraDir)
+        self.paraPaths = {}
+
+    def _para_path(self, nc):
+        if str(nc) not in self.paraPaths:
+            self.paraPaths[str(nc)] = '{}/{}_{}vcomp.fits'.format(self.paraDir, self.paraNameRoot, nc)
+        return self.paraPaths[str(nc)]
+
+    def read_model_fit(self, ncomps, read_conv=False, **kwargs):
+        for nc in ncomps:
+            super().load_model_fit(self._para_path(nc), ncomp=nc, calc_model=False)
+
+    def get_model_fit(self, ncomp, update=True, **kwargs):
+        """Fit (``update``) and save, then load the saved maps back -- the reference's resume contract."""
+        if not isinstance(ncomp, Iterable):
+            ncomp = [ncomp]
+        for nc in ncomp:
+            self._para_path(nc)
+        if update:
+            for nc in ncomp:
+                if 'multicore' not in kwargs:
+                    kwargs['multicore'] = self.n_cores
+                self.fit_cube(ncomp=[nc], **kwargs)
+                self.save_fit(self.paraPaths[str(nc)], nc)
+        for nc in ncomp:
+            self.load_model_fit(self.paraPaths[str(nc)], nc)
+
+
 def fit_cube(cube, pcube, fittype, simpfit=False, **kwargs):
     """Module-level dispatcher (UltraCube.py:777-801)."""
     if simpfit:

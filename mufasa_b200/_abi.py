@@ -85,7 +85,7 @@ SIGNATURES = {
     "b200fit_masked_moments": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp,
                                          _vp]),
     "b200fit_resid_stats": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
-    "b200fit_convolve_planes": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "b200fit_convolve_planes": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, C.c_double, _vp, _vp]),
     "b200fit_resample_bilinear": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, C.c_double, C.c_double,
                                             C.c_double, C.c_double, _vp]),
 }

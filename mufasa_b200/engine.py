@@ -281,8 +281,9 @@ class Engine(object):
             assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda)
         if include is not None:
             assert include.dtype == torch.uint8 and include.is_contiguous() and include.numel() == ny * nx
+        ksum = float(k2.double().sum()) if k2 is not None else float(kx.double().sum()) * float(ky.double().sum())
         rc = self.lib.b200fit_convolve_planes(self.ctx, _ptr(cube_dev), nchan, ny, nx, _ptr(include), ksize, _ptr(kx),
-                                              _ptr(ky), _ptr(k2), _ptr(out), self._stream())
+                                              _ptr(ky), _ptr(k2), ksum, _ptr(out), self._stream())
         self._check(rc, "b200fit_convolve_planes")
         return out
 

@@ -192,3 +192,39 @@ def test_two_step_fit_through_the_convolved_cube(engine):
     assert good.sum() > 0.4 * ny * nx
     dv = np.abs(p.parcube[0][good] - truth[0][good])
     assert np.median(dv) < 0.02 and np.median(np.abs(p.parcube[1][good] - truth[1][good])) < 0.03
+
+
+def test_region_iter_2comp_fit_from_fits_files(engine, tmp_path):
+    """Region + iter_2comp_fit (master_fitter.py:65-126, :682-775) from a FITS cube on disk: convolved cube and its
+    1- / 2-component parameter maps are written next to it, the full-resolution fits start from guesses regridded
+    from them, everything is saved in the reference's ``{root}_{n}vcomp.fits`` layout and can be resumed."""
+    import os
+    from mufasa_b200 import master_fitter as mf
+    from mufasa_b200.utils import fits_io
+    ny, nx, nchan = 48, 48, 500
+    syn = synth.make_cube(3, T.oracle_modelcube, shape=(ny, nx, nchan))
+    sc = SpecCube(syn["cube"], syn["v"], rest_value=23.6944955e9, header=_header(ny, nx))
+    path = str(tmp_path / "field.fits")
+    sc.write(path)
+    reg = mf.Region(path, "field", paraDir=str(tmp_path / "paras"), fittype=syn["fittype"], device=0)
+    mf.iter_2comp_fit(reg, snr_min=3.0)
+    for f in ("field_conv2Xbeam.fits", "paras/field_conv2Xbeam_1vcomp.fits", "paras/field_conv2Xbeam_2vcomp.fits",
+              "paras/field_1vcomp.fits", "paras/field_2vcomp.fits"):
+        assert os.path.isfile(str(tmp_path / f)), f
+    data, hdr = fits_io.read(str(tmp_path / "paras/field_2vcomp.fits"))
+    assert data.shape == (16, ny, nx) and hdr.value("PLANE1") is not None
+    assert reg.ucube_cnv.cube.shape == (nchan, ny // 2, nx // 2)
+    p1, p2 = reg.ucube.pcubes["1"], reg.ucube.pcubes["2"]
+    assert p1.has_fit.sum() > 0.3 * ny * nx and p2.has_fit.sum() > 0.2 * ny * nx
+    one = p1.has_fit & (syn["ncomp_true"] == 1)
+    assert one.sum() > 100
+    assert np.median(np.abs(p1.parcube[0][one] - syn["truth1"][0][one])) < 0.03
+    # model selection on top of the two-step fits picks 2 components mostly where the truth has 2
+    reg.ucube.get_best_2c_parcube()
+    two_true = (syn["ncomp_true"] == 2) & p2.has_fit
+    if two_true.sum() > 50:
+        assert (reg.ucube.ncomp_map[two_true] == 2).mean() > (reg.ucube.ncomp_map[one] == 2).mean()
+    # resume: a second Region reads the saved maps instead of fitting
+    reg2 = mf.Region(path, "field", paraDir=str(tmp_path / "paras"), fittype=syn["fittype"], device=0)
+    reg2.ucube.get_model_fit([1, 2], update=False)
+    np.testing.assert_array_equal(reg2.ucube.pcubes["2"].parcube, p2.parcube)
