@@ -411,6 +411,7 @@ def run_b200(args):
                 "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": float(e2e_t.item()) * 1e3,
+                        "samples_ms": [round(t * 1e3, 2) for t in e2e_times],
                         "api": "UltraCube.fit_cube([1, 2], simpfit) + get_best_2c_parcube()"},
                 "gpu_launches": int(launches_timed),
                 "fit2c_only": {"value": npix / t2, "unit": UNIT, "ms": t2 * 1e3},

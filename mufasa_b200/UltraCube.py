@@ -14,6 +14,7 @@ while every per-pixel computation is a kernel of libb200fit.so.  Differences tha
 import gc
 import logging
 import os
+import weakref
 from collections.abc import Iterable
 from copy import copy
 
@@ -43,6 +44,7 @@ class UltraCube(object):
         self.lnk_maps = {}
         self.ncomp_map = None
         self._master_model_mask = None
+        self._aicc_eager = None
         self._mask_ncomps = []            # which fits feed the lazily built master_model_mask
         self.snr_min = 0.0
         self.cnv_factor = cnv_factor
@@ -91,7 +93,7 @@ class UltraCube(object):
         self.cube_cnv = cnvtool.convolve_sky_byfactor(self.cube, factor, savename, edgetrim_width=edgetrim_width,
                                                       device=self.device)
 
-    def fit_cube(self, ncomp, simpfit=False, concurrent=True, **kwargs):
+    def fit_cube(self, ncomp, simpfit=False, concurrent=True, eager_aicc=True, **kwargs):
         """UltraCube.py:272-326.  With several ``ncomp`` the reference fits them one after the other; here the host
         drivers still run in that order, but the GPU fits are launched together (``concurrent``; Engine.fit_batch)
         so the slow tail of one fit overlaps the other.  Results are identical to sequential fits."""
@@ -116,16 +118,56 @@ class UltraCube(object):
             self.pcubes[str(nc)] = fit_cube(self.cube, self.pcubes[str(nc)], fittype=self.fittype, simpfit=simpfit,
                                             ncomp=nc, **kw)
             self.pcubes[str(nc)]._deferred = None
+        eager = None
         if batch:
             eng = batch[0]["pcube"].engine
             outs = eng.fit_batch(batch)
-            for job, out in zip(batch, outs):
-                job["pcube"].finish_fit(job, out)
+            # the model selection needs nothing from the host: queue it right behind the fits, on the parameters as
+            # they lie on the device, and bring the fit results back on a second stream meanwhile
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(eng.device))
+            if eager_aicc:
+                eager = self._launch_eager_aicc(batch, outs, eng)
+            if not hasattr(eng, "_side_stream"):
+                eng._side_stream = torch.cuda.Stream(device=eng.device)
+            with torch.cuda.stream(eng._side_stream):
+                eng._side_stream.wait_event(done)
+                for job, out in zip(batch, outs):           # both copies in flight before the first host wait
+                    job["pcube"].start_fit_readback(job, out)
+                for job, out in zip(batch, outs):
+                    job["pcube"].finish_fit(job, out)
         for nc in ncomp:
             p = self.pcubes[str(nc)]
             if p.has_fit.sum() > 0 and p.parcube is not None:
                 self._include_fit_in_mask(nc)
             self._invalidate_stats()
+        self._aicc_eager = eager
+
+    def _launch_eager_aicc(self, batch, outs, eng, expand=20, thr=(5.0, 5.0, 5.0)):
+        """AICc 0/1/2 selection of a batched 1- + 2-component fit, launched asynchronously on the device-resident fit
+        output (the same arrays ``_params_dev`` would rebuild from parcube: zeros where there is no fit).  Returns
+        (key, device result dict) for ``_run_aicc`` or None when the batch is not that pair."""
+        by_nc = {int(job["prob"].ncomp): (job, out) for job, out in zip(batch, outs)}
+        if set(by_nc) != {1, 2} or self.dist is not None:
+            return None
+        ref = batch[0]["pcube"]
+        ny, nx = self.cube.shape[1:]
+        pars = {}
+        for nc, (job, out) in by_nc.items():
+            if job["row_index"] is None:
+                pars[nc] = out["params"]
+            else:
+                full = torch.zeros((ny * nx, 4 * nc), dtype=torch.float64, device=eng.device)
+                full[job["row_index"]] = out["params"]
+                pars[nc] = full
+        prob = ref._problem(self.fittype, 1, ny * nx, [-1e30] * 4, [1e30] * 4)
+        model_f32 = self.cube._data.dtype == np.float32
+        out = eng.aicc_global(prob, ref.rows_on_device(), pars[1], pars[2], expand=expand, model_f32=model_f32, thr=thr)
+        out["host_stage"] = self._aicc_to_host(out, eng)
+        eng._aicc_stage_owner = weakref.ref(self)   # the pinned buffer is shared: a later selection takes it over
+        out["host_ready"] = torch.cuda.Event()
+        out["host_ready"].record(torch.cuda.current_stream(eng.device))
+        return (int(expand), tuple(float(t) for t in thr)), out, pars
 
     # ---- on-disk contract (SURVEY.md 8f #2) ------------------------------------------------------------------
     def save_fit(self, savename, ncomp, header_note=None):
@@ -151,6 +193,7 @@ class UltraCube(object):
                   self.rchisq_maps):
             d.clear()
         self.ncomp_map = None
+        self._aicc_eager = None        # a selection queued behind an earlier fit no longer describes the fits
 
     def has_fit(self, ncomp):
         """UltraCube.py:328-348."""
@@ -202,6 +245,14 @@ class UltraCube(object):
             par = np.zeros((ny * nx, P))
         return torch.from_numpy(par).to(eng.device, non_blocking=True)
 
+    @staticmethod
+    def _aicc_to_host(out, eng):
+        packed_d = torch.cat([out["rss"], out["nsamp"][:, None], out["lnk"], out["ncomp"].to(torch.float64)[:, None]],
+                             dim=1).t().contiguous()
+        stage = eng.pinned_stage(("aicc",) + tuple(packed_d.shape))
+        stage.copy_(packed_d, non_blocking=True)
+        return stage
+
     def _run_aicc(self, expand=20, thr=(5.0, 5.0, 5.0)):
         key = (int(expand), tuple(float(t) for t in thr))
         if self.lnk_maps.get("_key") == key:
@@ -209,20 +260,37 @@ class UltraCube(object):
         ref = self._ref_pcube if self._ref_pcube is not None else self.load_pcube()
         eng = ref.engine
         ny, nx = self.cube.shape[1:]
+        eager, self._aicc_eager = getattr(self, "_aicc_eager", None), None
+        if eager is not None and eager[0] == key:
+            out = eager[1]              # already computed behind the batched fit (fit_cube)
+        else:
+            out = None
         rows = ref.rows_on_device()
         prob = ref._problem(self.fittype, 1, ny * nx, [-1e30] * 4, [1e30] * 4)
-        p1 = self._params_dev(1, eng)
-        p2 = self._params_dev(2, eng)
         model_f32 = self.cube._data.dtype == np.float32
-        if self.dist is None:
+        if out is not None:
+            pass
+        elif self.dist is None:
+            p1 = self._params_dev(1, eng)
+            p2 = self._params_dev(2, eng)
             out = eng.aicc_global(prob, rows, p1, p2, expand=expand, model_f32=model_f32, thr=thr)
         else:       # row slab of a partitioned cube: the include_nosamp fill mask is global (dist.py)
             from . import dist as D
+            p1 = self._params_dev(1, eng)
+            p2 = self._params_dev(2, eng)
             out = D.aicc_distributed(eng, prob, rows, p1, p2, first_pixel=self.dist[1], expand=expand,
                                      model_f32=model_f32, thr=thr, group=self.dist[0])
-        # one field-major D2H copy: rss0..2, nsamp, lnk10/20/21, ncomp
-        packed = torch.cat([out["rss"], out["nsamp"][:, None], out["lnk"], out["ncomp"].to(torch.float64)[:, None]],
-                           dim=1).t().contiguous().cpu().numpy()
+        # one field-major D2H copy through a pinned buffer: rss0..2, nsamp, lnk10/20/21, ncomp
+        owner = getattr(eng, "_aicc_stage_owner", None)
+        if out.get("host_stage") is not None and owner is not None and owner() is self:
+            out["host_ready"].synchronize()         # the eager path started the copy right behind the kernels
+            packed = out["host_stage"].numpy()
+            eng._aicc_stage_owner = None
+        else:
+            eng._aicc_stage_owner = None
+            packed = self._aicc_to_host(out, eng)
+            torch.cuda.current_stream(eng.device).synchronize()
+            packed = packed.numpy()
         rss = packed[0:3].reshape(3, ny, nx)
         nsamp = packed[3].reshape(ny, nx)
         lnk = packed[4:7].reshape(3, ny, nx)

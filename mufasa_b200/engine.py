@@ -65,11 +65,11 @@ class Engine(object):
     def pinned_stage(self, shape, dtype=torch.float64):
         """Pinned host staging buffer for D2H copies, cached per shape (page-locking costs ~10 ms per call)."""
         cache = self.__dict__.setdefault("_pinned", {})
-        key = (tuple(shape), dtype)
+        key = (tuple(shape), dtype)         # a leading string in ``shape`` names a separate buffer of that shape
         if key not in cache:
             if len(cache) > 16:
                 cache.clear()
-            cache[key] = torch.empty(shape, dtype=dtype).pin_memory()
+            cache[key] = torch.empty([d for d in shape if not isinstance(d, str)], dtype=dtype).pin_memory()
         return cache[key]
 
     @staticmethod

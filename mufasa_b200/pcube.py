@@ -249,19 +249,27 @@ class PCube(object):
         out = eng.fit(prob, rows, g_dev, row_index=idx_dev)
         self.finish_fit(job, out)
 
-    def finish_fit(self, job, out):
-        """Copy the results of a (possibly batched) fit back into parcube / errcube / has_fit ..."""
-        pix = job["pix"]
-        P = self.npars
-        ny, nx = self.has_fit.shape
-        # one device-side transpose to field-major [2P + 4, npix], one D2H copy through a pinned buffer, then
-        # contiguous row copies into the maps
+    def start_fit_readback(self, job, out):
+        """Queue the D2H copy of a fit's results on the current stream (no host synchronisation): one device-side
+        transpose to field-major [2P + 4, npix], one copy into a pinned buffer."""
         packed_d = torch.cat([out["params"], out["perr"], out["chi2"][:, None], out["err_used"][:, None],
                               out["status"].to(torch.float64)[:, None],
                               out["counts"][:, 0].to(torch.float64)[:, None]], dim=1).t().contiguous()
         stage = self.engine.pinned_stage(tuple(packed_d.shape))   # pinned staging buffers live with the engine
         stage.copy_(packed_d, non_blocking=True)
-        torch.cuda.current_stream(packed_d.device).synchronize()
+        job["host_stage"] = stage
+        return stage
+
+    def finish_fit(self, job, out):
+        """Copy the results of a (possibly batched) fit back into parcube / errcube / has_fit ..."""
+        pix = job["pix"]
+        P = self.npars
+        ny, nx = self.has_fit.shape
+        # readback (start_fit_readback), then contiguous row copies into the maps
+        stage = job.get("host_stage")
+        if stage is None:
+            stage = self.start_fit_readback(job, out)
+        torch.cuda.current_stream(out["params"].device).synchronize()
         packed = stage.numpy()
         flat = lambda a: a.reshape(a.shape[0], ny * nx) if a.ndim == 3 else a.reshape(ny * nx)
         if pix.size == ny * nx:

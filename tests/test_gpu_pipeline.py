@@ -201,3 +201,23 @@ def test_dist_fit_and_select_single_rank_matches_ultracube():
     assert np.array_equal(res["best_parcube"], par, equal_nan=True)
     assert np.array_equal(res["lnk21"], l21, equal_nan=True)
     assert np.array_equal(res["ncomp"].astype(np.int8), uc.ncomp_map)
+
+
+def test_eager_selection_survives_interleaved_cubes():
+    """fit_cube([1, 2]) queues the AICc selection and its read-back behind the fits (a pinned buffer shared per
+    engine).  Fitting a second cube before asking the first for its maps must not mix the two."""
+    syn_a = synth.make_cube(2, T.oracle_modelcube, shape=(12, 16, 800))
+    syn_b = synth.make_cube(2, T.oracle_modelcube, shape=(12, 16, 800), seed_offset=3)
+    def run(syn, eager):
+        uc = _ucube(syn)
+        uc.fit_cube(ncomp=[1, 2], simpfit=True, eager_aicc=eager,
+                    guesses={1: syn["guess1"].copy(), 2: syn["guess2"].copy()})
+        return uc
+    ref_a = run(syn_a, False).get_best_2c_parcube()
+    ua = run(syn_a, True)
+    ub = run(syn_b, True)                       # takes over the shared staging buffer
+    got_a = ua.get_best_2c_parcube()
+    got_b = ub.get_best_2c_parcube()
+    for x, y in zip(got_a, ref_a):
+        np.testing.assert_array_equal(x, y)
+    assert not np.array_equal(got_b[2], got_a[2], equal_nan=True)
