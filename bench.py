@@ -48,6 +48,9 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
 
 
+NCU_DRAM_BYTES_PER_EVAL = (166.019072e6 + 19.493888e6) / 65536.0   # profiles/r1m_fit2c_ncu_full_summary.txt
+
+
 class ClockSampler(object):
     """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md).  NVML is polled from a thread
     (nvidia_ml_py); a polling `nvidia-smi -lms` process takes the driver lock for milliseconds per query and slows a
@@ -379,7 +382,11 @@ def run_b200(args):
     t2 = (prof2["prologue_ms"] + prof2["eval_ms"] + prof2["solve_ms"]) * 1e-3   # seconds per 2c fit run on its own
     roofline = {"bound": bound, "kernel": "fit_eval_kernel<2>", "achieved": ach[bound] / 1e12,
                 "peak": pk[bound] / 1e12, "unit": "TFLOP/s" if bound != "xu" else "Top/s", "frac": frac[bound],
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch with all 65 536 pixels active (ncu --set
+                # full, profiles/r1m_fit2c_ncu_full_summary.txt: 166.0 + 19.5 MB = 2831 B per pixel-evaluation: the
+                # windowed part of the spectrum + the per-pixel LM state), scaled to the average launch of this run
+                "traffic": NCU_DRAM_BYTES_PER_EVAL * evals / launches_eval,
+                "traffic_source": "ncu capture r1m (2831 B per pixel-evaluation) x evaluations per launch of this run",
                 "definition": "ALGORITHMIC work (SURVEY 8d per-evaluation figures x evaluations counted by the kernel) "
                               "/ summed CUDA-event duration of the kernel's launches in one 2c fit; the kernel skips "
                               "gaussians beyond 6.2 sigma (exactly 0 in fp32), see frac_executed",
