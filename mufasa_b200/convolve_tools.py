@@ -9,7 +9,8 @@ restated in oracle/convolve.py.
 """
 import numpy as np
 import torch
-from scipy.interpolate import griddata
+from scipy.interpolate import CloughTocher2DInterpolator, griddata
+from scipy.spatial import Delaunay
 
 from . import signals
 from .cube import SpecCube
@@ -211,3 +212,29 @@ def regrid(image, header1, header2, dmask=None, method='cubic'):
         dmask = np.ones(grid1[0].shape, dtype=bool)
     return griddata((X[mask], Y[mask]), image[mask], (grid1[1] * dmask, grid1[0] * dmask), method=method,
                     fill_value=np.nan)
+
+
+def regrid_many(images, header1, header2, method='cubic'):
+    """``regrid`` of several maps [k, ny, nx] at once, with results identical to k separate calls: maps that share
+    their finite footprint share one Delaunay triangulation and one point location (the triangulation is 60 % of a
+    cubic griddata call on a 256 x 256 map, the point location most of the rest)."""
+    images = np.asarray(images)
+    if method != 'cubic':
+        return np.array([regrid(im, header1, header2, method=method) for im in images])
+    grid1 = get_pixel_mapping(header1, header2)
+    X, Y = np.meshgrid(np.arange(images.shape[2]), np.arange(images.shape[1]))
+    out = np.empty((images.shape[0],) + grid1[0].shape)
+    finite = np.isfinite(images)
+    done = np.zeros(images.shape[0], bool)
+    for k in range(images.shape[0]):
+        if done[k]:
+            continue
+        same = [j for j in range(k, images.shape[0]) if not done[j] and np.array_equal(finite[j], finite[k])]
+        m = finite[k]
+        tri = Delaunay(np.column_stack([X[m], Y[m]]))
+        ip = CloughTocher2DInterpolator(tri, np.stack([images[j][m] for j in same], axis=1), fill_value=np.nan)
+        res = ip(grid1[1], grid1[0])
+        for i, j in enumerate(same):
+            out[j] = res[..., i]
+            done[j] = True
+    return out

@@ -139,7 +139,7 @@ def refine_each_comp(guess_comp, mask=None, v_range=None, sig_range=None, tau_th
 def guess_from_cnvpara(data_cnv, header_cnv, header_target, mask=None, tau_thresh=1, clean_map=True):
     """Guesses [4 ncomp, ny, nx] on the grid of ``header_target`` from the parameter + error maps
     [8 ncomp, ny_c, nx_c] fitted to the convolved cube."""
-    from .convolve_tools import get_celestial_hdr, regrid
+    from .convolve_tools import get_celestial_hdr, regrid_many
     npara = 4
     ncomp = int(data_cnv.shape[0] / npara / 2)
     data_cnv = data_cnv.copy()
@@ -155,11 +155,11 @@ def guess_from_cnvpara(data_cnv, header_cnv, header_target, mask=None, tau_thres
                                                                tau_thresh=tau_thresh)
     hdr_conv, hdr_final = get_celestial_hdr(header_cnv), get_celestial_hdr(header_target)
     newmask = signals.remove_small_holes(np.any(np.isfinite(data_cnv), axis=0), 25)
+    # per map: fill the footprint, regrid (cubic griddata), grow the footprint back by two pixels.  The regridding
+    # of all maps shares one triangulation (convolve_tools.regrid_many; same values as map-by-map calls)
+    filled = np.array([interpolate.iter_expand(gss, mask=newmask) for gss in data_cnv])
     guesses_final = []
-    for gss in data_cnv:
-        g = interpolate.iter_expand(gss, mask=newmask)
-        g = regrid(g, hdr_conv, hdr_final, dmask=None)
-        # regridding can shrink the footprint: grow it back by two pixels
+    for g in regrid_many(filled, hdr_conv, hdr_final):
         mask_l = signals.binary_dilation(np.isfinite(g), signals.disk(2))
         guesses_final.append(interpolate.iter_expand(g, mask=mask_l))
     return np.array(guesses_final)

@@ -181,3 +181,19 @@ def test_guess_from_cnvpara_fills_the_target_grid():
     row = g[0, 16, 10:26]
     assert np.allclose(np.diff(row), 0.025, atol=5e-3)
     assert np.nanmax(np.abs(g[1][fine] - 0.3)) < 1e-6 and np.nanmax(np.abs(g[2][fine] - 6.0)) < 1e-6
+
+
+def test_regrid_many_equals_map_by_map_regrid():
+    from mufasa_b200.convolve_tools import regrid, regrid_many
+    rng = np.random.default_rng(9)
+    ny, nx = 20, 24
+    maps = rng.normal(size=(5, ny, nx))
+    yy, xx = np.mgrid[:ny, :nx]
+    maps[:, (yy - 10) ** 2 + (xx - 12) ** 2 > 81] = np.nan
+    maps[3:, 5, 5] = np.nan                              # two maps with a different footprint
+    h = {"NAXIS1": 2 * nx, "NAXIS2": 2 * ny, "CRPIX1": 24.0, "CRPIX2": 20.0, "CDELT1": -0.002, "CDELT2": 0.002,
+         "CTYPE1": "RA---TAN", "CTYPE2": "DEC--TAN", "CRVAL1": 52.0, "CRVAL2": 31.0}
+    hc, _ = oc.downsample_map(h, 2)
+    many = regrid_many(maps, hc, h)
+    for k in range(5):
+        np.testing.assert_array_equal(many[k], regrid(maps[k], hc, h))
