@@ -105,6 +105,7 @@ class UltraCube(object):
             ncomp = [ncomp]
         ncomp = list(ncomp)
         batch = [] if (concurrent and len(ncomp) > 1) else None
+        pending = []
         for nc in ncomp:
             if self.pcubes:
                 _, pcube_ref = next(iter(self.pcubes.items()))
@@ -115,8 +116,19 @@ class UltraCube(object):
             kw = dict(kwargs)
             if isinstance(kw.get('guesses'), dict):          # per-ncomp guesses for a batched call
                 kw['guesses'] = kw['guesses'].get(nc)
+            if simpfit and batch is not None:
+                # first half of every driver (host work on the guesses) while the cube is still uploading; the
+                # halves that need the device follow below
+                steps = mvf.cubefit_simp_steps(self.cube, self.pcubes[str(nc)], fittype=self.fittype, ncomp=nc, **kw)
+                next(steps)
+                pending.append((nc, steps))
+                continue
             self.pcubes[str(nc)] = fit_cube(self.cube, self.pcubes[str(nc)], fittype=self.fittype, simpfit=simpfit,
                                             ncomp=nc, **kw)
+            self.pcubes[str(nc)]._deferred = None
+        for nc, steps in pending:
+            for _ in steps:
+                pass
             self.pcubes[str(nc)]._deferred = None
         eager = None
         if batch:

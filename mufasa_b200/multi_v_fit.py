@@ -143,6 +143,17 @@ def cubefit_simp(cube, pcube, ncomp, guesses, multicore=None, maskmap=None, fitt
                  **kwargs):
     """multi_v_fit.py:126-208.  Mutates ``guesses`` in place exactly like the reference (zero velocities -> NaN,
     clamps with +-eps)."""
+    for _ in cubefit_simp_steps(cube, pcube, ncomp, guesses, multicore=multicore, maskmap=maskmap, fittype=fittype,
+                                snr_min=snr_min, **kwargs):
+        pass
+    return pcube
+
+
+def cubefit_simp_steps(cube, pcube, ncomp, guesses, multicore=None, maskmap=None, fittype='nh3_multi_v', snr_min=None,
+                       **kwargs):
+    """``cubefit_simp`` as a two-step generator: everything up to the ``yield`` is host work on the guesses that does
+    not need the cube on the device; the rest (footprint, pixel selection, the fit) does.  A caller preparing several
+    fits of one cube runs the first half of all of them while the cube is still uploading (UltraCube.fit_cube)."""
     mod_info = MetaModel(fittype, ncomp)
     Texmin, Texmax = mod_info.Texmin, mod_info.Texmax
     sigmin, sigmax = mod_info.sigmin, mod_info.sigmax
@@ -183,6 +194,7 @@ def cubefit_simp(cube, pcube, ncomp, guesses, multicore=None, maskmap=None, fitt
     impose_lim(guesses[1::4], sigmin, sigmax, eps)
     impose_lim(guesses[2::4], Texmin, Texmax, eps)
     impose_lim(guesses[3::4], taumin, taumax, eps)
+    yield
 
     # (the reference builds the footprint first, multi_v_fit.py:150; nothing above depends on it)
     footprint_mask = pcube.footprint() if hasattr(pcube, "footprint") else np.any(np.isfinite(data), axis=0)
@@ -203,7 +215,7 @@ def cubefit_simp(cube, pcube, ncomp, guesses, multicore=None, maskmap=None, fitt
     kwargs.setdefault('verbose', False)
 
     pcube.fiteach(fittype=fittype, guesses=guesses, **kwargs)
-    return pcube
+    yield
 
 
 def cubefit_gen(cube, pcube, ncomp=2, paraname=None, modname=None, chisqname=None, guesses=None, errmap11name=None,
