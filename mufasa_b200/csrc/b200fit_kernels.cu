@@ -79,6 +79,13 @@ struct FitQueues {               // head of the workspace
 };
 
 constexpr int EVAL_WARPS = 4;    // warps per block, evaluation / prologue kernels
+// From this round on a block (not a warp) evaluates a pixel (fit_eval_kernel).  A team spends ~1.8x the warp-time of
+// a single warp on a pixel (set-up, reduction and barriers do not shrink), so it pays once a round holds fewer
+// pixels than warp slots / 4: measured on 65 536 NH3 spectra, round 96 for 1 component (evaluation 8.6 -> 7.5 ms),
+// while 2-component fits keep ~3000 pixels (the ones running to maxiter) until round ~200, where teams from round
+// 96 cost +4 %; they switch only for the final stretch.
+template <int NC>
+constexpr int fit_team_round() { return NC == 1 ? 96 : 288; }
 constexpr int SOLVE_THREADS = 64;
 
 // ---- packed fp32 pairs --------------------------------------------------------------------------------------
@@ -248,11 +255,20 @@ struct LineGroups<B200FIT_MODEL_N2HP_10> {  // -8.0 (1) | -0.6 .. 1.0 (3) | 5.5 
     __host__ __device__ static constexpr int start(int g) { return g == 0 ? 0 : g == 1 ? 1 : g == 2 ? 4 : 7; }
 };
 
-template <int NC, int MODEL>
+//
+// TEAM = warps per pixel.  TEAM = 1: a warp owns a pixel.  TEAM = EVAL_WARPS: a block owns a pixel and its warps take
+// the active chunks round-robin -- a quarter of the evaluation latency, which is what the late rounds of a fit are
+// made of (a few thousand pixels crawling to maxiter; profiles/r1m launch list).  The two variants sum the fp32
+// per-lane accumulators in different groupings, so WHICH one evaluates a pixel must not depend on what else is being
+// fitted: the host switches at a fixed round number (fit_team_round<NC>()), and since every active pixel is evaluated
+// exactly once per round that is a function of the pixel's own evaluation count -- results stay independent of
+// how the pixels are partitioned over calls or GPUs.
+template <int NC, int MODEL, int TEAM>
 __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)   // measured: 96 regs help 1c, hurt 2c
     fit_eval_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
                     const long long* __restrict__ row_index, PixState<4 * NC>* __restrict__ states,
                     const unsigned* __restrict__ list, FitQueues* __restrict__ fq, int cur) {
+    static_assert(TEAM == 1 || TEAM == EVAL_WARPS, "a pixel belongs to one warp or to one block");
     constexpr int P = 4 * NC;
     constexpr int NH = P * (P + 1) / 2;
     constexpr int NACC = NH + P + 1;
@@ -261,29 +277,32 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)   // measu
     constexpr int NG = LG::NG;
     __shared__ FitTables tb;
     __shared__ EvalScratch<NC> scratch[EVAL_WARPS];
+    __shared__ double part[(TEAM > 1) ? EVAL_WARPS : 1][NACC + 2];   // per-warp partial sums of a team
     load_fit_tables(pr, tb);
-    const int lane = threadIdx.x & 31;
-    EvalScratch<NC>& w = scratch[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    EvalScratch<NC>& w = scratch[(TEAM > 1) ? 0 : warp];   // line records: per warp, or shared by the team
+    EvalScratch<NC>& wr = scratch[warp];                    // reduction tile: always per warp
     const unsigned count = fq->count[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) fq->count[cur ^ 1] = 0;   // the list this round's solver appends to
-    const unsigned warp0 = blockIdx.x * EVAL_WARPS + (threadIdx.x >> 5);
-    const unsigned nwarps = gridDim.x * EVAL_WARPS;
+    const unsigned unit0 = (TEAM > 1) ? blockIdx.x : blockIdx.x * EVAL_WARPS + warp;
+    const unsigned nunits = (TEAM > 1) ? gridDim.x : gridDim.x * EVAL_WARPS;
     const int nhf = pr.nhf;
     const int nchunks = (pr.nchan + 31) >> 5;
     const int nhalf = (nchunks > 32) ? 2 : 1;
     const float ic0 = (float)pr.ic0;
 
-    for (unsigned idx = warp0; idx < count; idx += nwarps) {
+    for (unsigned idx = unit0; idx < count; idx += nunits) {
         const long long px = list[idx];
         PixState<P>& ps = states[px];
         const long long row = row_index ? row_index[px] : px;
         const float* __restrict__ spec = spectra + row * stride;
-        // 1. fp64 line set-up, one line per lane
+        // 1. fp64 line set-up, one line per lane (a team: one component per warp)
         if (lane < nhf) {
             const double c1 = tb.c1mrho[lane], rho = tb.rho[lane], kdv = tb.kdv[lane];
             const float lw = tb.lw[lane];
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
+                if (TEAM > 1 && c != warp) continue;
                 LineCoef lc;
                 float lo, hi;
                 line_coef(c1, rho, kdv, lw, pr.v0, pr.inv_dv, ps.st.pt[4 * c], ps.inv_sigma[c], lc, lo, hi);
@@ -295,7 +314,10 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)   // measu
         CompCoef cc[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) cc[c] = ps.cc[c];
-        __syncwarp();
+        if (TEAM > 1)
+            __syncthreads();
+        else
+            __syncwarp();
         // 2. which line groups reach chunk `lane` (and chunk `lane + 32`): bit 8c + g
         unsigned packed[2] = {0u, 0u};
         unsigned my_lines = 0;   // gaussians this lane's chunks will cost (roofline accounting)
@@ -332,10 +354,17 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)   // measu
         for (int k = 0; k < PH; ++k) b2[k] = 0ull;
         unsigned n_chunks = 0;
 
+        int ordinal = 0;   // running index of the active chunks of this pixel (a team deals them round-robin)
 #pragma unroll 1
         for (int h = 0; h < nhalf; ++h) {
             const unsigned mypk = h ? packed[1] : packed[0];
             unsigned act = __ballot_sync(FULL, mypk != 0u);
+            if (TEAM > 1) {
+                unsigned mine = 0u;
+                for (unsigned a = act; a; a &= a - 1u)
+                    if ((ordinal++ & (TEAM - 1)) == warp) mine |= a & (0u - a);
+                act = mine;
+            }
             int jn = act ? (__ffs(act) - 1) : 0;
             float ynext = act ? __ldg(spec + (((jn + 32 * h) << 5) + lane)) : 0.f;
             while (act) {
@@ -419,20 +448,22 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)   // measu
         for (int base = 0; base < NACC; base += RR) {
 #pragma unroll
             for (int e = 0; e < RR; ++e)
-                if (base + e < NACC) w.red[e][lane] = acc[base + e];
+                if (base + e < NACC) wr.red[e][lane] = acc[base + e];
             __syncwarp();
             const int e = base + lane;
             if (lane < RR && e < NACC) {
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
                 for (int m = 0; m < 32; m += 4) {
-                    s0 += (double)w.red[lane][m];
-                    s1 += (double)w.red[lane][m + 1];
-                    s2 += (double)w.red[lane][m + 2];
-                    s3 += (double)w.red[lane][m + 3];
+                    s0 += (double)wr.red[lane][m];
+                    s1 += (double)wr.red[lane][m + 1];
+                    s2 += (double)wr.red[lane][m + 2];
+                    s3 += (double)wr.red[lane][m + 3];
                 }
                 const double s = (s0 + s1) + (s2 + s3);
-                if (e < NH)
+                if (TEAM > 1)
+                    part[warp][e] = s;
+                else if (e < NH)
                     ps.st.Ht[e] = s;
                 else if (e < NH + P)
                     ps.st.bt[e - NH] = s;
@@ -442,7 +473,31 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)   // measu
             __syncwarp();
         }
         const unsigned n_gauss = (unsigned)warp_sum_i((int)my_lines);
-        if (lane == 0) {
+        if (TEAM > 1) {
+            // every warp computed the same chunk masks, so n_gauss is already the pixel's; chunks were shared out
+            if (lane == 0) part[warp][NACC] = (double)n_chunks;
+            __syncthreads();
+            if (warp == 0) {
+                for (int e = lane; e < NACC; e += 32) {
+                    double s = part[0][e];
+#pragma unroll
+                    for (int t = 1; t < TEAM; ++t) s += part[t][e];
+                    if (e < NH)
+                        ps.st.Ht[e] = s;
+                    else if (e < NH + P)
+                        ps.st.bt[e - NH] = s;
+                    else
+                        ps.st.chi2t = ps.sumsq + s;
+                }
+                if (lane == 0) {
+                    double nc = 0.0;
+#pragma unroll
+                    for (int t = 0; t < TEAM; ++t) nc += part[t][NACC];
+                    ps.n_gauss += n_gauss;
+                    ps.n_chunks += (unsigned)nc;
+                }
+            }
+        } else if (lane == 0) {
             ps.n_gauss += n_gauss;
             ps.n_chunks += n_chunks;
         }
@@ -1227,7 +1282,7 @@ struct FitJob {
     unsigned* lists[2] = {nullptr, nullptr};
     void* states = nullptr;
     cudaStream_t stream = nullptr;
-    unsigned egrid = 0, sgrid = 0;
+    unsigned egrid = 0, egrid_team = 0, sgrid = 0;
     int r = 0, max_rounds = 0, nchecks = 0, slot0 = 0;
     bool finished = false, prof = false;
 };
@@ -1278,19 +1333,22 @@ static int job_begin(b200fit_ctx* ctx, FitJob& jb, void* d_workspace) {
     }
     int eval_per_sm = 0;
     if (jb.model_id == B200FIT_MODEL_NH3_11)
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC, B200FIT_MODEL_NH3_11>,
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, 1>,
                                                          EVAL_WARPS * 32, 0));
     else
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10>,
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, 1>,
                                                          EVAL_WARPS * 32, 0));
     if (eval_per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit_eval_kernel does not fit on an SM");
     long long egrid = (long long)ctx->num_sms * eval_per_sm;        // a whole number of CTAs per SM
+    long long egrid_team = egrid;                                    // block-per-pixel rounds: same launch bounds
+    if (egrid_team > pr.npix) egrid_team = pr.npix;
     if (egrid > pwarps) egrid = pwarps;
     const long long sgroups = SOLVE_THREADS / P;                     // pixels per solver block and pass
     const long long sblocks = (pr.npix + sgroups - 1) / sgroups;
     long long sgrid = (long long)ctx->num_sms * 32;
     if (sgrid > sblocks) sgrid = sblocks;
     jb.egrid = (unsigned)egrid;
+    jb.egrid_team = (unsigned)egrid_team;
     jb.sgrid = (unsigned)sgrid;
     jb.max_rounds = 2 * pr.max_iter + 3;
     jb.r = 0;
@@ -1304,12 +1362,15 @@ static int job_round(b200fit_ctx* ctx, FitJob& jb) {
     constexpr int P = 4 * NC;
     cudaStream_t stream = jb.stream;
     const int r = jb.r, cur = r & 1;
-    if (jb.model_id == B200FIT_MODEL_NH3_11)
-        fit_eval_kernel<NC, B200FIT_MODEL_NH3_11><<<jb.egrid, EVAL_WARPS * 32, 0, stream>>>(
-            jb.pr, jb.d_spectra, jb.stride, jb.d_row_index, (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
-    else
-        fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10><<<jb.egrid, EVAL_WARPS * 32, 0, stream>>>(
-            jb.pr, jb.d_spectra, jb.stride, jb.d_row_index, (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
+    // late rounds: a block per pixel (see fit_eval_kernel); a function of the round only
+    const bool team = r >= fit_team_round<NC>();
+    auto* ek = (jb.model_id == B200FIT_MODEL_NH3_11)
+                   ? (team ? fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, EVAL_WARPS>
+                           : fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, 1>)
+                   : (team ? fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, EVAL_WARPS>
+                           : fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, 1>);
+    ek<<<team ? jb.egrid_team : jb.egrid, EVAL_WARPS * 32, 0, stream>>>(jb.pr, jb.d_spectra, jb.stride, jb.d_row_index,
+                                                 (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
     if (jb.prof) ctx->next_event(stream);   // [2 + 2r] after the evaluation of round r
     fit_solve_kernel<NC><<<jb.sgrid, SOLVE_THREADS, 0, stream>>>(jb.pr, (PixState<P>*)jb.states, jb.lists[cur],
                                                                  jb.lists[cur ^ 1], jb.fq, cur, jb.d_params, jb.d_perr,
