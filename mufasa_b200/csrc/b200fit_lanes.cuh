@@ -141,8 +141,9 @@ __device__ __forceinline__ double lane_dnorm(const LaneGroup<P>& g, double dg, d
     return sqrt(g.sum(t * t));
 }
 
-// Right-looking Cholesky of A = H_free + par*diag^2 (fixed rows/cols -> identity).  Lane i ends up with row i of
-// L in lrow[0..i] and 1/L_ii in linv.  Returns false (group-uniform) if A is not numerically positive definite.
+// Right-looking Cholesky of A = H_free + par*diag^2 (fixed rows/cols -> identity).  Lane i ends up with the
+// strictly lower part of row i of L in lrow[0..i-1] (zeros from the diagonal on, which lets the triangular solves
+// run without per-lane conditions) and 1/L_ii in linv.  Returns false (group-uniform) if A is not numerically positive definite.
 template <int P>
 __device__ __forceinline__ bool lane_chol(const LaneGroup<P>& g, const double (&H)[P], double diag, double par,
                                           unsigned fixed, double (&lrow)[P], double& linv) {
@@ -164,15 +165,15 @@ __device__ __forceinline__ bool lane_chol(const LaneGroup<P>& g, const double (&
     linv = 0.0;
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-        double d = g.bcast(a[j], j);             // updated diagonal, held by lane j
-        const double d0 = g.bcast(dorig, j);
-        if (!(d > 1e-14 * d0)) {                 // rank deficient in this direction
-            ok = false;
-            d = (d0 > 0.0) ? d0 : 1.0;
-        }
+        // the pivot test runs on every lane's own (a[j], dorig) -- only lane j's is the diagonal -- so that one
+        // broadcast and one vote replace two broadcasts
+        const bool good = a[j] > 1e-14 * dorig;  // false: rank deficient in this direction
+        const double dj = good ? a[j] : ((dorig > 0.0) ? dorig : 1.0);
+        const double d = g.bcast(dj, j);         // (repaired) updated diagonal, held by lane j
+        const unsigned votes = g.ballot(good);   // unconditionally: a collective must not sit behind ``ok &&``
+        ok = ok && ((votes >> j) & 1u);
         const double inv = rsqrt(d);             // 1 / L_jj  (rsqrt + one multiply instead of sqrt + divide)
-        const double s = d * inv;
-        const double l = (i > j) ? a[j] * inv : ((i == j) ? s : 0.0);   // L_ij
+        const double l = (i > j) ? a[j] * inv : 0.0;   // L_ij below the diagonal; the diagonal lives in linv only
         lrow[j] = l;
         if (i == j) linv = inv;
 #pragma unroll
@@ -188,14 +189,15 @@ __device__ __forceinline__ bool lane_chol(const LaneGroup<P>& g, const double (&
 template <int P>
 __device__ __forceinline__ double lane_fwd(const LaneGroup<P>& g, const double (&lrow)[P], double linv, double rhs) {
     const int i = g.gl;
-    double acc = rhs, y = 0.0;
+    double acc = rhs;
 #pragma unroll
     for (int j = 0; j < P; ++j) {
         const double yj = g.bcast(acc * linv, j);
-        if (i == j) y = yj;
-        if (i > j) acc -= lrow[j] * yj;
+        acc -= lrow[j] * yj;                     // lrow[j] == 0 for j >= i: lane i's acc is final after step i - 1
     }
-    return y;
+    (void)i;
+    return __dmul_rn(acc, linv);                 // rounded here, as in the serial restatement (no FMA contraction
+                                                 // with the caller's subtraction)
 }
 
 // L^T x = y; lane i returns x_i
@@ -206,7 +208,7 @@ __device__ __forceinline__ double lane_bwd(const LaneGroup<P>& g, const double (
 #pragma unroll
     for (int jj = 0; jj < P; ++jj) {
         const int j = P - 1 - jj;
-        const double s = g.sum((i > j) ? lrow[j] * x : 0.0);
+        const double s = g.sum(lrow[j] * x);     // lanes i <= j contribute 0: lrow[j] == 0 (and x is still 0)
         if (i == j) x = (y - s) * linv;
     }
     return x;
@@ -230,6 +232,8 @@ __device__ __forceinline__ double lane_par(const LaneGroup<P>& g, const double (
     const bool fixedbit = (fixed >> g.gl) & 1u;
     double lrow[P], linv, x = 0.0, xout = 0.0;
     double dxnorm = INFINITY, fp = INFINITY, parl = 0.0, paru = 0.0;
+    const double t0 = rhs / dg;
+    const double gnorm = sqrt(g.sum(t0 * t0));   // |D^-1 b|: the same in every iteration
 #pragma unroll 1
     for (int it = 0; it <= 10; ++it) {
         if (!g.any_in_warp(live)) break;
@@ -242,8 +246,6 @@ __device__ __forceinline__ double lane_par(const LaneGroup<P>& g, const double (
         const double dxs = lane_dnorm<P>(g, dg, xs);
         // Newton correction (fp / delta) / |L^-1 (D^2 x / |D x|)|^2
         const double den = lane_newton_den<P>(g, lrow, linv, dg, xs, dxs, fixedbit);
-        const double t = rhs / dg;
-        const double gnorm = sqrt(g.sum(t * t));
         if (!live) continue;
         if (solved) {
             x = xs;
