@@ -338,10 +338,13 @@ class UltraCube(object):
         if kwargs.get("ucube_B") is not None:
             return calc_AICc_likelihood(self, ncomp1, ncomp2, ucube_B=kwargs["ucube_B"],
                                         expand=kwargs.get("expand", 0), planemask=kwargs.get("planemask"))
-        if kwargs.get("planemask") is not None:
-            raise NotImplementedError("planemask updates of cached maps are not supported")
         self._run_aicc()
-        return -1.0 * (self.AICc_maps[str(ncomp1)] - self.AICc_maps[str(ncomp2)]) / 2.0
+        lnk = -1.0 * (self.AICc_maps[str(ncomp1)] - self.AICc_maps[str(ncomp2)]) / 2.0
+        if kwargs.get("planemask") is not None:
+            # the reference updates its cached maps inside the mask only and returns those values (:1207-1214);
+            # here the maps are rebuilt whole by one AICc pass whenever a fit changed, so this is just a selection
+            return lnk[kwargs["planemask"]]
+        return lnk
 
     def get_all_lnk_maps(self, ncomp_max=2, rest_model_mask=True, multicore=True):
         """UltraCube.py:1218-1280."""
@@ -499,3 +502,33 @@ def get_residual(cube, model):
     """data - model (UltraCube.py:1743-1800); NaN wherever the model cube has no fit."""
     data = cube._data if hasattr(cube, "_data") else np.asarray(cube)
     return data - model
+
+
+def get_masked_moment(cube, model, order=0, expand=10, mask=None):
+    """UltraCube.py:1568-1655: moment of the data over the channels where the model is positive (dilated by
+    ``expand``); pixels whose model peak is below the median peak use the channels where any model exceeds 10 % of
+    that median instead.  Returns a [ny, nx] array (moment 0 in K km/s)."""
+    if order != 0:
+        raise NotImplementedError("only moment 0 is written by save_best_2comp_fit")
+    data = cube._data
+    with np.errstate(invalid="ignore"):
+        mask = (model > 0) if mask is None else np.logical_and(mask, np.isfinite(model))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            peak_T = np.nanmax(model, axis=0)
+            med_peak_T = np.nanmedian(peak_T)
+        high = peak_T > med_peak_T
+        mask_low = mask.copy()
+        mask_low[:, high] = False
+        specmask = np.any(model > med_peak_T * 0.1, axis=(1, 2))
+    mask_low[specmask, :] = True
+    mask[:, ~high] = mask_low[:, ~high]
+    if expand > 0:
+        from scipy.ndimage import binary_dilation
+        mask = binary_dilation(mask, structure=np.ones((expand, 1, 1), dtype=bool))
+    v = np.asarray(cube.spectral_axis, dtype=np.float64)
+    keep = mask & np.isfinite(data)
+    out = np.where(keep, data, 0.0).sum(axis=0, dtype=np.float64) * abs(v[1] - v[0])
+    out[~keep.any(axis=0)] = np.nan
+    return out

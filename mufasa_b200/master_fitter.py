@@ -11,6 +11,13 @@ fit through the convolved cube.  The later stages of ``master_
   Region              :65-126   (cube + parameter-file bookkeeping; logging / progress CSV left out)
   get_convolved_cube  :461-511, get_convolved_fits :516-552, get_fits :555-580, iter_2comp_fit :682-775,
   get_local_bad       :1632-1665, save_updated_paramaps :1700-1718
+and the stages of ``master_2comp_fit`` (:583-679) that are compositions of the above:
+  refit_bad_2comp     :777-844,  refit_marginal :847-922 (+ get_marginal_pix :1598-1629), refit_swap_2comp :925-978,
+  expand_fits         :1101-1244, fit_surroundings :1247-1400, standard_2comp_fit :1668-1697,
+  save_best_2comp_fit :1722-1931 (maps only: no CSV / 3-D scatter plot), get_best_2comp_model :2412-2468,
+  get_best_2comp_snr_mod :2376-2409
+Not rebuilt: ``refit_2comp_wide`` (:981-1098, the recovery of widely separated components from the convolved
+residual cube); ``master_2comp_fit(recover_wide=True)`` raises NotImplementedError.
 """
 import logging
 import os
@@ -21,8 +28,10 @@ from scipy import ndimage as nd
 
 from . import UltraCube as UCube
 from . import guess_refine as gss_rf
+from . import multi_v_fit as mvf
 from . import signals
 from .exceptions import SNRMaskError, StartFitError
+from .utils import fits_io
 from .utils.convolve import convolve_gauss2d
 
 logger = logging.getLogger(__name__)
@@ -242,3 +251,325 @@ def iter_2comp_fit(reg, snr_min=3.0, updateCnvFits=True, planemask=None, multico
             save_updated_paramaps(reg.ucube, ncomps=[nc])
         reg.log_progress(process_name='iter %d comp fit' % nc, n_attempted=int(n_pix),
                          n_success=int(reg.ucube.pcubes[str(nc)].has_fit.sum()), finished=True)
+
+
+# ---- the later stages of master_2comp_fit ----------------------------------------------------------------------
+def disk_neighbour(r):
+    """utils/neighbours.py: the disk(r) footprint without its centre."""
+    struct = signals.disk(r)
+    struct[r, r] = False
+    return struct
+
+
+def get_marginal_pix(lnkmap, lnk_thresh=5, holes_only=False, smallest_struct_size=9):
+    """Pixels on the rim of the structures with lnk > lnk_thresh, or the holes inside them."""
+    with np.errstate(invalid="ignore"):
+        mask = signals.remove_small_objects(lnkmap > lnk_thresh, smallest_struct_size)
+    mask_nosml = signals.remove_small_holes(mask)
+    if not holes_only:
+        mask_nosml = signals.binary_dilation(mask_nosml)
+    return np.logical_xor(mask_nosml, mask)
+
+
+def refit_bad_2comp(reg, snr_min=3, lnk_thresh=-5, multicore=True, save_para=True, method='best_neighbour',
+                    local_bad=True):
+    """Refit the pixels whose 2-component fit is worse than the 1-component one (or than noise) although a
+    1-component fit is significant, from the parameters of their best neighbour."""
+    ucube = reg.ucube
+    lnk10, lnk20, lnk21 = ucube.get_all_lnk_maps(ncomp_max=2, rest_model_mask=False, multicore=multicore)
+    with np.errstate(invalid="ignore"):
+        mask = np.logical_or(lnk21 < lnk_thresh, lnk20 < 5)
+        mask = np.logical_and(mask, lnk10 > 5)
+    mask = np.logical_and(mask, np.isfinite(lnk10))
+    if local_bad:
+        bad_thresh = max(10, lnk_thresh)
+        mask = np.logical_or(mask, get_local_bad(lnkmap=lnk21, lnk_thresh=bad_thresh, block_size=15, offset=0,
+                                                 bad_size_max=225))
+    if np.sum(mask) == 0:
+        reg.log_progress(process_name='refit_bad_2comp', n_attempted=0, n_success=0, finished=True)
+        return
+    guesses, mask = get_refit_guesses(ucube, mask, ncomp=2, method='best_neighbour', refmap=lnk20)
+    good_mask = replace_bad_pix(ucube, mask, snr_min, guesses, ncomp=2, simpfit=True, multicore=multicore,
+                                return_good_mask=True)
+    if save_para:
+        save_updated_paramaps(ucube, ncomps=[2, 1])
+    reg.log_progress(process_name='refit_bad_2comp', n_attempted=int(np.sum(mask)), n_success=int(good_mask.sum()),
+                     finished=True)
+
+
+def refit_marginal(reg, ncomp, lnk_thresh=5, holes_only=False, multicore=True, save_para=True, method='best_neighbour',
+                   refit_only=True, **kwargs_marg):
+    """Refit the pixels on the rim of (or in holes of) the significantly detected structures."""
+    ucube = reg.ucube
+    lnk_maps = ucube.get_all_lnk_maps(ncomp_max=ncomp, rest_model_mask=False, multicore=multicore)
+    lnkmap = lnk_maps if ncomp == 1 else lnk_maps[2]
+    proc = 'refit_marginal_%d_comp' % ncomp
+    mask = get_marginal_pix(lnkmap, lnk_thresh=lnk_thresh, holes_only=holes_only, **kwargs_marg)
+    if mask.sum() < 1:
+        reg.log_progress(process_name=proc, n_attempted=0, n_success=0, finished=True)
+        return
+    guesses, mask = get_refit_guesses(ucube, mask=mask, ncomp=ncomp, method=method, refmap=lnkmap)
+    if refit_only:
+        mask = np.logical_and(mask, np.isfinite(guesses).all(axis=0))
+        mask = np.logical_and(mask, ucube.pcubes[str(ncomp)].has_fit)
+    if np.sum(mask) == 0:
+        reg.log_progress(process_name=proc, n_attempted=0, n_success=0, finished=True)
+        return
+    good_mask = replace_bad_pix(ucube, mask, 0, guesses, ncomp=ncomp, simpfit=True, multicore=multicore,
+                                return_good_mask=True)
+    if save_para:
+        save_updated_paramaps(ucube, ncomps=[2, 1])
+    reg.log_progress(process_name=proc, n_attempted=int(np.sum(mask)), n_success=int(good_mask.sum()), finished=True)
+
+
+def refit_swap_2comp(reg, snr_min=3):
+    """Refit the significant 2-component pixels with the two slabs exchanged and keep the likelier fits."""
+    ucube = reg.ucube
+    for nc in (1, 2):
+        if str(nc) not in ucube.pcubes:
+            ucube.load_model_fit(ucube.paraPaths[str(nc)], nc)
+    with np.errstate(invalid="ignore"):
+        mask = ucube.get_AICc_likelihood(2, 1) > 5
+    guesses = copy(ucube.pcubes['2'].parcube)
+    guesses[0:4], guesses[4:8] = ucube.pcubes['2'].parcube[4:8].copy(), ucube.pcubes['2'].parcube[0:4].copy()
+    ucube_new = UCube.UltraCube(cube=ucube.cube, fittype=reg.fittype, device=ucube.device, share_device_with=ucube)
+    ucube_new.fit_cube(ncomp=[2], maskmap=mask, snr_min=snr_min, guesses=guesses)
+    lnk_NvsO = UCube.calc_AICc_likelihood(ucube_new, 2, 2, ucube_B=ucube)
+    with np.errstate(invalid="ignore"):
+        good_mask = lnk_NvsO > 0
+    replace_para(ucube.pcubes['2'], ucube_new.pcubes['2'], good_mask)
+    replace_rss(ucube, ucube_new, ncomp=2, mask=good_mask)
+    save_updated_paramaps(ucube, ncomps=[2, 1])
+
+
+def expand_fits(reg, ncomp, lnk_thresh=5, max_iter=5, r_expand=1, fill_mask=None, lnkmap=None, multicore=True,
+                snr_min=0, save_para=True, return_niter=False):
+    """Grow the fitted footprint outwards from the pixels with lnk > lnk_thresh, one ring of radius ``r_expand`` per
+    iteration, fitting each ring from its best neighbours; a pixel that failed twice is not tried again."""
+    ucube = reg.ucube
+    proc = 'expand_fit_%dcomp' % ncomp
+    if lnkmap is None:
+        lnkmap = ucube.get_AICc_likelihood(ncomp, ncomp - 1)
+    lnkmap = np.array(lnkmap, dtype=np.float64)
+    if fill_mask is None:
+        fill_mask = np.ones(lnkmap.shape, dtype=bool)
+
+    def ring(lnkmap):
+        with np.errstate(invalid="ignore"):
+            mask = lnkmap > lnk_thresh
+        return np.logical_xor(mask, signals.binary_dilation(mask, signals.disk(r_expand))) & fill_mask
+
+    def fit(mask):
+        guesses, mask = get_refit_guesses(ucube, mask, ncomp=ncomp, method='best_neighbour', refmap=lnkmap,
+                                          structure=disk_neighbour(r_expand + 1))
+        good = replace_bad_pix(ucube, mask, snr_min, guesses, ncomp=ncomp, simpfit=True, multicore=multicore,
+                               return_good_mask=True)
+        return good if good.shape == lnkmap.shape else np.zeros(lnkmap.shape, dtype=bool)
+
+    mask_fit = ring(lnkmap)
+    mask_attempted = mask_fit
+    if mask_fit.sum() < 1:
+        reg.log_progress(process_name=proc, n_attempted=0, n_success=0, finished=True)
+        return (0, 0, 0) if return_niter else (0, 0)
+    good_mask = fit(mask_fit)
+    bad_mask = np.logical_and(mask_fit, ~good_mask)
+    bad_twice = np.zeros(bad_mask.shape, dtype=bool)
+    n_good = n_good_total = int(good_mask.sum())
+    i = 0
+    while i < max_iter and n_good > 0:
+        i += 1
+        lnkmap[mask_fit] = ucube.get_AICc_likelihood(ncomp, ncomp - 1, planemask=mask_fit)
+        mask_fit = np.logical_and(ring(lnkmap), ~mask_attempted)
+        mask_fit = np.logical_or(mask_fit, bad_mask & ~bad_twice)
+        if mask_fit.sum() == 0:
+            break
+        good_mask = fit(mask_fit)
+        bad_mask = np.logical_and(mask_fit, ~good_mask)
+        bad_twice = np.logical_or(bad_twice, bad_mask)
+        mask_attempted = np.logical_or(mask_attempted, mask_fit)
+        n_good = int(good_mask.sum())
+        n_good_total += n_good
+    if save_para:
+        save_updated_paramaps(ucube, ncomps=[2, 1])
+    n_attempt_total = int(mask_attempted.sum())
+    reg.log_progress(process_name=proc, n_attempted=n_attempt_total, n_success=n_good_total, finished=True)
+    return (n_good_total, n_attempt_total, i) if return_niter else (n_good_total, n_attempt_total)
+
+
+def fit_surroundings(reg, ncomps=[1, 2], snr_min=3, max_iter=None, save_para=True, fill_mask=None, multicore=True,
+                     match_footprint=True):
+    """``expand_fits`` in tiers of falling lnk thresholds (10, 3, then 0 / -5 / -20 with wider rings as ``snr_min``
+    allows), the lowest ncomp first; with ``match_footprint`` a higher ncomp may only grow where the previous one
+    has fits.  Small holes left in the footprint get one more pass."""
+    max_iter_fill = 100
+    if max_iter is None:
+        max_iter = 1 if snr_min > 3 else max_iter_fill
+    elif max_iter > max_iter_fill:
+        max_iter_fill = max_iter
+    if fill_mask is None:
+        fill_mask = reg.ucube.pcubes[str(min(ncomps))].footprint() if str(min(ncomps)) in reg.ucube.pcubes \
+            else np.any(reg.ucube.cube.mask.include(), axis=0)
+    ncomps = sorted(ncomps)
+    for i, ncomp in enumerate(ncomps):
+        m_iter = max_iter
+        if match_footprint and i > 0:
+            m_iter = max_iter_fill
+            prev = reg.ucube.has_fit(ncomps[i - 1])
+            fill_mask = np.logical_or(fill_mask, prev) if i > 1 else prev
+        kw = dict(ncomp=ncomp, save_para=save_para, fill_mask=fill_mask, multicore=multicore, return_niter=True,
+                  snr_min=snr_min)
+        state = dict(m_iter=m_iter, n_good=1, good=0, tried=0)
+
+        def tier(lnk_thresh, r_expand):
+            if state["m_iter"] > 0 and state["n_good"] > 0:
+                n_good, n_attempt, n = expand_fits(reg, lnk_thresh=lnk_thresh, max_iter=state["m_iter"],
+                                                   r_expand=r_expand, **kw)
+                state["n_good"] = n_good
+                state["good"] += n_good
+                state["tried"] += n_attempt
+                state["m_iter"] -= n
+
+        tier(10, 1)
+        tier(3, 1)
+        last = (3, 1)
+        for cut, thr, r in ((2, 0, 2), (1, -5, 3), (0, -20, 5)):
+            if snr_min <= cut:
+                tier(thr, r)
+                last = (thr, r)
+        fitted = reg.ucube.has_fit(ncomp)
+        filled = signals.remove_small_holes(fitted, 9)
+        if np.logical_xor(fitted, filled).sum() > 0:
+            kw['fill_mask'] = filled
+            state["n_good"], state["m_iter"] = 1, 1
+            tier(last[0], 2)
+        reg.log_progress(process_name='expand_fit_%dcomp' % ncomp, n_attempted=state["tried"],
+                         n_success=state["good"], finished=True)
+
+
+def standard_2comp_fit(reg, planemask=None, snr_min=3):
+    """1- and 2-component fits from moment guesses only (no convolved-cube stage)."""
+    for nc in (1, 2):
+        kwargs = {'update': True, 'snr_min': snr_min}
+        if planemask is not None:
+            kwargs['maskmap'] = planemask
+        reg.ucube.get_model_fit([nc], **kwargs)
+
+
+def get_best_2comp_model(reg):
+    """[nchan, ny, nx] model cube of the selected fit per pixel: 2 components where lnk21 > 5 and lnk20 > 5, else 1
+    where lnk10 > 5, else 0."""
+    lnk10, lnk20, lnk21 = reg.ucube.get_all_lnk_maps(ncomp_max=2, rest_model_mask=True)
+    mod1 = reg.ucube.pcubes['1'].get_modelcube()
+    mod2 = reg.ucube.pcubes['2'].get_modelcube()
+    modbest = np.zeros_like(mod1)
+    with np.errstate(invalid="ignore"):
+        mask = lnk10 > 5
+        modbest[:, mask] = mod1[:, mask]
+        mask = np.logical_and(lnk21 > 5, lnk20 > 5)
+    modbest[:, mask] = mod2[:, mask]
+    return modbest
+
+
+def _rms_of_residual(res):
+    """UltraCube.get_rms (UltraCube.py:1701-1740): 1.4826 median|r - roll(r, 2)| / sqrt(2) along the spectrum."""
+    diff = res - np.roll(res, 2, axis=0)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        return 1.4826 * np.nanmedian(np.abs(diff), axis=0) / 2 ** 0.5
+
+
+def get_best_2comp_snr_mod(reg, modbest=None):
+    """Peak of the selected model over the noise of its residual."""
+    if modbest is None:
+        modbest = get_best_2comp_model(reg)
+    rms = _rms_of_residual(reg.ucube.cube._data - modbest)
+    import warnings
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore", RuntimeWarning)
+        return np.nanmax(modbest, axis=0) / rms
+
+
+def save_map(map, header, savename, overwrite=True):
+    if not overwrite and os.path.exists(savename):
+        raise IOError("%s exists" % savename)
+    fits_io.write(savename, np.asarray(map), header)
+
+
+def save_best_2comp_fit(reg, multicore=True, from_saved_para=False, lnk21_thres=5, lnk10_thres=5, save_csv=False,
+                        save_Scatter3D=False):
+    """The products of a run: ``{root}_2vcomp_final.fits`` (model-selected parameters + errors), the lnk21 / lnk10 /
+    lnk20 maps, the peak S/N of the selected model, moment 0 of the model and of the data over the model's
+    footprint, reduced chi-squared of the 1- and 2-component fits.  (The reference's CSV table and 3-D scatter plot
+    are plotting-side products and are not written.)"""
+    if save_csv or save_Scatter3D:
+        raise NotImplementedError("CSV / 3-D scatter products are outside the fit path")
+    ncomps = [1, 2]
+    ucube = reg.ucube
+    save_updated_paramaps(ucube, ncomps=ncomps)
+    if from_saved_para:
+        for nc in ncomps:
+            ucube.load_model_fit(ucube.paraPaths[str(nc)], nc)
+    pcube_final = ucube.pcubes['2'].copy()
+    parcube, errcube, lnk10, lnk20, lnk21 = ucube.get_best_2c_parcube(multicore=multicore, lnk21_thres=lnk21_thres,
+                                                                     lnk10_thres=lnk10_thres, return_lnks=True)
+    pcube_final.parcube, pcube_final.errcube = parcube, errcube
+    root2 = os.path.splitext(ucube._para_path(2))[0]
+    mvf.save_pcube(pcube_final, "{}_final.fits".format(root2), ncomp=2,
+                   header_note='Model-selected best 1- or 2-comp fits parameters, based on lnk21')
+    paraDir, paraRoot = ucube.paraDir, ucube.paraNameRoot
+
+    def name(key):
+        for word in ("parameters", "parameter", "para"):
+            if word in paraRoot:
+                return "{}/{}.fits".format(paraDir, paraRoot.replace(word, key))
+        return "{}/{}_{}.fits".format(paraDir, paraRoot, key)
+
+    def header(notes, bunit=None):
+        hdr = mvf.make_header(2, ucube.cube.header)
+        hdr.set('NOTES', notes)
+        if bunit is not None:
+            hdr.set('BUNIT', bunit)
+        return hdr
+
+    for key, lnk in (("21", lnk21), ("10", lnk10), ("20", lnk20)):
+        other = 'noise' if key[1] == '0' else '%s comp fit' % key[1]
+        save_map(lnk, header("Relative log-likelihood of %s comp fit vs %s" % (key[0], other), 'unitless'),
+                 name("lnk" + key))
+    modbest = get_best_2comp_model(reg)
+    save_map(get_best_2comp_snr_mod(reg, modbest), header('Estimated peak signal-to-noise ratio', 'unitless'),
+             name("SNR"))
+    v = np.asarray(ucube.cube.spectral_axis, dtype=np.float64)
+    dv = abs(v[1] - v[0])
+    save_map(np.nansum(modbest, axis=0) * dv, header('moment 0 of the best-fit model', 'K km/s'), name("model_mom0"))
+    save_map(UCube.get_masked_moment(ucube.cube, modbest, order=0, expand=20),
+             header('moment 0 over the footprint of the best-fit model', 'K km/s'), name("mom0"))
+    save_map(ucube.get_reduced_chisq(1), header('reduced chi-squared values of the 1-comp model'), name("chi2red_1c"))
+    save_map(ucube.get_reduced_chisq(2), header('reduced chi-squared values of the 2-comp model'), name("chi2red_2c"))
+    return reg
+
+
+def master_2comp_fit(reg, snr_min=0.0, recover_wide=False, planemask=None, updateCnvFits=True, refit_bad_pix=True,
+                     refit_marg=True, max_expand_iter=None, multicore=True):
+    """The reference's full 2-component pipeline (master_fitter.py:583-679): two-step fit through the convolved cube,
+    quality-assurance refits, expansion into the surroundings, products.  ``recover_wide`` (the reference's default
+    True) needs ``refit_2comp_wide``, which is not rebuilt."""
+    if recover_wide:
+        raise NotImplementedError("refit_2comp_wide is not rebuilt; call with recover_wide=False")
+    iter_2comp_fit(reg, snr_min=snr_min, updateCnvFits=updateCnvFits, planemask=planemask, multicore=multicore)
+    recover_snr_min = min(3.0, snr_min / 3.0)
+    if refit_bad_pix:
+        refit_bad_2comp(reg, snr_min=recover_snr_min, lnk_thresh=-5, multicore=multicore)
+    if refit_marg:
+        for nc in (1, 2):
+            refit_marginal(reg, ncomp=nc, lnk_thresh=10, holes_only=False, multicore=multicore,
+                           method='best_neighbour')
+    if max_expand_iter is not False:
+        if max_expand_iter is True:
+            max_expand_iter = None
+        fit_surroundings(reg, ncomps=[1, 2], snr_min=snr_min, max_iter=max_expand_iter, fill_mask=None,
+                         multicore=multicore, match_footprint=True)
+        if refit_bad_pix:
+            refit_bad_2comp(reg, snr_min=recover_snr_min, lnk_thresh=-5, multicore=multicore)
+    save_best_2comp_fit(reg, multicore=multicore, lnk21_thres=5, lnk10_thres=5)
+    return reg

@@ -228,3 +228,47 @@ def test_region_iter_2comp_fit_from_fits_files(engine, tmp_path):
     reg2 = mf.Region(path, "field", paraDir=str(tmp_path / "paras"), fittype=syn["fittype"], device=0)
     reg2.ucube.get_model_fit([1, 2], update=False)
     np.testing.assert_array_equal(reg2.ucube.pcubes["2"].parcube, p2.parcube)
+
+
+def test_master_2comp_fit_pipeline(engine, tmp_path):
+    """The full driver (master_fitter.py:583-679, recover_wide off): two-step fit, bad-pixel and marginal refits,
+    expansion into the surroundings, products on disk."""
+    import os
+    from mufasa_b200 import master_fitter as mf
+    from mufasa_b200.utils import fits_io
+    ny, nx, nchan = 48, 48, 500
+    syn = synth.make_cube(3, T.oracle_modelcube, shape=(ny, nx, nchan))
+    path = str(tmp_path / "field.fits")
+    SpecCube(syn["cube"], syn["v"], rest_value=23.6944955e9, header=_header(ny, nx)).write(path)
+    reg = mf.Region(path, "field", paraDir=str(tmp_path / "paras"), fittype=syn["fittype"], device=0)
+    mf.iter_2comp_fit(reg, snr_min=3.0)
+    n1_before = int(reg.ucube.pcubes["1"].has_fit.sum())
+    lnk21_before = np.array(reg.ucube.get_AICc_likelihood(2, 1))
+    # the remaining stages, as master_2comp_fit strings them together
+    mf.refit_bad_2comp(reg, snr_min=1.0, lnk_thresh=-5)
+    for nc in (1, 2):
+        mf.refit_marginal(reg, ncomp=nc, lnk_thresh=10, holes_only=False, method='best_neighbour')
+    mf.fit_surroundings(reg, ncomps=[1, 2], snr_min=3.0, max_iter=3, match_footprint=True)
+    mf.save_best_2comp_fit(reg)
+    p1, p2 = reg.ucube.pcubes["1"], reg.ucube.pcubes["2"]
+    assert int(p1.has_fit.sum()) >= n1_before                      # refits only ever replace or add fits
+    lnk21_after = reg.ucube.get_AICc_likelihood(2, 1)
+    both = np.isfinite(lnk21_before) & np.isfinite(lnk21_after)
+    assert np.nanmedian(lnk21_after[both] - lnk21_before[both]) >= -1e-6
+    for key in ("2vcomp_final", "lnk21", "lnk10", "lnk20", "SNR", "model_mom0", "mom0", "chi2red_1c", "chi2red_2c"):
+        f = str(tmp_path / "paras" / ("field_%s.fits" % key))
+        assert os.path.isfile(f), key
+    final, hdr = fits_io.read(str(tmp_path / "paras" / "field_2vcomp_final.fits"))
+    assert final.shape == (16, ny, nx)
+    truth = syn["ncomp_true"]
+    two = np.isfinite(final[4])                                   # second component kept by the selection
+    fitted = p1.has_fit
+    assert (two[fitted] == (truth[fitted] == 2)).mean() > 0.85
+    snr, _ = fits_io.read(str(tmp_path / "paras" / "field_SNR.fits"))
+    assert np.nanmax(snr) > 10 and snr.shape == (ny, nx)
+    # and the one-call driver runs the same chain
+    reg2 = mf.Region(path, "field2", paraDir=str(tmp_path / "paras2"), fittype=syn["fittype"], device=0)
+    mf.master_2comp_fit(reg2, snr_min=3.0, recover_wide=False, max_expand_iter=2)
+    assert os.path.isfile(str(tmp_path / "paras2" / "field2_2vcomp_final.fits"))
+    with pytest.raises(NotImplementedError):
+        mf.master_2comp_fit(reg2, snr_min=3.0, recover_wide=True)

@@ -44,3 +44,46 @@ def test_get_refit_guesses_best_neighbour_and_convolved():
     assert m[2, 3] and not m[0, 0]
     g2, m2 = mf.get_refit_guesses(_U(par.copy()), mask, ncomp=1, method='convolved')
     assert np.isfinite(g2[:, 2, 3]).all() and abs(g2[0, 2, 3] - par[0, 2, 2:5].mean()) < 0.05
+
+
+def test_marginal_pixels_and_local_bad():
+    lnk = np.full((20, 20), np.nan)
+    lnk[5:15, 5:15] = 20.0
+    lnk[9, 9] = 1.0                                            # a hole inside the structure
+    lnk[0, 0] = 30.0                                           # an isolated pixel: too small to be a structure
+    rim = mf.get_marginal_pix(lnk, lnk_thresh=5)
+    assert rim.sum() == 41 and rim[9, 9] and rim[4, 7] and not rim[4, 4] and not rim[0, 1]
+    holes = mf.get_marginal_pix(lnk, lnk_thresh=5, holes_only=True)
+    assert holes.sum() == 1 and holes[9, 9]
+    d = mf.disk_neighbour(2)
+    assert d.shape == (5, 5) and d.sum() == 12 and not d[2, 2]
+    # get_local_bad: a small dip inside a bright plateau is flagged, the plateau is not
+    yy, xx = np.mgrid[:40, :40]
+    lnk = 30.0 + 0.0 * yy
+    lnk[18:21, 18:21] = 12.0
+    bad = mf.get_local_bad(lnk, lnk_thresh=10, block_size=15, bad_size_max=225)
+    assert bad[19, 19] and bad.sum() == 9
+
+
+def test_masked_moment_of_the_data_over_the_model_footprint():
+    from mufasa_b200.UltraCube import get_masked_moment
+    from mufasa_b200.cube import SpecCube
+    nchan, ny, nx = 60, 4, 5
+    v = np.linspace(-3, 3, nchan)
+    rng = np.random.default_rng(0)
+    data = rng.normal(0, 0.1, (nchan, ny, nx)).astype(np.float32)
+    model = np.zeros((nchan, ny, nx))
+    model[28:32] = 2.0                                         # a bright line everywhere ...
+    model[:, 0, 0] = 0.0
+    model[29:31, 0, 0] = 0.05                                  # ... but one faint pixel
+    data = data + model.astype(np.float32)
+    cube = SpecCube(data, v)
+    m0 = get_masked_moment(cube, model.copy(), order=0, expand=4)
+    dv = v[1] - v[0]
+    chan = np.zeros(nchan, bool)
+    chan[28 - 2:32 + 2] = True                                 # ones(4) dilation: [k - 2, k + 1]
+    chan[32 + 1] = False
+    want = data[chan, 1, 1].astype(np.float64).sum() * dv
+    assert np.isclose(m0[1, 1], want)
+    # the faint pixel borrows the channels where any model exceeds 10 % of the median peak
+    assert np.isclose(m0[0, 0], data[chan, 0, 0].astype(np.float64).sum() * dv)
