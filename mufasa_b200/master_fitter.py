@@ -496,6 +496,61 @@ def save_map(map, header, savename, overwrite=True):
     fits_io.write(savename, np.asarray(map), header)
 
 
+def _best_model_products(reg, expand=20):
+    """SNR, model moment 0 and masked data moment 0 of the selected model, from the device-resident rows.
+
+    The reference builds three [nchan, ny, nx] host cubes for these maps (two model cubes + the selected one,
+    master_fitter.py:2412-2468, then get_masked_moment, UltraCube.py:1568-1655); at 512 x 512 x 1000 that is minutes
+    of numpy.  Here the 1- and 2-component models are evaluated by ``b200fit_model`` into pixel-major rows, the
+    per-pixel choice is the integer map of the AICc kernel, and what is left are row reductions on the device (torch
+    tensor ops: plumbing around the kernels, off the fit path)."""
+    import torch
+    ucube = reg.ucube
+    ucube.get_all_lnk_maps(ncomp_max=2, rest_model_mask=True)
+    ref = ucube._ref_pcube if ucube._ref_pcube is not None else ucube.load_pcube()
+    eng = ref.engine
+    nchan, ny, nx = ucube.cube.shape
+    npix = ny * nx
+    rows = ref.rows_on_device()[:, :nchan]
+    ncomp = torch.from_numpy(ucube.ncomp_map.astype(np.int64).ravel()).to(eng.device)
+    best = torch.zeros((npix, nchan), dtype=torch.float64, device=eng.device)
+    for nc in (1, 2):
+        sel = torch.nonzero(ncomp == nc).ravel()
+        if sel.numel() == 0:
+            continue
+        par = ucube._params_dev(nc, eng)[sel].contiguous()
+        prob = ref._problem(ucube.fittype, nc, int(sel.numel()), [-1e30] * (4 * nc), [1e30] * (4 * nc))
+        best[sel] = eng.model(prob, par)[:, :nchan]
+    best = torch.nan_to_num(best, nan=0.0)
+    peak = best.amax(dim=1)
+    v = np.asarray(ucube.cube.spectral_axis, dtype=np.float64)
+    dv = abs(v[1] - v[0])
+    # S/N: peak of the selected model over the noise of its residual (get_rms of the selected fit's residual)
+    rms = torch.full((npix,), float("nan"), dtype=torch.float64, device=eng.device)
+    for nc in (1, 2):
+        m = torch.from_numpy(np.ascontiguousarray(ucube.get_rms(nc)).ravel()).to(eng.device)
+        rms = torch.where(ncomp == nc, m, rms)
+    snr = torch.where(ncomp > 0, peak / rms, torch.zeros_like(peak))
+    model_mom0 = best.sum(dim=1) * dv
+    # get_masked_moment: channels where the model is positive; pixels fainter than the median peak use the channels
+    # where any model exceeds 10 % of that median; dilated by ones(expand) -> [k - expand/2, k + expand/2 - 1]
+    mask = best > 0
+    med = torch.nanmedian(peak)
+    high = peak > med
+    spec = (best > 0.1 * med).any(dim=0)
+    mask = torch.where(high[:, None], mask, mask | spec[None, :])
+    if expand > 0:
+        lo, hi = expand // 2, expand - expand // 2 - 1
+        padded = torch.nn.functional.pad(mask.to(torch.float32)[:, None, :], (hi, lo))
+        mask = torch.nn.functional.max_pool1d(padded, kernel_size=expand, stride=1)[:, 0, :] > 0
+    keep = mask & torch.isfinite(rows)
+    mom0 = torch.where(keep, rows.to(torch.float64), torch.zeros((), dtype=torch.float64, device=eng.device)).sum(1) * dv
+    mom0 = torch.where(keep.any(dim=1), mom0, torch.full_like(mom0, float("nan")))
+    _, _, flip = ref.xarr.v0_dv_flip           # rows are stored with ascending velocity; sums do not care
+    out = torch.stack([snr, model_mom0, mom0]).cpu().numpy().reshape(3, ny, nx)
+    return dict(SNR=out[0], model_mom0=out[1], mom0=out[2])
+
+
 def save_best_2comp_fit(reg, multicore=True, from_saved_para=False, lnk21_thres=5, lnk10_thres=5, save_csv=False,
                         save_Scatter3D=False):
     """The products of a run: ``{root}_2vcomp_final.fits`` (model-selected parameters + errors), the lnk21 / lnk10 /
@@ -536,14 +591,10 @@ def save_best_2comp_fit(reg, multicore=True, from_saved_para=False, lnk21_thres=
         other = 'noise' if key[1] == '0' else '%s comp fit' % key[1]
         save_map(lnk, header("Relative log-likelihood of %s comp fit vs %s" % (key[0], other), 'unitless'),
                  name("lnk" + key))
-    modbest = get_best_2comp_model(reg)
-    save_map(get_best_2comp_snr_mod(reg, modbest), header('Estimated peak signal-to-noise ratio', 'unitless'),
-             name("SNR"))
-    v = np.asarray(ucube.cube.spectral_axis, dtype=np.float64)
-    dv = abs(v[1] - v[0])
-    save_map(np.nansum(modbest, axis=0) * dv, header('moment 0 of the best-fit model', 'K km/s'), name("model_mom0"))
-    save_map(UCube.get_masked_moment(ucube.cube, modbest, order=0, expand=20),
-             header('moment 0 over the footprint of the best-fit model', 'K km/s'), name("mom0"))
+    maps = _best_model_products(reg, expand=20)
+    save_map(maps["SNR"], header('Estimated peak signal-to-noise ratio', 'unitless'), name("SNR"))
+    save_map(maps["model_mom0"], header('moment 0 of the best-fit model', 'K km/s'), name("model_mom0"))
+    save_map(maps["mom0"], header('moment 0 over the footprint of the best-fit model', 'K km/s'), name("mom0"))
     save_map(ucube.get_reduced_chisq(1), header('reduced chi-squared values of the 1-comp model'), name("chi2red_1c"))
     save_map(ucube.get_reduced_chisq(2), header('reduced chi-squared values of the 2-comp model'), name("chi2red_2c"))
     return reg

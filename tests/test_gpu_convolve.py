@@ -266,6 +266,19 @@ def test_master_2comp_fit_pipeline(engine, tmp_path):
     assert (two[fitted] == (truth[fitted] == 2)).mean() > 0.85
     snr, _ = fits_io.read(str(tmp_path / "paras" / "field_SNR.fits"))
     assert np.nanmax(snr) > 10 and snr.shape == (ny, nx)
+    # the device-side product maps against the reference's host recipe on full model cubes
+    from mufasa_b200.UltraCube import get_masked_moment
+    modbest = mf.get_best_2comp_model(reg)
+    snr_host = mf.get_best_2comp_snr_mod(reg, modbest)
+    sel = reg.ucube.ncomp_map > 0
+    np.testing.assert_allclose(snr[sel], snr_host[sel], rtol=1e-5)
+    mm0, _ = fits_io.read(str(tmp_path / "paras" / "field_model_mom0.fits"))
+    dv = syn["v"][1] - syn["v"][0]
+    np.testing.assert_allclose(mm0, np.nansum(modbest.astype(np.float64), axis=0) * dv, rtol=1e-5, atol=1e-6)
+    m0, _ = fits_io.read(str(tmp_path / "paras" / "field_mom0.fits"))
+    m0_host = get_masked_moment(reg.ucube.cube, modbest.astype(np.float64), order=0, expand=20)
+    assert np.array_equal(np.isnan(m0), np.isnan(m0_host))
+    np.testing.assert_allclose(m0[np.isfinite(m0)], m0_host[np.isfinite(m0)], rtol=1e-6, atol=1e-5)
     # and the one-call driver runs the same chain
     reg2 = mf.Region(path, "field2", paraDir=str(tmp_path / "paras2"), fittype=syn["fittype"], device=0)
     mf.master_2comp_fit(reg2, snr_min=3.0, recover_wide=False, max_expand_iter=2)
