@@ -16,6 +16,9 @@ struct b200fit_ctx {
     cudaStream_t job_stream[B200FIT_MAX_BATCH];
     cudaEvent_t fork_ev, join_ev[B200FIT_MAX_BATCH];
     unsigned long long launches = 0;          // kernels launched by this context (all entry points)
+    double* d_chan = nullptr;                 // per-channel constants of the fp64 model (3 x B200FIT_MAX_NCHAN)
+    int chan_n = 0;                           // ... valid for this spectral axis: nchan, {v0, dv, nu_ref}
+    double chan_key[3] = {0.0, 0.0, 0.0};
     int profiling = 0;                        // record CUDA events around the fit's kernels
     std::vector<cudaEvent_t> prof_ev;         // event pool (grown on demand)
     size_t prof_used = 0;

@@ -604,10 +604,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
 
 // ---------------------------------------------------------------------------------------------------------
 // fp64 model in the reference's operation order (HyperfineModel.py:41-58, 91-107; BaseModel.py:191-192).
-// Explicit _rn intrinsics keep nvcc from contracting mul+add into FMA, so the arithmetic is the numpy sequence.
-// Hyperfine terms below exp(-90) relative are skipped: they cannot change the rounded sum (see DESIGN.md).
+// Explicit _rn intrinsics keep nvcc from contracting mul+add into FMA, so the arithmetic is the numpy sequence,
+// with two exceptions inside the hyperfine sum, which is ~80 % of this model's instructions: the gaussian argument
+// is -(a*a) * (1 / (2 w^2)) with the reciprocal taken once per line (numpy divides: last-bit differences in a
+// quarter of the terms) and its exponential is ``exp_neg`` below (CUDA's exp already differs from glibc's in the
+// last bit).  Both are far inside the 1e-13 agreement the parity tests ask of the model, and the sample mask
+// ``model > 0`` can only change for a channel whose optical depth sits within ~1e-12 (relative) of the 1.1e-16
+// where 1 - exp(-tau) leaves zero -- rarer than the platform dependence of that channel documented in DESIGN.md.
+// Hyperfine terms below exp(-90) relative are skipped: they cannot change the rounded sum.
+// Quantities that depend on the channel only (frequency, h nu / k, J(T_CMB)) come from a per-context table
+// (chan_tables_kernel) instead of two to five divisions and an exponential per pixel and channel; same values.
 struct CompF64 {
-    double tex, tau, nuoff[MAXHF_FULL], inv2w2[MAXHF_FULL], tw[MAXHF_FULL];
+    double tex, tau, nuoff[MAXHF_FULL], rcp2w2[MAXHF_FULL], tw[MAXHF_FULL];   // rcp2w2 = 1 / (2 nuwidth^2)
     double acut[MAXHF_FULL];   // |x + nuoff - line| beyond which the term is below exp(-90): skipped without the divide
     int clo[MAXHF_FULL], chi[MAXHF_FULL];   // per line group: channels outside [clo, chi] are beyond every acut (+2 margin)
 };
@@ -626,7 +634,7 @@ __device__ __forceinline__ void comp_setup_f64(const DeviceProblem& pr, const do
         const double nuwidth = fabs(__dmul_rn(__ddiv_rn(width, CKMS), line));
         c.nuoff[k] = __dmul_rn(__ddiv_rn(vel, CKMS), line);
         const double d = __dmul_rn(2.0, __dmul_rn(nuwidth, nuwidth));   // 2.0 * nuwidth**2 (the divisor)
-        c.inv2w2[k] = d;
+        c.rcp2w2[k] = __ddiv_rn(1.0, d);
         c.tw[k] = __dmul_rn(tau, pr.wts_full[k]);
         c.acut[k] = sqrt(90.0 * d) * (1.0 + 1e-9);   // generous: the exact arg > -90 test still follows
     }
@@ -653,6 +661,29 @@ __device__ __forceinline__ double xarr_ghz(const DeviceProblem& pr, int i) {
     return __ddiv_rn(__dmul_rn(__dmul_rn(pr.nu_ref_ghz, 1e9), __dsub_rn(1.0, __ddiv_rn(v, CKMS))), 1e9);
 }
 
+// exp(x) for -90 <= x <= 0, ~1 ulp: x = n ln2 + r, |r| <= ln2 / 2, degree-13 Taylor, exponent added in place.
+// Half the instructions of exp(): no overflow / subnormal handling is needed on this range.
+__device__ __forceinline__ double exp_neg(double x) {
+    const double n = rint(x * 1.4426950408889634);
+    double r = fma(n, -6.93147180369123816490e-01, x);
+    r = fma(n, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                 // 1 / 13!
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.388888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + ((int)n << 20), __double2loint(p));
+}
+
 // exp(x) as numpy evaluates it.  glibc's exp is within ~0.51 ulp, i.e. practically correctly rounded; CUDA's is
 // within 1 ulp.  The difference matters in exactly one place: exp(-tau) for tau ~ 1e-16 decides whether
 // 1 - exp(-tau) is 0 or 1.1e-16, i.e. whether a channel at the edge of a hyperfine window belongs to the AICc sample
@@ -674,8 +705,8 @@ __device__ __forceinline__ double tauprof_f64(const DeviceProblem& pr, const Com
         for (int k = pr.gstart_full[g]; k < pr.gstart_full[g + 1]; ++k) {
             const double a = __dsub_rn(__dadd_rn(x, cp.nuoff[k]), pr.lines_full[k]);
             if (fabs(a) > cp.acut[k]) continue;
-            const double arg = __ddiv_rn(-__dmul_rn(a, a), cp.inv2w2[k]);
-            if (arg > -90.0) tauprof = __dadd_rn(tauprof, __dmul_rn(cp.tw[k], exp(arg)));
+            const double arg = __dmul_rn(-__dmul_rn(a, a), cp.rcp2w2[k]);
+            if (arg > -90.0) tauprof = __dadd_rn(tauprof, __dmul_rn(cp.tw[k], exp_neg(arg)));
         }
     }
     return tauprof;
@@ -694,15 +725,28 @@ __device__ __forceinline__ double planck_T0(double x) {
     return __ddiv_rn(__dmul_rn(__dmul_rn(H_CGS, x), 1e9), KB_CGS);
 }
 
+// per-channel constants of the fp64 model: tab[i] = frequency (GHz), tab[MAX + i] = h nu / k, tab[2 MAX + i] =
+// J(T_CMB, nu) -- the same operation sequences model_f64 used to run per pixel
+__global__ void chan_tables_kernel(const DeviceProblem pr, double* __restrict__ tab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pr.nchan) return;
+    const double x = xarr_ghz(pr, i);
+    const double T0 = planck_T0(x);
+    tab[i] = x;
+    tab[B200FIT_MAX_NCHAN + i] = T0;
+    tab[2 * B200FIT_MAX_NCHAN + i] = t_antenna(T0, TCMB);
+}
+
 // model of ``ncomp`` (<= 2) components at channel i; comps in shared/local memory.  A channel outside every
 // hyperfine window is exactly 0 (bg0 - bg0) and costs only the window tests.
-__device__ __forceinline__ double model_f64(const DeviceProblem& pr, const CompF64* comps, int ncomp, int i) {
-    const double x = xarr_ghz(pr, i);
+__device__ __forceinline__ double model_f64(const DeviceProblem& pr, const double* __restrict__ tab,
+                                            const CompF64* comps, int ncomp, int i) {
+    const double x = __ldg(tab + i);
     const double t0 = tauprof_f64(pr, comps[0], x, i);
     const double t1 = (ncomp > 1) ? tauprof_f64(pr, comps[1], x, i) : 0.0;
     if (t0 == 0.0 && t1 == 0.0) return 0.0;
-    const double T0 = planck_T0(x);
-    const double bg0 = t_antenna(T0, TCMB);
+    const double T0 = __ldg(tab + B200FIT_MAX_NCHAN + i);
+    const double bg0 = __ldg(tab + 2 * B200FIT_MAX_NCHAN + i);
     double bg = slab_f64(bg0, T0, comps[0].tex, t0);
     if (ncomp > 1) bg = slab_f64(bg, T0, comps[1].tex, t1);
     return __dsub_rn(bg, bg0);
@@ -711,9 +755,10 @@ __device__ __forceinline__ double model_f64(const DeviceProblem& pr, const CompF
 // model A (comps[0 .. nA)) and model B (comps[2 .. 2 + nB)) of one pixel at channel i, sharing the frequency axis and
 // the Planck terms.  A = the 1-component fit, B = the 2-component fit in get_all_lnk_maps; A = a new fit, B = the
 // old fit with the same number of components in replace_bad_pix (master_fitter.py:1449).
-__device__ __forceinline__ void model_pair_f64(const DeviceProblem& pr, const CompF64* comps, bool vA, bool vB, int nA,
-                                               int nB, int i, double& mA, double& mB) {
-    const double x = xarr_ghz(pr, i);
+__device__ __forceinline__ void model_pair_f64(const DeviceProblem& pr, const double* __restrict__ tab,
+                                               const CompF64* comps, bool vA, bool vB, int nA, int nB, int i,
+                                               double& mA, double& mB) {
+    const double x = __ldg(tab + i);
     const double a0 = vA ? tauprof_f64(pr, comps[0], x, i) : 0.0;
     const double a1 = (vA && nA > 1) ? tauprof_f64(pr, comps[1], x, i) : 0.0;
     const double b0 = vB ? tauprof_f64(pr, comps[2], x, i) : 0.0;
@@ -721,8 +766,8 @@ __device__ __forceinline__ void model_pair_f64(const DeviceProblem& pr, const Co
     mA = 0.0;
     mB = 0.0;
     if (a0 == 0.0 && a1 == 0.0 && b0 == 0.0 && b1 == 0.0) return;
-    const double T0 = planck_T0(x);
-    const double bg0 = t_antenna(T0, TCMB);
+    const double T0 = __ldg(tab + B200FIT_MAX_NCHAN + i);
+    const double bg0 = __ldg(tab + 2 * B200FIT_MAX_NCHAN + i);
     if (a0 != 0.0 || a1 != 0.0)
         mA = __dsub_rn(slab_f64(slab_f64(bg0, T0, comps[0].tex, a0), T0, comps[1].tex, a1), bg0);
     if (b0 != 0.0 || b1 != 0.0)
@@ -746,8 +791,8 @@ struct AuxShared {
 
 // get_modelcube: one warp per pixel
 __global__ void __launch_bounds__(AUX_WARPS * 32)
-    model_kernel(const DeviceProblem pr, const double* __restrict__ params, double* __restrict__ model,
-                 long long stride) {
+    model_kernel(const DeviceProblem pr, const double* __restrict__ tab, const double* __restrict__ params,
+                 double* __restrict__ model, long long stride) {
     __shared__ AuxShared sh[AUX_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int P = 4 * pr.ncomp;
@@ -759,7 +804,7 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
             for (int c = 0; c < pr.ncomp; ++c) comp_setup_f64(pr, p + 4 * c, sh[warp].comps[c], lane);
         for (int i = lane; i < (int)stride; i += 32) {
             double m = NAN;
-            if (valid && i < pr.nchan) m = model_f64(pr, sh[warp].comps, pr.ncomp, i);
+            if (valid && i < pr.nchan) m = model_f64(pr, tab, sh[warp].comps, pr.ncomp, i);
             model[pix * stride + i] = m;
         }
         __syncwarp();
@@ -809,7 +854,7 @@ __device__ __forceinline__ void setup_pixel_models(const DeviceProblem& pr, AuxS
 // Un-dilated union mask (model1 > 0) | (model2 > 0) of ONE pixel, written as a bit set: the spectral mask the
 // include_nosamp rule copies into pixels without samples (UltraCube.py:1423-1438).
 __global__ void __launch_bounds__(32)
-    mask_bits_kernel(const DeviceProblem pr, int nA, int nB, const double* __restrict__ params1,
+    mask_bits_kernel(const DeviceProblem pr, const double* __restrict__ tab, int nA, int nB, const double* __restrict__ params1,
                      const double* __restrict__ params2, int model_f32, const long long* __restrict__ best /* {count, pix} or null */, long long pix_arg,
                      unsigned* __restrict__ bits_out) {
     __shared__ AuxShared sh;
@@ -829,7 +874,7 @@ __global__ void __launch_bounds__(32)
         bool on = false;
         if (wd < nwords && i < pr.nchan) {
             double m1, m2;
-            model_pair_f64(pr, sh.comps, v1, v2, nA, nB, i, m1, m2);
+            model_pair_f64(pr, tab, sh.comps, v1, v2, nA, nB, i, m1, m2);
             on = model_f32 ? (((float)m1 > 0.f) || ((float)m2 > 0.f)) : ((m1 > 0.0) || (m2 > 0.0));
         }
         const unsigned b = __ballot_sync(FULL, on);
@@ -865,7 +910,8 @@ __global__ void mask_argmax_finish_kernel(const unsigned long long* __restrict__
 //   pass 2 (only_empty = 1): only the pixels with mask_counts[pix] == 0, with fill_bits (the global include_nosamp
 //                            mask, known only after pass 1 has seen every pixel of every rank).
 __global__ void __launch_bounds__(AUX_WARPS * 32)
-    aicc_kernel(const DeviceProblem pr, int nA, int nB, const float* __restrict__ spectra, long long stride,
+    aicc_kernel(const DeviceProblem pr, const double* __restrict__ tab, int nA, int nB,
+                const float* __restrict__ spectra, long long stride,
                 const long long* __restrict__ row_index, const double* __restrict__ params1,
                 const double* __restrict__ params2, const unsigned* __restrict__ fill_bits, int only_empty, int expand,
                 int model_f32, double thr10, double thr20, double thr21, double* __restrict__ rss_out,
@@ -892,7 +938,7 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
             bool on = false;
             if (i < pr.nchan) {
                 double m1, m2;
-                model_pair_f64(pr, sh[warp].comps, v1, v2, nA, nB, i, m1, m2);
+                model_pair_f64(pr, tab, sh[warp].comps, v1, v2, nA, nB, i, m1, m2);
                 if (model_f32) {
                     m1s[i] = (float)m1;
                     m2s[i] = (float)m2;
@@ -1000,7 +1046,8 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
 //   chisq_red = nansum((r * mask)^2) / sum(mask) / rms^2,  mask = dilate(model > 0, expand)
 // The median is taken with a warp-wide bitonic sort of |diff| in shared memory.
 __global__ void __launch_bounds__(AUX_WARPS * 32)
-    resid_stats_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
+    resid_stats_kernel(const DeviceProblem pr, const double* __restrict__ tab, const float* __restrict__ spectra,
+                       long long stride,
                        const long long* __restrict__ row_index, const double* __restrict__ params, int expand,
                        int model_f32, int npow2, double* __restrict__ rms_out, double* __restrict__ chisq_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1029,7 +1076,7 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
             const int i = (wd << 5) + lane;
             bool on = false;
             if (i < nchan) {
-                const double m = model_f64(pr, sh[warp].comps, pr.ncomp, i);
+                const double m = model_f64(pr, tab, sh[warp].comps, pr.ncomp, i);
                 const float d = y[i];
                 if (model_f32) {
                     const float mf = (float)m;
@@ -1399,6 +1446,22 @@ static int job_round(b200fit_ctx* ctx, FitJob& jb) {
     return B200FIT_OK;
 }
 
+// (Re)build the per-channel table of the fp64 model when the spectral axis differs from the cached one.
+static int ensure_chan_tables(b200fit_ctx* ctx, const DeviceProblem& pr, cudaStream_t stream) {
+    if (!ctx->d_chan) CK(cudaMalloc((void**)&ctx->d_chan, 3 * B200FIT_MAX_NCHAN * sizeof(double)));
+    if (ctx->chan_n == pr.nchan && ctx->chan_key[0] == pr.v0 && ctx->chan_key[1] == pr.dv &&
+        ctx->chan_key[2] == pr.nu_ref_ghz)
+        return B200FIT_OK;
+    chan_tables_kernel<<<(pr.nchan + 127) / 128, 128, 0, stream>>>(pr, ctx->d_chan);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->chan_n = pr.nchan;
+    ctx->chan_key[0] = pr.v0;
+    ctx->chan_key[1] = pr.dv;
+    ctx->chan_key[2] = pr.nu_ref_ghz;
+    return B200FIT_OK;
+}
+
 extern "C" {
 
 int b200fit_abi_version(void) { return B200FIT_ABI_VERSION; }
@@ -1450,6 +1513,7 @@ void b200fit_destroy(b200fit_ctx* ctx) {
     cudaEventDestroy(ctx->fork_ev);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->h_count) cudaFreeHost((void*)ctx->h_count);
+    if (ctx->d_chan) cudaFree(ctx->d_chan);
     delete ctx;
 }
 
@@ -1628,8 +1692,9 @@ int b200fit_model(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d
     if (pr.npix == 0) return B200FIT_OK;
     if (!d_params || !d_model || nchan_stride < pr.nchan) return fail(ctx, B200FIT_E_ARG, "model: bad argument");
     CK(cudaSetDevice(ctx->device));
-    model_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, 0, (cudaStream_t)stream>>>(pr, d_params, d_model,
-                                                                                                 nchan_stride);
+    if (int rc = ensure_chan_tables(ctx, pr, (cudaStream_t)stream)) return rc;
+    model_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        pr, ctx->d_chan, d_params, d_model, nchan_stride);
     CK(cudaGetLastError());
     ctx->launches += 1;
     return B200FIT_OK;
@@ -1665,8 +1730,9 @@ int b200fit_mask_bits_pair(b200fit_ctx* ctx, const b200fit_problem* prob, int32_
     if (rc) return fail(ctx, rc, "mask_bits: invalid problem description");
     if (!d_bits || (!d_params1 && !d_params2)) return fail(ctx, B200FIT_E_ARG, "mask_bits: bad argument");
     CK(cudaSetDevice(ctx->device));
-    mask_bits_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pr, ncomp_a, ncomp_b, d_params1, d_params2, model_f32,
-                                                        (const long long*)d_best, pix, d_bits);
+    if (int rc = ensure_chan_tables(ctx, pr, (cudaStream_t)stream)) return rc;
+    mask_bits_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pr, ctx->d_chan, ncomp_a, ncomp_b, d_params1, d_params2,
+                                                        model_f32, (const long long*)d_best, pix, d_bits);
     CK(cudaGetLastError());
     ctx->launches += 1;
     return B200FIT_OK;
@@ -1698,8 +1764,9 @@ int b200fit_aicc_pair(b200fit_ctx* ctx, const b200fit_problem* prob, int32_t nco
     const double t10 = thr ? thr[0] : 5.0, t20 = thr ? thr[1] : 5.0, t21 = thr ? thr[2] : 5.0;
     const size_t smem = (size_t)AUX_WARPS * 2 * nchan_stride * (model_f32 ? sizeof(float) : sizeof(double));
     CK(cudaFuncSetAttribute(aicc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = ensure_chan_tables(ctx, pr, (cudaStream_t)stream)) return rc;
     aicc_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        pr, ncomp_a, ncomp_b, d_spectra, nchan_stride, (const long long*)d_row_index, d_params1, d_params2, d_fill_bits,
+        pr, ctx->d_chan, ncomp_a, ncomp_b, d_spectra, nchan_stride, (const long long*)d_row_index, d_params1, d_params2, d_fill_bits,
         only_empty, expand, model_f32, t10, t20, t21, d_rss, d_nsamp, d_lnk, d_ncomp, d_mask_counts);
     CK(cudaGetLastError());
     ctx->launches += 1;
@@ -1753,8 +1820,9 @@ int b200fit_resid_stats(b200fit_ctx* ctx, const b200fit_problem* prob, const flo
     while (npow2 < pr.nchan) npow2 <<= 1;
     const size_t smem = (size_t)AUX_WARPS * 2 * npow2 * sizeof(double);
     CK(cudaFuncSetAttribute(resid_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = ensure_chan_tables(ctx, pr, (cudaStream_t)stream)) return rc;
     resid_stats_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, smem, (cudaStream_t)stream>>>(
-        pr, d_spectra, nchan_stride, (const long long*)d_row_index, d_params, expand, model_f32, npow2, d_rms,
+        pr, ctx->d_chan, d_spectra, nchan_stride, (const long long*)d_row_index, d_params, expand, model_f32, npow2, d_rms,
         d_chisq_red);
     CK(cudaGetLastError());
     ctx->launches += 1;
