@@ -611,12 +611,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
 // last bit).  Both are far inside the 1e-13 agreement the parity tests ask of the model, and the sample mask
 // ``model > 0`` can only change for a channel whose optical depth sits within ~1e-12 (relative) of the 1.1e-16
 // where 1 - exp(-tau) leaves zero -- rarer than the platform dependence of that channel documented in DESIGN.md.
-// Hyperfine terms below exp(-90) relative are skipped: they cannot change the rounded sum.
+// Hyperfine terms below exp(-50) = 2e-22 relative are skipped: where such a term is the largest one the optical
+// depth is far below the 5.6e-17 at which 1 - exp(-tau) leaves zero (the model is exactly 0 there either way), and
+// next to larger terms it is below their rounding error.
 // Quantities that depend on the channel only (frequency, h nu / k, J(T_CMB)) come from a per-context table
 // (chan_tables_kernel) instead of two to five divisions and an exponential per pixel and channel; same values.
 struct CompF64 {
     double tex, tau, nuoff[MAXHF_FULL], rcp2w2[MAXHF_FULL], tw[MAXHF_FULL];   // rcp2w2 = 1 / (2 nuwidth^2)
-    double acut[MAXHF_FULL];   // |x + nuoff - line| beyond which the term is below exp(-90): skipped without the divide
+    double acut[MAXHF_FULL];   // |x + nuoff - line| beyond which the term is below exp(-50): skipped before the multiply
     int clo[MAXHF_FULL], chi[MAXHF_FULL];   // per line group: channels outside [clo, chi] are beyond every acut (+2 margin)
 };
 
@@ -636,7 +638,7 @@ __device__ __forceinline__ void comp_setup_f64(const DeviceProblem& pr, const do
         const double d = __dmul_rn(2.0, __dmul_rn(nuwidth, nuwidth));   // 2.0 * nuwidth**2 (the divisor)
         c.rcp2w2[k] = __ddiv_rn(1.0, d);
         c.tw[k] = __dmul_rn(tau, pr.wts_full[k]);
-        c.acut[k] = sqrt(90.0 * d) * (1.0 + 1e-9);   // generous: the exact arg > -90 test still follows
+        c.acut[k] = sqrt(50.0 * d) * (1.0 + 1e-9);   // generous: the exact arg > -50 test still follows
     }
     __syncwarp();
     // channel range of every line group (integer pre-test; x decreases with the channel index)
@@ -661,7 +663,7 @@ __device__ __forceinline__ double xarr_ghz(const DeviceProblem& pr, int i) {
     return __ddiv_rn(__dmul_rn(__dmul_rn(pr.nu_ref_ghz, 1e9), __dsub_rn(1.0, __ddiv_rn(v, CKMS))), 1e9);
 }
 
-// exp(x) for -90 <= x <= 0, ~1 ulp: x = n ln2 + r, |r| <= ln2 / 2, degree-13 Taylor, exponent added in place.
+// exp(x) for -50 <= x <= 0 (valid down to ~ -700), ~1 ulp: x = n ln2 + r, |r| <= ln2 / 2, degree-13 Taylor, exponent added in place.
 // Half the instructions of exp(): no overflow / subnormal handling is needed on this range.
 __device__ __forceinline__ double exp_neg(double x) {
     const double n = rint(x * 1.4426950408889634);
@@ -696,8 +698,8 @@ __device__ __forceinline__ double t_antenna(double T0, double T) {
     return __ddiv_rn(T0, __dsub_rn(exp(__ddiv_rn(T0, T)), 1.0));
 }
 
-// optical depth profile of one component at frequency x (HyperfineModel.py:99-103); terms below exp(-90) of their
-// peak are skipped (they cannot change the rounded sum: exp(-90) = 8e-40)
+// optical depth profile of one component at frequency x (HyperfineModel.py:99-103); terms below exp(-50) of their
+// peak are skipped (see the note above CompF64)
 __device__ __forceinline__ double tauprof_f64(const DeviceProblem& pr, const CompF64& cp, double x, int i) {
     double tauprof = 0.0;
     for (int g = 0; g < pr.ngroups_full; ++g) {
@@ -706,7 +708,7 @@ __device__ __forceinline__ double tauprof_f64(const DeviceProblem& pr, const Com
             const double a = __dsub_rn(__dadd_rn(x, cp.nuoff[k]), pr.lines_full[k]);
             if (fabs(a) > cp.acut[k]) continue;
             const double arg = __dmul_rn(-__dmul_rn(a, a), cp.rcp2w2[k]);
-            if (arg > -90.0) tauprof = __dadd_rn(tauprof, __dmul_rn(cp.tw[k], exp_neg(arg)));
+            if (arg > -50.0) tauprof = __dadd_rn(tauprof, __dmul_rn(cp.tw[k], exp_neg(arg)));
         }
     }
     return tauprof;
