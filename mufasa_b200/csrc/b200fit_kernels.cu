@@ -616,10 +616,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
 // next to larger terms it is below their rounding error.
 // Quantities that depend on the channel only (frequency, h nu / k, J(T_CMB)) come from a per-context table
 // (chan_tables_kernel) instead of two to five divisions and an exponential per pixel and channel; same values.
+constexpr int MASK_WORDS = B200FIT_MAX_NCHAN / 32;   // spectral masks are bit sets of at most 64 words
+static_assert(MASK_WORDS == 64, "comp_setup_f64 fills two words per lane");
+
 struct CompF64 {
     double tex, tau, nuoff[MAXHF_FULL], rcp2w2[MAXHF_FULL], tw[MAXHF_FULL];   // rcp2w2 = 1 / (2 nuwidth^2)
     double acut[MAXHF_FULL];   // |x + nuoff - line| beyond which the term is below exp(-50): skipped before the multiply
-    int clo[MAXHF_FULL], chi[MAXHF_FULL];   // per line group: channels outside [clo, chi] are beyond every acut (+2 margin)
+    unsigned char gbits[MASK_WORDS];        // per 32-channel word: bit g set when line group g (< 8) reaches into it
 };
 
 // Warp-cooperative set-up of one component: lane k prepares line k (the divisions and the square root are the
@@ -641,7 +644,9 @@ __device__ __forceinline__ void comp_setup_f64(const DeviceProblem& pr, const do
         c.acut[k] = sqrt(50.0 * d) * (1.0 + 1e-9);   // generous: the exact arg > -50 test still follows
     }
     __syncwarp();
-    // channel range of every line group (integer pre-test; x decreases with the channel index)
+    // channel range [clo, chi] of every line group (x decreases with the channel index; +2 channels of margin):
+    // channels outside it are beyond every acut of the group
+    int clo = 1, chi = 0;
     if (lane < pr.ngroups_full) {
         const int g = lane;
         double xmin = INFINITY, xmax = -INFINITY;
@@ -652,9 +657,19 @@ __device__ __forceinline__ void comp_setup_f64(const DeviceProblem& pr, const do
         }
         const double ilo = ((1.0 - xmax / pr.nu_ref_ghz) * CKMS - pr.v0) / pr.dv;
         const double ihi = ((1.0 - xmin / pr.nu_ref_ghz) * CKMS - pr.v0) / pr.dv;
-        c.clo[g] = (int)fmax(fmin(floor(ilo) - 2.0, 1e9), -1e9);
-        c.chi[g] = (int)fmax(fmin(ceil(ihi) + 2.0, 1e9), -1e9);
+        clo = (int)fmax(fmin(floor(ilo) - 2.0, 1e9), -1e9);
+        chi = (int)fmax(fmin(ceil(ihi) + 2.0, 1e9), -1e9);
     }
+    // which groups can contribute to each 32-channel word: the hyperfine sum then walks only those (a word outside
+    // every window costs one byte load instead of a test per group, channel and component)
+    unsigned m0 = 0u, m1 = 0u;   // words lane and lane + 32
+    for (int g = 0; g < pr.ngroups_full; ++g) {
+        const int lo = __shfl_sync(FULL, clo, g), hi = __shfl_sync(FULL, chi, g);
+        if (!((lane << 5) + 31 < lo || (lane << 5) > hi)) m0 |= 1u << g;
+        if (!(((lane + 32) << 5) + 31 < lo || ((lane + 32) << 5) > hi)) m1 |= 1u << g;
+    }
+    c.gbits[lane] = (unsigned char)m0;
+    c.gbits[lane + 32] = (unsigned char)m1;
     __syncwarp();
 }
 
@@ -663,15 +678,16 @@ __device__ __forceinline__ double xarr_ghz(const DeviceProblem& pr, int i) {
     return __ddiv_rn(__dmul_rn(__dmul_rn(pr.nu_ref_ghz, 1e9), __dsub_rn(1.0, __ddiv_rn(v, CKMS))), 1e9);
 }
 
-// exp(x) for -50 <= x <= 0 (valid down to ~ -700), ~1 ulp: x = n ln2 + r, |r| <= ln2 / 2, degree-13 Taylor, exponent added in place.
+// exp(x) for -50 <= x <= 0 (valid down to ~ -700), ~1 ulp: x = n ln2 + r, |r| <= ln2 / 2, degree-13 Taylor,
+// exponent added in place.
 // Half the instructions of exp(): no overflow / subnormal handling is needed on this range.
 __device__ __forceinline__ double exp_neg(double x) {
     const double n = rint(x * 1.4426950408889634);
     double r = fma(n, -6.93147180369123816490e-01, x);
     r = fma(n, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;                 // 1 / 13!
-    p = fma(p, r, 2.08767569878681e-09);
-    p = fma(p, r, 2.505210838544172e-08);
+    double p = 1.6059043836821613e-10;                 // 1 / 13!  (Horner; an Estrin tree, 5 deep instead of 13,
+    p = fma(p, r, 2.08767569878681e-09);               //  measured the same: the term loop's branches, not this
+    p = fma(p, r, 2.505210838544172e-08);              //  chain, are what the warps wait on)
     p = fma(p, r, 2.755731922398589e-07);
     p = fma(p, r, 2.7557319223985893e-06);
     p = fma(p, r, 2.48015873015873e-05);
@@ -702,11 +718,11 @@ __device__ __forceinline__ double t_antenna(double T0, double T) {
 // peak are skipped (see the note above CompF64)
 __device__ __forceinline__ double tauprof_f64(const DeviceProblem& pr, const CompF64& cp, double x, int i) {
     double tauprof = 0.0;
-    for (int g = 0; g < pr.ngroups_full; ++g) {
-        if (i < cp.clo[g] || i > cp.chi[g]) continue;   // integer pre-test: the whole group is out of reach
+    for (unsigned m = cp.gbits[i >> 5]; m; m &= m - 1u) {   // groups in reach of this word, ascending as in the sum
+        const int g = __ffs(m) - 1;
         for (int k = pr.gstart_full[g]; k < pr.gstart_full[g + 1]; ++k) {
             const double a = __dsub_rn(__dadd_rn(x, cp.nuoff[k]), pr.lines_full[k]);
-            if (fabs(a) > cp.acut[k]) continue;
+            if (fabs(a) > cp.acut[k]) continue;   // (a branch-free form that weights skipped terms by 0 was 65 % slower)
             const double arg = __dmul_rn(-__dmul_rn(a, a), cp.rcp2w2[k]);
             if (arg > -50.0) tauprof = __dadd_rn(tauprof, __dmul_rn(cp.tw[k], exp_neg(arg)));
         }
@@ -815,7 +831,6 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
 
 // ---------------------------------------------------------------------------------------------------------
 // Spectral masks are bit sets: bits[w] bit b <-> channel 32*w + b, at most 64 words (B200FIT_MAX_NCHAN = 2048).
-constexpr int MASK_WORDS = B200FIT_MAX_NCHAN / 32;
 
 // Dilation along the spectral axis: True at k spreads to [k - e/2, k + (e-1)/2] (scipy binary_dilation with
 // ones(e), origin 0 -- UltraCube.expand_mask :1658-1698; e = 20: [k-10, k+9]).  Word-parallel, e <= 64.
@@ -1450,6 +1465,7 @@ static int job_round(b200fit_ctx* ctx, FitJob& jb) {
 
 // (Re)build the per-channel table of the fp64 model when the spectral axis differs from the cached one.
 static int ensure_chan_tables(b200fit_ctx* ctx, const DeviceProblem& pr, cudaStream_t stream) {
+    if (pr.ngroups_full > 8) return fail(ctx, B200FIT_E_MODEL, "fp64 model: more than 8 hyperfine line groups");
     if (!ctx->d_chan) CK(cudaMalloc((void**)&ctx->d_chan, 3 * B200FIT_MAX_NCHAN * sizeof(double)));
     if (ctx->chan_n == pr.nchan && ctx->chan_key[0] == pr.v0 && ctx->chan_key[1] == pr.dv &&
         ctx->chan_key[2] == pr.nu_ref_ghz)
@@ -1679,9 +1695,14 @@ int b200fit_fit(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_sp
     return b200fit_fit_batch(ctx, &a, 1, stream);
 }
 
+// Grid of the warp-per-pixel statistics kernels.  Pixels differ a lot in cost (no fit / 1 / 2 components, line width),
+// so the work is cut into many more blocks than fit on the device -- 4 pixels per warp -- and the hardware scheduler
+// balances them; a grid of exactly 8 blocks per SM left a second, partly filled wave (5-6 blocks are resident).
 static long long aux_blocks(const b200fit_ctx* ctx, long long npix) {
-    long long blocks = (long long)ctx->num_sms * 8;
     const long long need = (npix + AUX_WARPS - 1) / AUX_WARPS;
+    long long blocks = (need + 3) / 4;
+    const long long floor_blocks = (long long)ctx->num_sms * 8;
+    if (blocks < floor_blocks) blocks = floor_blocks;
     return blocks < need ? blocks : (need > 0 ? need : 1);
 }
 
