@@ -142,7 +142,8 @@ typedef struct {
 int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* jobs, int32_t njobs, void* stream);
 
 /* Model evaluation: replaces pcube.get_modelcube() (one multi_v_spectrum call per pixel,
- * HyperfineModel.py:22-109), in fp64 with the reference's frequency-space operation order.
+ * HyperfineModel.py:22-109), in fp64 with the reference's frequency-space operation order (except that the gaussian
+ * argument of a hyperfine term multiplies by a per-line reciprocal and uses a lean exp: last-bit differences).
  *   d_params [npix][P]; all-zero or non-finite rows produce NaN rows (pyspeckit convention)
  *   d_model  [npix][nchan_stride] fp64 */
 int b200fit_model(b200fit_ctx* ctx, const b200fit_problem* prob, const double* d_params,
