@@ -6,13 +6,13 @@
 //   pcube.get_modelcube, UltraCube.get_rss / expand_mask / AICc ...  mufasa/UltraCube.py:322-325, 1384-1475, 1658-1698
 //
 // Design:
-//   * fit_kernel<NC>: persistent warps, ONE WARP PER PIXEL, pixels pulled from an atomic queue (iteration counts
-//     vary by >10x between pixels).  The spectrum is staged in shared memory with coalesced float4 loads; lanes
-//     own channels (32-channel chunks).  Per evaluation the warp computes the fp32 model and its analytic
-//     Jacobian only over the chunks a hyperfine window touches, accumulates J^T J / J^T r / chi2 per lane in
-//     fp32, reduces across lanes in fp64 through shared memory, and lane 0 advances the LM state machine
-//     (fp64 Cholesky on the damped normal equations, mpfit-style limits) from b200fit_common.h.
-//   * model/aicc/mask/stat kernels: fp64 model in the reference's frequency-space operation order (the AICc
+//   * the fit is a ROUND LOOP of small uniform kernels over a compacted list of the pixels still iterating
+//     (fit_prologue / fit_eval / fit_solve / fit_finalize below): a warp (late rounds: a block) evaluates the fp32
+//     model and its analytic Jacobian of one pixel over the chunks a hyperfine window touches and accumulates
+//     J^T J / J^T r / chi2 (packed fp32 FMAs per lane, fp64 across lanes); P lanes advance the pixel's LM state
+//     machine (fp64 Cholesky on the damped normal equations, mpfit-style limits; b200fit_lanes.cuh, serial
+//     restatement in b200fit_common.h).  Several fits -- or parts of one -- run in flight together.
+//   * model / aicc / mask / stat kernels: fp64 model in the reference's frequency-space operation order (the AICc
 //     sample mask is ``model > 0``, decided by fp64 round-off), one warp per pixel.
 //   * gather_kernel: FITS channel-major cube -> compacted pixel-major rows (smem tile transpose).
 // No tensor cores: the per-pixel systems are 4x4 / 8x8.  No CPU fallback anywhere in this library.
@@ -55,8 +55,9 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 //                        active list 0
 //   fit_eval_kernel      warp per ACTIVE pixel: fp32 model + analytic Jacobian over the hyperfine windows,
 //                        J^T J / J^T r / chi2 (fp32 per lane, fp64 across lanes) at the pixel's trial point
-//   fit_solve_kernel     THREAD per active pixel: one step of the LM state machine (fp64 Cholesky trust-region
-//                        solve, mpfit limits); finished pixels write their results, the rest join the next list
+//   fit_solve_kernel     P lanes per active pixel: one step of the LM state machine (fp64 Cholesky trust-region
+//                        solve, mpfit limits); finished pixels leave the list, the rest join the next one
+//   fit_finalize_kernel  once: parameter errors from (J^T J)^-1 and the result rows
 // Why not one fused persistent kernel (rounds 1a-1c, profiles/): the solver is ~5k instructions of branchy fp64
 // scalar code per step.  Fused, it ran on 1 (v1) or ~4 (v2, pixel groups) lanes of a warp, and evaluation +
 // solver code together (107-263 KB) thrashed the 32 KB instruction cache -- >50 % of all stall samples were
