@@ -254,27 +254,30 @@ def run_b200(args):
         res = uc.get_best_2c_parcube()
         return uc, res
 
-    uc, res = e2e_step()                           # also the source of the limits the device arm uses
-    torch.cuda.synchronize()
-    h2d = cube_host.nbytes + syn["guess1"].nbytes + syn["guess2"].nbytes + npix * 12 * 8
-    d2h = sum(uc.pcubes[k].parcube.nbytes * 2 + npix * (8 + 8 + 8 + 8) for k in ("1", "2")) + npix * (3 + 1 + 3) * 8 \
-        + npix
+    # Steady state of a caller that processes one cube after another: the previous step's objects are released
+    # before the next step starts.  (Keeping an older UltraCube alive costs ~7 ms per step in first-touch page
+    # faults of the freshly mapped result arrays -- host allocator behaviour, not device work.)
     e2e_times = []
     n_e2e = max(2, min(args.steps, 5))
-    for it in range(1 + n_e2e):
+    for it in range(2 + n_e2e):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         uc_i, res_i = e2e_step()
         torch.cuda.synchronize()
-        if it >= 1:
+        if it >= 2:
             e2e_times.append(time.perf_counter() - t0)
         del uc_i, res_i
     e2e_t = torch.tensor([float(np.mean(e2e_times))], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = npix * world / float(e2e_t.item())
+    uc, res = e2e_step()                           # kept: the source of the rows and limits the device arm uses
+    torch.cuda.synchronize()
+    h2d = cube_host.nbytes + syn["guess1"].nbytes + syn["guess2"].nbytes + npix * 12 * 8
+    d2h = sum(uc.pcubes[k].parcube.nbytes * 2 + npix * (8 + 8 + 8 + 8) for k in ("1", "2")) + npix * (3 + 1 + 3) * 8 \
+        + npix
 
     # ---------------- device arm: rows resident in HBM --------------------------------------------------------
     rows = uc._ref_pcube.rows_on_device()

@@ -140,10 +140,9 @@ class UltraCube(object):
             done.record(torch.cuda.current_stream(eng.device))
             if eager_aicc:
                 eager = self._launch_eager_aicc(batch, outs, eng)
-            if not hasattr(eng, "_side_stream"):
-                eng._side_stream = torch.cuda.Stream(device=eng.device)
-            with torch.cuda.stream(eng._side_stream):
-                eng._side_stream.wait_event(done)
+            back = eng.side_stream("d2h")
+            with torch.cuda.stream(back):
+                back.wait_event(done)
                 for job, out in zip(batch, outs):           # both copies in flight before the first host wait
                     job["pcube"].start_fit_readback(job, out)
                 for job, out in zip(batch, outs):

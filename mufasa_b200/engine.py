@@ -73,6 +73,14 @@ class Engine(object):
             cache[key] = torch.empty([d for d in shape if not isinstance(d, str)], dtype=dtype).pin_memory()
         return cache[key]
 
+    def side_stream(self, name):
+        """A second CUDA stream of this engine (created on first use), e.g. for copies that must not queue behind
+        the main stream's work."""
+        streams = self.__dict__.setdefault("_side_streams", {})
+        if name not in streams:
+            streams[name] = torch.cuda.Stream(device=self.device)
+        return streams[name]
+
     @staticmethod
     def nchan_stride(nchan):
         return (int(nchan) + 31) // 32 * 32
@@ -163,6 +171,9 @@ class Engine(object):
             assert guesses.dtype == torch.float64 and guesses.is_contiguous() and tuple(guesses.shape) == (npix, P)
             assert job.get("row_index") is not None or spectra.shape[0] == npix
             results.append(job.get("out") or self.alloc_fit_out(prob))
+        for job in jobs:                      # inputs uploaded on another stream (PCube.fiteach)
+            if job.get("ready") is not None:
+                torch.cuda.current_stream(self.device).wait_event(job["ready"])
         jobs = self._split_jobs(jobs, results)
         n = len(jobs)
         arr = (_abi.FitArgs * max(n, 1))()

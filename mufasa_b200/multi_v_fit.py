@@ -196,8 +196,13 @@ def cubefit_simp_steps(cube, pcube, ncomp, guesses, multicore=None, maskmap=None
     impose_lim(guesses[3::4], taumin, taumax, eps)
     yield
 
-    # (the reference builds the footprint first, multi_v_fit.py:150; nothing above depends on it)
-    footprint_mask = pcube.footprint() if hasattr(pcube, "footprint") else np.any(np.isfinite(data), axis=0)
+    # The reference also removes the pixels without a finite channel here (footprint_mask, multi_v_fit.py:150, :193).
+    # On the device that would be a host synchronisation with the cube upload; the fit kernel returns "not fitted"
+    # (zeros, has_fit False) for such spectra by itself, so they are left in the mask and the maps come out the same.
+    if hasattr(pcube, "rows_on_device"):
+        footprint_mask = True
+    else:
+        footprint_mask = np.any(np.isfinite(data), axis=0)
     if maskmap is not None:
         maskmap = maskmap & planemask & footprint_mask
     else:

@@ -237,15 +237,31 @@ class PCube(object):
         prob = self._problem(fittype, ncomp, npix, list(minpars), list(maxpars), signal_cut=float(signal_cut or 0.0),
                              maxiter=maxiter)
         rows = self.rows_on_device()
-        gsel = np.ascontiguousarray(guesses.reshape(P, ny * nx)[:, pix].T)
-        g_dev = torch.from_numpy(gsel).to(dev, non_blocking=True)
-        idx_dev = None if npix == ny * nx else torch.from_numpy(pix.astype(np.int64)).to(dev, non_blocking=True)
-        job = dict(prob=prob, spectra=rows, guesses=g_dev, row_index=idx_dev, pcube=self, pix=pix)
+        # guesses (and the pixel list) go up through pinned memory on a second stream: a copy from pageable memory
+        # on the main stream would make the host wait for the cube upload queued ahead of it
+        main = torch.cuda.current_stream(dev)
+        up = eng.side_stream("h2d")
+        g_stage = eng.pinned_stage(("guesses", npix, P))
+        np.copyto(g_stage.numpy(), guesses.reshape(P, ny * nx)[:, pix].T)
+        i_stage = None
+        if npix != ny * nx:
+            i_stage = eng.pinned_stage(("pixels", npix), dtype=torch.int64)
+            np.copyto(i_stage.numpy(), pix)
+        with torch.cuda.stream(up):
+            g_dev = g_stage.to(dev, non_blocking=True)
+            idx_dev = None if i_stage is None else i_stage.to(dev, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(up)
+        g_dev.record_stream(main)
+        if idx_dev is not None:
+            idx_dev.record_stream(main)
+        job = dict(prob=prob, spectra=rows, guesses=g_dev, row_index=idx_dev, pcube=self, pix=pix, ready=ready)
         if self._deferred is not None:
             # UltraCube.fit_cube over several ncomp: the fits are launched together (Engine.fit_batch) so that the
             # latency-bound late rounds of one overlap the other; results are filled in by finish_fit()
             self._deferred.append(job)
             return
+        main.wait_event(ready)
         out = eng.fit(prob, rows, g_dev, row_index=idx_dev)
         self.finish_fit(job, out)
 
