@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200FIT_ABI_VERSION 3
+#define B200FIT_ABI_VERSION 4
 
 enum {
     B200FIT_OK = 0,
@@ -138,8 +138,17 @@ typedef struct {
     int32_t* d_status;
     uint32_t* d_counts;
     void* d_workspace;
+    void* wait_event;   /* cudaEvent_t or NULL: this job's kernels are ordered after the event (inputs of the job that
+                         * are still being uploaded on another stream, see b200fit_upload_slab) */
 } b200fit_fit_args;
 int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* jobs, int32_t njobs, void* stream);
+
+/* Host -> device copy of a row slab of a FITS-order cube [nchan][ny][nx] (pinned host memory): the ``count``
+ * elements starting ``first`` elements into every plane, i.e. h_cube[c * plane + first + k] -> d_dst[c * count + k]
+ * (one cudaMemcpy2DAsync on ``stream``).  Lets the fit of the first rows start while the rest of the cube is still
+ * crossing PCIe; replaces the single read of the cube file in UltraCube.load_pcube (mufasa/UltraCube.py:185-200). */
+int b200fit_upload_slab(b200fit_ctx* ctx, const float* h_cube, int32_t nchan, int64_t plane, int64_t first, int64_t count,
+                        float* d_dst, void* stream);
 
 /* Model evaluation: replaces pcube.get_modelcube() (one multi_v_spectrum call per pixel,
  * HyperfineModel.py:22-109), in fp64 with the reference's frequency-space operation order (except that the gaussian

@@ -8,7 +8,7 @@ LIB_PATH = os.environ.get("B200FIT_LIB", os.path.join(HERE, "csrc", "libb200fit.
 
 MODEL_IDS = {"nh3_multi_v": 0, "n2hp_multi_v": 1}
 MAX_NCHAN = 2048
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Problem(C.Structure):
@@ -40,7 +40,8 @@ class FitArgs(C.Structure):
     _fields_ = [("prob", C.POINTER(Problem)), ("d_spectra", C.c_void_p), ("nchan_stride", C.c_int64),
                 ("d_row_index", C.c_void_p), ("d_guesses", C.c_void_p), ("d_err", C.c_void_p),
                 ("d_params", C.c_void_p), ("d_perr", C.c_void_p), ("d_chi2", C.c_void_p), ("d_err_used", C.c_void_p),
-                ("d_status", C.c_void_p), ("d_counts", C.c_void_p), ("d_workspace", C.c_void_p)]
+                ("d_status", C.c_void_p), ("d_counts", C.c_void_p), ("d_workspace", C.c_void_p),
+                ("wait_event", C.c_void_p)]
 
 
 MAX_BATCH = 4
@@ -85,6 +86,7 @@ SIGNATURES = {
     "b200fit_masked_moments": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp,
                                          _vp]),
     "b200fit_resid_stats": (C.c_int, [_vp, _PP, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "b200fit_upload_slab": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp]),
     "b200fit_convolve_planes": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, C.c_double, _vp, _vp]),
     "b200fit_resample_bilinear": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, C.c_double, C.c_double,
                                             C.c_double, C.c_double, _vp]),

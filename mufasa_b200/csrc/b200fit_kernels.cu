@@ -1348,6 +1348,7 @@ struct FitJob {
     void* states = nullptr;
     cudaStream_t stream = nullptr;
     unsigned egrid = 0, egrid_team = 0, sgrid = 0;
+    void* wait_event = nullptr;
     int r = 0, max_rounds = 0, nchecks = 0, slot0 = 0;
     bool finished = false, prof = false;
 };
@@ -1592,6 +1593,18 @@ int b200fit_gather_spectra(b200fit_ctx* ctx, const float* d_cube, int32_t nchan,
     return B200FIT_OK;
 }
 
+int b200fit_upload_slab(b200fit_ctx* ctx, const float* h_cube, int32_t nchan, int64_t plane, int64_t first, int64_t count,
+                        float* d_dst, void* stream) {
+    if (!ctx) return B200FIT_E_ARG;
+    if (nchan == 0 || count == 0) return B200FIT_OK;
+    if (!h_cube || !d_dst || nchan < 0 || plane <= 0 || first < 0 || count < 0 || first + count > plane)
+        return fail(ctx, B200FIT_E_ARG, "upload_slab: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(d_dst, (size_t)count * sizeof(float), h_cube + first, (size_t)plane * sizeof(float),
+                         (size_t)count * sizeof(float), (size_t)nchan, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return B200FIT_OK;
+}
+
 int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* args, int32_t njobs, void* stream_) {
     if (!ctx || !args) return fail(ctx, B200FIT_E_ARG, "fit: null context/arguments");
     if (njobs < 0 || njobs > B200FIT_MAX_BATCH) return fail(ctx, B200FIT_E_ARG, "fit: njobs must be in [0, B200FIT_MAX_BATCH]");
@@ -1623,6 +1636,7 @@ int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* args, int32_t nj
         jb.d_err_used = a.d_err_used;
         jb.d_status = a.d_status;
         jb.d_counts = a.d_counts;
+        jb.wait_event = a.wait_event;
         jb.slot0 = live * FIT_RING;
         jb.states = a.d_workspace;   // resolved in job_begin
         ++live;
@@ -1636,6 +1650,7 @@ int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* args, int32_t nj
         jb.stream = forked ? ctx->job_stream[j] : stream;
         jb.prof = ctx->profiling != 0 && j == 0 && !forked;
         if (forked) CK(cudaStreamWaitEvent(jb.stream, ctx->fork_ev, 0));
+        if (jb.wait_event) CK(cudaStreamWaitEvent(jb.stream, (cudaEvent_t)jb.wait_event, 0));
         void* ws = jb.states;
         const int rc = (jb.nc == 1) ? job_begin<1>(ctx, jb, ws) : job_begin<2>(ctx, jb, ws);
         if (rc) return rc;
@@ -1693,6 +1708,7 @@ int b200fit_fit(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_sp
     a.d_status = d_status;
     a.d_counts = d_counts;
     a.d_workspace = d_workspace;
+    a.wait_event = nullptr;
     return b200fit_fit_batch(ctx, &a, 1, stream);
 }
 

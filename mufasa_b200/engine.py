@@ -115,6 +115,15 @@ class Engine(object):
         self._check(rc, "b200fit_gather_spectra")
         return out
 
+    def upload_slab(self, host_cube, first, count, dst):
+        """Pinned host cube [nchan, nplane] fp32 -> dst [nchan, count]: elements [first, first + count) of every
+        plane, one 2-D copy on the current stream (b200fit_upload_slab)."""
+        assert host_cube.dtype == torch.float32 and host_cube.is_contiguous() and host_cube.dim() == 2
+        assert dst.dtype == torch.float32 and dst.is_contiguous() and tuple(dst.shape) == (host_cube.shape[0], count)
+        rc = self.lib.b200fit_upload_slab(self.ctx, C.c_void_p(host_cube.data_ptr()), int(host_cube.shape[0]),
+                                          int(host_cube.shape[1]), int(first), int(count), _ptr(dst), self._stream())
+        self._check(rc, "b200fit_upload_slab")
+
     def fit(self, prob, spectra, guesses, err=None, want_counts=True, row_index=None, out=None):
         """Batched LM fit.  spectra [nrows, stride] fp32, guesses [npix, P] fp64 (device); ``row_index`` [npix] int64
         maps pixel k to its spectrum row (None: row k).  Returns a dict of device tensors: params, perr [npix, P];
@@ -199,6 +208,7 @@ class Engine(object):
             a.d_status = out["status"].data_ptr()
             a.d_counts = out["counts"].data_ptr() if out.get("counts") is not None else None
             a.d_workspace = ws.data_ptr()
+            a.wait_event = job["wait"].cuda_event if job.get("wait") is not None else None
             outs.append(out)
             keep.append((prob, spectra, guesses, row_index))
         rc = self.lib.b200fit_fit_batch(self.ctx, arr, n, self._stream())
@@ -212,6 +222,9 @@ class Engine(object):
         (contiguous views of the same inputs and outputs).  Pixels do not interact, so the results are those of the
         undivided fit; two half-sized round loops interleave on the GPU where one full-sized loop leaves it partly
         idle between its dependent kernels (measured: 2-component fit of 65 536 spectra 34.7 -> 32.7 ms)."""
+        slabbed = [j for j in jobs if j.get("slab_ready") is not None]
+        if slabbed and not getattr(self, "_profiling", False):
+            return self._split_by_slab(jobs, results)
         limit = min(_abi.MAX_BATCH, int(os.environ.get("B200FIT_SPLIT_LIMIT", 3)))   # measured: 3 beats 2 and 4
         parts = [1] * len(jobs)
         weight = [int(j["prob"].npix) * int(j["prob"].ncomp) ** 2 for j in jobs]
@@ -238,6 +251,44 @@ class Engine(object):
                                  row_index=None if ri is None else ri[a:b],
                                  err=None if job.get("err") is None else job["err"][a:b],
                                  out={key: (None if t is None else t[a:b]) for key, t in out.items()}))
+        return work
+
+    def _split_by_slab(self, jobs, results):
+        """Jobs whose spectra are still being uploaded slab by slab (PCube.rows_on_device): a job is cut at the slab
+        boundaries when the batch has room, and every part waits only for the event of the last slab it reads --
+        the first rows are being fitted while the rest of the cube crosses PCIe."""
+        nslab = max(len(j["slab_ready"][0]) for j in jobs if j.get("slab_ready") is not None)
+        cut = len(jobs) * nslab <= _abi.MAX_BATCH
+        work = []
+        for job, out in zip(jobs, results):
+            prob, npix = job["prob"], int(job["prob"].npix)
+            sr = job.get("slab_ready")
+            if sr is None:
+                work.append(dict(job, out=out))
+                continue
+            bounds, events = sr
+            pix = job.get("pix")                      # ascending pixel indices of a masked fit, or None / all
+            if job.get("row_index") is None:
+                ends = [min(b, npix) for b in bounds]
+            else:
+                ends = [int(np.searchsorted(pix, b)) for b in bounds]
+            if not cut:
+                last = min(k for k in range(len(ends)) if ends[k] >= npix)   # the slab holding its last pixel
+                work.append(dict(job, out=out, wait=events[last]))
+                continue
+            ri, a = job.get("row_index"), 0
+            for k, b in enumerate(ends):
+                if b <= a:
+                    continue
+                p = _abi.Problem()
+                C.memmove(C.byref(p), C.byref(prob), C.sizeof(p))
+                p.npix = b - a
+                work.append(dict(prob=p, guesses=job["guesses"][a:b], wait=events[k],
+                                 spectra=job["spectra"] if ri is not None else job["spectra"][a:b],
+                                 row_index=None if ri is None else ri[a:b],
+                                 err=None if job.get("err") is None else job["err"][a:b],
+                                 out={key: (None if t is None else t[a:b]) for key, t in out.items()}))
+                a = b
         return work
 
     def model(self, prob, params, stride=None):

@@ -165,7 +165,7 @@ def cubefit_simp_steps(cube, pcube, ncomp, guesses, multicore=None, maskmap=None
 
     data = _cube_data(cube)
     if hasattr(pcube, "rows_on_device"):
-        pcube.rows_on_device()          # start the (asynchronous) upload + layout pass; host logic below overlaps it
+        pcube.rows_on_device(wait=False)   # start the (asynchronous) upload + layout pass; host logic below overlaps it
     planemask = np.any(np.isfinite(guesses), axis=0)
     peaksnr, planemask, kwargs = handle_snr(pcube, snr_min, planemask, **kwargs)
 

@@ -101,22 +101,53 @@ class PCube(object):
     def engine(self):
         return get_engine(self._device)
 
-    def rows_on_device(self):
+    def rows_on_device(self, wait=True):
         """The cube as pixel-major rows [ny*nx, stride] fp32 on the GPU (NaN padded, velocity ascending).
 
-        Uploaded ONCE per data cube -- pinned host memory -> channel-major staging buffer -> ``b200fit_gather_spectra``
-        transpose -- and shared between the PCubes of one UltraCube (``share_device``).  The reference instead
-        re-reads the FITS file for every ncomp (UltraCube.py:191)."""
+        Uploaded ONCE per data cube and shared between the PCubes of one UltraCube (``share_device``); the reference
+        instead re-reads the FITS file for every ncomp (UltraCube.py:191).  A large cube in pinned memory goes up as
+        two row slabs on a second stream (``b200fit_upload_slab`` + ``b200fit_gather_spectra`` per slab), each with
+        an event: fit jobs that only touch the first slab start while the second is still crossing PCIe
+        (``slab_ready``, used by Engine.fit_batch).  ``wait=True`` orders the current stream after the whole upload
+        -- what every consumer other than the batched fit wants."""
         if self._dev.get("rows") is None:
             nchan, ny, nx = self.cube.shape
             eng = self.engine
             host = self.cube if self.cube.dtype == np.float32 else self.cube.astype(np.float32)
             t = torch.from_numpy(np.ascontiguousarray(host).reshape(nchan, ny * nx))
-            staging = t.to(eng.device, non_blocking=True)       # async when the cube lives in pinned memory
             _, _, flip = self.xarr.v0_dv_flip
-            self._dev["rows"] = eng.gather(staging, None, flip=flip)
+            nslab = 2 if (t.is_pinned() and ny * nx >= 2 * eng.SPLIT_MIN_PIXELS and ny >= 2) else 1
+            if nslab == 1:
+                staging = t.to(eng.device, non_blocking=True)       # async when the cube lives in pinned memory
+                self._dev["rows"] = eng.gather(staging, None, flip=flip)
+                del staging
+            else:
+                rows = torch.empty((ny * nx, eng.nchan_stride(nchan)), dtype=torch.float32, device=eng.device)
+                up = eng.side_stream("h2d_cube")
+                up.wait_stream(torch.cuda.current_stream(eng.device))   # the allocation above is ordered before
+                bounds, events = [], []
+                for k in range(nslab):
+                    first, last = (k * ny // nslab) * nx, ((k + 1) * ny // nslab) * nx
+                    with torch.cuda.stream(up):
+                        staging = torch.empty((nchan, last - first), dtype=torch.float32, device=eng.device)
+                        # in pieces of ~16 MB: a copy cannot be overtaken, and the (small) upload of the guesses
+                        # issued later on another stream must not sit behind the whole slab
+                        step = max(1, (16 << 20) // (4 * (last - first)))
+                        for c0 in range(0, nchan, step):
+                            c1 = min(nchan, c0 + step)
+                            eng.upload_slab(t[c0:c1], first, last - first, staging[c0:c1])
+                        eng.gather(staging, None, flip=flip, out=rows[first:last])
+                        ev = torch.cuda.Event()
+                        ev.record(up)
+                        del staging
+                    bounds.append(last)
+                    events.append(ev)
+                self._dev["rows"] = rows
+                self._dev["slab_ready"] = (bounds, events)
+                self._dev["host_cube"] = t                      # keeps the pinned source alive until the copies ran
             self._dev["h2d_bytes"] = t.numel() * 4
-            del staging
+        if wait and self._dev.get("slab_ready") is not None:
+            torch.cuda.current_stream(self.engine.device).wait_event(self._dev["slab_ready"][1][-1])
         return self._dev["rows"]
 
     def footprint(self):
@@ -236,7 +267,7 @@ class PCube(object):
         dev = eng.device
         prob = self._problem(fittype, ncomp, npix, list(minpars), list(maxpars), signal_cut=float(signal_cut or 0.0),
                              maxiter=maxiter)
-        rows = self.rows_on_device()
+        rows = self.rows_on_device(wait=False)
         # guesses (and the pixel list) go up through pinned memory on a second stream: a copy from pageable memory
         # on the main stream would make the host wait for the cube upload queued ahead of it
         main = torch.cuda.current_stream(dev)
@@ -255,14 +286,14 @@ class PCube(object):
         g_dev.record_stream(main)
         if idx_dev is not None:
             idx_dev.record_stream(main)
-        job = dict(prob=prob, spectra=rows, guesses=g_dev, row_index=idx_dev, pcube=self, pix=pix, ready=ready)
+        job = dict(prob=prob, spectra=rows, guesses=g_dev, row_index=idx_dev, pcube=self, pix=pix, ready=ready,
+                   slab_ready=self._dev.get("slab_ready"))
         if self._deferred is not None:
             # UltraCube.fit_cube over several ncomp: the fits are launched together (Engine.fit_batch) so that the
             # latency-bound late rounds of one overlap the other; results are filled in by finish_fit()
             self._deferred.append(job)
             return
-        main.wait_event(ready)
-        out = eng.fit(prob, rows, g_dev, row_index=idx_dev)
+        out = eng.fit_batch([job])[0]
         self.finish_fit(job, out)
 
     def start_fit_readback(self, job, out):

@@ -26,7 +26,7 @@ for _ in range(3): step()
 ts=[]
 for _ in range(5):
     t0 = time.perf_counter(); step(); ts.append((time.perf_counter() - t0) * 1e3)
-print("e2e steps ms", ["%.1f" % t for t in ts])
+print("e2e steps ms", ["%.1f" % t for t in ts], "slabs", len((step()._ref_pcube._dev.get("slab_ready") or ([None], 0))[0]))
 pr = cProfile.Profile(); pr.enable(); step(); pr.disable()
 pstats.Stats(pr).sort_stats("tottime").print_stats(25)
 pstats.Stats(pr).sort_stats("cumulative").print_stats(12)
