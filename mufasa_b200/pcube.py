@@ -272,14 +272,16 @@ class PCube(object):
         # on the main stream would make the host wait for the cube upload queued ahead of it
         main = torch.cuda.current_stream(dev)
         up = eng.side_stream("h2d")
-        g_stage = eng.pinned_stage(("guesses", npix, P))
-        np.copyto(g_stage.numpy(), guesses.reshape(P, ny * nx)[:, pix].T)
+        # [P, npix] on the host (a plain copy when every pixel is fitted), transposed to [npix, P] on the device
+        g_stage = eng.pinned_stage(("guesses", P, npix))
+        gflat = guesses.reshape(P, ny * nx)
+        np.copyto(g_stage.numpy(), gflat if npix == ny * nx else gflat[:, pix])
         i_stage = None
         if npix != ny * nx:
             i_stage = eng.pinned_stage(("pixels", npix), dtype=torch.int64)
             np.copyto(i_stage.numpy(), pix)
         with torch.cuda.stream(up):
-            g_dev = g_stage.to(dev, non_blocking=True)
+            g_dev = g_stage.to(dev, non_blocking=True).t().contiguous()
             idx_dev = None if i_stage is None else i_stage.to(dev, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(up)
