@@ -221,3 +221,47 @@ def test_eager_selection_survives_interleaved_cubes():
     for x, y in zip(got_a, ref_a):
         np.testing.assert_array_equal(x, y)
     assert not np.array_equal(got_b[2], got_a[2], equal_nan=True)
+
+
+def test_slab_upload_and_slab_split_jobs_equal_single_upload():
+    """A cube in pinned memory with >= 32768 pixels goes up as two row slabs and its batched fits are cut at the slab
+    boundary (PCube.rows_on_device, Engine._split_by_slab).  Results must equal those of the same cube from pageable
+    memory (one upload, one job per fit): all pixels, a masked fit (row_index path), and a descending velocity axis."""
+    import torch
+    ny, nx, nchan = 128, 256, 160
+    syn = synth.make_cube(2, T.oracle_modelcube, shape=(8, nx, nchan))          # 8 rows of spectra, tiled to 128
+    reps = ny // 8
+    cube = np.tile(syn["cube"], (1, reps, 1))
+    cube += np.random.default_rng(0).normal(0, 0.02, cube.shape).astype(np.float32)
+    g1 = np.tile(syn["guess1"], (1, reps, 1))
+    g2 = np.tile(syn["guess2"], (1, reps, 1))
+    mask = np.zeros((ny, nx), bool)
+    mask[3:120:2, 5:250] = True                                    # crosses the slab boundary at row 64
+    pinned = torch.empty((nchan, ny, nx), dtype=torch.float32).pin_memory()
+    pinned.numpy()[:] = cube
+
+    def run(data, v, maskmap):
+        from mufasa_b200.UltraCube import UltraCube
+        uc = UltraCube(cube=SpecCube(data, v), fittype=syn["fittype"], device=0)
+        uc.fit_cube(ncomp=[1, 2], simpfit=True, maskmap=maskmap, guesses={1: g1.copy(), 2: g2.copy()})
+        best = uc.get_best_2c_parcube()
+        return uc, best
+
+    for v, flip in ((syn["v"], False), (syn["v"][::-1].copy(), True)):
+        for maskmap in (None, mask):
+            src_p = pinned.numpy()[::-1] if flip else pinned.numpy()
+            src_h = cube[::-1].copy() if flip else cube
+            if flip:                                               # keep the pinned buffer contiguous in file order
+                pinned_f = torch.empty((nchan, ny, nx), dtype=torch.float32).pin_memory()
+                pinned_f.numpy()[:] = src_h
+                src_p = pinned_f.numpy()
+            up, bp = run(src_p, v, maskmap)
+            uh, bh = run(src_h, v, maskmap)
+            assert up._ref_pcube._dev.get("slab_ready") is not None and uh._ref_pcube._dev.get("slab_ready") is None
+            for nc in ("1", "2"):
+                np.testing.assert_array_equal(up.pcubes[nc].parcube, uh.pcubes[nc].parcube)
+                np.testing.assert_array_equal(up.pcubes[nc].errcube, uh.pcubes[nc].errcube)
+                np.testing.assert_array_equal(up.pcubes[nc].has_fit, uh.pcubes[nc].has_fit)
+            for a, b in zip(bp, bh):
+                np.testing.assert_array_equal(a, b)
+            assert up.pcubes["2"].has_fit.sum() > (0.3 if maskmap is not None else 0.8) * (mask.sum() if maskmap is not None else ny * nx)
