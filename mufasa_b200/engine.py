@@ -225,6 +225,8 @@ class Engine(object):
         slabbed = [j for j in jobs if j.get("slab_ready") is not None]
         if slabbed and not getattr(self, "_profiling", False):
             return self._split_by_slab(jobs, results)
+        for j in slabbed:                     # profiled fits run undivided: order them after the whole upload
+            torch.cuda.current_stream(self.device).wait_event(j["slab_ready"][1][-1])
         limit = min(_abi.MAX_BATCH, int(os.environ.get("B200FIT_SPLIT_LIMIT", 3)))   # measured: 3 beats 2 and 4
         parts = [1] * len(jobs)
         weight = [int(j["prob"].npix) * int(j["prob"].ncomp) ** 2 for j in jobs]
