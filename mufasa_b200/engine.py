@@ -222,7 +222,9 @@ class Engine(object):
         (contiguous views of the same inputs and outputs).  Pixels do not interact, so the results are those of the
         undivided fit; two half-sized round loops interleave on the GPU where one full-sized loop leaves it partly
         idle between its dependent kernels (measured: 2-component fit of 65 536 spectra 34.7 -> 32.7 ms)."""
-        slabbed = [j for j in jobs if j.get("slab_ready") is not None]
+        # slab events matter only while the upload is in flight; a resident cube takes the generic split below
+        slabbed = [j for j in jobs if j.get("slab_ready") is not None
+                   and not all(ev.query() for ev in j["slab_ready"][1])]
         if slabbed and not getattr(self, "_profiling", False):
             return self._split_by_slab(jobs, results)
         for j in slabbed:                     # profiled fits run undivided: order them after the whole upload
@@ -260,7 +262,8 @@ class Engine(object):
         boundaries when the batch has room, and every part waits only for the event of the last slab it reads --
         the first rows are being fitted while the rest of the cube crosses PCIe."""
         nslab = max(len(j["slab_ready"][0]) for j in jobs if j.get("slab_ready") is not None)
-        cut = len(jobs) * nslab <= _abi.MAX_BATCH
+        cut = len(jobs) * nslab <= _abi.MAX_BATCH and all(
+            int(j["prob"].npix) >= 2 * self.SPLIT_MIN_PIXELS for j in jobs if j.get("slab_ready") is not None)
         work = []
         for job, out in zip(jobs, results):
             prob, npix = job["prob"], int(job["prob"].npix)
