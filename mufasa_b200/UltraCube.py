@@ -16,7 +16,6 @@ import logging
 import os
 import weakref
 from collections.abc import Iterable
-from copy import copy
 
 import numpy as np
 import torch

@@ -14,7 +14,7 @@ import torch
 from . import _abi
 from .engine import get_engine
 from .exceptions import FitTypeError
-from .spec_models.meta_model import FITTYPE_ALIASES, MetaModel
+from .spec_models.meta_model import FITTYPE_ALIASES
 
 
 class _Registry(object):
