@@ -7,6 +7,9 @@
  *     pcube.get_modelcube()                                             mufasa/UltraCube.py:324, :978
  *     UltraCube.get_rss / get_AICc / get_all_lnk_maps / get_best_2c_parcube
  *                                                                       mufasa/UltraCube.py:432-498, :1218-1379
+ * and, either side of the fit, the voxel work of
+ *     signals.get_moments / get_rms_robust / get_snr                    mufasa/signals.py:24-121, :329-396
+ *     convolve_tools.convolve_sky_byfactor                              mufasa/convolve_tools.py:37-138
  * Each entry point below names the reference call it stands in for.  A reference-side binding is a
  * ctypes stub.  Plain pointers and sizes only; no torch / CUDA types in signatures
  * (``stream`` is a cudaStream_t passed as void*; NULL = default stream).
