@@ -265,7 +265,9 @@ struct LineGroups<B200FIT_MODEL_N2HP_10> {  // -8.0 (1) | -0.6 .. 1.0 (3) | 5.5 
 // exactly once per round that is a function of the pixel's own evaluation count -- results stay independent of
 // how the pixels are partitioned over calls or GPUs.
 template <int NC, int MODEL, int TEAM>
-__global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)   // measured: 96 regs help 1c, hurt 2c
+// blocks per SM: 5 (96 registers) help the 1-component kernel; the 2-component one compiles to 96 registers with
+// next to no spills as well, but runs 16 % slower there (24.1 vs 20.7 ms per fit) than at 4 blocks / 128 registers
+__global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
     fit_eval_kernel(const DeviceProblem pr, const float* __restrict__ spectra, long long stride,
                     const long long* __restrict__ row_index, PixState<4 * NC>* __restrict__ states,
                     const unsigned* __restrict__ list, FitQueues* __restrict__ fq, int cur) {
