@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
 // (profiles/): thread per pixel on global state 30 ms per 2c fit, the same staged through shared memory 63 ms
 // (copy loops serialise global round trips), both bound by the ~20k-instruction dependent chain of one serial step.
 template <int NC>
-__global__ void __launch_bounds__(SOLVE_THREADS, 8)   // 128 regs (a few spills) beat 168 / 202: latency bound
+__global__ void __launch_bounds__(SOLVE_THREADS, 8)   // 128 regs (a few spills) beat 168 / 202 and 96 / 80 / 64 (measured)
     fit_solve_kernel(const DeviceProblem pr, PixState<4 * NC>* __restrict__ states, const unsigned* __restrict__ list,
                      unsigned* __restrict__ next_list, FitQueues* __restrict__ fq, int cur,
                      double* __restrict__ params, double* __restrict__ perr, double* __restrict__ chi2,
