@@ -55,17 +55,27 @@ def maxref_neighbor_coords(mask, ref, fill_coord=(0, 0), structure=None):
     dy, dx = np.where(structure)
     dy, dx = dy - cy, dx - cx
     ny, nx = ref.shape
-    out = []
-    for y, x in zip(*np.where(mask)):
-        best, best_val = None, None
-        for yy, xx in zip(dy + y, dx + x):
-            if yy >= ny or xx >= nx or yy < -ny or xx < -nx:
-                continue
-            val = ref[yy, xx]
-            if best is None or val > best_val:      # python max(): the first of equal / incomparable values stays
-                best, best_val = (yy, xx), val
-        out.append(best if best is not None else fill_coord)
-    return out
+    ys, xs = np.where(mask)
+    if ys.size == 0:
+        return []
+    if dy.size == 0:
+        return [fill_coord] * ys.size
+    # all pixels at once; python's sequential max() restated: the first usable neighbour stays the best when its
+    # value is NaN (nothing compares greater), otherwise the first occurrence of the largest non-NaN value wins
+    yy, xx = ys[:, None] + dy[None, :], xs[:, None] + dx[None, :]
+    usable = (yy < ny) & (xx < nx) & (yy >= -ny) & (xx >= -nx)
+    vals = np.asarray(ref)[np.where(usable, yy, 0), np.where(usable, xx, 0)]
+    isnan = vals != vals
+    first = np.argmax(usable, axis=1)
+    rows = np.arange(ys.size)
+    cand = usable & ~isnan
+    with np.errstate(invalid="ignore"):
+        top = np.max(np.where(cand, vals, -np.inf), axis=1)
+        pick = np.argmax(cand & (vals == top[:, None]), axis=1)
+    pick = np.where(isnan[rows, first], first, pick)
+    has = usable.any(axis=1)
+    by, bx = yy[rows, pick], xx[rows, pick]
+    return [(by[i], bx[i]) if has[i] else fill_coord for i in range(ys.size)]
 
 
 def get_refit_guesses(ucube, mask, ncomp, method='best_neighbour', refmap=None, structure=None):

@@ -79,11 +79,11 @@ def write(path, data, header=None):
     cards.append("END".ljust(80))
     head = "".join(cards)
     head += " " * (-len(head) % BLOCK)
-    raw = np.ascontiguousarray(data, dtype=_BITPIX[bitpix]).tobytes()
-    raw += b"\0" * (-len(raw) % BLOCK)
+    raw = np.ascontiguousarray(data, dtype=_BITPIX[bitpix])   # the one copy: byte order (and layout, if strided)
     with open(path, "wb") as f:
         f.write(head.encode("ascii"))
-        f.write(raw)
+        f.write(raw.reshape(-1).data)                          # straight from the array's buffer
+        f.write(b"\0" * (-raw.nbytes % BLOCK))
 
 
 def _parse_value(s):

@@ -20,6 +20,44 @@ def test_square_neighbour_and_best_neighbour_lookup():
     assert ref[yy, xx] == ref[-1, -1]
 
 
+def _neighbour_loop(mask, ref, fill_coord=(0, 0), structure=None):
+    """The reference's per-pixel loop (utils/neighbours.py:17-60) restated literally: python max() over the
+    neighbours in structure order, IndexError-style skipping of indices past the far edges only."""
+    if structure is None:
+        structure = mf.square_neighbour(1)
+    cy, cx = int(np.ceil(structure.shape[0] / 2)) - 1, int(np.ceil(structure.shape[1] / 2)) - 1
+    dy, dx = np.where(structure)
+    dy, dx = dy - cy, dx - cx
+    ny, nx = ref.shape
+    out = []
+    for y, x in zip(*np.where(mask)):
+        best, best_val = None, None
+        for yy, xx in zip(dy + y, dx + x):
+            if yy >= ny or xx >= nx or yy < -ny or xx < -nx:
+                continue
+            val = ref[yy, xx]
+            if best is None or val > best_val:
+                best, best_val = (yy, xx), val
+        out.append(best if best is not None else fill_coord)
+    return out
+
+
+def test_best_neighbour_lookup_matches_the_sequential_loop():
+    """NaN and -inf reference values, ties, wrap-around at the near edges, empty structures, 1-pixel maps."""
+    rng = np.random.default_rng(1)
+    for trial in range(25):
+        ny, nx = int(rng.integers(1, 12)), int(rng.integers(1, 12))
+        ref = rng.integers(0, 4, size=(ny, nx)).astype(float)
+        ref[rng.random((ny, nx)) < 0.3] = np.nan
+        if trial % 3 == 0:
+            ref[rng.random((ny, nx)) < 0.2] = -np.inf
+        mask = rng.random((ny, nx)) < 0.6
+        for st in (None, mf.square_neighbour(2), mf.disk_neighbour(2), np.zeros((3, 3), bool)):
+            want = _neighbour_loop(mask, ref, structure=st)
+            got = mf.maxref_neighbor_coords(mask, ref, structure=st)
+            assert [tuple(int(v) for v in c) for c in got] == [tuple(int(v) for v in c) for c in want]
+
+
 class _P(object):
     def __init__(self, parcube):
         self.parcube = parcube
