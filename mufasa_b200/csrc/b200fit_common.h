@@ -81,6 +81,7 @@ struct DeviceProblem {
     // with width sigma*rho[k];  rho[k] = (1 - voff_k/c) * nu0/nu_ref;  kdv[k] = KAPPA0*dv/rho[k]
     double rho[MAXHF_FIT], c1mrho[MAXHF_FIT], kdv[MAXHF_FIT];
     float lw[MAXHF_FIT];           // log2(normalised weight)
+    double wfit[MAXHF_FIT];        // normalised weight (fp64 evaluation of the polish phase)
     // Planck terms, linear in channel offset di = i - ic0:  T0_i = T0c + dT0*di
     double ic0, T0c, dT0, Jbg0, Jbg1;
     // fp64 reference-order model (frequency space, HyperfineModel.py:91-107)
@@ -205,6 +206,102 @@ B2_HD void rt_channel(const float* G, const float* A, const float* B, float di, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// fp64 evaluation (the POLISH phase of a fit: the last iterations of every pixel, from the point where the fp32
+// evaluation above stops resolving chi2, run on this model with mpfit's tests at face value -- DESIGN.md 3.1).
+// Same velocity-space form; natural units: q = (V_i - cen_k) / (sigma rho_k), g = w_k exp(-q^2 / 2),
+//   G = sum g, A = sum g q, B = sum g q^2;  dtau/dv = tau0 A / sigma,  dtau/dsigma = tau0 B / sigma.
+// The Planck terms J(T; T0_i) are a quadratic through their exact values at the first, centre and last channel
+// (T0 is exactly linear in the channel index; the cubic remainder is ~(band / nu)^3 ~ 2e-12 relative).
+constexpr double QCUT2_64 = 80.0;   // gaussians below exp(-40) = 4e-18 of their peak are skipped
+
+struct CompCoef64 {
+    double tau0, inv_sigma;
+    double dJ[3];     // J(Tex) - J(Tbg) = dJ[0] + di (dJ[1] + di dJ[2])
+    double dJT[3];    // dJ/dTex, likewise
+};
+
+struct LineCoef64 {
+    double ic, a, w;  // q(i) = (i - ic) * a
+};
+
+B2_HD void planck_exact(double T, double T0, double& J, double& JT) {   // BaseModel.py:176-193 and its T-derivative
+    const double x = T0 / T;
+    const double em1 = expm1(x);
+    J = T0 / em1;
+    JT = x * x * (em1 + 1.0) / (em1 * em1);
+}
+
+B2_HD void comp_coefs64(double T0c, double dT0, double ic0, const double* p4, CompCoef64& cc) {
+    const double h = (ic0 > 0.5) ? ic0 : 0.5;   // half the band, in channels
+    double fj[3], ft[3];
+    B2_ROLL
+    for (int m = 0; m < 3; ++m) {
+        const double T0 = T0c + dT0 * (double)(m - 1) * h;
+        double Jx, JTx, Jb, JTb;
+        planck_exact(p4[2], T0, Jx, JTx);
+        planck_exact(TCMB, T0, Jb, JTb);
+        fj[m] = Jx - Jb;
+        ft[m] = JTx;
+    }
+    cc.tau0 = p4[3];
+    cc.inv_sigma = 1.0 / p4[1];
+    cc.dJ[0] = fj[1];
+    cc.dJ[1] = (fj[2] - fj[0]) / (2.0 * h);
+    cc.dJ[2] = (fj[2] - 2.0 * fj[1] + fj[0]) / (2.0 * h * h);
+    cc.dJT[0] = ft[1];
+    cc.dJT[1] = (ft[2] - ft[0]) / (2.0 * h);
+    cc.dJT[2] = (ft[2] - 2.0 * ft[1] + ft[0]) / (2.0 * h * h);
+}
+
+// line k of a component at velocity v: channel position, scale, weight; the window [wlo, whi] (in channels) outside
+// which the gaussian is skipped
+B2_HD void line_coef64(double c1mrho_k, double rho_k, double w_k, double v0, double inv_dv, double dv, double v,
+                       double inv_sigma, LineCoef64& lc, double& wlo, double& whi) {
+    const double cen = c1mrho_k + rho_k * v;
+    lc.ic = (cen - v0) * inv_dv;
+    lc.a = dv * inv_sigma / rho_k;
+    lc.w = w_k;
+    const double hw = 8.944271909999159 / lc.a;   // sqrt(QCUT2_64)
+    wlo = lc.ic - hw;
+    whi = lc.ic + hw;
+}
+
+B2_HD void gauss_accum64(double fi, const LineCoef64& lc, double& G, double& A, double& B) {
+    const double q = (fi - lc.ic) * lc.a;
+    const double q2 = q * q;
+    if (q2 < QCUT2_64) {
+        const double g = lc.w * exp(-0.5 * q2);
+        G += g;
+        A = fma(g, q, A);
+        B = fma(g, q2, B);
+    }
+}
+
+template <int NC>
+B2_HD void rt_channel64(const double* G, const double* A, const double* B, double di, const CompCoef64* cc, double& m,
+                        double* J) {
+    double Mprev = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const double tau = cc[c].tau0 * G[c];
+        const double e = exp(-tau);
+        const double ome = -expm1(-tau);
+        const double dJ = fma(di, fma(di, cc[c].dJ[2], cc[c].dJ[1]), cc[c].dJ[0]);
+        const double dJT = fma(di, fma(di, cc[c].dJT[2], cc[c].dJT[1]), cc[c].dJT[0]);
+        const double D = (dJ - Mprev) * e;
+        const double ts = cc[c].tau0 * cc[c].inv_sigma;
+#pragma unroll
+        for (int q = 0; q < 4 * c; ++q) J[q] *= e;
+        J[4 * c + 0] = D * ts * A[c];
+        J[4 * c + 1] = D * ts * B[c];
+        J[4 * c + 2] = dJT * ome;
+        J[4 * c + 3] = D * G[c];
+        Mprev = fma(dJ, ome, Mprev * e);
+    }
+    m = Mprev;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Levenberg-Marquardt state machine: MINPACK-style trust region on the NORMAL EQUATIONS.
 //   H = J^T J (packed upper triangle), b = J^T r with r = y - M, chi2 = r^T r   (UNWEIGHTED sums: the per-pixel
 //   weight 1/err^2 is a common factor -- it cancels in the step and is applied to chi2 / covariance at the end).
@@ -242,7 +339,8 @@ struct LMState {
     double H[NH], Ht[NH];
     double chi2, chi2t, chi2_last, delta, par, xnorm, pnorm, alpha, sHs;
     int status, iters, nevals, nrej, first, fresh;
-    unsigned peg, pad_;
+    unsigned peg;
+    int mode;   // 0: fp32 evaluation (noise-aware tests); 1: polish phase, fp64 evaluation, mpfit's tests at face value
 };
 
 template <int P>
@@ -407,7 +505,7 @@ B2_HD unsigned lm_pegged(const LMState<P>& s, const LMConfig& cf) {
     B2_ROLL
     for (int j = 0; j < P; ++j) {
         const double hjj = s.H[hidx<P>(j, j)];
-        const double thr = 3.0 * LM_NOISE_REL * sqrt((hjj > 0.0 ? hjj : 0.0) * s.chi2);
+        const double thr = s.mode ? 0.0 : 3.0 * LM_NOISE_REL * sqrt((hjj > 0.0 ? hjj : 0.0) * s.chi2);
         if (s.p[j] <= cf.lo[j] && s.b[j] < thr) peg |= 1u << j;
         if (s.p[j] >= cf.hi[j] && s.b[j] > -thr) peg |= 1u << j;
     }
@@ -440,6 +538,7 @@ B2_HD bool lm_init(LMState<P>& s, const double* guess, const LMConfig& cf) {
     s.peg = 0;
     s.first = 1;
     s.fresh = 1;
+    s.mode = 0;
     s.chi2 = 0.0;
     s.chi2t = 0.0;
     s.chi2_last = 0.0;
@@ -460,6 +559,40 @@ B2_HD int lm_adopt_first(LMState<P>& s) {
     for (int j = 0; j < P; ++j) s.b[j] = s.bt[j];
     B2_ROLL
     for (int q = 0; q < LMState<P>::NH; ++q) s.H[q] = s.Ht[q];
+    return LM_CONTINUE;
+}
+
+// Polish phase.  A pixel the fp32 phase declared converged (status 1-4 or 6) goes on from its current point with
+// fp64 evaluations and mpfit's tests at face value: the point is re-evaluated (pt = p), the result adopted, and the
+// iteration continues with the trust region, damping and scaling it had, until mpfit's own tests fire.
+template <int P>
+B2_HD bool lm_wants_polish(const LMState<P>& s) {
+    return s.mode == 0 && (s.status == 1 || s.status == 2 || s.status == 3 || s.status == 4 || s.status == 6);
+}
+
+template <int P>
+B2_HD void lm_begin_polish(LMState<P>& s) {
+    s.mode = 1;
+    s.status = 0;
+    B2_ROLL
+    for (int j = 0; j < P; ++j) s.pt[j] = s.p[j];
+}
+
+// After the fp64 re-evaluation at the current point (stored in the *t slots).
+template <int P>
+B2_HD int lm_adopt_polish(LMState<P>& s) {
+    s.nevals += 1;
+    if (!(s.chi2t == s.chi2t) || isinf(s.chi2t)) {
+        s.status = -16;
+        return LM_DONE;
+    }
+    s.chi2 = s.chi2t;
+    s.chi2_last = s.chi2t;
+    B2_ROLL
+    for (int j = 0; j < P; ++j) s.b[j] = s.bt[j];
+    B2_ROLL
+    for (int q = 0; q < LMState<P>::NH; ++q) s.H[q] = s.Ht[q];
+    s.fresh = 1;
     return LM_CONTINUE;
 }
 
@@ -566,7 +699,7 @@ B2_HD int lm_update(LMState<P>& s, const LMConfig& cf) {
     double trap = 0.0;
     B2_ROLL
     for (int j = 0; j < P; ++j) trap += (s.pt[j] - s.p[j]) * (s.b[j] + s.bt[j]);
-    const double act_abs = (fabs(direct) > 40.0 * LM_NOISE_REL * s.chi2) ? direct : trap;
+    const double act_abs = (s.mode || fabs(direct) > 40.0 * LM_NOISE_REL * s.chi2) ? direct : trap;
     double actred = -1.0;
     if (0.01 * s.chi2t < s.chi2) actred = act_abs / s.chi2;
     // mpfit applies alpha a second time to |J s| (temp1) -- kept
@@ -603,7 +736,7 @@ B2_HD int lm_update(LMState<P>& s, const LMConfig& cf) {
     }
     int st = 0;
     if (fabs(actred) <= cf.ftol && prered <= cf.ftol && 0.5 * ratio <= 1.0) st = 1;
-    else if (fabs(actred) <= LM_FTOL_NOISE && prered <= LM_FTOL_NOISE && 0.5 * ratio <= 1.0) st = 6;
+    else if (!s.mode && fabs(actred) <= LM_FTOL_NOISE && prered <= LM_FTOL_NOISE && 0.5 * ratio <= 1.0) st = 6;
     if (s.delta <= LM_XTOL * s.xnorm) st = (st == 1) ? 3 : 2;
     if (st != 0) {
         s.status = st;

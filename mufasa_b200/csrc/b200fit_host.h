@@ -74,6 +74,7 @@ inline int make_device_problem(const b200fit_problem& in, DeviceProblem& out) {
         out.c1mrho[k] = CKMS * (1.0 - rho);
         out.kdv[k] = KAPPA0 * in.dv / rho;
         out.lw[k] = (float)std::log2(v[k].second / wsum);
+        out.wfit[k] = v[k].second / wsum;
     }
     // windowing groups: neighbouring hyperfines closer than GROUP_GAP km/s share one channel window
     const double GROUP_GAP = 3.0;

@@ -12,7 +12,8 @@ installed here, so this file restates the published algorithm:
     snapping to the limit, and ``perror = sqrt(diag(covar))`` with zero for pegged parameters.
 Defaults are mpfit's: ftol = xtol = gtol = 1e-10, maxiter = 200, factor = 100, forward differences with
 relative step sqrt(machep).  [RECALLED -- PARITY UNPINNED: no golden vector from the reference exists for
-the solver; cross-checked against scipy's real MINPACK in tests/test_oracle_mpfit.py]
+the solver.  Cross-checked against scipy's real MINPACK in tests/test_oracle_mpfit.py: same minimum as lmdif on
+interior solutions (<= 0.05 sigma, chi2 to 1e-6), same chi2 as the bounded trf solver where a parameter is pegged]
 
 Supported subset: every parameter free, optional lower/upper limits per parameter, no ties, no
 ``mpmaxstep``, one-sided automatic derivatives -- exactly what SpectralModel.fitter builds for MUFASA

@@ -38,11 +38,36 @@ def limits_vectors(fittype, ncomp, vmin=-3.5, vmax=4.5):
     return lo, hi
 
 
-def oracle_fit(tile, ncomp, lo, hi, guesses, perturb=0.0, cores=None):
+def _central_jacobian(fcn, x, fvec, qulim, ulim, res):
+    """Drop-in for oracle.mpfit._fdjac2: central differences with a 1e-6 relative step (error ~1e-11 instead of the
+    forward difference's ~1e-8) -- mpfit as it would run with an accurate Jacobian."""
+    n = len(x)
+    fjac = np.zeros([len(fvec), n])
+    h = 1e-6 * np.abs(x)
+    h[h == 0] = 1e-6
+    for j in range(n):
+        xp, xm = x.copy(), x.copy()
+        xp[j] += h[j]
+        xm[j] -= h[j]
+        fjac[:, j] = (fcn(xp) - fcn(xm)) / (2 * h[j])
+        res.nfev += 1
+    return fjac
+
+
+def oracle_fit(tile, ncomp, lo, hi, guesses, perturb=0.0, cores=None, jacobian="forward"):
+    """jacobian='forward': mpfit as the reference runs it; 'central': the same algorithm with an accurate
+    Jacobian (used to measure how reproducible mpfit's own answer is, tests/test_parity_floor.py)."""
+    from oracle import mpfit as MP
     g = guesses if perturb == 0.0 else np.clip(guesses * (1 + perturb), np.array(lo)[:, None, None],
                                                 np.array(hi)[:, None, None])
-    return F.fiteach(tile["cube"], tile["v"], g, lo, hi, tile["fittype"],
-                     multicore=cores or min(8, F.default_cores() + 1))
+    keep = MP._fdjac2
+    if jacobian == "central":
+        MP._fdjac2 = _central_jacobian          # inherited by the forked workers
+    try:
+        return F.fiteach(tile["cube"], tile["v"], g, lo, hi, tile["fittype"],
+                         multicore=cores or min(8, F.default_cores() + 1))
+    finally:
+        MP._fdjac2 = keep
 
 
 def pixel_major(tile, guesses):
@@ -101,7 +126,9 @@ def build_emul():
     return C.CDLL(lib)
 
 
-def emul_fit(lib, prob, spec, gg):
+def emul_fit(lib, prob, spec, gg, mode=0):
+    """mode 0: the kernels' algorithm; 1: + fp64 polish phase; 2: fp64 throughout (measured alternatives)."""
+    lib.emul_set_mode(C.c_int(mode))
     npix, P = gg.shape
     out = dict(params=np.zeros((npix, P)), perr=np.zeros((npix, P)), chi2=np.zeros(npix), err_used=np.zeros(npix),
                status=np.zeros(npix, np.int32), counts=np.zeros((npix, 4), np.uint32))

@@ -5,6 +5,7 @@
 // It is never built into libb200fit.so and never imported by the mufasa_b200 package.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -13,6 +14,13 @@
 using namespace b200fit;
 
 namespace {
+
+// 0 = the kernels' algorithm: fp32 evaluation, noise-aware tests (default)
+// 1 = the same followed by an fp64 POLISH phase (fp64 model, mpfit's tests at face value) -- measured alternative
+// 2 = fp64 evaluation and mpfit's tests throughout -- measured alternative
+// The alternatives exist to quantify what evaluation precision contributes to the disagreement with mpfit on
+// multi-modal 2-component spectra (tests/test_parity_floor.py): nothing measurable.
+int g_emul_mode = 0;
 
 template <int NC>
 struct Eval {
@@ -94,6 +102,59 @@ struct Eval {
     }
 };
 
+// fp64 evaluation of the polish phase (shared source: comp_coefs64 / line_coef64 / gauss_accum64 / rt_channel64)
+template <int NC>
+struct Eval64 {
+    static constexpr int P = 4 * NC;
+    static constexpr int NH = P * (P + 1) / 2;
+    const DeviceProblem& pr;
+    const float* spec;
+    double sumsq;
+    uint64_t n_gauss = 0;
+    Eval64(const DeviceProblem& p, const float* s, double sq) : pr(p), spec(s), sumsq(sq) {}
+
+    void run(const double* p, double* H, double* b, double& chi2) {
+        CompCoef64 cc[NC];
+        LineCoef64 lc[NC][MAXHF_FIT];
+        double wlo[NC][MAXHF_FIT], whi[NC][MAXHF_FIT];
+        for (int c = 0; c < NC; ++c) {
+            comp_coefs64(pr.T0c, pr.dT0, pr.ic0, p + 4 * c, cc[c]);
+            for (int k = 0; k < pr.nhf; ++k)
+                line_coef64(pr.c1mrho[k], pr.rho[k], pr.wfit[k], pr.v0, pr.inv_dv, pr.dv, p[4 * c], cc[c].inv_sigma,
+                            lc[c][k], wlo[c][k], whi[c][k]);
+        }
+        for (int q = 0; q < NH; ++q) H[q] = 0.0;
+        for (int u = 0; u < P; ++u) b[u] = 0.0;
+        double chi = 0.0;
+        for (int i = 0; i < pr.nchan; ++i) {
+            const float yf = spec[i];
+            if (!(yf == yf)) continue;
+            const double y = (double)yf, fi = (double)i;
+            double G[NC], A[NC], B[NC];
+            bool any = false;
+            for (int c = 0; c < NC; ++c) {
+                G[c] = A[c] = B[c] = 0.0;
+                for (int k = 0; k < pr.nhf; ++k)
+                    if (fi >= wlo[c][k] && fi <= whi[c][k]) {
+                        gauss_accum64(fi, lc[c][k], G[c], A[c], B[c]);
+                        ++n_gauss;
+                        any = true;
+                    }
+            }
+            if (!any) continue;
+            double m, J[P];
+            rt_channel64<NC>(G, A, B, fi - pr.ic0, cc, m, J);
+            const double r = y - m;
+            int q = 0;
+            for (int u = 0; u < P; ++u)
+                for (int v = u; v < P; ++v) H[q] = fma(J[u], J[v], H[q]), ++q;
+            for (int u = 0; u < P; ++u) b[u] = fma(J[u], r, b[u]);
+            chi = fma(m, m - 2.0 * y, chi);
+        }
+        chi2 = sumsq + chi;
+    }
+};
+
 // weights as the kernel's prologue computes them: one pass, fp64
 static double spectrum_stats(const DeviceProblem& pr, const float* spec, double& sumsq, double& ymax) {
     double sum = 0.0;
@@ -131,20 +192,43 @@ void fit_pixel(const DeviceProblem& pr, const float* spec, const double* guess, 
     LMState<P> s;
     if (!lm_init<P>(s, guess, cf)) return;
     Eval<NC> ev(pr, spec, sumsq);
-    ev.run(s.pt, s.Ht, s.bt, s.chi2t);
-    int done = lm_adopt_first<P>(s);
+    Eval64<NC> ev64(pr, spec, sumsq);
+    const int emul_mode = g_emul_mode;
+    int done;
+    if (emul_mode == 2) {
+        s.mode = 1;
+        ev64.run(s.pt, s.Ht, s.bt, s.chi2t);
+    } else {
+        ev.run(s.pt, s.Ht, s.bt, s.chi2t);
+    }
+    done = lm_adopt_first<P>(s);
     while (!done) {
         done = lm_propose<P>(s, cf);
         if (done) break;
-        ev.run(s.pt, s.Ht, s.bt, s.chi2t);
+        if (s.mode)
+            ev64.run(s.pt, s.Ht, s.bt, s.chi2t);
+        else
+            ev.run(s.pt, s.Ht, s.bt, s.chi2t);
         done = lm_update<P>(s, cf);
+    }
+    int n32 = s.nevals;
+    if (emul_mode == 1 && lm_wants_polish<P>(s)) {
+        lm_begin_polish<P>(s);
+        ev64.run(s.pt, s.Ht, s.bt, s.chi2t);
+        done = lm_adopt_polish<P>(s);
+        while (!done) {
+            done = lm_propose<P>(s, cf);
+            if (done) break;
+            ev64.run(s.pt, s.Ht, s.bt, s.chi2t);
+            done = lm_update<P>(s, cf);
+        }
     }
     *status = s.status;
     if (counts) {
         counts[0] = (uint32_t)s.nevals;
         counts[1] = (uint32_t)s.nrej;
         counts[2] = (uint32_t)ev.n_gauss;
-        counts[3] = (uint32_t)ev.n_chunks;
+        counts[3] = (uint32_t)(s.nevals - n32);   // evaluations of the polish phase
     }
     if (s.status > 0) {
         const double err2 = err * err;
@@ -155,6 +239,8 @@ void fit_pixel(const DeviceProblem& pr, const float* spec, const double* guess, 
 }
 
 }  // namespace
+
+extern "C" void emul_set_mode(int mode) { g_emul_mode = mode; }
 
 extern "C" int emul_fit(const b200fit_problem* prob, const float* spectra, int64_t nchan_stride, const double* guesses,
                         const double* err, double* params, double* perr, double* chi2, double* err_used,
