@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the B200 per-pixel spectral fitter on BASELINE.json's metric.
 
-metric   : spectra fitted / second, 2-component NH3(1,1) model selection workload
-workload : BASELINE.json configs[1] -- synthetic NH3(1,1) cube 256 x 256 x 800 channels; one STEP = the whole job
-           on one cube: 1-component fit + 2-component fit of every spectrum + AICc 0/1/2-component selection
-           (UltraCube.fit_cube(1), fit_cube(2), get_best_2c_parcube in the reference's terms).
-           N GPUs: every rank owns one such cube (independent noise realisation) -- pixels are independent, no
-           collective on the data path -> "scaling": "weak".
-value    : (spectra of all ranks) / (max-over-ranks device time per step), cube rows already resident in HBM.
-e2e      : the same job through the public host API (mufasa_b200.UltraCube) starting from HOST (pinned) buffers:
-           H2D of the cube and guesses, all kernels, D2H of parameter / error / lnk / ncomp maps, host bookkeeping.
-roofline : dominant kernel = fit_eval_kernel<2> (model + Jacobian + normal equations of the 2-component fit).  The path is compute bound: the
-           fraction reported is algorithmic pipe work / time / pipe peak for the binding pipe (FP32 FMA, XU ex2,
-           FP64), with the HBM figure alongside.
+metric   : spectra fitted / second, 2-component NH3(1,1) model-selection workload
+workload : BASELINE.json configs[4] (the configuration the north-star target is quoted on) -- ONE synthetic NH3(1,1)
+           cube, 1024 x 1024 pixels x 1000 channels.  One STEP = the whole job on the whole cube: 1-component fit +
+           2-component fit of every spectrum + AICc 0/1/2-component selection + assembly of the best-model parameter
+           cube (UltraCube.fit_cube([1, 2]) + get_best_2c_parcube in the reference's terms).
+           N GPUs: the SAME cube partitioned by row slabs (mufasa_b200.dist.partition_rows), rank r holds rows
+           [r ny / N, (r + 1) ny / N) -> "scaling": "strong".  Pixels are independent: no collective inside the fit
+           loop; NCCL carries the global arg-max of the AICc include_nosamp rule (16 bytes per rank + one 256-byte
+           broadcast) and ONE gather of the [44, rows, nx] result block per step.
+value    : 1 048 576 spectra / (max-over-ranks device time per step), slab rows and guesses already resident in HBM;
+           the step runs from the launch of the two fits to the gathered result block on rank 0's GPU.
+e2e      : the same job through the public host API, mufasa_b200.dist.fit_and_select, starting from HOST (pinned)
+           buffers: H2D of each rank's slab and guesses, all kernels, the NCCL gather, D2H of the 44 result maps on
+           rank 0; wall clock between barriers, max over ranks.
+roofline : dominant kernel = fit_eval_kernel<2> (model + analytic Jacobian + normal equations of the 2-component
+           fit).  The path is compute bound.  ``frac`` is the EXECUTED fraction of the binding pipe
+           (XU: ex2 actually issued / kernel time / peak); the algorithmic figure (what the reference's arithmetic
+           would need, most of which the kernel's windows skip) is reported beside it as ``frac_algorithmic``.
 cpu_baseline / --impl reference: the CPU oracle (numpy restatement of the reference's pyspeckit/mpfit path; the
            reference itself is pure Python on un-vendored pyspeckit and cannot be installed here) timed on this
-           box's host cores on a bounded sample of the same cube.
+           box's host cores on ONE fixed sample of the same cube (REF_ROWS x every REF_XSTEP-th column).
 
 Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 """
@@ -33,9 +39,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CFG = 2
+CFG = 5                                  # synth.CONFIGS key of BASELINE.json configs[4]
 METRIC = "spectra fitted/sec, 2-comp NH3(1,1)"
 UNIT = "spectra/s"
+REF_NROWS, REF_XSTEP = 8, 32             # the CPU sample: 8 rows x every 32nd column of the cube = 256 spectra
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -46,9 +53,6 @@ def measured_peaks():
             d = json.load(f)
         return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured")
     return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
-
-
-NCU_DRAM_BYTES_PER_EVAL = (166.019072e6 + 19.493888e6) / 65536.0   # profiles/r1m_fit2c_ncu_full_summary.txt
 
 
 class ClockSampler(object):
@@ -116,33 +120,48 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------------------------------------------------------
 def oracle_modelcube(parcube, v, fittype):
+    """Model cube for synth.make_cube from the CPU oracle -- only at the sampled columns (the generator draws the
+    noise of whole rows, so the sampled spectra are those of the full cube; the other columns are not used)."""
     from oracle import model as M
-    return M.modelcube(v, parcube, fittype)
+    out = np.zeros((len(v),) + parcube.shape[1:])
+    out[:, :, ::REF_XSTEP] = M.modelcube(v, parcube[:, :, ::REF_XSTEP], fittype)
+    return out
 
 
 def sample_rows(ny, nrows):
     return [int(y) for y in np.linspace(20, ny - 21, nrows)]
 
 
-def cpu_job(cfg, rows, xstep, cores, seed_offset=0):
-    """The reference's job on a sample of the workload cube, on the host: 1c fit + 2c fit (cubefit_simp semantics:
-    guesses clamped into the limits, err = std(spectrum), mpfit) + get_all_lnk_maps / get_best_2c_parcube.
-    Returns (nspectra, seconds)."""
+def cpu_sample(cfg):
+    """The fixed CPU sample of the workload cube (same cube, same guesses as the GPU arm: synth.make_cube is
+    reproducible per row): dict(cube, g1, g2, v, fittype, vstats-free limits)."""
+    from mufasa_b200 import synth
+    fittype, ny, nx, nchan, dv = synth.CONFIGS[cfg]
+    parts = [synth.make_cube(cfg, oracle_modelcube, rows=(y, y + 1)) for y in sample_rows(ny, REF_NROWS)]
+    cube = np.ascontiguousarray(np.concatenate([p["cube"][:, :, ::REF_XSTEP] for p in parts], axis=1))
+    g1 = np.concatenate([p["guess1"][:, :, ::REF_XSTEP] for p in parts], axis=1)
+    g2 = np.concatenate([p["guess2"][:, :, ::REF_XSTEP] for p in parts], axis=1)
+    return dict(cube=cube, g1=g1, g2=g2, v=parts[0]["v"], fittype=fittype,
+                what="%d spectra (%d rows x every %d-th column of the %dx%dx%d cube)" % (
+                    cube.shape[1] * cube.shape[2], REF_NROWS, REF_XSTEP, ny, nx, nchan))
+
+
+def cpu_job(sample, cores):
+    """The reference's job on the sample, on the host: 1c fit + 2c fit (cubefit_simp semantics: guesses clamped into
+    the limits, err = std(spectrum), mpfit) + get_all_lnk_maps / get_best_2c_parcube.  Returns (nspectra, seconds)."""
     from mufasa_b200 import synth
     from oracle import constants as K
     from oracle import fiteach as F
     from oracle import model as M
     from oracle import stats as ST
-    parts = [synth.make_cube(cfg, oracle_modelcube, rows=(y, y + 1), seed_offset=seed_offset) for y in rows]
-    cube = np.ascontiguousarray(np.concatenate([p["cube"][:, :, ::xstep] for p in parts], axis=1))
-    g1 = np.concatenate([p["guess1"][:, :, ::xstep] for p in parts], axis=1)
-    g2 = np.concatenate([p["guess2"][:, :, ::xstep] for p in parts], axis=1)
-    v, fittype = parts[0]["v"], parts[0]["fittype"]
+    cube, v, fittype = sample["cube"], sample["v"], sample["fittype"]
     L = K.limits(fittype)
     lo1 = [-3.5, L["sigmin"], L["Texmin"], L["taumin"]]
     hi1 = [4.5, L["sigmax"], L["Texmax"], L["taumax"]]
-    g1 = synth.clamp_guesses(g1, lo1, hi1)
-    g2 = synth.clamp_guesses(g2, lo1 * 2, hi1 * 2)
+    g1 = synth.clamp_guesses(sample["g1"], lo1, hi1)
+    g2 = synth.clamp_guesses(sample["g2"], lo1 * 2, hi1 * 2)
+    nspec = cube.shape[1] * cube.shape[2]
+    assert nspec >= 2 * cores, "oracle.fiteach runs serially below 2 spectra per core"
     t0 = time.perf_counter()
     o1 = F.fiteach(cube, v, g1, lo1, hi1, fittype, multicore=cores)
     o2 = F.fiteach(cube, v, g2, lo1 * 2, hi1 * 2, fittype, multicore=cores)
@@ -152,8 +171,7 @@ def cpu_job(cfg, rows, xstep, cores, seed_offset=0):
         Lk = ST.all_lnk_maps(cube, m1, m2, expand=20)
         ST.best_2c_parcube(o1["parcube"], o1["errcube"], o2["parcube"], o2["errcube"], Lk["lnk10"], Lk["lnk20"],
                            Lk["lnk21"])
-    dt = time.perf_counter() - t0
-    return cube.shape[1] * cube.shape[2], dt
+    return nspec, time.perf_counter() - t0
 
 
 def host_cores():
@@ -164,60 +182,76 @@ def host_cores():
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle restatement) on this box's host cores."""
+    """--impl reference: the reference's CPU path (oracle restatement) on this box's host cores, all of them, on the
+    fixed sample -- the same sample at every N and in the b200 arm's ``cpu_baseline``."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from mufasa_b200 import synth
-    fittype, ny, nx, nchan, dv = synth.CONFIGS[CFG]
-    cores = host_cores()
-    # pilot: one short row sample to size the per-step sample so that the whole run stays within ~3 minutes
-    n0, t0 = cpu_job(CFG, sample_rows(ny, 2), 16, cores)
-    rate = n0 / t0
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    want = int(min(2048, max(32, rate * budget)))
-    nrows = max(2, min(16, want // 32))
-    xstep = max(1, nx // max(1, want // nrows))
-    rows = sample_rows(ny, nrows)
-    times = []
-    nspec = 0
+    cores = min(host_cores(), REF_NROWS * (1024 // REF_XSTEP) // 4)     # >= 4 spectra per worker process
+    sample = cpu_sample(CFG)
+    times, nspec = [], 0
+    t_begin = time.perf_counter()
+    done_warm = 0
     for it in range(args.warmup + args.steps):
-        nspec, dt = cpu_job(CFG, rows, xstep, cores)
+        # CPU runs have no warm-up effect beyond the first repetition (fork + page cache): when the whole run would
+        # not fit in ~4 minutes the remaining warm-up repetitions are skipped, never the timed ones
+        if it < args.warmup and it >= 1 and times_est(t_begin, it) * (args.steps + args.warmup) > 240.0:
+            continue
+        nspec, dt = cpu_job(sample, cores)
         if it >= args.warmup:
             times.append(dt)
+        else:
+            done_warm += 1
     tstep = float(np.mean(times))
     value = nspec / tstep
-    sample = "%d spectra per step (%d rows x every %d-th column of the %dx%dx%d cube); 1c fit + 2c fit + AICc" % (
-        nspec, nrows, xstep, ny, nx, nchan)
+    what = "%s per step; 1c fit + 2c fit + AICc; %d worker processes; %d of %d warm-up repetitions run" % (
+        sample["what"], cores, done_warm, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tstep * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": what},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = pure-Python MUFASA on un-vendored pyspeckit/mpfit (not installable offline); timed "
-                    "here: the numpy oracle restatement of that path (oracle/), multiprocessing over all host cores"}
+                    "here: the numpy oracle restatement of that path (oracle/), multiprocessing over the host cores"}
     print(json.dumps(line))
     return 0
 
 
+def times_est(t_begin, reps_done):
+    return (time.perf_counter() - t_begin) / max(1, reps_done)
+
+
 def workload_config(n):
-    return {"workload": "BASELINE configs[1]: synthetic NH3(1,1) cube 256x256x800 ch per GPU; step = 1-comp fit + "
-                        "2-comp fit + AICc ncomp selection of all 65536 spectra",
-            "spectra_per_gpu": 65536, "nchan": 800, "fittype": "nh3_multi_v",
-            "partition": "one cube per rank (pixels independent, no data-path collective)" if n > 1 else "single GPU",
-            "cache": "inputs larger than L2 (210 MB of spectra per GPU vs 126 MB L2), streamed once per kernel"}
+    return {"workload": "BASELINE configs[4]: ONE synthetic NH3(1,1) cube 1024x1024x1000 ch; step = 1-comp fit + "
+                        "2-comp fit + AICc ncomp selection + best-model cube of all 1048576 spectra",
+            "spectra": 1048576, "nchan": 1000, "fittype": "nh3_multi_v",
+            "partition": ("row slabs of the one cube over %d GPUs (%d rows each), result block gathered to rank 0 "
+                          "over NCCL" % (n, 1024 // n)) if n > 1 else "single GPU, whole cube",
+            "cache": "inputs larger than L2 (%.1f GB of spectra per GPU vs 126 MB L2), streamed from HBM by every "
+                     "kernel" % (4.29 / max(1, n))}
 
 
 # ------------------------------------------------------------------------------------------------------------------
+class RowSlabView(object):
+    """[nchan, ny, nx] stand-in that only holds rows y0:y1 -- what a loader that reads slabs hands fit_and_select."""
+
+    def __init__(self, slab, ny, y0):
+        self.slab, self.y0 = slab, y0
+        self.shape = (slab.shape[0], ny, slab.shape[2])
+
+    def __getitem__(self, key):
+        rows = key[1]
+        assert key[0] == slice(None) and (rows.start, rows.stop) == (self.y0, self.y0 + self.slab.shape[1])
+        return self.slab
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     from mufasa_b200 import _abi, synth
-    from mufasa_b200.cube import SpecCube
+    from mufasa_b200 import dist as D
     from mufasa_b200.engine import get_engine
-    from mufasa_b200.spec_models.meta_model import MetaModel
-    from mufasa_b200.UltraCube import UltraCube
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -229,223 +263,229 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = get_engine(local)
     dev = eng.device
+    warmup = max(3, args.warmup)
 
     fittype, ny, nx, nchan, dv = synth.CONFIGS[CFG]
-    npix = ny * nx
+    if args.small:                              # smoke-size run of the same code path (not a bench line)
+        ny, nx = 64 * world, 128
+    nspec = ny * nx
+    y0, y1 = D.partition_rows(ny, world, rank)
+    ry = y1 - y0
 
     def gpu_modelcube(parcube, v, ft):
-        P, ry, rx = parcube.shape
-        prob = _abi.make_problem(ft, P // 4, len(v), ry * rx, v[0], v[1] - v[0], [-1e30] * P, [1e30] * P)
-        par = torch.from_numpy(np.ascontiguousarray(parcube.reshape(P, ry * rx).T)).to(dev)
-        m = eng.model(prob, par)[:, :len(v)]
-        return m.cpu().numpy().T.reshape(len(v), ry, rx)
+        P, py, px = parcube.shape
+        prob = _abi.make_problem(ft, P // 4, len(v), py * px, v[0], v[1] - v[0], [-1e30] * P, [1e30] * P)
+        par = torch.from_numpy(np.ascontiguousarray(parcube.reshape(P, py * px).T)).to(dev)
+        return eng.model(prob, par)[:, :len(v)].float().cpu().numpy().T.reshape(len(v), py, px)
 
-    pinned = torch.empty((nchan, ny, nx), dtype=torch.float32).pin_memory()
-    syn = synth.make_cube(CFG, gpu_modelcube, seed_offset=rank, out=pinned.numpy())
-    cube_host = syn["cube"]                       # numpy view of the pinned buffer
-    v = syn["v"]
-    mm = MetaModel(fittype, 1)
-    spec = SpecCube(cube_host, v)
+    # ---------------- synthesis (untimed): this rank's slab into pinned memory, 64 rows at a time ------------------
+    t_syn = time.perf_counter()
+    slab_t = torch.empty((nchan, ry, nx), dtype=torch.float32, pin_memory=True)
+    slab = slab_t.numpy()
+    g1s, g2s = np.empty((4, ry, nx)), np.empty((8, ry, nx))
+    shape = (ny, nx, nchan) if args.small else None
+    for a in range(0, ry, 64):
+        b = min(ry, a + 64)
+        part = synth.make_cube(CFG, gpu_modelcube, rows=(y0 + a, y0 + b), shape=shape, out=slab[:, a:b, :])
+        g1s[:, a:b], g2s[:, a:b] = part["guess1"], part["guess2"]
+        v = part["v"]
+    torch.cuda.empty_cache()
 
-    # ---------------- end-to-end arm: the public API from host buffers ----------------------------------------
-    def e2e_step():
-        uc = UltraCube(cube=spec, fittype=fittype, device=local)
-        uc.fit_cube(ncomp=[1, 2], simpfit=True, guesses={1: syn["guess1"].copy(), 2: syn["guess2"].copy()})
-        res = uc.get_best_2c_parcube()
-        return uc, res
+    def all_rows(a):                            # [k, ry, nx] slab maps of every rank -> [k, ny, nx] on every rank
+        if world == 1:
+            return a
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        pieces = [torch.empty((a.shape[0], D.partition_rows(ny, world, r)[1] - D.partition_rows(ny, world, r)[0], nx),
+                              dtype=t.dtype, device=dev) for r in range(world)]
+        dist.all_gather(pieces, t)
+        return torch.cat(pieces, dim=1).cpu().numpy()
 
-    # Steady state of a caller that processes one cube after another: the previous step's objects are released
-    # before the next step starts.  (Keeping an older UltraCube alive costs ~7 ms per step in first-touch page
-    # faults of the freshly mapped result arrays -- host allocator behaviour, not device work.)
-    e2e_times = []
-    n_e2e = max(2, min(args.steps, 5))
-    for it in range(2 + n_e2e):
+    g1_full, g2_full = all_rows(g1s), all_rows(g2s)
+    t_syn = time.perf_counter() - t_syn
+    cube_view = RowSlabView(slab, ny, y0)
+
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+
+    # ---------------- end-to-end arm: the public API from host buffers ------------------------------------------------
+    e2e_times = []
+    n_e2e = max(2, min(args.steps, 5))
+    res = None
+    for it in range(2 + n_e2e):
+        barrier()
         t0 = time.perf_counter()
-        uc_i, res_i = e2e_step()
-        torch.cuda.synchronize()
+        res = D.fit_and_select(cube_view, v, fittype, g1_full, g2_full, device=local)
+        barrier()
         if it >= 2:
-            e2e_times.append(time.perf_counter() - t0)
-        del uc_i, res_i
-    e2e_t = torch.tensor([float(np.mean(e2e_times))], device=dev, dtype=torch.float64)
+            e2e_times.append(max_over_ranks(time.perf_counter() - t0))
+    e2e_s = float(np.mean(e2e_times))
+    e2e_value = nspec / e2e_s
+    ncomp_hist_e2e = np.bincount(res["ncomp"].astype(int).ravel(), minlength=3).tolist() if rank == 0 else None
+    d2h = int(_abi.PACK_FIELDS * nspec * 8) + 16 * 2
+
+    # ---------------- device arm: slab rows and guesses resident in HBM -------------------------------------------------
+    job = D.SelectionJob(cube_view, v, fittype, g1_full, g2_full, device=local)
+    h2d_t = torch.tensor([float(job.h2d_bytes())], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = npix * world / float(e2e_t.item())
-    uc, res = e2e_step()                           # kept: the source of the rows and limits the device arm uses
-    torch.cuda.synchronize()
-    h2d = cube_host.nbytes + syn["guess1"].nbytes + syn["guess2"].nbytes + npix * 12 * 8
-    d2h = sum(uc.pcubes[k].parcube.nbytes * 2 + npix * (8 + 8 + 8 + 8) for k in ("1", "2")) + npix * (3 + 1 + 3) * 8 \
-        + npix
-
-    # ---------------- device arm: rows resident in HBM --------------------------------------------------------
-    rows = uc._ref_pcube.rows_on_device()
-    p1h, p2h = uc.pcubes["1"], uc.pcubes["2"]
-    # same guesses / limits the drivers produced (cubefit_simp clamps + velocity window)
-    lims = {}
-    for nc in (1, 2):
-        g = syn["guess%d" % nc].copy()
-        from mufasa_b200 import multi_v_fit as mvf
-        vg = g[::4]
-        vmed, v99, v1p = mvf.get_vstats(vg)
-        vmax = max(vmed + 10, v99 + mm.sigmax)
-        vmin = min(vmed - 10, v1p - mm.sigmax)
-        lo = [vmin, mm.sigmin, mm.Texmin, mm.taumin] * nc
-        hi = [vmax, mm.sigmax, mm.Texmax, mm.taumax] * nc
-        g = synth.clamp_guesses(g, lo, hi, eps=mm.eps)
-        lims[nc] = (lo, hi, torch.from_numpy(np.ascontiguousarray(g.reshape(4 * nc, npix).T)).to(dev))
-    prob1 = _abi.make_problem(fittype, 1, nchan, npix, v[0], dv, lims[1][0], lims[1][1])
-    prob2 = _abi.make_problem(fittype, 2, nchan, npix, v[0], dv, lims[2][0], lims[2][1])
-    out1 = eng.fit(prob1, rows, lims[1][2])
-    out2 = eng.fit(prob2, rows, lims[2][2])
-    aout = eng.aicc_alloc(npix)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-
-    def dev_step(timers=None):
-        if timers is not None:
-            ev[0].record()
-        # the 1- and the 2-component fit in flight together (b200fit_fit_batch): same results as two calls, the
-        # latency-bound late rounds of one overlap the other
-        eng.fit_batch([dict(prob=prob1, spectra=rows, guesses=lims[1][2], out=out1),
-                       dict(prob=prob2, spectra=rows, guesses=lims[2][2], out=out2)])
-        if timers is not None:
-            ev[1].record()
-            ev[2].record()
-        eng.aicc_pass(prob1, rows, out1["params"], out2["params"], aout)
-        best = eng.mask_argmax(aout["mask_counts"])
-        bits = eng.mask_bits(prob1, out1["params"], out2["params"], best=best)
-        eng.aicc_pass(prob1, rows, out1["params"], out2["params"], aout, fill_bits=bits, only_empty=True)
-        if timers is not None:
-            ev[3].record()
-
-    for _ in range(max(3, args.warmup)):
-        dev_step()
-    torch.cuda.synchronize()
+        dist.all_reduce(h2d_t)
+    h2d = int(h2d_t.item())
+    for _ in range(warmup):
+        packed = job.run()
+    barrier()
     sampler = ClockSampler(local)
     if rank == 0 and not args.no_clock_sampler:
         sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_fit1 = t_fit2 = t_aicc = 0.0
     launches0 = eng.launch_count()
     start.record()
-    per = []
     for _ in range(args.steps):
-        dev_step(timers=True)
-        per.append(list(ev))
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        packed = job.run()
     stop.record()
-    torch.cuda.synchronize()
+    barrier()
     launches_timed = eng.launch_count() - launches0
-    if world > 1:
-        dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = start.elapsed_time(stop)
-    for e in per:
-        t_fit1 += e[0].elapsed_time(e[1])
-        t_fit2 += e[1].elapsed_time(e[2])
-        t_aicc += e[2].elapsed_time(e[3])
-    tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    ms_per_step = max_over_ranks(start.elapsed_time(stop)) / args.steps
+    value = nspec / (ms_per_step * 1e-3)
+    ncomp_hist = None
+    if rank == 0:
+        ncomp_hist = torch.bincount(packed[43].to(torch.int64).ravel(), minlength=3).tolist()
+    st2 = job.fits[2]["status"]
+    conv = torch.tensor([float((((st2 >= 1) & (st2 <= 4)) | (st2 == 6)).sum()), float((st2 == 5).sum()),
+                         float(job.fits[2]["counts"][:, 0].sum()), float(job.fits[1]["counts"][:, 0].sum())],
+                        dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tt.item()) / args.steps
-    value = npix * world / (ms_per_step * 1e-3)
+        dist.all_reduce(conv)
 
-    # ---------------- roofline of the dominant kernel (fit_eval_kernel<2>) on rank 0 ---------------------------
-    # One extra, untimed-for-`value` step with CUDA events recorded by the library around every kernel of the fit
-    # (b200fit_set_profiling: events on the launching stream).
+    # per-stage device times of one more step on this rank (fits | selection + assembly + gather), max over ranks
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    barrier()
+    ev[0].record()
+    outs = eng.fit_batch(job.batch)
+    ev[1].record()
+    sel = D.aicc_distributed(eng, job.prob, job.ref.rows_on_device(), outs[job.jobs[1]]["params"],
+                             outs[job.jobs[2]]["params"], first_pixel=y0 * nx, model_f32=True)
+    eng.pack_selection(outs[job.jobs[1]], outs[job.jobs[2]], sel)
+    ev[2].record()
+    barrier()
+    t_fits = max_over_ranks(ev[0].elapsed_time(ev[1]))
+    t_sel = max_over_ranks(ev[1].elapsed_time(ev[2]))
+    del outs, sel
+
+    # ---------------- roofline of the dominant kernel (fit_eval_kernel<2>) on rank 0's slab -------------------------
+    # One extra fit of each kind, outside the timed region, with CUDA events recorded by the library around every
+    # kernel on the launching stream (b200fit_set_profiling); a profiled fit runs undivided.
     peaks = measured_peaks()
+    j1, j2 = job.batch[job.jobs[1]], job.batch[job.jobs[2]]
     eng.set_profiling(True)
-    eng.fit(prob1, rows, lims[1][2], out=out1)
+    o1 = eng.fit(j1["prob"], j1["spectra"], j1["guesses"], row_index=j1["row_index"])
     prof1 = eng.get_profile()
-    eng.fit(prob2, rows, lims[2][2], out=out2)
+    o2 = eng.fit(j2["prob"], j2["spectra"], j2["guesses"], row_index=j2["row_index"])
     prof2 = eng.get_profile()
     eng.set_profiling(False)
-    cnt = out2["counts"].to(torch.float64)
-    evals = float(cnt[:, 0].sum().item())                 # fused model + Jacobian evaluations, summed over pixels
-    exec_gauss = float(cnt[:, 2].sum().item()) * 32.0      # gaussians actually evaluated (windowed)
-    exec_chan = float(cnt[:, 3].sum().item()) * 32.0       # channels actually visited (active 32-channel chunks)
+    npix_r = int(j2["prob"].npix)
+    cnt = o2["counts"].to(torch.float64)
+    evals = float(cnt[:, 0].sum().item())                  # fused model + Jacobian evaluations, summed over pixels
+    exec_gauss = float(cnt[:, 2].sum().item()) * 32.0       # gaussians actually evaluated (windowed)
+    exec_chan = float(cnt[:, 3].sum().item()) * 32.0        # channels actually visited (active 32-channel chunks)
     H, C, P = 18, 2, 8
-    sfu = evals * nchan * C * (H + 2)                      # SFU_J = N*C*(H+2)
-    f32 = evals * nchan * C * (12 * H + 30)                # F32_J = N*C*(12H+30)
-    f64 = evals * nchan * (P * (P + 1) + 2 * P + 2)        # F64_J = N*(P(P+1)+2P+2)
-    sfu_exec = exec_gauss + exec_chan * C                  # ex2 actually issued: gaussians + e^-tau per component
+    sfu = evals * nchan * C * (H + 2)                       # SFU_J = N*C*(H+2)
+    f32 = evals * nchan * C * (12 * H + 30)                 # F32_J = N*C*(12H+30)
+    f64 = evals * nchan * (P * (P + 1) + 2 * P + 2)         # F64_J = N*(P(P+1)+2P+2)
+    sfu_exec = exec_gauss + exec_chan * C                   # ex2 actually issued: gaussians + e^-tau per component
+    f32_exec = exec_gauss * 8.0 + exec_chan * (40.0 + 2.0 * 45.0)   # per gaussian 8, per channel RT 40 + 45 FMA
     launches_eval = max(1, prof2["rounds"])
-    t_eval = prof2["eval_ms"] * 1e-3                       # sum over the launches of one fit
+    t_eval = prof2["eval_ms"] * 1e-3                        # sum over the launches of one fit
     clk = peaks["sm_max_mhz"] * 1e6
     nsm = eng.num_sms
     pk = {"fp32": nsm * 128 * 2 * clk, "xu": nsm * 16 * clk, "fp64": nsm * 64 * 2 * clk}
     ach = {"fp32": f32 / t_eval, "xu": sfu / t_eval, "fp64": f64 / t_eval}
-    frac = {k: ach[k] / pk[k] for k in pk}
-    bound = max(frac, key=lambda k: frac[k])
-    hbm_bytes = npix * (nchan * 4 + P * 8 + (2 * P + 2) * 8 + 4 + 16)
-    t2 = (prof2["prologue_ms"] + prof2["eval_ms"] + prof2["solve_ms"]) * 1e-3   # seconds per 2c fit run on its own
-    roofline = {"bound": bound, "kernel": "fit_eval_kernel<2>", "achieved": ach[bound] / 1e12,
-                "peak": pk[bound] / 1e12, "unit": "TFLOP/s" if bound != "xu" else "Top/s", "frac": frac[bound],
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch with all 65 536 pixels active (ncu --set
-                # full, profiles/r1m_fit2c_ncu_full_summary.txt: 166.0 + 19.5 MB = 2831 B per pixel-evaluation: the
-                # windowed part of the spectrum + the per-pixel LM state), scaled to the average launch of this run
-                "traffic": NCU_DRAM_BYTES_PER_EVAL * evals / launches_eval,
-                "traffic_source": "ncu capture r1m (2831 B per pixel-evaluation) x evaluations per launch of this run",
-                "definition": "ALGORITHMIC work (SURVEY 8d per-evaluation figures x evaluations counted by the kernel) "
-                              "/ summed CUDA-event duration of the kernel's launches in one 2c fit; the kernel skips "
-                              "gaussians beyond 6.2 sigma (exactly 0 in fp32), see frac_executed",
-                "frac_executed": {"xu": sfu_exec / t_eval / pk["xu"]},
-                "pipes": {k: {"achieved_T": ach[k] / 1e12, "peak_T": pk[k] / 1e12, "frac": frac[k]} for k in pk},
-                "peak_source": "derived: %d SMs x lanes x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json, %s)" % (
+    frac_alg = {k: ach[k] / pk[k] for k in pk}
+    frac_exec = {"xu": sfu_exec / t_eval / pk["xu"], "fp32": f32_exec / t_eval / pk["fp32"]}
+    t2 = (prof2["prologue_ms"] + prof2["eval_ms"] + prof2["solve_ms"]) * 1e-3   # one 2c fit of this slab on its own
+    hbm_bytes = npix_r * (nchan * 4 + P * 8 + (2 * P + 2) * 8 + 4 + 16)
+    traffic = ncu_traffic_per_eval() * evals / launches_eval
+    roofline = {"bound": "xu", "kernel": "fit_eval_kernel<2>", "achieved": sfu_exec / t_eval / 1e12,
+                "peak": pk["xu"] / 1e12, "unit": "Top/s", "frac": frac_exec["xu"],
+                "definition": "EXECUTED ex2 (gaussians inside the 6.2-sigma windows + one e^-tau per channel and "
+                              "component, counted by the kernel) / summed CUDA-event duration of the kernel's launches "
+                              "in one undivided 2c fit of rank 0's slab / XU peak",
+                "frac_algorithmic": frac_alg, "frac_executed": frac_exec,
+                "algorithmic_definition": "SURVEY 8d per-evaluation figures x evaluations counted by the kernel; the "
+                                          "kernel skips gaussians beyond 6.2 sigma (exactly 0 in fp32), ~90 % of them",
+                "traffic": traffic,
+                "traffic_source": "dram bytes per pixel-evaluation of the latest ncu --set full capture under "
+                                  "profiles/ (%.0f B) x evaluations per launch of this run" % ncu_traffic_per_eval(),
+                "peak_source": "derived: %d SMs x 16 XU lanes x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json, %s)" % (
                     nsm, peaks["sm_max_mhz"], peaks["source"]),
                 "hbm": {"achieved": hbm_bytes / t2 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": hbm_bytes / t2 / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"]},
                 "per_launch": {"launches": launches_eval, "avg_ms": prof2["eval_ms"] / launches_eval,
-                               "xu_ops": sfu / launches_eval, "fp32_flop": f32 / launches_eval,
-                               "fp64_flop": f64 / launches_eval},
-                "algorithmic_per_fit": {"evaluations": evals, "xu_ops": sfu, "fp32_flop": f32, "fp64_flop": f64,
-                                        "executed_gaussians": exec_gauss, "algorithmic_gaussians": evals * nchan * C * H},
+                               "xu_ops_executed": sfu_exec / launches_eval, "xu_ops_algorithmic": sfu / launches_eval},
+                "per_fit": {"pixels": npix_r, "evaluations": evals, "executed_gaussians": exec_gauss,
+                            "algorithmic_gaussians": evals * nchan * C * H},
                 "fit_2c_ms": {"prologue": prof2["prologue_ms"], "eval": prof2["eval_ms"], "solve": prof2["solve_ms"],
                               "rounds": prof2["rounds"]},
                 "fit_1c_ms": {"prologue": prof1["prologue_ms"], "eval": prof1["eval_ms"], "solve": prof1["solve_ms"],
                               "rounds": prof1["rounds"]},
-                "share_of_step": {"fits_1c_and_2c_batched": t_fit1 / total_ms, "aicc": t_aicc / total_ms,
-                                  "fit_eval_kernel<2>": prof2["eval_ms"] / ms_per_step,
-                                  "fit_solve_kernel<2>": prof2["solve_ms"] / ms_per_step}}
+                "share_of_step": {"fits_1c_and_2c_batched": t_fits / (t_fits + t_sel),
+                                  "selection_assembly_gather": t_sel / (t_fits + t_sel)}}
+    del o1, o2
 
     line = None
     if rank == 0:
-        st2 = out2["status"].cpu().numpy()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 model+Jacobian, f64 normal equations/solve",
+                "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32 model+Jacobian, f64 normal equations/solve",
                 "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h), "ms_per_step": float(e2e_t.item()) * 1e3,
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                         "samples_ms": [round(t * 1e3, 2) for t in e2e_times],
-                        "api": "UltraCube.fit_cube([1, 2], simpfit) + get_best_2c_parcube()"},
+                        "api": "mufasa_b200.dist.fit_and_select(cube slab view, v, fittype, guesses1, guesses2): "
+                               "pinned host slab in, 44 gathered maps out on rank 0; wall clock, max over ranks"},
                 "gpu_launches": int(launches_timed),
-                "fit2c_only": {"value": npix / t2, "unit": UNIT, "ms": t2 * 1e3},
+                "stage_ms": {"fits_1c_2c": t_fits, "selection_assembly_gather": t_sel},
                 "roofline": roofline, "clocks": clocks,
-                "fit_stats": {"converged_2c": float(np.isin(st2, [1, 2, 3, 4, 6]).mean()),
-                              "maxiter_2c": float((st2 == 5).mean()),
-                              "mean_evals_2c": evals / npix,
-                              "mean_evals_1c": float(out1["counts"][:, 0].to(torch.float64).mean().item())}}
-    if world > 1:
-        dist.barrier()
-    # ---------------- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
+                "fit_stats": {"converged_2c": conv[0].item() / nspec, "maxiter_2c": conv[1].item() / nspec,
+                              "mean_evals_2c": conv[2].item() / nspec, "mean_evals_1c": conv[3].item() / nspec,
+                              "ncomp_hist": ncomp_hist, "ncomp_hist_e2e": ncomp_hist_e2e},
+                "synthesis_s": round(t_syn, 1)}
+        if args.small:
+            line["config"]["workload"] = "SMOKE-SIZE run (%dx%dx%d), not a bench line" % (ny, nx, nchan)
+    barrier()
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = host_cores()
-        rows_s = sample_rows(ny, 8)
-        nspec, dt = cpu_job(CFG, rows_s, 8, cores)
-        line["cpu_baseline"] = {"value": nspec / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d spectra (8 rows x every 8th column of the same cube), 1c fit + 2c fit + "
-                                          "AICc with the numpy oracle (mpfit restatement), %d processes, %.1f s" % (
-                                              nspec, cores, dt)}
+        cores = min(host_cores(), REF_NROWS * (1024 // REF_XSTEP) // 4)
+        sample = cpu_sample(CFG)
+        ns, dt = cpu_job(sample, cores)
+        line["cpu_baseline"] = {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%s, 1c fit + 2c fit + AICc with the numpy oracle (mpfit restatement), %d "
+                                          "worker processes, %.1f s" % (sample["what"], cores, dt)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ncu_traffic_per_eval():
+    """dram__bytes_read.sum + dram__bytes_write.sum per pixel-evaluation of fit_eval_kernel<2> from the latest
+    ncu --set full capture of a launch with every pixel active (profiles/NCU_TRAFFIC.json, written next to the
+    capture's summary)."""
+    path = os.path.join(ROOT, "profiles", "NCU_TRAFFIC.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_pixel_eval"])
+    except Exception:
+        return (166.019072e6 + 19.493888e6) / 65536.0   # profiles/r1m_fit2c_ncu_full_summary.txt
 
 
 def main():
@@ -456,6 +496,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostics only")
+    ap.add_argument("--small", action="store_true", help="smoke-size cube through the same code path (diagnostics)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B200FIT_ABI_VERSION 4
+#define B200FIT_ABI_VERSION 5
 
 enum {
     B200FIT_OK = 0,
@@ -207,6 +207,17 @@ int b200fit_mask_argmax(b200fit_ctx* ctx, const int32_t* d_mask_counts, int64_t 
 int b200fit_mask_bits(b200fit_ctx* ctx, const b200fit_problem* prob,
                       const double* d_params1, const double* d_params2, int32_t model_f32,
                       const int64_t* d_best, int64_t pix, uint32_t* d_bits, void* stream);
+
+/* UltraCube.get_best_2c_parcube (UltraCube.py:1283-1379; include_1c=True, return_lnks=True) assembled on the device
+ * from the two fits and the output of b200fit_aicc, field-major d_out[B200FIT_PACK_FIELDS][out_stride]:
+ *   [0,4) parcube1  [4,8) errcube1  [8,16) parcube2  [16,24) errcube2  [24,32) best parcube  [32,40) best errcube
+ *   (the 2-component fit where ncomp == 2; the 1-component fit in planes 0-3, NaN in 4-7 where ncomp == 1; NaN where
+ *   ncomp == 0 -- :1350-1367)  [40,43) lnk10, lnk20, lnk21  [43] ncomp.   These rows are what a row-slab partitioned
+ *   run gathers over NCCL (mufasa_b200/dist.py); d_lnk [npix][3] and d_ncomp [npix] come from b200fit_aicc. */
+#define B200FIT_PACK_FIELDS 44
+int b200fit_pack_selection(b200fit_ctx* ctx, int64_t npix, const double* d_params1, const double* d_perr1,
+                           const double* d_params2, const double* d_perr2, const double* d_lnk,
+                           const signed char* d_ncomp, double* d_out, int64_t out_stride, void* stream);
 
 /* Residual statistics of one fitted model: replaces UltraCube.get_rms / get_chisq(reduced=True)
  * (UltraCube.py:1701-1740, :1478-1565; prob->ncomp selects the model, d_params [npix][4*ncomp]).

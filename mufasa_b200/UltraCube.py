@@ -22,6 +22,7 @@ import torch
 
 from . import multi_v_fit as mvf
 from .cube import SpecCube
+from .exceptions import StartFitError
 from .pcube import PCube
 from .spec_models.meta_model import MetaModel
 
@@ -42,6 +43,7 @@ class UltraCube(object):
         self.AICc_maps = {}
         self.lnk_maps = {}
         self.ncomp_map = None
+        self._ncomp_thr = None
         self._master_model_mask = None
         self._aicc_eager = None
         self._mask_ncomps = []            # which fits feed the lazily built master_model_mask
@@ -105,47 +107,65 @@ class UltraCube(object):
         ncomp = list(ncomp)
         batch = [] if (concurrent and len(ncomp) > 1) else None
         pending = []
-        for nc in ncomp:
-            if self.pcubes:
-                _, pcube_ref = next(iter(self.pcubes.items()))
-                self.pcubes[str(nc)] = self.load_pcube(pcube_ref=pcube_ref)
-            else:
-                self.pcubes[str(nc)] = self.load_pcube()
-            self.pcubes[str(nc)]._deferred = batch
-            kw = dict(kwargs)
-            if isinstance(kw.get('guesses'), dict):          # per-ncomp guesses for a batched call
-                kw['guesses'] = kw['guesses'].get(nc)
-            if simpfit and batch is not None:
-                # first half of every driver (host work on the guesses) while the cube is still uploading; the
-                # halves that need the device follow below
-                steps = mvf.cubefit_simp_steps(self.cube, self.pcubes[str(nc)], fittype=self.fittype, ncomp=nc, **kw)
-                next(steps)
-                pending.append((nc, steps))
-                continue
-            self.pcubes[str(nc)] = fit_cube(self.cube, self.pcubes[str(nc)], fittype=self.fittype, simpfit=simpfit,
-                                            ncomp=nc, **kw)
-            self.pcubes[str(nc)]._deferred = None
-        for nc, steps in pending:
-            for _ in steps:
-                pass
-            self.pcubes[str(nc)]._deferred = None
         eager = None
-        if batch:
-            eng = batch[0]["pcube"].engine
-            outs = eng.fit_batch(batch)
-            # the model selection needs nothing from the host: queue it right behind the fits, on the parameters as
-            # they lie on the device, and bring the fit results back on a second stream meanwhile
-            done = torch.cuda.Event()
-            done.record(torch.cuda.current_stream(eng.device))
-            if eager_aicc:
-                eager = self._launch_eager_aicc(batch, outs, eng)
-            back = eng.side_stream("d2h")
-            with torch.cuda.stream(back):
-                back.wait_event(done)
-                for job, out in zip(batch, outs):           # both copies in flight before the first host wait
-                    job["pcube"].start_fit_readback(job, out)
-                for job, out in zip(batch, outs):
-                    job["pcube"].finish_fit(job, out)
+        try:
+            for nc in ncomp:
+                if self.pcubes:
+                    _, pcube_ref = next(iter(self.pcubes.items()))
+                    self.pcubes[str(nc)] = self.load_pcube(pcube_ref=pcube_ref)
+                else:
+                    self.pcubes[str(nc)] = self.load_pcube()
+                self.pcubes[str(nc)]._deferred = batch
+                kw = dict(kwargs)
+                if isinstance(kw.get('guesses'), dict):          # per-ncomp guesses for a batched call
+                    kw['guesses'] = kw['guesses'].get(nc)
+                if simpfit and batch is not None:
+                    # first half of every driver (host work on the guesses) while the cube is still uploading; the
+                    # halves that need the device follow below
+                    steps = mvf.cubefit_simp_steps(self.cube, self.pcubes[str(nc)], fittype=self.fittype, ncomp=nc,
+                                                   **kw)
+                    next(steps)
+                    pending.append((nc, steps))
+                    continue
+                self.pcubes[str(nc)] = fit_cube(self.cube, self.pcubes[str(nc)], fittype=self.fittype,
+                                                simpfit=simpfit, ncomp=nc, **kw)
+            for nc, steps in pending:
+                for _ in steps:
+                    pass
+            if batch:
+                eng = batch[0]["pcube"].engine
+                outs = eng.fit_batch(batch)
+                # the model selection needs nothing from the host: queue it right behind the fits, on the parameters
+                # as they lie on the device, and bring the fit results back on a second stream meanwhile
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(eng.device))
+                if eager_aicc:
+                    eager = self._launch_eager_aicc(batch, outs, eng)
+                back = eng.side_stream("d2h")
+                with torch.cuda.stream(back):
+                    back.wait_event(done)
+                    for job, out in zip(batch, outs):           # both copies in flight before the first host wait
+                        job["pcube"].start_fit_readback(job, out)
+                    for job, out in zip(batch, outs):
+                        try:
+                            job["pcube"].finish_fit(job, out)
+                        except AssertionError as e:
+                            # the reference's contract at this point (multi_v_fit.py:388-403, :456-478): cubefit_gen
+                            # turns "no pixel yielded a fit" into StartFitError (every pixel was tried here, so the
+                            # retry from another start pixel has nothing left to do); cubefit_simp lets it through
+                            if simpfit:
+                                raise
+                            raise StartFitError("The first two attempts to fit a pixel did not yield a fit. Message "
+                                                "from the fitter: " + str(e))
+                for job in batch:                                # writers the drivers deferred until the maps exist
+                    save = getattr(job["pcube"], "_save_after_fit", None)
+                    if save is not None:
+                        mvf.save_pcube(job["pcube"], save[0], ncomp=save[1])
+                        job["pcube"]._save_after_fit = None
+        finally:
+            for nc in ncomp:
+                if str(nc) in self.pcubes:
+                    self.pcubes[str(nc)]._deferred = None
         for nc in ncomp:
             p = self.pcubes[str(nc)]
             if p.has_fit.sum() > 0 and p.parcube is not None:
@@ -203,6 +223,7 @@ class UltraCube(object):
                   self.rchisq_maps):
             d.clear()
         self.ncomp_map = None
+        self._ncomp_thr = None
         self._aicc_eager = None        # a selection queued behind an earlier fit no longer describes the fits
 
     def has_fit(self, ncomp):
@@ -263,16 +284,38 @@ class UltraCube(object):
         stage.copy_(packed_d, non_blocking=True)
         return stage
 
-    def _run_aicc(self, expand=20, thr=(5.0, 5.0, 5.0)):
-        key = (int(expand), tuple(float(t) for t in thr))
-        if self.lnk_maps.get("_key") == key:
+    def _select_ncomp(self, thr):
+        """The integer 0/1/2 map for the thresholds ``thr`` = (lnk10, lnk20, lnk21), from the likelihood maps as the
+        reference selects (UltraCube.py:1350-1367): 2 where lnk21 > t21 and lnk20 > t20, else 1, and 0 where not
+        lnk10 > t10 (comparisons with NaN are False)."""
+        with np.errstate(invalid="ignore"):
+            lnk10 = -1.0 * (self.AICc_maps["1"] - self.AICc_maps["0"]) / 2.0
+            lnk20 = -1.0 * (self.AICc_maps["2"] - self.AICc_maps["0"]) / 2.0
+            lnk21 = -1.0 * (self.AICc_maps["2"] - self.AICc_maps["1"]) / 2.0
+            two = np.logical_and(lnk21 > thr[2], lnk20 > thr[1])
+            nc = np.where(two, 2, 1).astype(np.int8)
+            nc[~(lnk10 > thr[0])] = 0
+        self.ncomp_map = nc
+        self._ncomp_thr = tuple(float(t) for t in thr)
+
+    def _run_aicc(self, expand=20, thr=None):
+        """One AICc pass per (fits, expand): rss_0/1/2, N, AICc_0/1/2, the lnk maps and the selection map.  The
+        statistics do not depend on the selection thresholds, so a call with other thresholds reuses the cached maps
+        and only redoes the selection (``thr`` None: whatever selection is there stays)."""
+        if self.lnk_maps.get("_key") == int(expand):
+            if thr is not None and tuple(float(t) for t in thr) != self._ncomp_thr:
+                self._select_ncomp(thr)
             return
+        thr = (5.0, 5.0, 5.0) if thr is None else tuple(float(t) for t in thr)
+        key = (int(expand), thr)
         ref = self._ref_pcube if self._ref_pcube is not None else self.load_pcube()
         eng = ref.engine
         ny, nx = self.cube.shape[1:]
         eager, self._aicc_eager = getattr(self, "_aicc_eager", None), None
-        if eager is not None and eager[0] == key:
+        kernel_thr = thr
+        if eager is not None and eager[0][0] == int(expand):
             out = eager[1]              # already computed behind the batched fit (fit_cube)
+            kernel_thr = eager[0][1]    # ... with these thresholds; the selection is redone below if others are asked
         else:
             out = None
         rows = ref.rows_on_device()
@@ -312,8 +355,11 @@ class UltraCube(object):
                 p = 4 * nc
                 self.AICc_maps[str(nc)] = ns * np.log(self.rss_maps[str(nc)] / ns) + 2 * p + \
                     (2 * p * (p + 1)) / (ns - p - 1)
-        self.lnk_maps = {"_key": key, "10": lnk[0].copy(), "20": lnk[1].copy(), "21": lnk[2].copy()}
-        self.ncomp_map = packed[7].astype(np.int8).reshape(ny, nx)
+        self.lnk_maps = {"_key": int(expand), "10": lnk[0].copy(), "20": lnk[1].copy(), "21": lnk[2].copy()}
+        self.ncomp_map = packed[7].astype(np.int8).reshape(ny, nx)     # the kernel's selection
+        self._ncomp_thr = kernel_thr
+        if kernel_thr != thr:
+            self._select_ncomp(thr)
 
     def get_rss(self, ncomp, mask=None, planemask=None, update=True, expand=20):
         """Residual sum of squares over the dilated union model mask (UltraCube.py:432-451)."""

@@ -8,7 +8,7 @@ LIB_PATH = os.environ.get("B200FIT_LIB", os.path.join(HERE, "csrc", "libb200fit.
 
 MODEL_IDS = {"nh3_multi_v": 0, "n2hp_multi_v": 1}
 MAX_NCHAN = 2048
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Problem(C.Structure):
@@ -45,6 +45,7 @@ class FitArgs(C.Structure):
 
 
 MAX_BATCH = 4
+PACK_FIELDS = 44
 
 
 class B200FitError(RuntimeError):
@@ -77,6 +78,7 @@ SIGNATURES = {
     "b200fit_mask_bits_pair": (C.c_int, [_vp, _PP, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "b200fit_mask_argmax": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "b200fit_mask_bits": (C.c_int, [_vp, _PP, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
+    "b200fit_pack_selection": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "b200fit_rms_snr": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, C.c_double, _i32, _vp, _vp, _vp, _vp]),
     "b200fit_signal_bits": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, C.c_double, _vp, _vp]),
     "b200fit_bits_morph": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp]),

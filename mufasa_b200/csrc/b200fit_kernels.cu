@@ -1061,6 +1061,59 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// get_best_2c_parcube (UltraCube.py:1283-1379, include_1c, return_lnks) assembled on the device, field-major:
+//   out[ 0.. 3] parcube1   out[ 4.. 7] errcube1   out[ 8..15] parcube2   out[16..23] errcube2
+//   out[24..31] best parcube: the 2-component fit where ncomp == 2; the 1-component fit in planes 0-3 and NaN in
+//               4-7 where ncomp == 1; NaN where ncomp == 0            out[32..39] best errcube, likewise
+//   out[40..42] lnk10, lnk20, lnk21 (NaN where the fit does not exist)   out[43] ncomp
+// One thread per pixel; every plane is written coalesced.  This is what a partitioned run gathers: [44][npix] rows.
+constexpr int PACK_FIELDS = 44;
+__global__ void __launch_bounds__(256)
+    pack_selection_kernel(long long npix, const double* __restrict__ params1, const double* __restrict__ perr1,
+                          const double* __restrict__ params2, const double* __restrict__ perr2,
+                          const double* __restrict__ lnk, const signed char* __restrict__ ncomp,
+                          double* __restrict__ out, long long out_stride) {
+    for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < npix;
+         px += (long long)gridDim.x * blockDim.x) {
+        const int nc = ncomp[px];
+        double p1[4], e1[4], p2[8], e2[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            p1[j] = params1[px * 4 + j];
+            e1[j] = perr1[px * 4 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            p2[j] = params2[px * 8 + j];
+            e2[j] = perr2[px * 8 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            out[(0 + j) * out_stride + px] = p1[j];
+            out[(4 + j) * out_stride + px] = e1[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            out[(8 + j) * out_stride + px] = p2[j];
+            out[(16 + j) * out_stride + px] = e2[j];
+            double bp = NAN, be = NAN;
+            if (nc == 2) {
+                bp = p2[j];
+                be = e2[j];
+            } else if (nc == 1 && j < 4) {
+                bp = p1[j];
+                be = e1[j];
+            }
+            out[(24 + j) * out_stride + px] = bp;
+            out[(32 + j) * out_stride + px] = be;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) out[(40 + k) * out_stride + px] = lnk[px * 3 + k];
+        out[43 * out_stride + px] = (double)nc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // get_rms + reduced get_chisq of one fitted model (UltraCube.py:1701-1740, :1478-1565), one warp per pixel:
 //   r = data - model;  rms = 1.4826 * nanmedian(|r - roll(r, 2)|) / sqrt(2);
 //   chisq_red = nansum((r * mask)^2) / sum(mask) / rms^2,  mask = dilate(model > 0, expand)
@@ -1822,6 +1875,23 @@ int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_s
                  void* stream) {
     return b200fit_aicc_pair(ctx, prob, 1, 2, d_spectra, nchan_stride, d_row_index, d_params1, d_params2, d_fill_bits,
                              only_empty, expand, model_f32, thr, d_rss, d_nsamp, d_lnk, d_ncomp, d_mask_counts, stream);
+}
+
+int b200fit_pack_selection(b200fit_ctx* ctx, int64_t npix, const double* d_params1, const double* d_perr1,
+                           const double* d_params2, const double* d_perr2, const double* d_lnk,
+                           const signed char* d_ncomp, double* d_out, int64_t out_stride, void* stream) {
+    if (!ctx) return B200FIT_E_ARG;
+    if (npix == 0) return B200FIT_OK;
+    if (!d_params1 || !d_perr1 || !d_params2 || !d_perr2 || !d_lnk || !d_ncomp || !d_out || npix < 0 || out_stride < npix)
+        return fail(ctx, B200FIT_E_ARG, "pack_selection: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    long long blocks = (npix + 255) / 256;
+    if (blocks > (long long)ctx->num_sms * 16) blocks = (long long)ctx->num_sms * 16;
+    pack_selection_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(npix, d_params1, d_perr1, d_params2, d_perr2,
+                                                                               d_lnk, d_ncomp, d_out, out_stride);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    return B200FIT_OK;
 }
 
 int b200fit_rms_snr(b200fit_ctx* ctx, int32_t nchan, int64_t npix, const float* d_spectra, int64_t nchan_stride,

@@ -51,20 +51,37 @@ def global_best(local_best, group=None):
     return best
 
 
+def _global_rank(group, r):
+    """torch.distributed takes GLOBAL ranks for src / dst; ``r`` is a rank within ``group``."""
+    return r if group is None else dist.get_global_rank(group, r)
+
+
 def gather_maps(local, ny, group=None, dst=0):
-    """Gather row-slab maps ``local[..., ry, nx]`` (any leading dims) to ``[..., ny, nx]`` on rank ``dst``
-    (None elsewhere).  Slabs follow ``partition_rows``; uneven slabs are padded to the largest for the collective."""
+    """Gather row-slab maps ``local[..., ry, nx]`` (any leading dims) to ``[..., ny, nx]`` on rank ``dst`` of the
+    group (None elsewhere).  Slabs follow ``partition_rows``; uneven slabs are padded to the largest for the
+    collective.  One collective whatever the number of maps: callers stack their maps along the leading dimension."""
     world, rank = _world(group)
     if world == 1:
         return local
     lead, nx = local.shape[:-2], local.shape[-1]
     rmax = -(-int(ny) // world)
-    pad = torch.zeros(lead + (rmax, nx), dtype=local.dtype, device=local.device)
-    pad[..., :local.shape[-2], :] = local
-    pieces = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-    dist.gather(pad, pieces, dst=dst, group=group)
+    if local.shape[-2] == rmax:
+        pad = local.contiguous()
+    else:
+        pad = torch.zeros(lead + (rmax, nx), dtype=local.dtype, device=local.device)
+        pad[..., :local.shape[-2], :] = local
+    if rank == dst:
+        buf = torch.empty((world,) + tuple(pad.shape), dtype=local.dtype, device=local.device)
+        pieces = list(buf.unbind(0))
+    else:
+        buf, pieces = None, None
+    dist.gather(pad, pieces, dst=_global_rank(group, dst), group=group)
     if rank != dst:
         return None
+    if int(ny) == world * rmax:          # even slabs: the gathered buffer is the result, rank-major along the rows
+        nl = len(lead)
+        perm = tuple(range(1, nl + 1)) + (0, nl + 1, nl + 2)
+        return buf.permute(perm).reshape(lead + (int(ny), nx))
     out = torch.empty(lead + (int(ny), nx), dtype=local.dtype, device=local.device)
     for r, t in enumerate(pieces):
         y0, y1 = partition_rows(ny, world, r)
@@ -88,7 +105,7 @@ def aicc_distributed(engine, prob, rows, params1, params2, first_pixel, expand=2
     else:
         bits = torch.zeros(64, dtype=torch.int32, device=engine.device)
     if world > 1:
-        dist.broadcast(bits, src=owner, group=group)
+        dist.broadcast(bits, src=_global_rank(group, owner), group=group)
     engine.aicc_pass(prob, rows, params1, params2, out, fill_bits=bits, only_empty=True, expand=expand,
                      model_f32=model_f32, thr=thr, row_index=row_index)
     out["fill_bits"] = bits
@@ -96,61 +113,186 @@ def aicc_distributed(engine, prob, rows, params1, params2, first_pixel, expand=2
     return out
 
 
-def fit_and_select(cube, v_kms, fittype, guesses1, guesses2, device=None, group=None, gather=True):
-    """The model-selection job (1c fit + 2c fit + AICc 0/1/2 selection; UltraCube.fit_cube([1, 2]) +
+def percentiles_like_numpy(values, qs):
+    """``np.percentile(values, qs)`` (method 'linear') of a 1-D float64 torch tensor on ANY device, bit for bit:
+    sort, virtual index (n - 1) q / 100, numpy's two-sided lerp.  Used for the global statistics of the velocity
+    guesses (multi_v_fit.get_vstats, multi_v_fit.py:634-644), which every rank of a partitioned run needs and which
+    cost 0.1 s per map of a 1024 x 1024 cube with numpy on the host."""
+    import numpy as np
+    n = int(values.numel())
+    if n == 0:
+        return [float("nan")] * len(qs)
+    srt = torch.sort(values).values
+    want, meta = [], []
+    for q in qs:
+        virt = (n - 1) * float(np.true_divide(q, np.float64(100)))
+        prev = int(np.floor(virt))
+        prev = min(max(prev, 0), n - 1)
+        nxt = min(prev + 1, n - 1)
+        want += [prev, nxt]
+        meta.append(virt - np.floor(virt))
+    got = srt[torch.tensor(want, device=srt.device)].cpu().numpy()
+    out = []
+    for k, t in enumerate(meta):
+        a, b = np.float64(got[2 * k]), np.float64(got[2 * k + 1])
+        d = b - a
+        out.append(float(b - d * (1 - t)) if t >= 0.5 else float(a + d * t))
+    return out
+
+
+def median_like_numpy(values):
+    """``np.median`` of a 1-D float64 torch tensor: the middle value, or the mean of the two middle values."""
+    n = int(values.numel())
+    if n == 0:
+        return float("nan")
+    k = torch.tensor([(n - 1) // 2, n // 2], device=values.device)
+    lo, hi = torch.sort(values).values[k].tolist()
+    return lo if n % 2 else (lo + hi) / 2.0
+
+
+def global_vstats(vmaps, device):
+    """(median, 99th, 1st percentile) of the finite, non-zero velocity guesses ``vmaps`` [k, ny, nx] -- the numbers
+    cubefit_simp derives its velocity window from (multi_v_fit.py:163-176) -- computed on ``device``."""
+    import numpy as np
+    t = torch.from_numpy(np.ascontiguousarray(vmaps, dtype=np.float64)).to(device, non_blocking=True).ravel()
+    t = t[torch.isfinite(t) & (t != 0)]
+    p99, p1 = percentiles_like_numpy(t, [99, 1])
+    return median_like_numpy(t), p99, p1
+
+
+FIELDS = (("parcube1", 0, 4), ("errcube1", 4, 8), ("parcube2", 8, 16), ("errcube2", 16, 24), ("best_parcube", 24, 32),
+          ("best_errcube", 32, 40), ("lnk10", 40, 41), ("lnk20", 41, 42), ("lnk21", 42, 43), ("ncomp", 43, 44))
+
+
+class SelectionJob(object):
+    """One rank's share of the model-selection job (see ``fit_and_select``), split at the points a caller may want
+    to time or repeat: ``__init__`` = host work on the guesses + upload of the slab and the guesses; ``run`` =
+    everything on the device, from the two fits to the gathered result block; ``to_host`` = the one copy back."""
+
+    def __init__(self, cube, v_kms, fittype, guesses1, guesses2, device=None, group=None, vstats=None):
+        import numpy as np
+        from . import _abi
+        from . import multi_v_fit as mvf
+        from .cube import SpecCube
+        from .engine import get_engine
+        from .exceptions import SNRMaskError, StartFitError
+        from .pcube import PCube
+        self.group = group
+        self.world, self.rank = _world(group)
+        nchan, ny, nx = cube.shape
+        self.ny, self.nx, self.fittype = int(ny), int(nx), fittype
+        y0, y1 = partition_rows(ny, self.world, self.rank)
+        self.y0, self.ry = y0, y1 - y0
+        self.npix = npix = self.ry * nx
+        dev = torch.cuda.current_device() if device is None else device
+        self.eng = eng = get_engine(dev)
+        slab = cube[:, y0:y1, :]
+        if not (isinstance(slab, np.ndarray) and slab.flags["C_CONTIGUOUS"]):
+            slab = np.ascontiguousarray(slab)
+        spec = SpecCube(slab, v_kms)
+        self.model_f32 = spec._data.dtype == np.float32
+        self.ref = ref = PCube(spec._data, spec.xarr(), header=spec.header, unit=spec.unit, device=dev)
+        if npix:
+            ref.rows_on_device(wait=False)                   # the upload starts now; host work below overlaps it
+        if vstats is None:
+            vstats = {1: global_vstats(guesses1[::4], eng.device), 2: global_vstats(guesses2[::4], eng.device)}
+        self.vstats = vstats
+        # the two drivers: host work on the guesses, then the device-side job descriptions; nothing is fitted yet
+        self.batch, self.jobs = [], {}
+        for nc, full in ((1, guesses1), (2, guesses2)):
+            g = np.array(full[:, y0:y1, :], dtype=np.float64)
+            p = PCube(spec._data, spec.xarr(), header=spec.header, unit=spec.unit, device=dev)
+            p.share_device(ref)
+            p._deferred = self.batch
+            before = len(self.batch)
+            try:
+                if npix:
+                    mvf.cubefit_simp(spec, p, ncomp=nc, guesses=g, fittype=fittype, vstats=vstats[nc])
+            except (SNRMaskError, StartFitError, AssertionError, ValueError):
+                del self.batch[before:]                      # this slab has nothing to fit for this model
+            finally:
+                p._deferred = None
+            self.jobs[nc] = before if len(self.batch) > before else None
+        if npix:
+            self.prob = ref._problem(fittype, 1, npix, [-1e30] * 4, [1e30] * 4)
+        else:                                                # an empty slab still answers the collectives
+            v0, dv, _ = ref.xarr.v0_dv_flip
+            self.prob = _abi.make_problem(fittype, 1, nchan, 0, v0, dv, [-1e30] * 4, [1e30] * 4)
+            self._no_rows = torch.zeros((0, eng.nchan_stride(nchan)), dtype=torch.float32, device=eng.device)
+
+    def h2d_bytes(self):
+        """Bytes this rank's ``__init__`` sends to its GPU: the slab and the guesses of the fitted pixels."""
+        n = int(self.ref.cube.nbytes) if self.npix else 0
+        for job in self.batch:
+            n += int(job["guesses"].numel()) * 8 + (0 if job["row_index"] is None else int(job["row_index"].numel()) * 8)
+        return n
+
+    def run(self, gather=True):
+        """Both fits in flight together, the AICc selection (global include_nosamp rule) and the assembly of the
+        result block on the fit results where they lie, then ONE gather.  Returns the [44, ny, nx] block on rank 0
+        (None elsewhere), or this rank's [44, rows, nx] block when ``gather`` is False.  Device tensors; no copy
+        to the host except the 16 bytes per rank of the global arg-max."""
+        from . import _abi
+        eng, npix = self.eng, self.npix
+        outs = eng.fit_batch(self.batch) if self.batch else []
+        fits = {}
+        for nc in (1, 2):
+            P = 4 * nc
+            if self.jobs[nc] is None:
+                fits[nc] = dict(params=torch.zeros((npix, P), dtype=torch.float64, device=eng.device),
+                                perr=torch.zeros((npix, P), dtype=torch.float64, device=eng.device))
+                continue
+            out, job = outs[self.jobs[nc]], self.batch[self.jobs[nc]]
+            if job["row_index"] is None:
+                fits[nc] = out
+            else:                                            # masked fit: scatter to the slab's pixel order
+                full_p = torch.zeros((npix, P), dtype=torch.float64, device=eng.device)
+                full_e = torch.zeros((npix, P), dtype=torch.float64, device=eng.device)
+                full_p[job["row_index"]] = out["params"]
+                full_e[job["row_index"]] = out["perr"]
+                fits[nc] = dict(params=full_p, perr=full_e, status=out["status"], counts=out.get("counts"))
+        self.fits = fits
+        rows = self.ref.rows_on_device() if npix else self._no_rows
+        self.sel = sel = aicc_distributed(eng, self.prob, rows, fits[1]["params"], fits[2]["params"],
+                                          first_pixel=self.y0 * self.nx, model_f32=self.model_f32, group=self.group)
+        packed = eng.pack_selection(fits[1], fits[2], sel).reshape(_abi.PACK_FIELDS, self.ry, self.nx)
+        if gather and self.world > 1:
+            if dist.get_backend(self.group) != "nccl":
+                packed = packed.cpu()
+            packed = gather_maps(packed, self.ny, group=self.group, dst=0)
+        return packed
+
+    def to_host(self, packed):
+        """The result block as a dict of numpy views of ONE pinned host buffer (valid until the next call)."""
+        if packed is None:
+            return None
+        stage = self.eng.pinned_stage(("select",) + tuple(packed.shape))
+        stage.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream(self.eng.device).synchronize()
+        host = stage.numpy()
+        return {name: (host[a] if b - a == 1 else host[a:b]) for name, a, b in FIELDS}
+
+
+def fit_and_select(cube, v_kms, fittype, guesses1, guesses2, device=None, group=None, gather=True, vstats=None):
+    """The model-selection job (1c fit + 2c fit + AICc 0/1/2 selection; UltraCube.fit_cube([1, 2], simpfit=True) +
     get_best_2c_parcube) on a cube partitioned by row slabs over the ranks of ``group``.
 
     ``cube`` [nchan, ny, nx], ``guesses1`` [4, ny, nx], ``guesses2`` [8, ny, nx]: the WHOLE arrays on every rank
     (each rank touches only its slab; a loader that reads slabs directly can pass views of a larger virtual array).
     Global couplings are resolved before partitioning: cubefit_simp's velocity window comes from the statistics of
-    the whole guess map, the include_nosamp fill mask from ``aicc_distributed``.  Per-pixel results are identical
-    to a single-GPU run.  Returns dict(parcube1, errcube1, parcube2, errcube2, best_parcube, best_errcube, lnk10,
-    lnk20, lnk21, ncomp) of [.., ny, nx] numpy arrays on rank 0 (None elsewhere) when ``gather``, else the slab's."""
-    import numpy as np
-    from . import multi_v_fit as mvf
-    from .cube import SpecCube
-    from .UltraCube import UltraCube
-    world, rank = _world(group)
-    nchan, ny, nx = cube.shape
-    y0, y1 = partition_rows(ny, world, rank)
-    dev = torch.cuda.current_device() if device is None else device
-    slab = np.ascontiguousarray(cube[:, y0:y1, :])
-    uc = UltraCube(cube=SpecCube(slab, v_kms), fittype=fittype, device=dev)
-    uc.dist = (group, y0 * nx)
-    g = {1: np.array(guesses1[:, y0:y1, :], dtype=np.float64), 2: np.array(guesses2[:, y0:y1, :], dtype=np.float64)}
-    vstats = {}
-    for nc, full in ((1, guesses1), (2, guesses2)):      # global statistics of the velocity guesses (cubefit_simp)
-        vg = np.array(full[::4], dtype=np.float64)
-        vg[vg == 0] = np.nan
-        vstats[nc] = mvf.get_vstats(vg)
-    for nc in (1, 2):
-        uc.pcubes.pop(str(nc), None)
-    # the two fits in flight together; each driver gets the global velocity statistics of its own guess map
-    batch = []
-    for nc in (1, 2):
-        p = uc.load_pcube(pcube_ref=uc._ref_pcube)
-        p._deferred = batch
-        uc.pcubes[str(nc)] = mvf.cubefit_simp(uc.cube, p, ncomp=nc, guesses=g[nc], fittype=fittype,
-                                              vstats=vstats[nc])
-        p._deferred = None
-    if batch:
-        outs = batch[0]["pcube"].engine.fit_batch(batch)
-        for job, out in zip(batch, outs):
-            job["pcube"].finish_fit(job, out)
-    for nc in (1, 2):
-        uc._include_fit_in_mask(nc)
-    best_par, best_err, lnk10, lnk20, lnk21 = uc.get_best_2c_parcube()
-    local = dict(parcube1=uc.pcubes["1"].parcube, errcube1=uc.pcubes["1"].errcube, parcube2=uc.pcubes["2"].parcube,
-                 errcube2=uc.pcubes["2"].errcube, best_parcube=best_par, best_errcube=best_err,
-                 lnk10=lnk10[None], lnk20=lnk20[None], lnk21=lnk21[None],
-                 ncomp=uc.ncomp_map.astype(np.float64)[None])
-    if not gather or world == 1:
-        return {k: (v[0] if k.startswith("lnk") or k == "ncomp" else v) for k, v in local.items()}
-    out = {}
-    device_t = torch.device("cuda", dev) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    for k, v in local.items():
-        t = gather_maps(torch.from_numpy(np.ascontiguousarray(v)).to(device_t), ny, group=group, dst=0)
-        if rank == 0:
-            a = t.cpu().numpy()
-            out[k] = a[0] if k.startswith("lnk") or k == "ncomp" else a
-    return out if rank == 0 else None
+    the whole guess map (``vstats`` = {1: (median, p99, p1), 2: ...} if the caller has them, else computed here on
+    the GPU), the include_nosamp fill mask from ``aicc_distributed``.  Per-pixel results are identical to a
+    single-GPU run.
+
+    Device-resident from the upload to the gather: the slab goes up (pinned host memory: asynchronously, in two
+    pieces, the first being fitted while the second crosses PCIe), both fits run in flight together, the AICc
+    selection and the assembly of the best-model cube (b200fit_pack_selection) read the fit results where they lie,
+    ONE NCCL gather brings the [44, rows, nx] result block of every rank to rank 0, ONE copy brings it to the host.
+    A slab that cannot be fitted at all (no finite guess: SNRMaskError; no pixel yields a fit) comes back as
+    "nothing fitted" -- the rank still takes part in every collective.
+
+    Returns dict(parcube1, errcube1, parcube2, errcube2, best_parcube, best_errcube, lnk10, lnk20, lnk21, ncomp) of
+    [.., ny, nx] numpy arrays on rank 0 (None elsewhere) when ``gather``, else the slab's.  The arrays are views of
+    a pinned staging buffer that the next call on this device reuses: copy what must outlive it."""
+    job = SelectionJob(cube, v_kms, fittype, guesses1, guesses2, device=device, group=group, vstats=vstats)
+    return job.to_host(job.run(gather=gather))

@@ -358,6 +358,22 @@ class Engine(object):
         out["fill_bits"] = bits
         return out
 
+    def pack_selection(self, fit1, fit2, sel, out=None):
+        """get_best_2c_parcube assembled on the device (b200fit_pack_selection): ``fit1`` / ``fit2`` = result dicts
+        of the 1- and 2-component fits over the same pixels (params, perr), ``sel`` = output of aicc_global /
+        aicc_distributed.  Returns the field-major [PACK_FIELDS, npix] fp64 device tensor."""
+        npix = int(fit1["params"].shape[0])
+        if out is None:
+            out = torch.empty((_abi.PACK_FIELDS, npix), dtype=torch.float64, device=self.device)
+        assert out.is_contiguous() and tuple(out.shape) == (_abi.PACK_FIELDS, npix)
+        for t, w in ((fit1["params"], 4), (fit1["perr"], 4), (fit2["params"], 8), (fit2["perr"], 8)):
+            assert t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == (npix, w)
+        rc = self.lib.b200fit_pack_selection(self.ctx, npix, _ptr(fit1["params"]), _ptr(fit1["perr"]),
+                                             _ptr(fit2["params"]), _ptr(fit2["perr"]), _ptr(sel["lnk"]),
+                                             _ptr(sel["ncomp"]), _ptr(out), npix, self._stream())
+        self._check(rc, "b200fit_pack_selection")
+        return out
+
     def rms_snr(self, nchan, spectra, planemask=None, sigma_cut=2.5, expand=20, row_index=None):
         """signals.get_rms_robust + the peak for get_snr / snr_estimate, per pixel on the GPU.  Returns device
         tensors rms0 (plain mad_std), rms (refined), peak (max over the included channels)."""

@@ -58,8 +58,9 @@ def get_vstats(velocities, signal_mask=None):
     if signal_mask is not None:
         mask = np.logical_and(mask, signal_mask)
     m1_good = m1[mask]
-    # one selection pass for the three order statistics (np.median == the 50th percentile with linear interpolation)
-    v_median, v_99p, v_1p = np.percentile(m1_good, [50, 99, 1])
+    # np.median is the mean of the two middle values; the 50th percentile's lerp can differ from it in the last bit
+    v_median = np.median(m1_good)
+    v_99p, v_1p = np.percentile(m1_good, [99, 1])
     return v_median, v_99p, v_1p
 
 
@@ -89,11 +90,9 @@ def snr_estimate(pcube, errmap, smooth=True):
     cube = pcube.cube if hasattr(pcube, 'cube') else pcube
     peak = None
     if errmap is None:
-        if hasattr(pcube, "rms_robust"):     # per-pixel MAD + peak on the GPU (b200fit_rms_snr), same values
-            r = pcube.rms_robust()
-            errmap, peak = r["rms0"], r["peak"]
-        else:
-            errmap = signals.mad_std(cube, axis=0)
+        # per-pixel MAD + peak on the GPU (b200fit_rms_snr): mad_std(cube, axis=0) and nanmax(cube, axis=0)
+        r = pcube.rms_robust()
+        errmap, peak = r["rms0"], r["peak"]
     err_med = np.nanmedian(errmap)
     err_mask = errmap < err_med * 3.0
     with np.errstate(all="ignore"):
@@ -225,11 +224,11 @@ def cubefit_simp_steps(cube, pcube, ncomp, guesses, multicore=None, maskmap=None
 
 def cubefit_gen(cube, pcube, ncomp=2, paraname=None, modname=None, chisqname=None, guesses=None, errmap11name=None,
                 multicore=None, mask_function=None, snr_min=0.0, momedgetrim=True, saveguess=False,
-                fittype='nh3_multi_v', gpu_prepass=True, **kwargs):
+                fittype='nh3_multi_v', **kwargs):
     """multi_v_fit.py:211-417: moment maps -> guesses -> tautex_renorm -> clamps -> masks -> fiteach.
 
-    ``gpu_prepass=False`` runs the moment / rms / S/N pre-pass with the numpy mirror (mufasa_b200/signals.py)
-    instead of the GPU kernels (mufasa_b200/prepass.py); the two agree (tests/test_gpu_pipeline.py).
+    The moment / rms / S/N pre-pass (signals.get_moments, get_snr) runs on the GPU (mufasa_b200/prepass.py); there
+    is no host path for it (its numpy restatement is test infrastructure, oracle/signals.py).
 
     ``paraname`` / ``modname`` / ``chisqname`` (FITS writers) are outside the fit path and not supported here."""
     from . import signals
@@ -246,25 +245,17 @@ def cubefit_gen(cube, pcube, ncomp=2, paraname=None, modname=None, chisqname=Non
 
     linewidth_sigma = False
     trim = 3
-    if gpu_prepass and hasattr(pcube, "rows_on_device"):
-        # the whole pre-pass on the GPU (mufasa_b200/prepass.py): the include-mask of the trimmed cube is
-        # isfinite(cube) & cube_plane, so only the 2-D footprint is trimmed on the host (signals.trim_cube_edge)
-        from . import prepass
-        cube_plane = pcube.footprint().copy()
-        if np.sum(cube_plane) > 1000:
-            cube_plane = signals.trim_edge(cube_plane, trim=trim)
-        m0, m1, m2, rms = prepass.get_moments(pcube, cube_plane, window_hwidth=mod_info.window_hwidth,
-                                              linewidth_sigma=linewidth_sigma,
-                                              central_win_hwidth=mod_info.central_win_hwidth, return_rms=True)
-        with np.errstate(all="ignore"):
-            peaksnr = pcube._dev["prepass_peak"] / rms
-    else:
-        include = signals.trim_cube_edge(cube, trim=trim)    # bool [nchan, ny, nx] (the masked cube of the reference)
-        m0, m1, m2, rms = signals.get_moments(cube, include=include, window_hwidth=mod_info.window_hwidth,
-                                              linewidth_sigma=linewidth_sigma,
-                                              central_win_hwidth=mod_info.central_win_hwidth, return_rms=True)
-        peaksnr = signals.get_snr(cube, rms=rms, include=include)
-        cube_plane = np.any(include, axis=0)
+    # the whole pre-pass on the GPU (mufasa_b200/prepass.py): the include-mask of the trimmed cube is
+    # isfinite(cube) & cube_plane, so only the 2-D footprint is trimmed on the host (signals.trim_cube_edge :199-226)
+    from . import prepass
+    cube_plane = pcube.footprint().copy()
+    if np.sum(cube_plane) > 1000:
+        cube_plane = signals.trim_edge(cube_plane, trim=trim)
+    m0, m1, m2, rms = prepass.get_moments(pcube, cube_plane, window_hwidth=mod_info.window_hwidth,
+                                          linewidth_sigma=linewidth_sigma,
+                                          central_win_hwidth=mod_info.central_win_hwidth, return_rms=True)
+    with np.errstate(all="ignore"):
+        peaksnr = pcube._dev["prepass_peak"] / rms
 
     vmax = np.nanmax(m1) + sigmax / 2
     vmin = np.nanmin(m1) - sigmax / 2
@@ -349,7 +340,10 @@ def cubefit_gen(cube, pcube, ncomp=2, paraname=None, modname=None, chisqname=Non
         logger.warning("The starting fit position is somehow not among the valid: " + str(e))
         retry_fit(pcube, kwargs, start_point, peaksnr=peaksnr)
     if paraname is not None:
-        save_pcube(pcube, paraname, ncomp=ncomp)
+        if getattr(pcube, "_deferred", None) is not None:
+            pcube._save_after_fit = (paraname, ncomp)     # batched fit: the maps exist after finish_fit (UltraCube)
+        else:
+            save_pcube(pcube, paraname, ncomp=ncomp)
     if modname is not None or chisqname is not None:
         raise NotImplementedError("model-cube / legacy chi-square writers are not part of the fit path")
     return pcube

@@ -278,7 +278,9 @@ class PCube(object):
         np.copyto(g_stage.numpy(), gflat if npix == ny * nx else gflat[:, pix])
         i_stage = None
         if npix != ny * nx:
-            i_stage = eng.pinned_stage(("pixels", npix), dtype=torch.int64)
+            # one buffer per model size: the 1- and 2-component jobs of a batched fit may select different pixels, and
+            # the first job's (asynchronous) copy must not read the second job's list
+            i_stage = eng.pinned_stage(("pixels%d" % P, npix), dtype=torch.int64)
             np.copyto(i_stage.numpy(), pix)
         with torch.cuda.stream(up):
             g_dev = g_stage.to(dev, non_blocking=True).t().contiguous()

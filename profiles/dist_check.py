@@ -34,6 +34,8 @@ t0 = time.perf_counter()
 res = D.fit_and_select(syn["cube"], syn["v"], syn["fittype"], syn["guess1"].copy(), syn["guess2"].copy(), device=local)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
+if res is not None:
+    res = {k: v.copy() for k, v in res.items()}            # views of a pinned buffer the next call reuses
 if rank == 0:
     single = D.fit_and_select(syn["cube"], syn["v"], syn["fittype"], syn["guess1"].copy(), syn["guess2"].copy(),
                               device=local, group=dist.new_group([0]) if world > 1 else None)

@@ -41,6 +41,12 @@ def _worker(rank, world, port, ny, nx, q):
             assert torch.equal(got, full)
         else:
             assert got is None
+        # even slabs take the permute path (no per-rank copies); leading dims are kept
+        ne = 4 * world
+        full_e = torch.arange(2 * 3 * ne * nx, dtype=torch.float64).reshape(2, 3, ne, nx)
+        e0, e1 = D.partition_rows(ne, world, rank)
+        got = D.gather_maps(full_e[:, :, e0:e1, :].contiguous(), ne)
+        assert (rank == 0 and torch.equal(got, full_e)) or (rank != 0 and got is None)
         # global arg-max of the mask sizes: largest count, ties -> lowest GLOBAL index
         counts = torch.tensor([[5, 40], [7, 3]])            # rank 0: (count 5 at pixel 40); rank 1: (7 at 3)
         c, i, owner = D.global_best(counts[rank].clone())
@@ -76,3 +82,20 @@ def test_single_process_passthrough():
     t = torch.zeros(2, 4, 4)
     assert D.gather_maps(t, 4) is t
     assert D.global_best(torch.tensor([3, 11])) == (3, 11, 0)
+
+
+def test_vstats_on_device_equal_numpy():
+    """dist.global_vstats (torch sort + numpy's interpolation rules) == multi_v_fit.get_vstats (np.median,
+    np.percentile) bit for bit: the velocity window of a partitioned run is the single-GPU run's."""
+    from mufasa_b200 import multi_v_fit as mvf
+    rng = np.random.default_rng(2)
+    for n in (1, 2, 3, 4, 17, 18, 1000, 1001, 65536):
+        a = rng.normal(size=(2, n)) * 2
+        a[0, : n // 7] = 0
+        if n > 3:
+            a[1, n // 3] = np.nan
+        b = a.copy()
+        b[b == 0] = np.nan
+        assert tuple(mvf.get_vstats(b)) == tuple(D.global_vstats(a.reshape(2, 1, n), "cpu")), n
+    x = torch.from_numpy(rng.normal(size=4097))
+    assert D.percentiles_like_numpy(x, [0, 1, 50, 99, 100]) == list(np.percentile(x.numpy(), [0, 1, 50, 99, 100]))

@@ -29,43 +29,86 @@ def _gpu_fit(engine, tile, ncomp, lo, hi, guesses):
 
 
 CASES = [
-    # cfg, ncomp, nrows, xstep, min pass fraction on the oracle-stable converged set
-    (2, 1, 4, 8, 0.99),
-    (2, 2, 4, 8, 0.90),
-    (4, 2, 3, 16, 0.85),   # low-SNR N2H+ 2c is multi-modal: 0.89-0.93 measured, half of the misses have LOWER chi2
-    (4, 1, 3, 16, 0.97),
+    # cfg, ncomp, nrows, xstep
+    (2, 1, 4, 8),      # NH3 800 ch
+    (2, 2, 4, 8),
+    (4, 2, 3, 16),     # N2H+ 1200 ch, low S/N, guesses on limits
+    (4, 1, 3, 16),
+    (5, 2, 3, 32),     # NH3 1000 ch: the channel count of BASELINE configs[2] and configs[4]
+    (5, 1, 3, 32),
 ]
 
 
-@pytest.mark.parametrize("cfg,ncomp,nrows,xstep,min_frac", CASES)
-def test_fit_parity(engine, cfg, ncomp, nrows, xstep, min_frac):
+@pytest.mark.parametrize("cfg,ncomp,nrows,xstep", CASES)
+def test_fit_parity(engine, cfg, ncomp, nrows, xstep):
+    """North-star criteria 1 and 2 (parameters within 0.05 sigma of the reference's errors, relative chi2 within 1e-4
+    on the pixels both sides flag converged) against the CPU oracle, on ALL both-converged pixels -- next to the
+    same numbers for mpfit against ITSELF with an accurate Jacobian (the floor a perfect independent implementation
+    can expect: 2-component fits of spectra holding fewer components are chaotic in mpfit, tests/test_parity_floor.py)
+    and on the pixels where mpfit is reproducible.  Every miss goes to gpurun_out/parity_misses.jsonl."""
     tile = T.sample_tile(cfg, nrows=nrows, xstep=xstep)
     lo, hi = T.limits_vectors(tile["fittype"], ncomp)
     g = synth.clamp_guesses(tile["guess%d" % ncomp], lo, hi)
     P = 4 * ncomp
     o = T.oracle_fit(tile, ncomp, lo, hi, g)
+    npix = o["chi2"].size
     o2 = T.oracle_fit(tile, ncomp, lo, hi, g, perturb=1e-9)
     stable = T.stable_set(o, o2, P)
+    oc = T.oracle_fit(tile, ncomp, lo, hi, g, jacobian="central")
+    c_floor = T.criteria(oc["parcube"].reshape(P, npix).T, oc["chi2"].ravel(), oc["status"].ravel(), o, P,
+                         perr=oc["errcube"].reshape(P, npix).T)
+    floor_ok = (c_floor["par_ok"] & c_floor["chi2_ok"])[c_floor["both"]]
     out = _gpu_fit(engine, tile, ncomp, lo, hi, g)
     c = T.criteria(out["params"], out["chi2"], out["status"], o, P, perr=out["perr"])
-    sel = c["both"] & stable
     ok = c["par_ok"] & c["chi2_ok"]
-    rep = dict(cfg=cfg, ncomp=ncomp, npix=int(sel.size), oracle_converged=int(c["conv_o"].sum()),
-               gpu_converged=int(c["conv_g"].sum()), oracle_stable=int((stable & c["conv_o"]).sum()),
-               compared=int(sel.sum()), passed=int(ok[sel].sum()),
-               passed_all_converged=int(ok[c["both"]].sum()), both_converged=int(c["both"].sum()),
-               median_dsigma=float(np.median(c["mz"][sel])), evals_mean=float(out["counts"][:, 0].mean()),
+    both, sel = c["both"], c["both"] & stable
+    miss = both & ~ok
+    sg = (out["chi2"] - o["chi2"].ravel()) / np.maximum(o["chi2"].ravel(), 1e-300)
+    rep = dict(cfg=cfg, ncomp=ncomp, nchan=int(tile["nchan"]), npix=int(npix),
+               oracle_converged=int(c["conv_o"].sum()), gpu_converged=int(c["conv_g"].sum()),
+               both_converged=int(both.sum()), passed=int(ok[both].sum()),
+               oracle_self_both=int(c_floor["both"].sum()), oracle_self_passed=int(floor_ok.sum()),
+               oracle_stable=int((stable & c["conv_o"]).sum()), compared_stable=int(sel.sum()),
+               passed_stable=int(ok[sel].sum()), median_dsigma=float(np.median(c["mz"][both])),
+               misses=int(miss.sum()), miss_gpu_chi2_lower=int((sg[miss] < -1e-4).sum()),
+               miss_chi2_equal=int((np.abs(sg[miss]) <= 1e-4).sum()), miss_oracle_chi2_lower=int((sg[miss] > 1e-4).sum()),
+               miss_status6=int((out["status"][miss] == 6).sum()), status6_all=int((out["status"] == 6).sum()),
+               miss_truth_ncomp_below_fit=int((tile["ncomp_true"].ravel()[miss] < ncomp).sum()),
+               evals_mean=float(out["counts"][:, 0].mean()),
                err_used_rel=float(np.nanmax(np.abs(out["err_used"] - o["err"].ravel()) / o["err"].ravel())))
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/parity_fit.jsonl", "a") as f:
         f.write(json.dumps(rep) + "\n")
+    op = o["parcube"].reshape(P, npix).T
+    oe = o["errcube"].reshape(P, npix).T
+    with open("gpurun_out/parity_misses.jsonl", "a") as f:
+        for i in np.nonzero(miss)[0]:
+            f.write(json.dumps(dict(cfg=cfg, ncomp=ncomp, pixel=int(i), truth_ncomp=int(tile["ncomp_true"].ravel()[i]),
+                                    status_oracle=int(o["status"].ravel()[i]), status_gpu=int(out["status"][i]),
+                                    oracle_stable=bool(stable[i]), dchi2_rel=float(sg[i]),
+                                    lower_chi2="gpu" if sg[i] < -1e-4 else ("oracle" if sg[i] > 1e-4 else "equal"),
+                                    max_dsigma=float(c["mz"][i]),
+                                    pegged_oracle=[int(k) for k in np.nonzero(oe[i] == 0)[0]],
+                                    pegged_gpu=[int(k) for k in np.nonzero(out["perr"][i] == 0)[0]],
+                                    p_oracle=[float(x) for x in op[i]], p_gpu=[float(x) for x in out["params"][i]],
+                                    evals_gpu=int(out["counts"][i, 0]))) + "\n")
     print(rep)
     # has_fit agreement (status > 0 on both sides)
     assert np.array_equal(out["status"] > 0, o["status"].ravel() > 0)
     # weights: std of the spectrum (fp64 on the GPU, cube dtype in numpy) agree to fp32 round-off
     assert rep["err_used_rel"] < 5e-7
-    assert sel.sum() >= 0.5 * sel.size
-    assert ok[sel].mean() >= min_frac
+    assert both.sum() >= 0.85 * npix
+    frac, floor = ok[both].mean(), floor_ok.mean()
+    if ncomp == 1:
+        # well-posed fits: the criteria hold on (nearly) every pixel -- as they do for mpfit against itself
+        assert frac >= 0.95 and frac >= floor - 0.05
+    else:
+        # 2-component fits: at mpfit's own reproducibility (counting noise of ~100 pixels: two sigma ~ 0.07) ...
+        assert frac >= floor - 0.07, "below mpfit's own reproducibility: %.3f vs %.3f" % (frac, floor)
+        # ... on the pixels where mpfit is reproducible the criteria hold
+        assert ok[sel].mean() >= 0.90
+        # ... and the misses are not one-sided: the GPU's chi2 is the lower one about as often as mpfit's
+        assert rep["miss_oracle_chi2_lower"] <= max(4, 0.75 * rep["misses"])
     # typical agreement is orders of magnitude inside the 0.05-sigma criterion
     assert rep["median_dsigma"] < 5e-3
 

@@ -1,11 +1,12 @@
 """GPU parity of the moment / signal-mask pre-pass: bit-cube morphology vs scipy.ndimage with the
-structuring elements and border conventions of mufasa_b200/signals.py, and the composed get_moments vs the numpy
-mirror of mufasa/signals.py:329-396."""
+structuring elements and border conventions of oracle/signals.py, and the composed get_moments vs the numpy
+restatement of mufasa/signals.py:329-396 in oracle/signals.py."""
 import numpy as np
 import pytest
 
 import _tiles as T
-from mufasa_b200 import prepass, signals, synth
+from mufasa_b200 import prepass, synth
+from oracle import signals
 from mufasa_b200.cube import SpecCube
 
 pytestmark = pytest.mark.gpu

@@ -135,3 +135,27 @@ def test_meta(golden_dir):
         assert nu0 == meta[ft]["rest_value_hz"]
         assert list(voff) == meta[ft]["voffs"] and list(wts) == meta[ft]["tau_wts"]
     assert meta["bogus_raises"][0] == "FitTypeError" and "LookupError" in meta["bogus_raises"][1]
+
+
+def test_product_guess_recipes_against_reference_golden(golden_dir):
+    """The PRODUCT's host-side guess recipes (mufasa_b200.moment_guess.moment_guesses, guess_refine.tautex_renorm --
+    what cubefit_gen stages for the kernel; moment_guess.py:388-518, guess_refine.py:183-213) against the vectors
+    produced by executing the reference's own files (tests/golden/make_golden.py): bit for bit."""
+    from mufasa_b200 import guess_refine as GR
+    from mufasa_b200 import moment_guess as MG
+    g = _load(golden_dir, "guess_golden.npz")
+    with np.errstate(all="ignore"):
+        for nc in (1, 2):
+            mine = MG.moment_guesses(g["m1"].copy(), g["m2"].copy(), nc, sigmin=0.07, moment0=g["m0"].copy(),
+                                     linetype="nh3")
+            assert np.array_equal(mine, g["gg%d_nh3" % nc], equal_nan=True)
+            mine = MG.moment_guesses(g["m1"].copy(), g["m2"].copy(), nc, sigmin=0.05, moment0=g["m0"].copy(),
+                                     linetype="n2hp", mom0_floor=0.5)
+            assert np.array_equal(mine, g["gg%d_n2hp" % nc], equal_nan=True)
+        for key, nu in (("nh3", 23.6944955), ("n2hp", 93.1737637)):
+            t, x = GR.tautex_renorm(g["renorm_tau_in"].copy(), g["renorm_tex_in"].copy(), tau_thresh=0.1, nu=nu)
+            assert np.array_equal(t, g["renorm_tau_" + key], equal_nan=True)
+            assert np.array_equal(x, g["renorm_tex_" + key], equal_nan=True)
+        assert np.array_equal(MG.get_tex(g["Ta"], tau=0.7, nu=23.6944955), g["get_tex"])
+        assert np.array_equal(MG.get_tau(g["Ta"] * 0.3, tex=6.0, nu=23.6944955), g["get_tau"])
+        assert np.array_equal(MG.peakT(np.linspace(3, 12, 20), np.linspace(0.1, 5, 20), nu=93.1737637), g["peakT"])
