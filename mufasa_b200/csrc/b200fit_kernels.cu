@@ -64,12 +64,21 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 // "no instruction".  Split, every warp of a kernel runs the same few KB of code, the solver runs 32 pixels per
 // warp, pixels that converge early free their lanes at once (iteration counts differ by >10x), and the state
 // that crosses kernels (~1.1 KB per pixel and round) is noise next to the arithmetic: the path is compute bound.
+// What ONE evaluation reads of a pixel's state, contiguous and 16-byte aligned so that the evaluation kernel stages
+// it in shared memory with a single bulk-async copy next to the pixel's spectrum row (fit_eval_kernel).
+template <int NC>
+struct alignas(16) EvalIn {
+    CompCoef cc[NC];             // coefficients of the trial point st.pt (filled by the prologue / the solver)
+    double v[NC];                // st.pt[4 c]: velocity of component c at the trial point
+    double inv_sigma[NC];        // 1 / st.pt[4 c + 1]
+    double sumsq, err;           // sum of y^2 over the finite channels; weight (std of the finite channels)
+};
+static_assert(sizeof(EvalIn<1>) % 16 == 0 && sizeof(EvalIn<2>) % 16 == 0, "bulk copies move multiples of 16 bytes");
+
 template <int P>
-struct alignas(8) PixState {
+struct alignas(16) PixState {
+    EvalIn<P / 4> in;
     LMState<P> st;
-    CompCoef cc[P / 4];          // coefficients of the trial point st.pt (filled by the solver)
-    double inv_sigma[P / 4];
-    double err, sumsq;           // weight (std of the finite channels); sum of y^2 over the finite channels
     unsigned n_gauss, n_chunks;  // roofline accounting
     int fitted, pad_;            // 1 once the LM state is initialised (0: bad guess / no weight -> zeros, status 0)
 };
@@ -143,8 +152,9 @@ __device__ __forceinline__ void prepare_trial(const DeviceProblem& pr, PixState<
     for (int c = 0; c < NC; ++c) {
         CompCoef cc;
         comp_coefs(pr.T0c, pr.dT0, pr.Jbg0, pr.Jbg1, &ps.st.pt[4 * c], cc);
-        ps.cc[c] = cc;
-        ps.inv_sigma[c] = 1.0 / ps.st.pt[4 * c + 1];
+        ps.in.cc[c] = cc;
+        ps.in.v[c] = ps.st.pt[4 * c];
+        ps.in.inv_sigma[c] = 1.0 / ps.st.pt[4 * c + 1];
     }
 }
 
@@ -154,7 +164,7 @@ __device__ __forceinline__ void write_result(const PixState<P>& ps, long long pi
                                              double* __restrict__ chi2, double* __restrict__ err_used,
                                              int* __restrict__ status, unsigned* __restrict__ counts) {
     const bool good = fitted && ps.st.status > 0;
-    const double err2 = ps.err * ps.err;
+    const double err2 = ps.in.err * ps.in.err;
     double pe[P];
     if (good) lm_errors<P>(ps.st, cf, err2, pe);
 #pragma unroll 1
@@ -163,7 +173,7 @@ __device__ __forceinline__ void write_result(const PixState<P>& ps, long long pi
         perr[pix * P + j] = good ? pe[j] : 0.0;
     }
     chi2[pix] = good ? lm_reported_chi2<P>(ps.st) / err2 : 0.0;
-    err_used[pix] = ps.err;
+    err_used[pix] = ps.in.err;
     status[pix] = fitted ? ps.st.status : 0;
     if (counts) {
         counts[4 * pix + 0] = fitted ? (unsigned)ps.st.nevals : 0u;
@@ -218,8 +228,8 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32)
             const double var = (n > 0) ? fmax(sq / n - mean * mean, 0.0) : NAN;
             double err = sqrt(var);
             if (pr.weight_mode == 1 && err_in != nullptr) err = err_in[px];
-            ps.err = err;
-            ps.sumsq = sq;
+            ps.in.err = err;
+            ps.in.sumsq = sq;
             ps.n_gauss = 0;
             ps.n_chunks = 0;
             ps.fitted = 0;
@@ -264,6 +274,53 @@ struct LineGroups<B200FIT_MODEL_N2HP_10> {  // -8.0 (1) | -0.6 .. 1.0 (3) | 5.5 
 // fitted: the host switches at a fixed round number (fit_team_round<NC>()), and since every active pixel is evaluated
 // exactly once per round that is a function of the pixel's own evaluation count -- results stay independent of
 // how the pixels are partitioned over calls or GPUs.
+//
+// Staging.  A unit (warp or team) is a small software pipeline over its pixels: while it evaluates pixel k, the
+// spectrum row (stride x 4 bytes) and the EvalIn block of pixel k + 1 are already on their way into the other half of
+// its shared-memory buffer -- two 1-D bulk-async copies (cp.async.bulk, the TMA engine) issued by one lane and
+// completed on an mbarrier, so no thread waits on L2 / HBM latency inside the chunk loop (profiles/r1o: the scalar
+// __ldg loads of the previous version were the second largest stall, long_scoreboard 1.03 cycles per instruction).
+//
+// Uniform control.  Which line groups reach a chunk is a per-chunk bit mask held by the lane that owns the chunk;
+// the mask of the chunk being processed reaches every lane through redux.sync (warp-wide OR), whose result the
+// compiler keeps in a UNIFORM register: the per-group tests are uniform-datapath instructions and plain branches.
+// (The previous version proved uniformity to the compiler with one __any_sync vote per group and component -- 29 %
+// of all executed warp instructions, profiles/r1o_eval2c_source_summary.txt.)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+template <int NC>
+__host__ __device__ constexpr size_t eval_buf_bytes(long long stride) {   // one pipeline stage of one unit
+    return (size_t)stride * sizeof(float) + sizeof(EvalIn<NC>);
+}
+template <int NC, int TEAM>
+static size_t eval_dyn_smem(long long stride) {
+    return ((TEAM > 1) ? 1 : EVAL_WARPS) * 2 * eval_buf_bytes<NC>(stride);
+}
+
 template <int NC, int MODEL, int TEAM>
 // blocks per SM: 5 (96 registers) help the 1-component kernel; the 2-component one compiles to 96 registers with
 // next to no spills as well, but runs 16 % slower there (24.1 vs 20.7 ms per fit) than at 4 blocks / 128 registers
@@ -276,13 +333,26 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
     constexpr int NH = P * (P + 1) / 2;
     constexpr int NACC = NH + P + 1;
     constexpr int RR = EvalScratch<NC>::RED_ROWS;
+    constexpr int UNITS = (TEAM > 1) ? 1 : EVAL_WARPS;   // pixels in flight per block
     using LG = LineGroups<MODEL>;
     constexpr int NG = LG::NG;
+    extern __shared__ __align__(128) unsigned char stage_smem[];   // UNITS x 2 stages x (row, EvalIn)
     __shared__ FitTables tb;
     __shared__ EvalScratch<NC> scratch[EVAL_WARPS];
     __shared__ double part[(TEAM > 1) ? EVAL_WARPS : 1][NACC + 2];   // per-warp partial sums of a team
-    load_fit_tables(pr, tb);
+    __shared__ __align__(8) unsigned long long bars[UNITS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int unit = (TEAM > 1) ? 0 : warp;
+    const bool leader = (TEAM > 1) ? (threadIdx.x == 0) : (lane == 0);   // issues this unit's copies
+    const unsigned row_bytes = (unsigned)(stride * sizeof(float));
+    const unsigned buf_bytes = (unsigned)eval_buf_bytes<NC>(stride);
+    unsigned char* const ubase = stage_smem + (size_t)unit * 2 * buf_bytes;
+    if (leader) {
+        mbar_init(smem_u32(&bars[unit][0]), 1);
+        mbar_init(smem_u32(&bars[unit][1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    load_fit_tables(pr, tb);                                // (ends with __syncthreads: the barriers are visible)
     EvalScratch<NC>& w = scratch[(TEAM > 1) ? 0 : warp];   // line records: per warp, or shared by the team
     EvalScratch<NC>& wr = scratch[warp];                    // reduction tile: always per warp
     const unsigned count = fq->count[cur];
@@ -294,11 +364,30 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
     const int nhalf = (nchunks > 32) ? 2 : 1;
     const float ic0 = (float)pr.ic0;
 
-    for (unsigned idx = unit0; idx < count; idx += nunits) {
-        const long long px = list[idx];
+    // one lane starts the two bulk copies of a pixel into stage ``b``; they complete on that stage's barrier
+    auto issue = [&](unsigned px, int b) {
+        const long long row = row_index ? row_index[px] : (long long)px;
+        const unsigned bar = smem_u32(&bars[unit][b]);
+        const unsigned dst = smem_u32(ubase + (size_t)b * buf_bytes);
+        mbar_expect_tx(bar, buf_bytes);
+        bulk_g2s(dst, spectra + row * stride, row_bytes, bar);
+        bulk_g2s(dst + row_bytes, &states[px].in, (unsigned)sizeof(EvalIn<NC>), bar);
+    };
+    // pixel indices run two iterations ahead of the evaluation (their loads never sit on the critical path)
+    unsigned px_cur = (unit0 < count) ? list[unit0] : 0u;
+    unsigned px_nxt = (unit0 + nunits < count) ? list[unit0 + nunits] : 0u;
+    if (leader && unit0 < count) issue(px_cur, 0);
+
+    int k = 0;
+    for (unsigned idx = unit0; idx < count; idx += nunits, ++k) {
+        const int sb = k & 1;
+        const unsigned px = px_cur;
+        if (leader && idx + nunits < count) issue(px_nxt, sb ^ 1);   // stage sb^1 was released by the sync below
+        const unsigned px_far = (idx + 2 * nunits < count) ? list[idx + 2 * nunits] : 0u;
         PixState<P>& ps = states[px];
-        const long long row = row_index ? row_index[px] : px;
-        const float* __restrict__ spec = spectra + row * stride;
+        mbar_wait(smem_u32(&bars[unit][sb]), (unsigned)((k >> 1) & 1));
+        const float* __restrict__ srow = reinterpret_cast<const float*>(ubase + (size_t)sb * buf_bytes);
+        const EvalIn<NC>& in = *reinterpret_cast<const EvalIn<NC>*>(ubase + (size_t)sb * buf_bytes + row_bytes);
         // 1. fp64 line set-up, one line per lane (a team: one component per warp)
         if (lane < nhf) {
             const double c1 = tb.c1mrho[lane], rho = tb.rho[lane], kdv = tb.kdv[lane];
@@ -308,7 +397,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
                 if (TEAM > 1 && c != warp) continue;
                 LineCoef lc;
                 float lo, hi;
-                line_coef(c1, rho, kdv, lw, pr.v0, pr.inv_dv, ps.st.pt[4 * c], ps.inv_sigma[c], lc, lo, hi);
+                line_coef(c1, rho, kdv, lw, pr.v0, pr.inv_dv, in.v[c], in.inv_sigma[c], lc, lo, hi);
                 w.lines[c][lane] = lc;
                 w.wlo[c][lane] = lo;
                 w.whi[c][lane] = hi;
@@ -316,7 +405,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
         }
         CompCoef cc[NC];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) cc[c] = ps.cc[c];
+        for (int c = 0; c < NC; ++c) cc[c] = in.cc[c];
         if (TEAM > 1)
             __syncthreads();
         else
@@ -352,9 +441,9 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
 #pragma unroll
         for (int u = 0; u < P; ++u)
 #pragma unroll
-            for (int k = 0; k < PH; ++k) h2[u][k] = 0ull;
+            for (int kk = 0; kk < PH; ++kk) h2[u][kk] = 0ull;
 #pragma unroll
-        for (int k = 0; k < PH; ++k) b2[k] = 0ull;
+        for (int kk = 0; kk < PH; ++kk) b2[kk] = 0ull;
         unsigned n_chunks = 0;
 
         int ordinal = 0;   // running index of the active chunks of this pixel (a team deals them round-robin)
@@ -368,17 +457,21 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
                     if ((ordinal++ & (TEAM - 1)) == warp) mine |= a & (0u - a);
                 act = mine;
             }
+            // software pipeline over the active chunks: channel value and group mask of the next one are fetched
+            // (shared memory / warp-wide OR) while the current one is evaluated
             int jn = act ? (__ffs(act) - 1) : 0;
-            float ynext = act ? __ldg(spec + (((jn + 32 * h) << 5) + lane)) : 0.f;
+            float ynext = act ? srow[((jn + 32 * h) << 5) + lane] : 0.f;
+            unsigned pknext = __reduce_or_sync(FULL, (lane == jn) ? mypk : 0u);
             while (act) {
                 const int j = jn;
                 const float y = ynext;
+                const unsigned pk = pknext;     // warp-uniform (redux result)
                 act &= act - 1;
-                if (act) {   // prefetch the next active chunk of the row
+                if (act) {
                     jn = __ffs(act) - 1;
-                    ynext = __ldg(spec + (((jn + 32 * h) << 5) + lane));
+                    ynext = srow[((jn + 32 * h) << 5) + lane];
+                    pknext = __reduce_or_sync(FULL, (lane == jn) ? mypk : 0u);
                 }
-                const unsigned pk = __shfl_sync(FULL, mypk, j);
                 const int i = ((j + 32 * h) << 5) + lane;
                 const float fi = (float)i;
                 float Gs[NC], As[NC], Bs[NC];
@@ -387,10 +480,10 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
                     float g = 0.f, a = 0.f, b = 0.f;
 #pragma unroll
                     for (int gi = 0; gi < NG; ++gi) {
-                        if (__any_sync(FULL, (pk >> (8 * c + gi)) & 1u)) {   // pk is warp-uniform; the vote tells nvcc so
+                        if (pk & (1u << (8 * c + gi))) {
 #pragma unroll
-                            for (int k = LG::start(gi); k < LG::start(gi + 1); ++k) {
-                                const float4 q = *reinterpret_cast<const float4*>(&w.lines[c][k]);
+                            for (int kk = LG::start(gi); kk < LG::start(gi + 1); ++kk) {
+                                const float4 q = *reinterpret_cast<const float4*>(&w.lines[c][kk]);
                                 LineCoef lc;
                                 lc.nf = q.x;
                                 lc.b = q.y;
@@ -411,20 +504,21 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
                     const float r = y - m;
                     f32x2 Jp[PH];
 #pragma unroll
-                    for (int k = 0; k < PH; ++k) Jp[k] = pk2(J[2 * k], J[2 * k + 1]);
+                    for (int kk = 0; kk < PH; ++kk) Jp[kk] = pk2(J[2 * kk], J[2 * kk + 1]);
                     const f32x2 r2 = pk2(r, r);
 #pragma unroll
-                    for (int k = 0; k < PH; ++k) b2[k] = fma2(Jp[k], r2, b2[k]);
+                    for (int kk = 0; kk < PH; ++kk) b2[kk] = fma2(Jp[kk], r2, b2[kk]);
 #pragma unroll
                     for (int u = 0; u < P; ++u) {
                         const f32x2 ju = pk2(J[u], J[u]);
 #pragma unroll
-                        for (int k = u / 2; k < PH; ++k) h2[u][k] = fma2(ju, Jp[k], h2[u][k]);
+                        for (int kk = u / 2; kk < PH; ++kk) h2[u][kk] = fma2(ju, Jp[kk], h2[u][kk]);
                     }
                     chi = fmaf(m, m - 2.f * y, chi);
                 }
             }
         }
+        const double sumsq = in.sumsq;
         // canonical order of the reduction: packed upper triangle of H, b, chi2 term
         float acc[NACC];
         {
@@ -463,15 +557,15 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
                     s2 += (double)wr.red[lane][m + 2];
                     s3 += (double)wr.red[lane][m + 3];
                 }
-                const double s = (s0 + s1) + (s2 + s3);
+                const double sred = (s0 + s1) + (s2 + s3);
                 if (TEAM > 1)
-                    part[warp][e] = s;
+                    part[warp][e] = sred;
                 else if (e < NH)
-                    ps.st.Ht[e] = s;
+                    ps.st.Ht[e] = sred;
                 else if (e < NH + P)
-                    ps.st.bt[e - NH] = s;
+                    ps.st.bt[e - NH] = sred;
                 else
-                    ps.st.chi2t = ps.sumsq + s;
+                    ps.st.chi2t = sumsq + sred;
             }
             __syncwarp();
         }
@@ -482,28 +576,34 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
             __syncthreads();
             if (warp == 0) {
                 for (int e = lane; e < NACC; e += 32) {
-                    double s = part[0][e];
+                    double sred = part[0][e];
 #pragma unroll
-                    for (int t = 1; t < TEAM; ++t) s += part[t][e];
+                    for (int t = 1; t < TEAM; ++t) sred += part[t][e];
                     if (e < NH)
-                        ps.st.Ht[e] = s;
+                        ps.st.Ht[e] = sred;
                     else if (e < NH + P)
-                        ps.st.bt[e - NH] = s;
+                        ps.st.bt[e - NH] = sred;
                     else
-                        ps.st.chi2t = ps.sumsq + s;
+                        ps.st.chi2t = sumsq + sred;
                 }
                 if (lane == 0) {
                     double nc = 0.0;
 #pragma unroll
                     for (int t = 0; t < TEAM; ++t) nc += part[t][NACC];
-                    ps.n_gauss += n_gauss;
-                    ps.n_chunks += (unsigned)nc;
+                    atomicAdd(&ps.n_gauss, n_gauss);           // (result unused: a fire-and-forget reduction)
+                    atomicAdd(&ps.n_chunks, (unsigned)nc);
                 }
             }
-        } else if (lane == 0) {
-            ps.n_gauss += n_gauss;
-            ps.n_chunks += n_chunks;
+            __syncthreads();   // the stage and ``part`` are free for the next pixel
+        } else {
+            if (lane == 0) {
+                atomicAdd(&ps.n_gauss, n_gauss);
+                atomicAdd(&ps.n_chunks, n_chunks);
+            }
+            __syncwarp();      // every lane is done with this stage: the next copy may overwrite it
         }
+        px_cur = px_nxt;
+        px_nxt = px_far;
     }
 }
 
@@ -552,8 +652,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 8)   // 128 regs (a few spills)
                 CompCoef cc;
                 comp_coefs(pr.T0c, pr.dT0, pr.Jbg0, pr.Jbg1, p4[c], cc);
                 if (g.gl == 0) {
-                    ps.cc[c] = cc;
-                    ps.inv_sigma[c] = 1.0 / p4[c][1];
+                    ps.in.cc[c] = cc;
+                    ps.in.v[c] = p4[c][0];
+                    ps.in.inv_sigma[c] = 1.0 / p4[c][1];
                 }
             }
             if (g.gl == 0) next_list[atomicAdd(&fq->count[cur ^ 1], 1u)] = px;
@@ -585,7 +686,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
         LaneState<P> s;
         lane_load<P>(g, ps.st, cf, s);
         const bool good = ps.fitted && s.status > 0;
-        const double err = ps.err, err2 = err * err;
+        const double err = ps.in.err, err2 = err * err;
         const double pe_all = lane_error<P>(g, s, err2);   // warp-uniform collectives
         if (!ps.fitted || !inside) continue;   // zeros were written by the prologue
         const double pe = good ? pe_all : 0.0;
@@ -1403,6 +1504,7 @@ struct FitJob {
     void* states = nullptr;
     cudaStream_t stream = nullptr;
     unsigned egrid = 0, egrid_team = 0, sgrid = 0;
+    size_t esmem = 0, esmem_team = 0;   // dynamic shared memory of the evaluation kernels (staging buffers)
     void* wait_event = nullptr;
     int r = 0, max_rounds = 0, nchecks = 0, slot0 = 0;
     bool finished = false, prof = false;
@@ -1452,16 +1554,32 @@ static int job_begin(b200fit_ctx* ctx, FitJob& jb, void* d_workspace) {
         }
         if (!same) return fail(ctx, B200FIT_E_MODEL, "fit: hyperfine group table mismatch");
     }
-    int eval_per_sm = 0;
-    if (jb.model_id == B200FIT_MODEL_NH3_11)
+    // the evaluation kernels stage spectrum rows in dynamic shared memory: two stages per pixel in flight
+    jb.esmem = eval_dyn_smem<NC, 1>(jb.stride);
+    jb.esmem_team = eval_dyn_smem<NC, EVAL_WARPS>(jb.stride);
+    int eval_per_sm = 0, team_per_sm = 0;
+    if (jb.model_id == B200FIT_MODEL_NH3_11) {
+        CK(cudaFuncSetAttribute(fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, 1>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb.esmem));
+        CK(cudaFuncSetAttribute(fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, EVAL_WARPS>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb.esmem_team));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, 1>,
-                                                         EVAL_WARPS * 32, 0));
-    else
+                                                         EVAL_WARPS * 32, jb.esmem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &team_per_sm, fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, EVAL_WARPS>, EVAL_WARPS * 32, jb.esmem_team));
+    } else {
+        CK(cudaFuncSetAttribute(fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, 1>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb.esmem));
+        CK(cudaFuncSetAttribute(fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, EVAL_WARPS>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb.esmem_team));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, 1>,
-                                                         EVAL_WARPS * 32, 0));
-    if (eval_per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit_eval_kernel does not fit on an SM");
+                                                         EVAL_WARPS * 32, jb.esmem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &team_per_sm, fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, EVAL_WARPS>, EVAL_WARPS * 32, jb.esmem_team));
+    }
+    if (eval_per_sm < 1 || team_per_sm < 1) return fail(ctx, B200FIT_E_ARG, "fit_eval_kernel does not fit on an SM");
     long long egrid = (long long)ctx->num_sms * eval_per_sm;        // a whole number of CTAs per SM
-    long long egrid_team = egrid;                                    // block-per-pixel rounds: same launch bounds
+    long long egrid_team = (long long)ctx->num_sms * team_per_sm;   // block-per-pixel rounds
     if (egrid_team > pr.npix) egrid_team = pr.npix;
     if (egrid > pwarps) egrid = pwarps;
     const long long sgroups = SOLVE_THREADS / P;                     // pixels per solver block and pass
@@ -1490,8 +1608,8 @@ static int job_round(b200fit_ctx* ctx, FitJob& jb) {
                            : fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, 1>)
                    : (team ? fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, EVAL_WARPS>
                            : fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, 1>);
-    ek<<<team ? jb.egrid_team : jb.egrid, EVAL_WARPS * 32, 0, stream>>>(jb.pr, jb.d_spectra, jb.stride, jb.d_row_index,
-                                                 (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
+    ek<<<team ? jb.egrid_team : jb.egrid, EVAL_WARPS * 32, team ? jb.esmem_team : jb.esmem, stream>>>(
+        jb.pr, jb.d_spectra, jb.stride, jb.d_row_index, (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
     if (jb.prof) ctx->next_event(stream);   // [2 + 2r] after the evaluation of round r
     fit_solve_kernel<NC><<<jb.sgrid, SOLVE_THREADS, 0, stream>>>(jb.pr, (PixState<P>*)jb.states, jb.lists[cur],
                                                                  jb.lists[cur ^ 1], jb.fq, cur, jb.d_params, jb.d_perr,

@@ -166,10 +166,10 @@ def test_resid_stats(engine, fitted_tile):
 
 
 def test_rms_snr_matches_numpy_signals(engine):
-    """b200fit_rms_snr vs the numpy mirror of signals.get_rms_robust / get_snr / mad_std: bit-identical (fp64
-    medians of the same values), including NaN channels, a fully masked pixel and a planemask."""
+    """b200fit_rms_snr vs the numpy restatement of signals.get_rms_robust / get_snr / mad_std (oracle/signals.py):
+    bit-identical (fp64 medians of the same values), including NaN channels, a fully masked pixel and a planemask."""
     import torch
-    from mufasa_b200 import signals
+    from oracle import signals
     tile = T.sample_tile(2, nrows=2, xstep=16)
     cube = tile["cube"].copy()
     cube[100:130, 0, 3] = np.nan
