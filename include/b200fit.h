@@ -126,7 +126,7 @@ int b200fit_fit(b200fit_ctx* ctx, const b200fit_problem* prob,
  * UltraCube.fit_cube loops over, UltraCube.py:312-320): the rounds of the jobs are interleaved on internal streams, so
  * the latency-bound late rounds of one fit overlap the other's work.  Results are identical to separate b200fit_fit
  * calls.  Each job needs its own workspace and output buffers; ``stream`` orders the whole batch (fork / join). */
-#define B200FIT_MAX_BATCH 4
+#define B200FIT_MAX_BATCH 8
 typedef struct {
     const b200fit_problem* prob;
     const float* d_spectra;

@@ -44,7 +44,7 @@ class FitArgs(C.Structure):
                 ("wait_event", C.c_void_p)]
 
 
-MAX_BATCH = 4
+MAX_BATCH = 8
 PACK_FIELDS = 44
 
 

@@ -15,6 +15,8 @@ struct b200fit_ctx {
     volatile unsigned* h_count;   // pinned, 4 slots per job: active-pixel counts read back by the fit's round loop
     cudaStream_t job_stream[B200FIT_MAX_BATCH];
     cudaEvent_t fork_ev, join_ev[B200FIT_MAX_BATCH];
+    std::vector<cudaGraphExec_t> retired;     // executable graphs of earlier fit calls, destroyed once retired_ev fired
+    cudaEvent_t retired_ev = nullptr;
     unsigned long long launches = 0;          // kernels launched by this context (all entry points)
     double* d_chan = nullptr;                 // per-channel constants of the fp64 model (3 x B200FIT_MAX_NCHAN)
     int chan_n = 0;                           // ... valid for this spectral axis: nchan, {v0, dv, nu_ref}

@@ -266,6 +266,18 @@ struct LineGroups<B200FIT_MODEL_N2HP_10> {  // -8.0 (1) | -0.6 .. 1.0 (3) | 5.5 
     __host__ __device__ static constexpr int start(int g) { return g == 0 ? 0 : g == 1 ? 1 : g == 2 ? 4 : 7; }
 };
 
+// hyperfine lines a chunk with group mask ``pk`` (bit 8c + g) evaluates per channel: sum of the sizes of its groups
+template <int MODEL, int NC>
+__device__ __forceinline__ unsigned group_lines(unsigned pk) {
+    using LG = LineGroups<MODEL>;
+    unsigned n = 0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int g = 0; g < LG::NG; ++g) n += ((pk >> (8 * c + g)) & 1u) * (unsigned)(LG::start(g + 1) - LG::start(g));
+    return n;
+}
+
 //
 // TEAM = warps per pixel.  TEAM = 1: a warp owns a pixel.  TEAM = EVAL_WARPS: a block owns a pixel and its warps take
 // the active chunks round-robin -- a quarter of the evaluation latency, which is what the late rounds of a fit are
@@ -412,7 +424,6 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
             __syncwarp();
         // 2. which line groups reach chunk `lane` (and chunk `lane + 32`): bit 8c + g
         unsigned packed[2] = {0u, 0u};
-        unsigned my_lines = 0;   // gaussians this lane's chunks will cost (roofline accounting)
         for (int h = 0; h < nhalf; ++h) {
             const int ch = lane + 32 * h;
             const float lo_edge = 32.f * ch, hi_edge = 32.f * ch + 31.f;
@@ -423,10 +434,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
                         const bool on = (w.whi[c][LG::start(g + 1) - 1] >= lo_edge) && (w.wlo[c][LG::start(g)] <= hi_edge);
-                        if (on) {
-                            pk |= 1u << (8 * c + g);
-                            my_lines += LG::start(g + 1) - LG::start(g);
-                        }
+                        if (on) pk |= 1u << (8 * c + g);
                     }
                 }
             }
@@ -444,7 +452,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
             for (int kk = 0; kk < PH; ++kk) h2[u][kk] = 0ull;
 #pragma unroll
         for (int kk = 0; kk < PH; ++kk) b2[kk] = 0ull;
-        unsigned n_chunks = 0;
+        unsigned n_chunks = 0, n_lines = 0;   // roofline accounting: 32-channel chunks / hyperfine lines x chunks evaluated
 
         int ordinal = 0;   // running index of the active chunks of this pixel (a team deals them round-robin)
 #pragma unroll 1
@@ -457,27 +465,53 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
                     if ((ordinal++ & (TEAM - 1)) == warp) mine |= a & (0u - a);
                 act = mine;
             }
-            // software pipeline over the active chunks: channel value and group mask of the next one are fetched
-            // (shared memory / warp-wide OR) while the current one is evaluated
-            int jn = act ? (__ffs(act) - 1) : 0;
-            float ynext = act ? srow[((jn + 32 * h) << 5) + lane] : 0.f;
-            unsigned pknext = __reduce_or_sync(FULL, (lane == jn) ? mypk : 0u);
-            while (act) {
-                const int j = jn;
-                const float y = ynext;
-                const unsigned pk = pknext;     // warp-uniform (redux result)
+            // The active chunks are taken TWO at a time: both channels of a lane run through the same line records
+            // (one shared-memory load per line and pair), the same group tests (on the OR of the two chunks' masks;
+            // a group evaluated for a chunk just outside its window adds terms below 2^-28 of the line's peak) and two
+            // independent radiative-transfer / accumulation chains -- twice the instruction-level parallelism per
+            // warp at 4 warps per scheduler, where the single-chunk loop waited on its own dependent chain (ncu r2c:
+            // issue slots 57 % busy, top stalls fixed-latency "wait" 1.85 and short_scoreboard 0.73 cycles per issue).
+            // A pixel's pairs depend on its own chunk list only.  Channel values and the pair's mask are fetched one
+            // pair ahead (shared memory / redux.sync).
+            int ja = 0, jb = 0;
+            bool has_b = false;
+            auto next_pair = [&]() {
+                ja = __ffs(act) - 1;
                 act &= act - 1;
-                if (act) {
-                    jn = __ffs(act) - 1;
-                    ynext = srow[((jn + 32 * h) << 5) + lane];
-                    pknext = __reduce_or_sync(FULL, (lane == jn) ? mypk : 0u);
+                has_b = act != 0u;
+                jb = has_b ? (__ffs(act) - 1) : ja;
+                act &= act - 1;    // (0 & anything) == 0 when there was no second chunk
+            };
+            float yna = 0.f, ynb = 0.f;
+            unsigned pkn = 0u;
+            int jna = 0, jnb = 0;
+            bool hnb = false;
+            bool more = act != 0u;
+            if (more) {
+                next_pair();
+                jna = ja, jnb = jb, hnb = has_b;
+                yna = srow[((jna + 32 * h) << 5) + lane];
+                ynb = hnb ? srow[((jnb + 32 * h) << 5) + lane] : __int_as_float(0x7fc00000);
+                pkn = __reduce_or_sync(FULL, (lane == jna || lane == jnb) ? mypk : 0u);
+            }
+            while (more) {
+                const int j0 = jna, j1 = jnb;
+                const bool two = hnb;
+                const float y[2] = {yna, ynb};
+                const unsigned pk = pkn;        // warp-uniform (redux result)
+                more = act != 0u;
+                if (more) {
+                    next_pair();
+                    jna = ja, jnb = jb, hnb = has_b;
+                    yna = srow[((jna + 32 * h) << 5) + lane];
+                    ynb = hnb ? srow[((jnb + 32 * h) << 5) + lane] : __int_as_float(0x7fc00000);
+                    pkn = __reduce_or_sync(FULL, (lane == jna || lane == jnb) ? mypk : 0u);
                 }
-                const int i = ((j + 32 * h) << 5) + lane;
-                const float fi = (float)i;
-                float Gs[NC], As[NC], Bs[NC];
+                const float fi[2] = {(float)(((j0 + 32 * h) << 5) + lane), (float)(((j1 + 32 * h) << 5) + lane)};
+                float Gs[2][NC], As[2][NC], Bs[2][NC];
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    float g = 0.f, a = 0.f, b = 0.f;
+                    float g0 = 0.f, a0 = 0.f, b0 = 0.f, g1 = 0.f, a1 = 0.f, b1 = 0.f;
 #pragma unroll
                     for (int gi = 0; gi < NG; ++gi) {
                         if (pk & (1u << (8 * c + gi))) {
@@ -489,32 +523,37 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
                                 lc.b = q.y;
                                 lc.a = q.z;
                                 lc.lw = q.w;
-                                gauss_accum(fi, lc, g, a, b);
+                                gauss_accum(fi[0], lc, g0, a0, b0);
+                                gauss_accum(fi[1], lc, g1, a1, b1);
                             }
                         }
                     }
-                    Gs[c] = g;
-                    As[c] = a;
-                    Bs[c] = b;
+                    Gs[0][c] = g0, As[0][c] = a0, Bs[0][c] = b0;
+                    Gs[1][c] = g1, As[1][c] = a1, Bs[1][c] = b1;
                 }
-                n_chunks += 1;
-                float m, J[P];
-                rt_channel<NC>(Gs, As, Bs, fi - ic0, cc, m, J);
-                if (y == y) {   // NaN channels (and the NaN padding) carry no weight
-                    const float r = y - m;
-                    f32x2 Jp[PH];
+                n_chunks += two ? 2u : 1u;
+                n_lines += (two ? 2u : 1u) * group_lines<MODEL, NC>(pk);
+                float m[2], J[2][P];
+                rt_channel<NC>(Gs[0], As[0], Bs[0], fi[0] - ic0, cc, m[0], J[0]);
+                rt_channel<NC>(Gs[1], As[1], Bs[1], fi[1] - ic0, cc, m[1], J[1]);
 #pragma unroll
-                    for (int kk = 0; kk < PH; ++kk) Jp[kk] = pk2(J[2 * kk], J[2 * kk + 1]);
-                    const f32x2 r2 = pk2(r, r);
+                for (int t = 0; t < 2; ++t) {
+                    if (y[t] == y[t]) {   // NaN channels (the NaN padding, the filler of an odd last chunk): no weight
+                        const float r = y[t] - m[t];
+                        f32x2 Jp[PH];
 #pragma unroll
-                    for (int kk = 0; kk < PH; ++kk) b2[kk] = fma2(Jp[kk], r2, b2[kk]);
+                        for (int kk = 0; kk < PH; ++kk) Jp[kk] = pk2(J[t][2 * kk], J[t][2 * kk + 1]);
+                        const f32x2 r2 = pk2(r, r);
 #pragma unroll
-                    for (int u = 0; u < P; ++u) {
-                        const f32x2 ju = pk2(J[u], J[u]);
+                        for (int kk = 0; kk < PH; ++kk) b2[kk] = fma2(Jp[kk], r2, b2[kk]);
 #pragma unroll
-                        for (int kk = u / 2; kk < PH; ++kk) h2[u][kk] = fma2(ju, Jp[kk], h2[u][kk]);
+                        for (int u = 0; u < P; ++u) {
+                            const f32x2 ju = pk2(J[t][u], J[t][u]);
+#pragma unroll
+                            for (int kk = u / 2; kk < PH; ++kk) h2[u][kk] = fma2(ju, Jp[kk], h2[u][kk]);
+                        }
+                        chi = fmaf(m[t], m[t] - 2.f * y[t], chi);
                     }
-                    chi = fmaf(m, m - 2.f * y, chi);
                 }
             }
         }
@@ -569,10 +608,12 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
             }
             __syncwarp();
         }
-        const unsigned n_gauss = (unsigned)warp_sum_i((int)my_lines);
         if (TEAM > 1) {
-            // every warp computed the same chunk masks, so n_gauss is already the pixel's; chunks were shared out
-            if (lane == 0) part[warp][NACC] = (double)n_chunks;
+            // chunks (and the gaussians evaluated for them) were shared out over the warps of the team
+            if (lane == 0) {
+                part[warp][NACC] = (double)n_chunks;
+                part[warp][NACC + 1] = (double)n_lines;
+            }
             __syncthreads();
             if (warp == 0) {
                 for (int e = lane; e < NACC; e += 32) {
@@ -587,17 +628,20 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
                         ps.st.chi2t = sumsq + sred;
                 }
                 if (lane == 0) {
-                    double nc = 0.0;
+                    double nc = 0.0, nl = 0.0;
 #pragma unroll
-                    for (int t = 0; t < TEAM; ++t) nc += part[t][NACC];
-                    atomicAdd(&ps.n_gauss, n_gauss);           // (result unused: a fire-and-forget reduction)
+                    for (int t = 0; t < TEAM; ++t) {
+                        nc += part[t][NACC];
+                        nl += part[t][NACC + 1];
+                    }
+                    atomicAdd(&ps.n_gauss, (unsigned)nl);      // (result unused: a fire-and-forget reduction)
                     atomicAdd(&ps.n_chunks, (unsigned)nc);
                 }
             }
             __syncthreads();   // the stage and ``part`` are free for the next pixel
         } else {
             if (lane == 0) {
-                atomicAdd(&ps.n_gauss, n_gauss);
+                atomicAdd(&ps.n_gauss, n_lines);
                 atomicAdd(&ps.n_chunks, n_chunks);
             }
             __syncwarp();      // every lane is done with this stage: the next copy may overwrite it
@@ -1505,6 +1549,8 @@ struct FitJob {
     cudaStream_t stream = nullptr;
     unsigned egrid = 0, egrid_team = 0, sgrid = 0;
     size_t esmem = 0, esmem_team = 0;   // dynamic shared memory of the evaluation kernels (staging buffers)
+    bool use_graph = false;             // rounds are launched as captured groups (job_rounds)
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // ... one executable graph per evaluation variant
     void* wait_event = nullptr;
     int r = 0, max_rounds = 0, nchecks = 0, slot0 = 0;
     bool finished = false, prof = false;
@@ -1589,20 +1635,18 @@ static int job_begin(b200fit_ctx* ctx, FitJob& jb, void* d_workspace) {
     jb.egrid = (unsigned)egrid;
     jb.egrid_team = (unsigned)egrid_team;
     jb.sgrid = (unsigned)sgrid;
-    jb.max_rounds = 2 * pr.max_iter + 3;
+    jb.max_rounds = (2 * pr.max_iter + 3 + FIT_CHECK - 1) / FIT_CHECK * FIT_CHECK;   // whole groups of rounds
     jb.r = 0;
     jb.nchecks = 0;
     jb.finished = false;
     return B200FIT_OK;
 }
 
+// The two kernels of one round on the job's stream (directly, or recorded into a graph being captured there).
 template <int NC>
-static int job_round(b200fit_ctx* ctx, FitJob& jb) {
+static void launch_round(FitJob& jb, int cur, bool team) {
     constexpr int P = 4 * NC;
     cudaStream_t stream = jb.stream;
-    const int r = jb.r, cur = r & 1;
-    // late rounds: a block per pixel (see fit_eval_kernel); a function of the round only
-    const bool team = r >= fit_team_round<NC>();
     auto* ek = (jb.model_id == B200FIT_MODEL_NH3_11)
                    ? (team ? fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, EVAL_WARPS>
                            : fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, 1>)
@@ -1610,17 +1654,62 @@ static int job_round(b200fit_ctx* ctx, FitJob& jb) {
                            : fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, 1>);
     ek<<<team ? jb.egrid_team : jb.egrid, EVAL_WARPS * 32, team ? jb.esmem_team : jb.esmem, stream>>>(
         jb.pr, jb.d_spectra, jb.stride, jb.d_row_index, (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
-    if (jb.prof) ctx->next_event(stream);   // [2 + 2r] after the evaluation of round r
     fit_solve_kernel<NC><<<jb.sgrid, SOLVE_THREADS, 0, stream>>>(jb.pr, (PixState<P>*)jb.states, jb.lists[cur],
                                                                  jb.lists[cur ^ 1], jb.fq, cur, jb.d_params, jb.d_perr,
                                                                  jb.d_chi2, jb.d_err_used, jb.d_status, jb.d_counts);
-    ctx->launches += 2;
-    if (jb.prof) {
-        ctx->next_event(stream);            // [3 + 2r] after the solver step of round r
-        ctx->prof_rounds = r + 1;
+}
+
+// One GROUP of FIT_CHECK rounds, then the (asynchronous) look at the active count.  The group is a CUDA graph,
+// captured once per job and evaluation variant and replayed: the late rounds of a fit are a chain of small dependent
+// kernels, and a graph launch replaces 2 * FIT_CHECK stream launches (host time, and the gap between dependent
+// kernels on the device).  Rounds after the last pixel finished find an empty list and return at once.
+template <int NC>
+static int job_rounds(b200fit_ctx* ctx, FitJob& jb) {
+    cudaStream_t stream = jb.stream;
+    const int r0 = jb.r;
+    // late rounds: a block per pixel (see fit_eval_kernel); a function of the round only
+    static_assert(fit_team_round<NC>() % FIT_CHECK == 0, "the evaluation variant changes between groups of rounds");
+    const bool team = r0 >= fit_team_round<NC>();
+    if (jb.use_graph) {
+        cudaGraphExec_t& ge = jb.gexec[team ? 1 : 0];
+        if (!ge) {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            for (int r = 0; r < FIT_CHECK; ++r) launch_round<NC>(jb, r & 1, team);   // r0 is even: cur = r & 1
+            const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+            if (ce != cudaSuccess || !graph) return fail(ctx, B200FIT_E_CUDA, "fit: stream capture of a round group", ce);
+            const cudaError_t ci = cudaGraphInstantiate(&ge, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ci != cudaSuccess) return fail(ctx, B200FIT_E_CUDA, "fit: cudaGraphInstantiate", ci);
+        }
+        CK(cudaGraphLaunch(ge, stream));
+        ctx->launches += 2 * FIT_CHECK;
+        jb.r = r0 + FIT_CHECK;
+    } else {
+        for (int r = r0; r < r0 + FIT_CHECK; ++r) {
+            constexpr int P = 4 * NC;
+            const int cur = r & 1;
+            auto* ek = (jb.model_id == B200FIT_MODEL_NH3_11)
+                           ? (team ? fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, EVAL_WARPS>
+                                   : fit_eval_kernel<NC, B200FIT_MODEL_NH3_11, 1>)
+                           : (team ? fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, EVAL_WARPS>
+                                   : fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, 1>);
+            ek<<<team ? jb.egrid_team : jb.egrid, EVAL_WARPS * 32, team ? jb.esmem_team : jb.esmem, stream>>>(
+                jb.pr, jb.d_spectra, jb.stride, jb.d_row_index, (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
+            if (jb.prof) ctx->next_event(stream);   // [2 + 2r] after the evaluation of round r
+            fit_solve_kernel<NC><<<jb.sgrid, SOLVE_THREADS, 0, stream>>>(
+                jb.pr, (PixState<P>*)jb.states, jb.lists[cur], jb.lists[cur ^ 1], jb.fq, cur, jb.d_params, jb.d_perr,
+                jb.d_chi2, jb.d_err_used, jb.d_status, jb.d_counts);
+            ctx->launches += 2;
+            if (jb.prof) {
+                ctx->next_event(stream);            // [3 + 2r] after the solver step of round r
+                ctx->prof_rounds = r + 1;
+            }
+        }
+        jb.r = r0 + FIT_CHECK;
     }
-    jb.r = r + 1;
-    if ((r + 1) % FIT_CHECK == 0) {
+    {
+        const int cur = (jb.r - 1) & 1;             // the last round of the group appended to list cur ^ 1
         const int slot = jb.slot0 + jb.nchecks % FIT_RING;
         if (jb.nchecks >= FIT_RING - 2) {   // wait for the check issued (FIT_RING - 2) checks ago
             const int old = jb.slot0 + (jb.nchecks - (FIT_RING - 2)) % FIT_RING;
@@ -1636,6 +1725,17 @@ static int job_round(b200fit_ctx* ctx, FitJob& jb) {
     }
     if (jb.r >= jb.max_rounds) jb.finished = true;
     return B200FIT_OK;
+}
+
+// Executable graphs of finished calls are destroyed once the work that used them has completed.
+static void retire_graphs(b200fit_ctx* ctx, bool wait) {
+    if (ctx->retired.empty()) return;
+    if (wait)
+        cudaEventSynchronize(ctx->retired_ev);
+    else if (cudaEventQuery(ctx->retired_ev) != cudaSuccess)
+        return;
+    for (cudaGraphExec_t g : ctx->retired) cudaGraphExecDestroy(g);
+    ctx->retired.clear();
 }
 
 // (Re)build the per-channel table of the fp64 model when the spectral axis differs from the cached one.
@@ -1682,6 +1782,7 @@ int b200fit_create(b200fit_ctx** out, int device) {
         return B200FIT_E_CUDA;
     }
     bool okc = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    okc = okc && cudaEventCreateWithFlags(&ctx->retired_ev, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < B200FIT_MAX_BATCH * 4; ++i)
         okc = okc && cudaEventCreateWithFlags(&ctx->check_ev[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < B200FIT_MAX_BATCH; ++i) {
@@ -1698,6 +1799,8 @@ int b200fit_create(b200fit_ctx** out, int device) {
 
 void b200fit_destroy(b200fit_ctx* ctx) {
     if (!ctx) return;
+    retire_graphs(ctx, true);
+    cudaEventDestroy(ctx->retired_ev);
     for (int i = 0; i < B200FIT_MAX_BATCH * 4; ++i) cudaEventDestroy(ctx->check_ev[i]);
     for (int i = 0; i < B200FIT_MAX_BATCH; ++i) {
         cudaEventDestroy(ctx->join_ev[i]);
@@ -1816,12 +1919,18 @@ int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* args, int32_t nj
     }
     if (live == 0) return B200FIT_OK;
     CK(cudaSetDevice(ctx->device));
-    const bool forked = live > 1;
+    retire_graphs(ctx, false);
+    // Round groups are replayed as CUDA graphs, captured on the library's own streams (the caller's may be the legacy
+    // default stream, which cannot be captured): every job is forked off the caller's stream, also a single one.
+    // A profiled fit (events between the kernels of every round) is launched kernel by kernel on the caller's stream.
+    const bool profiled = ctx->profiling != 0 && live == 1;
+    const bool forked = !profiled;
     if (forked) CK(cudaEventRecord(ctx->fork_ev, stream));
     for (int j = 0; j < live; ++j) {
         FitJob& jb = jobs[j];
         jb.stream = forked ? ctx->job_stream[j] : stream;
-        jb.prof = ctx->profiling != 0 && j == 0 && !forked;
+        jb.prof = profiled;
+        jb.use_graph = forked;
         if (forked) CK(cudaStreamWaitEvent(jb.stream, ctx->fork_ev, 0));
         if (jb.wait_event) CK(cudaStreamWaitEvent(jb.stream, (cudaEvent_t)jb.wait_event, 0));
         void* ws = jb.states;
@@ -1833,7 +1942,7 @@ int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* args, int32_t nj
         for (int j = 0; j < live; ++j) {
             FitJob& jb = jobs[j];
             if (jb.finished) continue;
-            const int rc = (jb.nc == 1) ? job_round<1>(ctx, jb) : job_round<2>(ctx, jb);
+            const int rc = (jb.nc == 1) ? job_rounds<1>(ctx, jb) : job_rounds<2>(ctx, jb);
             if (rc) return rc;
             any = true;
         }
@@ -1860,6 +1969,10 @@ int b200fit_fit_batch(b200fit_ctx* ctx, const b200fit_fit_args* args, int32_t nj
             CK(cudaStreamWaitEvent(stream, ctx->join_ev[j], 0));
         }
     }
+    for (int j = 0; j < live; ++j)
+        for (cudaGraphExec_t g : jobs[j].gexec)
+            if (g) ctx->retired.push_back(g);
+    if (!ctx->retired.empty()) CK(cudaEventRecord(ctx->retired_ev, stream));
     CK(cudaGetLastError());
     return B200FIT_OK;
 }

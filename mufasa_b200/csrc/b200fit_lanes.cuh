@@ -19,6 +19,29 @@
 
 namespace b200fit {
 
+// 1 / sqrt(x) and sqrt(x) for x > 0 finite: the hardware's ~20-bit seed (MUFU.RSQ64H) and two Newton steps, ~10
+// branch-free instructions.  CUDA's rsqrt() / sqrt() are correctly rounded and handle every special case, at ~60 / ~30
+// instructions with slow-path branches -- 9 % of the solver's executed instructions for the pivots of the Cholesky
+// factorisation alone (profiles/r1o_solve2c_source_summary.txt), and each branch a break in the instruction stream
+// of a kernel whose top stall is instruction fetch.  The result is within ~1 ulp; the factorisation and the norms it
+// feeds are not sensitive to that (the test-only host emulation keeps the correctly rounded library calls).
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-h * r, r, 0.5);      // 0.5 (1 - x r^2)
+    r = fma(r, e, r);
+    e = fma(-h * r, r, 0.5);
+    r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ double sqrt_nonneg(double x) {   // x >= 0 finite (sums of squares)
+    const double r = rsqrt_pos(fmax(x, 1e-300));
+    double s = x * r;
+    s = fma(fma(-s, s, x), 0.5 * r, s);  // one Heron correction of the product
+    return s;
+}
+
 template <int P>
 struct LaneGroup {
     static constexpr unsigned FULLMASK = 0xffffffffu;
@@ -138,7 +161,7 @@ __device__ __forceinline__ void lane_store(const LaneGroup<P>& g, LMState<P>& st
 template <int P>
 __device__ __forceinline__ double lane_dnorm(const LaneGroup<P>& g, double dg, double x) {
     const double t = dg * x;
-    return sqrt(g.sum(t * t));
+    return sqrt_nonneg(g.sum(t * t));
 }
 
 // Right-looking Cholesky of A = H_free + par*diag^2 (fixed rows/cols -> identity).  Lane i ends up with the
@@ -172,7 +195,7 @@ __device__ __forceinline__ bool lane_chol(const LaneGroup<P>& g, const double (&
         const double d = g.bcast(dj, j);         // (repaired) updated diagonal, held by lane j
         const unsigned votes = g.ballot(good);   // unconditionally: a collective must not sit behind ``ok &&``
         ok = ok && ((votes >> j) & 1u);
-        const double inv = rsqrt(d);             // 1 / L_jj  (rsqrt + one multiply instead of sqrt + divide)
+        const double inv = rsqrt_pos(d);         // 1 / L_jj  (d > 0: the pivot was repaired above if it was not)
         const double l = (i > j) ? a[j] * inv : 0.0;   // L_ij below the diagonal; the diagonal lives in linv only
         lrow[j] = l;
         if (i == j) linv = inv;
@@ -233,7 +256,7 @@ __device__ __forceinline__ double lane_par(const LaneGroup<P>& g, const double (
     double lrow[P], linv, x = 0.0, xout = 0.0;
     double dxnorm = INFINITY, fp = INFINITY, parl = 0.0, paru = 0.0;
     const double t0 = rhs / dg;
-    const double gnorm = sqrt(g.sum(t0 * t0));   // |D^-1 b|: the same in every iteration
+    const double gnorm = sqrt_nonneg(g.sum(t0 * t0));   // |D^-1 b|: the same in every iteration
 #pragma unroll 1
     for (int it = 0; it <= 10; ++it) {
         if (!g.any_in_warp(live)) break;
@@ -282,7 +305,7 @@ __device__ __forceinline__ double lane_par(const LaneGroup<P>& g, const double (
 
 template <int P>
 __device__ __forceinline__ unsigned lane_pegged(const LaneGroup<P>& g, const LaneState<P>& s) {
-    const double thr = 3.0 * LM_NOISE_REL * sqrt((s.hd > 0.0 ? s.hd : 0.0) * s.chi2);
+    const double thr = 3.0 * LM_NOISE_REL * sqrt_nonneg((s.hd > 0.0 ? s.hd : 0.0) * s.chi2);
     const bool peg = (s.p <= s.lo && s.b < thr) || (s.p >= s.hi && s.b > -thr);
     return g.ballot(peg);
 }
@@ -380,8 +403,8 @@ __device__ __forceinline__ int lane_step(const LaneGroup<P>& g, LaneState<P>& s,
     const bool fresh = (done == LM_CONTINUE) && s.fresh;
     {
         const bool pegbit = (peg_new >> g.gl) & 1u;
-        const double fnorm = sqrt(s.chi2);
-        const double cn = pegbit ? 0.0 : sqrt(s.hd > 0.0 ? s.hd : 0.0);
+        const double fnorm = sqrt_nonneg(s.chi2);
+        const double cn = pegbit ? 0.0 : sqrt_nonneg(s.hd > 0.0 ? s.hd : 0.0);
         double diag_new = s.diag;
         if (s.first)
             diag_new = (cn == 0.0) ? 1.0 : cn;

@@ -116,7 +116,10 @@ class PCube(object):
             host = self.cube if self.cube.dtype == np.float32 else self.cube.astype(np.float32)
             t = torch.from_numpy(np.ascontiguousarray(host).reshape(nchan, ny * nx))
             _, _, flip = self.xarr.v0_dv_flip
-            nslab = 2 if (t.is_pinned() and ny * nx >= 2 * eng.SPLIT_MIN_PIXELS and ny >= 2) else 1
+            # slabs of at least SPLIT_MIN_PIXELS spectra, at most 4 (two fits x 4 slabs fill a batch of the library)
+            nslab = 1
+            if t.is_pinned():
+                nslab = int(max(1, min(4, ny, (ny * nx) // eng.SPLIT_MIN_PIXELS)))
             if nslab == 1:
                 staging = t.to(eng.device, non_blocking=True)       # async when the cube lives in pinned memory
                 self._dev["rows"] = eng.gather(staging, None, flip=flip)

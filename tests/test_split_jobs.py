@@ -82,10 +82,10 @@ def test_slab_split_waits_for_the_right_slab():
     jf, of = _job(first_rows.size, 2, masked=(ny * nx, first_rows), slab_ready=(bounds, events))
     parts = eng._split_jobs([jf], [of])
     assert len(parts) == 1 and parts[0]["wait"] is events[0]
-    # three fits do not fit in the batch cut in two: each waits for the slab of its last pixel
-    (j3, o3) = _job(ny * nx, 2, slab_ready=(bounds, events))
-    parts = eng._split_jobs([j1, j2, j3], [o1, o2, o3])
-    assert len(parts) == 3 and all(p["wait"] is events[1] for p in parts)
+    # five fits do not fit in the batch (8 entries) cut in two: each waits for the slab of its last pixel
+    more = [_job(ny * nx, 2, slab_ready=(bounds, events)) for _ in range(3)]
+    parts = eng._split_jobs([j1, j2] + [j for j, _ in more], [o1, o2] + [o for _, o in more])
+    assert len(parts) == 5 and all(p["wait"] is events[1] for p in parts)
     # once the upload has completed the generic split applies
     for e in events:
         e.done = True
