@@ -6,8 +6,8 @@ workload : BASELINE.json configs[4] (the configuration the north-star target is 
            cube, 1024 x 1024 pixels x 1000 channels.  One STEP = the whole job on the whole cube: 1-component fit +
            2-component fit of every spectrum + AICc 0/1/2-component selection + assembly of the best-model parameter
            cube (UltraCube.fit_cube([1, 2]) + get_best_2c_parcube in the reference's terms).
-           N GPUs: the SAME cube partitioned by row slabs (mufasa_b200.dist.partition_rows), rank r holds rows
-           [r ny / N, (r + 1) ny / N) -> "scaling": "strong".  Pixels are independent: no collective inside the fit
+           N GPUs: the SAME cube partitioned by pixel blocks (mufasa_b200.dist.partition_row_blocks: blocks of 8 rows
+           dealt round-robin, so every rank gets the same mix of easy and hard spectra) -> "scaling": "strong".  Pixels are independent: no collective inside the fit
            loop; NCCL carries the global arg-max of the AICc include_nosamp rule (16 bytes per rank + one 256-byte
            broadcast) and ONE gather of the [44, rows, nx] result block per step.
 value    : 1 048 576 spectra / (max-over-ranks device time per step), slab rows and guesses already resident in HBM;
@@ -226,23 +226,23 @@ def workload_config(n):
     return {"workload": "BASELINE configs[4]: ONE synthetic NH3(1,1) cube 1024x1024x1000 ch; step = 1-comp fit + "
                         "2-comp fit + AICc ncomp selection + best-model cube of all 1048576 spectra",
             "spectra": 1048576, "nchan": 1000, "fittype": "nh3_multi_v",
-            "partition": ("row slabs of the one cube over %d GPUs (%d rows each), result block gathered to rank 0 "
-                          "over NCCL" % (n, 1024 // n)) if n > 1 else "single GPU, whole cube",
+            "partition": ("blocks of 8 rows of the one cube dealt round-robin to %d GPUs (%d rows each), result block "
+                          "gathered to rank 0 over NCCL" % (n, 1024 // n)) if n > 1 else "single GPU, whole cube",
             "cache": "inputs larger than L2 (%.1f GB of spectra per GPU vs 126 MB L2), streamed from HBM by every "
                      "kernel" % (4.29 / max(1, n))}
 
 
 # ------------------------------------------------------------------------------------------------------------------
-class RowSlabView(object):
-    """[nchan, ny, nx] stand-in that only holds rows y0:y1 -- what a loader that reads slabs hands fit_and_select."""
+class RankRows(object):
+    """[nchan, ny, nx] stand-in that only holds this rank's rows (stacked, in pinned memory) -- what a loader that
+    reads its own rows hands fit_and_select (mufasa_b200.dist.take_rows)."""
 
-    def __init__(self, slab, ny, y0):
-        self.slab, self.y0 = slab, y0
+    def __init__(self, slab, ny, rows):
+        self.slab, self.rows = slab, np.asarray(rows)
         self.shape = (slab.shape[0], ny, slab.shape[2])
 
-    def __getitem__(self, key):
-        rows = key[1]
-        assert key[0] == slice(None) and (rows.start, rows.stop) == (self.y0, self.y0 + self.slab.shape[1])
+    def take_rows(self, rows):
+        assert np.array_equal(np.asarray(rows), self.rows)
         return self.slab
 
 
@@ -269,8 +269,8 @@ def run_b200(args):
     if args.small:                              # smoke-size run of the same code path (not a bench line)
         ny, nx = 64 * world, 128
     nspec = ny * nx
-    y0, y1 = D.partition_rows(ny, world, rank)
-    ry = y1 - y0
+    my_rows = D.owned_rows(ny, world, rank, "cyclic")      # blocks of 8 rows dealt round-robin: even load per rank
+    ry = int(my_rows.size)
 
     def gpu_modelcube(parcube, v, ft):
         P, py, px = parcube.shape
@@ -284,25 +284,33 @@ def run_b200(args):
     slab = slab_t.numpy()
     g1s, g2s = np.empty((4, ry, nx)), np.empty((8, ry, nx))
     shape = (ny, nx, nchan) if args.small else None
-    for a in range(0, ry, 64):
-        b = min(ry, a + 64)
-        part = synth.make_cube(CFG, gpu_modelcube, rows=(y0 + a, y0 + b), shape=shape, out=slab[:, a:b, :])
+    a = 0
+    while a < ry:                               # runs of consecutive rows (whole cube at N = 1: 64 rows at a time)
+        b = a + 1
+        while b < ry and my_rows[b] == my_rows[b - 1] + 1 and b - a < 64:
+            b += 1
+        part = synth.make_cube(CFG, gpu_modelcube, rows=(int(my_rows[a]), int(my_rows[b - 1]) + 1), shape=shape,
+                               out=slab[:, a:b, :])
         g1s[:, a:b], g2s[:, a:b] = part["guess1"], part["guess2"]
         v = part["v"]
+        a = b
     torch.cuda.empty_cache()
 
-    def all_rows(a):                            # [k, ry, nx] slab maps of every rank -> [k, ny, nx] on every rank
+    def all_rows(a):                            # [k, ry, nx] maps of every rank's rows -> [k, ny, nx] on every rank
         if world == 1:
             return a
         t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        pieces = [torch.empty((a.shape[0], D.partition_rows(ny, world, r)[1] - D.partition_rows(ny, world, r)[0], nx),
-                              dtype=t.dtype, device=dev) for r in range(world)]
+        pieces = [torch.empty((a.shape[0], D.owned_rows(ny, world, r, "cyclic").size, nx), dtype=t.dtype, device=dev)
+                  for r in range(world)]
         dist.all_gather(pieces, t)
-        return torch.cat(pieces, dim=1).cpu().numpy()
+        out = np.empty((a.shape[0], ny, nx), dtype=a.dtype)
+        for r, piece in enumerate(pieces):
+            out[:, D.owned_rows(ny, world, r, "cyclic"), :] = piece.cpu().numpy()
+        return out
 
     g1_full, g2_full = all_rows(g1s), all_rows(g2s)
     t_syn = time.perf_counter() - t_syn
-    cube_view = RowSlabView(slab, ny, y0)
+    cube_view = RankRows(slab, ny, my_rows)
 
     def max_over_ranks(x):
         t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
@@ -372,7 +380,8 @@ def run_b200(args):
     outs = eng.fit_batch(job.batch)
     ev[1].record()
     sel = D.aicc_distributed(eng, job.prob, job.ref.rows_on_device(), outs[job.jobs[1]]["params"],
-                             outs[job.jobs[2]]["params"], first_pixel=y0 * nx, model_f32=True)
+                             outs[job.jobs[2]]["params"], model_f32=True,
+                             local_to_global=lambda i: int(my_rows[i // nx]) * nx + i % nx)
     eng.pack_selection(outs[job.jobs[1]], outs[job.jobs[2]], sel)
     ev[2].record()
     barrier()

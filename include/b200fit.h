@@ -208,6 +208,14 @@ int b200fit_mask_bits(b200fit_ctx* ctx, const b200fit_problem* prob,
                       const double* d_params1, const double* d_params2, int32_t model_f32,
                       const int64_t* d_best, int64_t pix, uint32_t* d_bits, void* stream);
 
+/* The guess conditioning of cubefit_simp (multi_v_fit.py:156-190) on the device: a velocity guess of exactly 0 becomes
+ * NaN ("no guess", :158-159), every value outside [lo, hi] is moved just inside (lo + eps / hi - eps, :178-190).
+ *   d_raw [npar][npix] field-major (the caller's [npar, ny, nx] maps), d_guesses [npix][npar] (input of b200fit_fit);
+ *   lo / hi: HOST arrays of npar doubles (minpars / maxpars); npar = 4 or 8.  Pixels left with a non-finite guess are
+ *   reported "not fitted" by b200fit_fit (status 0, zeros), which is what the reference's maskmap does to them. */
+int b200fit_prepare_guesses(b200fit_ctx* ctx, int64_t npix, int32_t npar, const double* d_raw, const double* lo,
+                            const double* hi, double eps, double* d_guesses, void* stream);
+
 /* UltraCube.get_best_2c_parcube (UltraCube.py:1283-1379; include_1c=True, return_lnks=True) assembled on the device
  * from the two fits and the output of b200fit_aicc, field-major d_out[B200FIT_PACK_FIELDS][out_stride]:
  *   [0,4) parcube1  [4,8) errcube1  [8,16) parcube2  [16,24) errcube2  [24,32) best parcube  [32,40) best errcube

@@ -551,9 +551,10 @@ def get_residual(cube, model):
 def get_masked_moment(cube, model, order=0, expand=10, mask=None):
     """UltraCube.py:1568-1655: moment of the data over the channels where the model is positive (dilated by
     ``expand``); pixels whose model peak is below the median peak use the channels where any model exceeds 10 % of
-    that median instead.  Returns a [ny, nx] array (moment 0 in K km/s)."""
-    if order != 0:
-        raise NotImplementedError("only moment 0 is written by save_best_2comp_fit")
+    that median instead.  ``order`` 0, 1 or 2 with spectral_cube's definitions on the km/s axis (radio convention):
+    m0 = sum(I) |dv|, m1 = sum(I v) / sum(I), m2 = sum(I (v - m1)^2) / sum(I) (a variance).  Returns [ny, nx]."""
+    if order not in (0, 1, 2):
+        raise ValueError("order must be 0, 1 or 2")
     data = cube._data
     with np.errstate(invalid="ignore"):
         mask = (model > 0) if mask is None else np.logical_and(mask, np.isfinite(model))
@@ -573,6 +574,14 @@ def get_masked_moment(cube, model, order=0, expand=10, mask=None):
         mask = binary_dilation(mask, structure=np.ones((expand, 1, 1), dtype=bool))
     v = np.asarray(cube.spectral_axis, dtype=np.float64)
     keep = mask & np.isfinite(data)
-    out = np.where(keep, data, 0.0).sum(axis=0, dtype=np.float64) * abs(v[1] - v[0])
-    out[~keep.any(axis=0)] = np.nan
+    w = np.where(keep, data, 0.0)
+    s0 = w.sum(axis=0, dtype=np.float64)
+    empty = ~keep.any(axis=0)
+    if order == 0:
+        out = s0 * abs(v[1] - v[0])
+    else:
+        with np.errstate(all="ignore"):
+            m1 = (w * v[:, None, None]).sum(axis=0, dtype=np.float64) / s0
+            out = m1 if order == 1 else (w * (v[:, None, None] - m1) ** 2).sum(axis=0, dtype=np.float64) / s0
+    out[empty] = np.nan
     return out

@@ -78,6 +78,7 @@ SIGNATURES = {
     "b200fit_mask_bits_pair": (C.c_int, [_vp, _PP, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "b200fit_mask_argmax": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "b200fit_mask_bits": (C.c_int, [_vp, _PP, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
+    "b200fit_prepare_guesses": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, C.c_double, _vp, _vp]),
     "b200fit_pack_selection": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "b200fit_rms_snr": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, C.c_double, _i32, _vp, _vp, _vp, _vp]),
     "b200fit_signal_bits": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, C.c_double, _vp, _vp]),

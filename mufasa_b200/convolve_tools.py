@@ -33,15 +33,40 @@ class Beam(object):
             raise ValueError("minor axis larger than the major axis")
 
     def deconvolve(self, other):
-        """The beam that convolved with ``other`` gives this one.  Same-angle (or circular) beams only: the axes
-        subtract in quadrature, which is the case convolve_sky_byfactor produces (:51-59)."""
-        same_pa = abs(((self.pa - other.pa) + 90.0) % 180.0 - 90.0) < 1e-9
-        if not (same_pa or other.major == other.minor):
-            raise NotImplementedError("deconvolution of beams at different position angles")
-        maj2, min2 = self.major ** 2 - other.major ** 2, self.minor ** 2 - other.minor ** 2
-        if maj2 <= 0 or min2 <= 0:
+        """The beam that convolved with ``other`` gives this one (radio_beam ``Beam.deconvolve``, the AIPS / Miriad
+        relations for two elliptical Gaussians at any position angles; convolve_tools.py:90-138 needs it when the
+        target beam is not a scaled copy of the cube's beam) [RECALLED: radio_beam.utils.deconvolve].  For beams at
+        the same angle the axes subtract in quadrature."""
+        t1, t2 = np.radians(self.pa), np.radians(other.pa)
+        a1, b1, a2, b2 = self.major ** 2, self.minor ** 2, other.major ** 2, other.minor ** 2
+        alpha = a1 * np.cos(t1) ** 2 + b1 * np.sin(t1) ** 2 - a2 * np.cos(t2) ** 2 - b2 * np.sin(t2) ** 2
+        beta = a1 * np.sin(t1) ** 2 + b1 * np.cos(t1) ** 2 - a2 * np.sin(t2) ** 2 - b2 * np.cos(t2) ** 2
+        gamma = 2.0 * ((b1 - a1) * np.sin(t1) * np.cos(t1) - (b2 - a2) * np.sin(t2) * np.cos(t2))
+        s = alpha + beta
+        t = np.sqrt((alpha - beta) ** 2 + gamma ** 2)
+        tol = 1e-12 * max(a1, a2)
+        if alpha < -tol or beta < -tol or s - t <= tol:
             raise ValueError("beam could not be deconvolved")
-        return Beam(np.sqrt(maj2), np.sqrt(min2), self.pa)
+        major, minor = np.sqrt(0.5 * (s + t)), np.sqrt(0.5 * (s - t))
+        if abs(gamma) + abs(alpha - beta) <= tol:
+            pa = 0.0 if major != minor else self.pa
+        else:
+            pa = np.degrees(0.5 * np.arctan2(-gamma, alpha - beta))
+        if abs(((self.pa - other.pa) + 90.0) % 180.0 - 90.0) < 1e-9:
+            pa = self.pa                                          # same angle: keep it exactly
+        return Beam(major, minor, pa)
+
+    def convolve(self, other):
+        """The beam of this one convolved with ``other``: the second-moment matrices add."""
+        def cov(b):
+            t = np.radians(b.pa)
+            c, s_ = np.cos(t), np.sin(t)
+            R = np.array([[c, -s_], [s_, c]])
+            return R @ np.diag([b.major ** 2, b.minor ** 2]) @ R.T
+        w, vecs = np.linalg.eigh(cov(self) + cov(other))
+        major, minor = np.sqrt(w[1]), np.sqrt(w[0])
+        pa = np.degrees(np.arctan2(vecs[1, 1], vecs[0, 1])) if major != minor else 0.0
+        return Beam(major, minor, ((pa + 90.0) % 180.0) - 90.0)
 
     def as_kernel(self, pixscale, support_scaling=8):
         """Sampled kernel in pixels: dict(kx, ky) [K] float32 for a circular beam, dict(k2) [K, K] otherwise

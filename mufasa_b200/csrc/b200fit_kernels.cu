@@ -83,6 +83,10 @@ struct alignas(16) PixState {
     int fitted, pad_;            // 1 once the LM state is initialised (0: bad guess / no weight -> zeros, status 0)
 };
 
+struct DeviceLimits {            // box limits of the parameters, passed by value (prepare_guesses_kernel)
+    double lo[8], hi[8];
+};
+
 struct FitQueues {               // head of the workspace
     unsigned int count[2];       // sizes of the ping-pong active lists
     unsigned int pad[62];
@@ -1206,13 +1210,35 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// What cubefit_simp does to the caller's guesses before fiteach (multi_v_fit.py:156-190), per pixel, on the device:
+// a velocity guess of exactly 0 means "no guess" (-> NaN, :158-159); every parameter outside its limits is moved
+// just inside (value < min -> min + eps, value > max -> max - eps, :178-190; NaN stays NaN).  Input field-major
+// raw[P][npix] (the [P, ny, nx] maps as the caller holds them), output pixel-major out[npix][P] (what b200fit_fit
+// reads).  A pixel with a non-finite guess is "not fitted" by the fit kernel itself (status 0, zeros) -- the
+// reference's maskmap & all-finite rule -- so no compaction is needed.
+__global__ void __launch_bounds__(256)
+    prepare_guesses_kernel(long long npix, int P, const double* __restrict__ raw, DeviceLimits lim, double eps,
+                           double* __restrict__ out) {
+    for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < npix;
+         px += (long long)gridDim.x * blockDim.x) {
+        for (int j = 0; j < P; ++j) {
+            double v = raw[(long long)j * npix + px];
+            if ((j & 3) == 0 && v == 0.0) v = NAN;
+            if (v < lim.lo[j]) v = lim.lo[j] + eps;
+            if (v > lim.hi[j]) v = lim.hi[j] - eps;
+            out[px * P + j] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // get_best_2c_parcube (UltraCube.py:1283-1379, include_1c, return_lnks) assembled on the device, field-major:
 //   out[ 0.. 3] parcube1   out[ 4.. 7] errcube1   out[ 8..15] parcube2   out[16..23] errcube2
 //   out[24..31] best parcube: the 2-component fit where ncomp == 2; the 1-component fit in planes 0-3 and NaN in
 //               4-7 where ncomp == 1; NaN where ncomp == 0            out[32..39] best errcube, likewise
 //   out[40..42] lnk10, lnk20, lnk21 (NaN where the fit does not exist)   out[43] ncomp
 // One thread per pixel; every plane is written coalesced.  This is what a partitioned run gathers: [44][npix] rows.
-constexpr int PACK_FIELDS = 44;
+constexpr int PACK_FIELDS = B200FIT_PACK_FIELDS;
 __global__ void __launch_bounds__(256)
     pack_selection_kernel(long long npix, const double* __restrict__ params1, const double* __restrict__ perr1,
                           const double* __restrict__ params2, const double* __restrict__ perr2,
@@ -2106,6 +2132,26 @@ int b200fit_aicc(b200fit_ctx* ctx, const b200fit_problem* prob, const float* d_s
                  void* stream) {
     return b200fit_aicc_pair(ctx, prob, 1, 2, d_spectra, nchan_stride, d_row_index, d_params1, d_params2, d_fill_bits,
                              only_empty, expand, model_f32, thr, d_rss, d_nsamp, d_lnk, d_ncomp, d_mask_counts, stream);
+}
+
+int b200fit_prepare_guesses(b200fit_ctx* ctx, int64_t npix, int32_t npar, const double* d_raw, const double* lo,
+                            const double* hi, double eps, double* d_guesses, void* stream) {
+    if (!ctx) return B200FIT_E_ARG;
+    if (npix == 0) return B200FIT_OK;
+    if (!d_raw || !d_guesses || !lo || !hi || npix < 0 || (npar != 4 && npar != 8))
+        return fail(ctx, B200FIT_E_ARG, "prepare_guesses: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    DeviceLimits lim;
+    for (int j = 0; j < 8; ++j) {
+        lim.lo[j] = (j < npar) ? lo[j] : 0.0;
+        lim.hi[j] = (j < npar) ? hi[j] : 0.0;
+    }
+    long long blocks = (npix + 255) / 256;
+    if (blocks > (long long)ctx->num_sms * 16) blocks = (long long)ctx->num_sms * 16;
+    prepare_guesses_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(npix, npar, d_raw, lim, eps, d_guesses);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    return B200FIT_OK;
 }
 
 int b200fit_pack_selection(b200fit_ctx* ctx, int64_t npix, const double* d_params1, const double* d_perr1,

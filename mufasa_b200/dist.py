@@ -26,6 +26,49 @@ def partition_rows(ny, world, rank):
     return y0, y0 + base + (1 if rank < extra else 0)
 
 
+ROW_BLOCK = 8
+
+
+def partition_row_blocks(ny, world, rank, block=ROW_BLOCK):
+    """Rows of rank ``rank`` under the BLOCK-CYCLIC partition: blocks of ``block`` consecutive rows are dealt to the
+    ranks round-robin (ascending row indices, int64 array).  Spectra differ a lot in cost (a 2-component fit of a
+    faint or single-component spectrum takes several times the evaluations of a clean one) and the cost varies
+    smoothly over the sky, so contiguous slabs leave the ranks unevenly loaded; interleaved blocks do not."""
+    import numpy as np
+    ny, world, rank, block = int(ny), int(world), int(rank), int(block)
+    if world < 1 or not (0 <= rank < world) or block < 1:
+        raise ValueError("bad world/rank/block")
+    nblocks = -(-ny // block)
+    rows = [np.arange(b * block, min(ny, (b + 1) * block)) for b in range(rank, nblocks, world)]
+    return np.concatenate(rows).astype(np.int64) if rows else np.zeros(0, dtype=np.int64)
+
+
+def owned_rows(ny, world, rank, partition="cyclic"):
+    """Row indices of a rank: ``partition`` = 'cyclic' (partition_row_blocks) or 'slabs' (partition_rows)."""
+    import numpy as np
+    if partition == "slabs" or world == 1:
+        y0, y1 = partition_rows(ny, world, rank)
+        return np.arange(y0, y1, dtype=np.int64)
+    if partition != "cyclic":
+        raise ValueError("partition must be 'cyclic' or 'slabs'")
+    return partition_row_blocks(ny, world, rank)
+
+
+def take_rows(cube, rows):
+    """[nchan, len(rows), nx] C-contiguous array of the given rows of ``cube``: a plain ndarray [nchan, ny, nx], or
+    any object with a ``take_rows(rows)`` method (a loader that holds / reads only this rank's rows)."""
+    import numpy as np
+    if hasattr(cube, "take_rows"):
+        return cube.take_rows(rows)
+    if len(rows) and int(rows[-1]) - int(rows[0]) + 1 == len(rows):
+        slab = cube[:, int(rows[0]):int(rows[-1]) + 1, :]
+    else:
+        slab = cube[:, rows, :]
+    if not (isinstance(slab, np.ndarray) and slab.flags["C_CONTIGUOUS"]):
+        slab = np.ascontiguousarray(slab)
+    return slab
+
+
 def _world(group=None):
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group), dist.get_rank(group)
@@ -89,19 +132,58 @@ def gather_maps(local, ny, group=None, dst=0):
     return out
 
 
-def aicc_distributed(engine, prob, rows, params1, params2, first_pixel, expand=20, model_f32=True,
-                     thr=(5.0, 5.0, 5.0), row_index=None, group=None):
+def gather_rows(local, ny, partition="cyclic", group=None, dst=0):
+    """``gather_maps`` for any row partition: ``local[..., ry, nx]`` holds the rows ``owned_rows(ny, world, rank,
+    partition)`` of this rank; returns ``[..., ny, nx]`` on rank ``dst`` (None elsewhere).  One collective."""
+    world, rank = _world(group)
+    if world == 1 or partition == "slabs":
+        return gather_maps(local, ny, group=group, dst=dst)
+    lead, nx = local.shape[:-2], local.shape[-1]
+    rmax = max(len(owned_rows(ny, world, r, partition)) for r in range(world))
+    if local.shape[-2] == rmax:
+        pad = local.contiguous()
+    else:
+        pad = torch.zeros(lead + (rmax, nx), dtype=local.dtype, device=local.device)
+        pad[..., :local.shape[-2], :] = local
+    if rank == dst:
+        buf = torch.empty((world,) + tuple(pad.shape), dtype=local.dtype, device=local.device)
+        pieces = list(buf.unbind(0))
+    else:
+        pieces = None
+    dist.gather(pad, pieces, dst=_global_rank(group, dst), group=group)
+    if rank != dst:
+        return None
+    out = torch.empty(lead + (int(ny), nx), dtype=local.dtype, device=local.device)
+    for r, t in enumerate(pieces):
+        rows = torch.from_numpy(owned_rows(ny, world, r, partition)).to(local.device)
+        out.index_copy_(len(lead), rows, t[..., :rows.numel(), :])
+    return out
+
+
+def aicc_distributed(engine, prob, rows, params1, params2, first_pixel=0, expand=20, model_f32=True,
+                     thr=(5.0, 5.0, 5.0), row_index=None, group=None, local_to_global=None):
     """``Engine.aicc_global`` across ranks: pass 1 on the local pixels, global arg-max of the un-dilated mask size,
     the owner evaluates that pixel's mask bits and broadcasts them, pass 2 redoes the local empty-mask pixels.
-    ``first_pixel`` = global flat index of this rank's first pixel (y0 * nx)."""
+    ``first_pixel`` = global flat index of this rank's first pixel (y0 * nx) for a contiguous slab;
+    ``local_to_global`` (callable: local flat index -> global flat index, monotonic) for any other partition."""
     world, rank = _world(group)
     out = engine.aicc_alloc(int(prob.npix))
     engine.aicc_pass(prob, rows, params1, params2, out, expand=expand, model_f32=model_f32, thr=thr,
                      row_index=row_index)
-    best = engine.mask_argmax(out["mask_counts"], index_offset=first_pixel)
+    if local_to_global is None:
+        best = engine.mask_argmax(out["mask_counts"], index_offset=first_pixel)
+        to_local = lambda g: g - first_pixel
+    else:
+        # the first local pixel holding the local maximum is also the one with the lowest GLOBAL index (the map is
+        # monotonic); its global index enters the comparison across ranks
+        best = engine.mask_argmax(out["mask_counts"], index_offset=0)
+        c_loc, i_loc = (int(x) for x in best.tolist())
+        best = torch.tensor([c_loc, int(local_to_global(i_loc)) if c_loc > 0 else 0], dtype=torch.int64,
+                            device=best.device)
+        to_local = lambda g, _i=i_loc: _i
     count, index, owner = global_best(best, group=group)
     if rank == owner and count > 0:
-        bits = engine.mask_bits(prob, params1, params2, pix=index - first_pixel, model_f32=model_f32)
+        bits = engine.mask_bits(prob, params1, params2, pix=to_local(index), model_f32=model_f32)
     else:
         bits = torch.zeros(64, dtype=torch.int32, device=engine.device)
     if world > 1:
@@ -169,26 +251,27 @@ class SelectionJob(object):
     to time or repeat: ``__init__`` = host work on the guesses + upload of the slab and the guesses; ``run`` =
     everything on the device, from the two fits to the gathered result block; ``to_host`` = the one copy back."""
 
-    def __init__(self, cube, v_kms, fittype, guesses1, guesses2, device=None, group=None, vstats=None):
+    def __init__(self, cube, v_kms, fittype, guesses1, guesses2, device=None, group=None, vstats=None,
+                 partition="cyclic"):
         import numpy as np
         from . import _abi
         from . import multi_v_fit as mvf
         from .cube import SpecCube
         from .engine import get_engine
-        from .exceptions import SNRMaskError, StartFitError
         from .pcube import PCube
+        from .spec_models.meta_model import MetaModel
         self.group = group
         self.world, self.rank = _world(group)
         nchan, ny, nx = cube.shape
         self.ny, self.nx, self.fittype = int(ny), int(nx), fittype
-        y0, y1 = partition_rows(ny, self.world, self.rank)
-        self.y0, self.ry = y0, y1 - y0
+        self.partition = partition
+        self.rows = rows = owned_rows(ny, self.world, self.rank, partition)
+        self.ry = int(rows.size)
         self.npix = npix = self.ry * nx
+        contiguous = self.ry == 0 or int(rows[-1]) - int(rows[0]) + 1 == self.ry
         dev = torch.cuda.current_device() if device is None else device
         self.eng = eng = get_engine(dev)
-        slab = cube[:, y0:y1, :]
-        if not (isinstance(slab, np.ndarray) and slab.flags["C_CONTIGUOUS"]):
-            slab = np.ascontiguousarray(slab)
+        slab = take_rows(cube, rows)
         spec = SpecCube(slab, v_kms)
         self.model_f32 = spec._data.dtype == np.float32
         self.ref = ref = PCube(spec._data, spec.xarr(), header=spec.header, unit=spec.unit, device=dev)
@@ -197,22 +280,44 @@ class SelectionJob(object):
         if vstats is None:
             vstats = {1: global_vstats(guesses1[::4], eng.device), 2: global_vstats(guesses2[::4], eng.device)}
         self.vstats = vstats
-        # the two drivers: host work on the guesses, then the device-side job descriptions; nothing is fitted yet
+        # The front half of cubefit_simp (multi_v_fit.py:126-190) for both models, ON THE DEVICE: the rank's rows of the
+        # guess maps go up as they are (through one pinned staging buffer, on a second stream, while the cube is
+        # uploading), b200fit_prepare_guesses turns zero velocities into NaN and moves every value inside the limits,
+        # and every pixel of the slab enters the fit -- the fit kernel itself reports a pixel with a non-finite guess
+        # as "not fitted" (zeros), which is what the reference's maskmap & all-finite rule comes to.  On the host this
+        # conditioning costs ~0.2 s per 1024 x 1024 map (copies, masks, clamps) and sat in front of the fits.
         self.batch, self.jobs = [], {}
+        main = torch.cuda.current_stream(eng.device)
+        up = eng.side_stream("h2d")
         for nc, full in ((1, guesses1), (2, guesses2)):
-            g = np.array(full[:, y0:y1, :], dtype=np.float64)
-            p = PCube(spec._data, spec.xarr(), header=spec.header, unit=spec.unit, device=dev)
-            p.share_device(ref)
-            p._deferred = self.batch
-            before = len(self.batch)
-            try:
-                if npix:
-                    mvf.cubefit_simp(spec, p, ncomp=nc, guesses=g, fittype=fittype, vstats=vstats[nc])
-            except (SNRMaskError, StartFitError, AssertionError, ValueError):
-                del self.batch[before:]                      # this slab has nothing to fit for this model
-            finally:
-                p._deferred = None
-            self.jobs[nc] = before if len(self.batch) > before else None
+            P = 4 * nc
+            mm = MetaModel(fittype, nc)
+            v_median, v_99p, v_1p = vstats[nc]
+            if not npix or not np.isfinite(v_median):        # no finite velocity guess anywhere: nothing to fit
+                self.jobs[nc] = None
+                continue
+            vmax, vmin = v_median + 10, v_median - 10        # multi_v_fit.py:163-176
+            if v_99p + mm.sigmax > vmax:
+                vmax = v_99p + mm.sigmax
+            if v_1p - mm.sigmax < vmin:
+                vmin = v_1p - mm.sigmax
+            lo, hi = mm.limits(vmin, vmax)
+            stage = eng.pinned_stage(("rawguess", P, self.ry, nx))
+            if contiguous:
+                np.copyto(stage.numpy(), full[:, int(rows[0]):int(rows[-1]) + 1, :])
+            else:
+                np.take(full, rows, axis=1, out=stage.numpy())
+            with torch.cuda.stream(up):
+                raw = stage.to(eng.device, non_blocking=True).reshape(P, npix)
+                g_dev = eng.prepare_guesses(raw, lo, hi, mm.eps)
+                ready = torch.cuda.Event()
+                ready.record(up)
+            g_dev.record_stream(main)
+            prob = ref._problem(fittype, nc, npix, lo, hi, signal_cut=0.0)
+            self.jobs[nc] = len(self.batch)
+            self.batch.append(dict(prob=prob, spectra=ref.rows_on_device(wait=False), guesses=g_dev, row_index=None,
+                                   pcube=None, pix=None, ready=ready, slab_ready=ref._dev.get("slab_ready"),
+                                   lo=lo, hi=hi))
         if npix:
             self.prob = ref._problem(fittype, 1, npix, [-1e30] * 4, [1e30] * 4)
         else:                                                # an empty slab still answers the collectives
@@ -253,13 +358,15 @@ class SelectionJob(object):
                 fits[nc] = dict(params=full_p, perr=full_e, status=out["status"], counts=out.get("counts"))
         self.fits = fits
         rows = self.ref.rows_on_device() if npix else self._no_rows
+        nx, owned = self.nx, self.rows
         self.sel = sel = aicc_distributed(eng, self.prob, rows, fits[1]["params"], fits[2]["params"],
-                                          first_pixel=self.y0 * self.nx, model_f32=self.model_f32, group=self.group)
+                                          model_f32=self.model_f32, group=self.group,
+                                          local_to_global=lambda i: int(owned[i // nx]) * nx + i % nx)
         packed = eng.pack_selection(fits[1], fits[2], sel).reshape(_abi.PACK_FIELDS, self.ry, self.nx)
         if gather and self.world > 1:
             if dist.get_backend(self.group) != "nccl":
                 packed = packed.cpu()
-            packed = gather_maps(packed, self.ny, group=self.group, dst=0)
+            packed = gather_rows(packed, self.ny, partition=self.partition, group=self.group, dst=0)
         return packed
 
     def to_host(self, packed):
@@ -273,12 +380,15 @@ class SelectionJob(object):
         return {name: (host[a] if b - a == 1 else host[a:b]) for name, a, b in FIELDS}
 
 
-def fit_and_select(cube, v_kms, fittype, guesses1, guesses2, device=None, group=None, gather=True, vstats=None):
+def fit_and_select(cube, v_kms, fittype, guesses1, guesses2, device=None, group=None, gather=True, vstats=None,
+                   partition="cyclic"):
     """The model-selection job (1c fit + 2c fit + AICc 0/1/2 selection; UltraCube.fit_cube([1, 2], simpfit=True) +
-    get_best_2c_parcube) on a cube partitioned by row slabs over the ranks of ``group``.
+    get_best_2c_parcube) on a cube partitioned by blocks of rows over the ranks of ``group``: ``partition`` =
+    'cyclic' (blocks of ROW_BLOCK rows dealt round-robin: even load, see partition_row_blocks) or 'slabs' (one
+    contiguous slab per rank).
 
-    ``cube`` [nchan, ny, nx], ``guesses1`` [4, ny, nx], ``guesses2`` [8, ny, nx]: the WHOLE arrays on every rank
-    (each rank touches only its slab; a loader that reads slabs directly can pass views of a larger virtual array).
+    ``cube`` [nchan, ny, nx] (or a loader object with ``shape`` and ``take_rows(rows)``), ``guesses1`` [4, ny, nx],
+    ``guesses2`` [8, ny, nx]: the WHOLE arrays on every rank (each rank touches only its rows).
     Global couplings are resolved before partitioning: cubefit_simp's velocity window comes from the statistics of
     the whole guess map (``vstats`` = {1: (median, p99, p1), 2: ...} if the caller has them, else computed here on
     the GPU), the include_nosamp fill mask from ``aicc_distributed``.  Per-pixel results are identical to a
@@ -294,5 +404,6 @@ def fit_and_select(cube, v_kms, fittype, guesses1, guesses2, device=None, group=
     Returns dict(parcube1, errcube1, parcube2, errcube2, best_parcube, best_errcube, lnk10, lnk20, lnk21, ncomp) of
     [.., ny, nx] numpy arrays on rank 0 (None elsewhere) when ``gather``, else the slab's.  The arrays are views of
     a pinned staging buffer that the next call on this device reuses: copy what must outlive it."""
-    job = SelectionJob(cube, v_kms, fittype, guesses1, guesses2, device=device, group=group, vstats=vstats)
+    job = SelectionJob(cube, v_kms, fittype, guesses1, guesses2, device=device, group=group, vstats=vstats,
+                       partition=partition)
     return job.to_host(job.run(gather=gather))

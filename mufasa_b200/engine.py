@@ -358,6 +358,19 @@ class Engine(object):
         out["fill_bits"] = bits
         return out
 
+    def prepare_guesses(self, raw, lo, hi, eps):
+        """cubefit_simp's conditioning of the guesses on the device (b200fit_prepare_guesses): ``raw`` [P, npix] fp64
+        field-major device tensor -> [npix, P] with zero velocities -> NaN and every value moved inside [lo, hi]."""
+        P, npix = (int(x) for x in raw.shape)
+        assert raw.dtype == torch.float64 and raw.is_contiguous() and P in (4, 8) and len(lo) == P and len(hi) == P
+        out = torch.empty((npix, P), dtype=torch.float64, device=self.device)
+        lo_a = (C.c_double * P)(*[float(x) for x in lo])
+        hi_a = (C.c_double * P)(*[float(x) for x in hi])
+        rc = self.lib.b200fit_prepare_guesses(self.ctx, npix, P, _ptr(raw), C.cast(lo_a, C.c_void_p),
+                                              C.cast(hi_a, C.c_void_p), float(eps), _ptr(out), self._stream())
+        self._check(rc, "b200fit_prepare_guesses")
+        return out
+
     def pack_selection(self, fit1, fit2, sel, out=None):
         """get_best_2c_parcube assembled on the device (b200fit_pack_selection): ``fit1`` / ``fit2`` = result dicts
         of the 1- and 2-component fits over the same pixels (params, perr), ``sel`` = output of aicc_global /

@@ -31,7 +31,9 @@ def gpu_modelcube(parcube, v, ft):
 ny = int(os.environ.get("DIST_NY", "61"))                 # odd: uneven slabs
 syn = synth.make_cube(2, gpu_modelcube, rows=(100, 100 + ny), shape=(256, 96, 800))
 t0 = time.perf_counter()
-res = D.fit_and_select(syn["cube"], syn["v"], syn["fittype"], syn["guess1"].copy(), syn["guess2"].copy(), device=local)
+PART = os.environ.get("DIST_PARTITION", "cyclic")
+res = D.fit_and_select(syn["cube"], syn["v"], syn["fittype"], syn["guess1"].copy(), syn["guess2"].copy(), device=local,
+                       partition=PART)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 if res is not None:
@@ -48,8 +50,8 @@ if rank == 0:
         same = np.array_equal(res[k], single[k], equal_nan=True)
         ok = ok and same
         print("%-13s %s  identical to single GPU: %s" % (k, res[k].shape, same))
-    print("world %d: partitioned job %.1f ms; ncomp hist %s; ALL IDENTICAL: %s" % (
-        world, dt * 1e3, np.bincount(res["ncomp"].astype(int).ravel(), minlength=3).tolist(), ok))
+    print("partition %s, world %d: partitioned job %.1f ms; ncomp hist %s; ALL IDENTICAL: %s" % (
+        PART, world, dt * 1e3, np.bincount(res["ncomp"].astype(int).ravel(), minlength=3).tolist(), ok))
     assert ok
 dist.barrier()
 dist.destroy_process_group()

@@ -197,3 +197,23 @@ def test_regrid_many_equals_map_by_map_regrid():
     many = regrid_many(maps, hc, h)
     for k in range(5):
         np.testing.assert_array_equal(many[k], regrid(maps[k], hc, h))
+
+
+def test_beam_deconvolution_at_any_position_angle():
+    """Beam.deconvolve (radio_beam's relations for two elliptical Gaussians, convolve_tools.py:90-138) undoes
+    Beam.convolve (second-moment matrices add -- an independent route) for beams at different position angles."""
+    from mufasa_b200.convolve_tools import Beam
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        maj = rng.uniform(1, 3)
+        b2 = Beam(maj, maj * rng.uniform(0.3, 1), rng.uniform(-90, 90))
+        majk = rng.uniform(1, 3)
+        k = Beam(majk, majk * rng.uniform(0.3, 1), rng.uniform(-90, 90))
+        d = b2.convolve(k).deconvolve(b2)
+        dpa = abs(((d.pa - k.pa) + 90) % 180 - 90)
+        assert abs(d.major - k.major) < 1e-9 and abs(d.minor - k.minor) < 1e-9
+        assert np.radians(dpa) * (k.major - k.minor) < 1e-9          # the angle matters only for elongated beams
+    same = Beam(5, 3, 30).deconvolve(Beam(3, 2, 30))
+    assert abs(same.major - 4.0) < 1e-12 and abs(same.minor - np.sqrt(5.0)) < 1e-12 and same.pa == 30.0
+    with pytest.raises(ValueError):
+        Beam(3, 2, 10).deconvolve(Beam(3, 2.5, 60))

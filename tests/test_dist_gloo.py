@@ -21,6 +21,23 @@ def test_partition_rows_covers_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_block_cyclic_partition_covers_everything_evenly():
+    for ny in (1, 7, 64, 1024, 1027):
+        for world in (1, 2, 3, 8):
+            rows = [D.partition_row_blocks(ny, world, r) for r in range(world)]
+            allr = np.sort(np.concatenate(rows))
+            assert np.array_equal(allr, np.arange(ny))
+            for r in rows:
+                assert np.all(np.diff(r) > 0)                       # ascending: local order == global order
+            if ny % (D.ROW_BLOCK * world) == 0:
+                assert len({len(r) for r in rows}) == 1
+    assert np.array_equal(D.owned_rows(10, 1, 0, "cyclic"), np.arange(10))
+    assert np.array_equal(D.owned_rows(20, 2, 1, "slabs"), np.arange(10, 20))
+    cube = np.arange(2 * 20 * 3).reshape(2, 20, 3)
+    rows = D.partition_row_blocks(20, 2, 1)
+    assert np.array_equal(D.take_rows(cube, rows), cube[:, rows, :]) and D.take_rows(cube, rows).flags["C_CONTIGUOUS"]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -47,6 +64,12 @@ def _worker(rank, world, port, ny, nx, q):
         e0, e1 = D.partition_rows(ne, world, rank)
         got = D.gather_maps(full_e[:, :, e0:e1, :].contiguous(), ne)
         assert (rank == 0 and torch.equal(got, full_e)) or (rank != 0 and got is None)
+        # block-cyclic rows (blocks of ROW_BLOCK rows dealt round-robin), ragged last block
+        nc = 2 * D.ROW_BLOCK * world + 3
+        full_c = torch.arange(3 * nc * nx, dtype=torch.float64).reshape(3, nc, nx)
+        mine = torch.from_numpy(D.owned_rows(nc, world, rank, "cyclic"))
+        got = D.gather_rows(full_c[:, mine, :].contiguous(), nc, partition="cyclic")
+        assert (rank == 0 and torch.equal(got, full_c)) or (rank != 0 and got is None)
         # global arg-max of the mask sizes: largest count, ties -> lowest GLOBAL index
         counts = torch.tensor([[5, 40], [7, 3]])            # rank 0: (count 5 at pixel 40); rank 1: (7 at 3)
         c, i, owner = D.global_best(counts[rank].clone())

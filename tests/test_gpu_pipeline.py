@@ -305,9 +305,19 @@ def test_dist_fit_and_select_single_rank_matches_ultracube():
     get_best_2c_parcube.  The 2-GPU run is checked bit for bit by profiles/dist_check.py under torchrun."""
     from mufasa_b200 import dist as D
     syn = synth.make_cube(2, T.oracle_modelcube, rows=(100, 104), shape=(200, 32, 800))
-    res = D.fit_and_select(syn["cube"], syn["v"], syn["fittype"], syn["guess1"].copy(), syn["guess2"].copy(), device=0)
+    # guesses that exercise cubefit_simp's conditioning (done on the device by the partitioned job, on the host by
+    # UltraCube): a zero velocity (= no guess), values outside the limits, NaNs
+    g1, g2 = syn["guess1"].copy(), syn["guess2"].copy()
+    g1[0, 1, 3] = 0.0
+    g1[1, 2, 5], g1[3, 2, 6], g1[2, 0, 7] = 9.0, 1e-3, 100.0
+    g2[:, 0, 0] = np.nan
+    g2[5, 2, 4], g2[6, 3, 9], g2[4, 1, 1] = 100.0, 0.5, 0.0
+    res = D.fit_and_select(syn["cube"], syn["v"], syn["fittype"], g1.copy(), g2.copy(), device=0)
+    res = {k: v.copy() for k, v in res.items()}
     uc = _ucube(syn)
-    uc.fit_cube(ncomp=[1, 2], simpfit=True, guesses={1: syn["guess1"].copy(), 2: syn["guess2"].copy()})
+    uc.fit_cube(ncomp=[1, 2], simpfit=True, guesses={1: g1.copy(), 2: g2.copy()})
+    assert not uc.pcubes["1"].has_fit[1, 3] and not uc.pcubes["2"].has_fit[0, 0] and not uc.pcubes["2"].has_fit[1, 1]
+    assert uc.pcubes["1"].has_fit[2, 5] and uc.pcubes["2"].has_fit[2, 4]
     par, err, l10, l20, l21 = uc.get_best_2c_parcube()
     assert np.array_equal(res["parcube2"], uc.pcubes["2"].parcube)
     assert np.array_equal(res["best_parcube"], par, equal_nan=True)
