@@ -421,7 +421,8 @@ def run_b200(args):
     frac_exec = {"xu": sfu_exec / t_eval / pk["xu"], "fp32": f32_exec / t_eval / pk["fp32"]}
     t2 = (prof2["prologue_ms"] + prof2["eval_ms"] + prof2["solve_ms"]) * 1e-3   # one 2c fit of this slab on its own
     hbm_bytes = npix_r * (nchan * 4 + P * 8 + (2 * P + 2) * 8 + 4 + 16)
-    traffic = ncu_traffic_per_eval() * evals / launches_eval
+    row_bytes = (nchan + 31) // 32 * 32 * 4
+    traffic = ncu_traffic_per_eval(row_bytes) * evals / launches_eval
     roofline = {"bound": "xu", "kernel": "fit_eval_kernel<2>", "achieved": sfu_exec / t_eval / 1e12,
                 "peak": pk["xu"] / 1e12, "unit": "Top/s", "frac": frac_exec["xu"],
                 "definition": "EXECUTED ex2 (gaussians inside the 6.2-sigma windows + one e^-tau per channel and "
@@ -431,8 +432,10 @@ def run_b200(args):
                 "algorithmic_definition": "SURVEY 8d per-evaluation figures x evaluations counted by the kernel; the "
                                           "kernel skips gaussians beyond 6.2 sigma (exactly 0 in fp32), ~90 % of them",
                 "traffic": traffic,
-                "traffic_source": "dram bytes per pixel-evaluation of the latest ncu --set full capture under "
-                                  "profiles/ (%.0f B) x evaluations per launch of this run" % ncu_traffic_per_eval(),
+                "traffic_source": "dram bytes per pixel-evaluation from the latest ncu --set full capture under "
+                                  "profiles/ (NCU_TRAFFIC.json: %.0f B at this row length; algorithmic %d B) x "
+                                  "evaluations per launch of this run" % (ncu_traffic_per_eval(row_bytes),
+                                                                          row_bytes + 112 + 360 + 4),
                 "peak_source": "derived: %d SMs x 16 XU lanes x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json, %s)" % (
                     nsm, peaks["sm_max_mhz"], peaks["source"]),
                 "hbm": {"achieved": hbm_bytes / t2 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -485,16 +488,15 @@ def run_b200(args):
     return 0
 
 
-def ncu_traffic_per_eval():
-    """dram__bytes_read.sum + dram__bytes_write.sum per pixel-evaluation of fit_eval_kernel<2> from the latest
+def ncu_traffic_per_eval(row_bytes):
+    """dram__bytes_read.sum + dram__bytes_write.sum per pixel-evaluation of fit_eval_kernel<2>, from the latest
     ncu --set full capture of a launch with every pixel active (profiles/NCU_TRAFFIC.json, written next to the
-    capture's summary)."""
+    capture's summary): the part that does not depend on the channel count (per-pixel inputs, normal equations out)
+    as measured, plus the spectrum row of THIS workload (the kernel stages the whole row once per evaluation; the
+    capture's own row accounted for its 800 channels to within 5 %)."""
     path = os.path.join(ROOT, "profiles", "NCU_TRAFFIC.json")
-    try:
-        with open(path) as f:
-            return float(json.load(f)["dram_bytes_per_pixel_eval"])
-    except Exception:
-        return (166.019072e6 + 19.493888e6) / 65536.0   # profiles/r1m_fit2c_ncu_full_summary.txt
+    with open(path) as f:
+        return float(json.load(f)["dram_bytes_per_pixel_eval_minus_row"]) + float(row_bytes)
 
 
 def main():

@@ -192,6 +192,16 @@ int b200fit_aicc_pair(b200fit_ctx* ctx, const b200fit_problem* prob, int32_t nco
                       const double* d_params1, const double* d_params2, const uint32_t* d_fill_bits,
                       int32_t only_empty, int32_t expand, int32_t model_f32, const double* thr, double* d_rss,
                       double* d_nsamp, double* d_lnk, signed char* d_ncomp, int32_t* d_mask_counts, void* stream);
+/* The same with the caller's spectral mask: d_mask_bits [npix][B200FIT_MAX_NCHAN / 32] (bit b of word w = channel
+ * 32 w + b; NULL = b200fit_aicc_pair) replaces (model A > 0) | (model B > 0) as the un-dilated mask of every pixel --
+ * UltraCube.get_rss(ncomp, mask=...) / get_AICc(..., mask=...), mufasa/UltraCube.py:432-451, :474-486.  The
+ * include_nosamp rule and the dilation apply to it as they do to the model mask (:1423-1451). */
+int b200fit_aicc_pair_masked(b200fit_ctx* ctx, const b200fit_problem* prob, int32_t ncomp_a, int32_t ncomp_b,
+                             const float* d_spectra, int64_t nchan_stride, const int64_t* d_row_index,
+                             const double* d_params1, const double* d_params2, const uint32_t* d_mask_bits,
+                             const uint32_t* d_fill_bits, int32_t only_empty, int32_t expand, int32_t model_f32,
+                             const double* thr, double* d_rss, double* d_nsamp, double* d_lnk, signed char* d_ncomp,
+                             int32_t* d_mask_counts, void* stream);
 int b200fit_mask_bits_pair(b200fit_ctx* ctx, const b200fit_problem* prob, int32_t ncomp_a, int32_t ncomp_b,
                            const double* d_params1, const double* d_params2, int32_t model_f32, const int64_t* d_best,
                            int64_t pix, uint32_t* d_bits, void* stream);

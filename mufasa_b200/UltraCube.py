@@ -361,21 +361,70 @@ class UltraCube(object):
         if kernel_thr != thr:
             self._select_ncomp(thr)
 
-    def get_rss(self, ncomp, mask=None, planemask=None, update=True, expand=20):
-        """Residual sum of squares over the dilated union model mask (UltraCube.py:432-451)."""
-        if mask is not None or planemask is not None:
-            raise NotImplementedError("custom masks belong to the refit loop (SURVEY.md 8f #3)")
-        self._run_aicc(expand=expand)
-        return self.rss_maps[str(ncomp)]
+    def _masked_stats(self, mask, expand):
+        """rss_0/1/2 and N over the caller's spectral mask ``mask`` [nchan, ny, nx] bool (dilated by ``expand``, empty
+        pixels filled by the include_nosamp rule, UltraCube.py:1423-1451): one b200fit_aicc_pair_masked pass.
+        Returns (rss [3, ny, nx], nsamp [ny, nx])."""
+        ref = self._ref_pcube if self._ref_pcube is not None else self.load_pcube()
+        eng = ref.engine
+        nchan, ny, nx = self.cube.shape
+        mask = np.asarray(mask, dtype=bool)
+        if mask.shape != (nchan, ny, nx):
+            raise ValueError("mask must be [nchan, ny, nx]")
+        if ref.xarr.v0_dv_flip[2]:
+            mask = mask[::-1]                                 # the device rows run along ascending velocity
+        packed = np.packbits(mask, axis=0, bitorder="little")              # [ceil(nchan / 8), ny, nx] uint8
+        words = np.zeros((ny * nx, 256), dtype=np.uint8)                   # 64 words of 32 bits per pixel
+        words[:, :packed.shape[0]] = packed.reshape(packed.shape[0], ny * nx).T
+        bits = torch.from_numpy(words.view(np.int32)).to(eng.device)
+        prob = ref._problem(self.fittype, 1, ny * nx, [-1e30] * 4, [1e30] * 4)
+        out = eng.aicc_global(prob, ref.rows_on_device(), self._params_dev(1, eng), self._params_dev(2, eng),
+                              expand=expand, model_f32=self.cube._data.dtype == np.float32, mask_bits=bits)
+        host = torch.cat([out["rss"], out["nsamp"][:, None]], dim=1).t().contiguous().cpu().numpy()
+        return host[0:3].reshape(3, ny, nx), host[3].reshape(ny, nx)
 
-    def get_AICc(self, ncomp, update=False, planemask=None, expand=20, **kwargs):
-        """UltraCube.py:474-486 (p = 4 * ncomp; ncomp = 0: model == 0, no free parameter)."""
-        if planemask is not None:
-            raise NotImplementedError("planemask updates belong to the refit loop (SURVEY.md 8f #3)")
-        if update:
-            self.lnk_maps.clear()
-        self._run_aicc(expand=expand)
-        return self.AICc_maps[str(ncomp)]
+    def get_rss(self, ncomp, mask=None, planemask=None, update=True, expand=20):
+        """Residual sum of squares of the ``ncomp``-component model (0: y = 0) over the dilated mask
+        (UltraCube.py:432-451): ``mask`` None = the union model mask (master_model_mask), else the caller's
+        [nchan, ny, nx] bool cube; ``planemask`` [ny, nx]: only these pixels of the stored maps are updated."""
+        compID = str(ncomp)
+        if mask is None:
+            self._run_aicc(expand=expand)
+            if planemask is None:
+                return self.rss_maps[compID]
+            return self.rss_maps[compID]          # the default maps are whole-map results already
+        rss3, nsamp = self._masked_stats(mask, expand)
+        with np.errstate(invalid="ignore"):
+            rss = rss3[int(ncomp)].copy()
+            ns = np.where(np.isnan(rss), np.nan, nsamp)
+        if planemask is None or compID not in self.rss_maps:
+            self.rss_maps[compID], self.NSamp_maps[compID] = rss, ns
+        else:
+            self.rss_maps[compID][planemask] = rss[planemask]
+            self.NSamp_maps[compID][planemask] = ns[planemask]
+        return self.rss_maps[compID]
+
+    def get_AICc(self, ncomp, update=False, planemask=None, expand=20, mask=None, **kwargs):
+        """UltraCube.py:474-486 (p = 4 * ncomp; ncomp = 0: model == 0, no free parameter).  With ``mask`` (the
+        reference forwards it to get_rss through **kwargs) the statistics are taken over the caller's mask and stored,
+        inside ``planemask`` when given, like the reference does."""
+        compID = str(ncomp)
+        if mask is None:
+            if update and planemask is None:
+                self.lnk_maps.clear()
+            self._run_aicc(expand=expand)
+            return self.AICc_maps[compID]
+        self._run_aicc(expand=expand)              # the other maps exist before one of them is overwritten
+        self.get_rss(ncomp, mask=mask, planemask=planemask, expand=expand)
+        p = 4 * int(ncomp)
+        with np.errstate(all="ignore"):
+            rss, ns = self.rss_maps[compID], self.NSamp_maps[compID]
+            fresh = ns * np.log(rss / ns) + 2 * p + (2 * p * (p + 1)) / (ns - p - 1)
+        if planemask is None:
+            self.AICc_maps[compID] = fresh
+        else:
+            self.AICc_maps[compID][planemask] = fresh[planemask]
+        return self.AICc_maps[compID]
 
     def get_AICc_likelihood(self, ncomp1, ncomp2, **kwargs):
         """ln(L_A / L_B) = (AICc_B - AICc_A) / 2  (calc_AICc_likelihood, UltraCube.py:1120-1216)."""
@@ -519,17 +568,20 @@ def calc_AICc_likelihood(ucube, ncomp_A, ncomp_B, ucube_B=None, multicore=True, 
     if ucube_B is None:
         lnk = ucube.get_AICc_likelihood(ncomp_A, ncomp_B)
         return lnk if planemask is None else lnk[planemask]
-    if ncomp_A not in (1, 2) or ncomp_B not in (1, 2):
-        raise NotImplementedError("the CUDA path compares 1- and 2-component models")
+    if ncomp_A not in (0, 1, 2) or ncomp_B not in (0, 1, 2):
+        raise ValueError("models of 0, 1 or 2 components can be compared")
     ref = ucube._ref_pcube if ucube._ref_pcube is not None else ucube.load_pcube()
     eng = ref.engine
     ny, nx = ucube.cube.shape[1:]
     rows = ref.rows_on_device()
     prob = ref._problem(ucube.fittype, 1, ny * nx, [-1e30] * 4, [1e30] * 4)
-    pA = ucube._params_dev(ncomp_A, eng)
-    pB = ucube_B._params_dev(ncomp_B, eng)
+    # a 0-component model is y = 0 with no free parameter: an all-zero ("no fit") 1-component parameter block
+    kA, kB = max(ncomp_A, 1), max(ncomp_B, 1)
+    zeros = lambda: torch.zeros((ny * nx, 4), dtype=torch.float64, device=eng.device)
+    pA = ucube._params_dev(ncomp_A, eng) if ncomp_A > 0 else zeros()
+    pB = ucube_B._params_dev(ncomp_B, eng) if ncomp_B > 0 else zeros()
     out = eng.aicc_global(prob, rows, pA, pB, expand=expand, model_f32=ucube.cube._data.dtype == np.float32,
-                          ncomp_pair=(ncomp_A, ncomp_B))
+                          ncomp_pair=(kA, kB))
     packed = torch.cat([out["rss"], out["nsamp"][:, None]], dim=1).t().contiguous().cpu().numpy()
     with np.errstate(all="ignore"):
         aicc = []

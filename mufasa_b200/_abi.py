@@ -75,6 +75,8 @@ SIGNATURES = {
                                _vp, _vp]),
     "b200fit_aicc_pair": (C.c_int, [_vp, _PP, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp,
                                     _vp, _vp, _vp, _vp]),
+    "b200fit_aicc_pair_masked": (C.c_int, [_vp, _PP, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp,
+                                           _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200fit_mask_bits_pair": (C.c_int, [_vp, _PP, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "b200fit_mask_argmax": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "b200fit_mask_bits": (C.c_int, [_vp, _PP, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),

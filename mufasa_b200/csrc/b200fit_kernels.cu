@@ -270,17 +270,31 @@ struct LineGroups<B200FIT_MODEL_N2HP_10> {  // -8.0 (1) | -0.6 .. 1.0 (3) | 5.5 
     __host__ __device__ static constexpr int start(int g) { return g == 0 ? 0 : g == 1 ? 1 : g == 2 ? 4 : 7; }
 };
 
-// hyperfine lines a chunk with group mask ``pk`` (bit 8c + g) evaluates per channel: sum of the sizes of its groups
+// hyperfine lines a chunk with group mask ``pk`` (bit 8c + g, c < 2) evaluates per channel: the sizes of its groups
+// summed -- groups of equal size share one population count (roofline accounting only; ``pk`` is warp-uniform)
 template <int MODEL, int NC>
-__device__ __forceinline__ unsigned group_lines(unsigned pk) {
-    using LG = LineGroups<MODEL>;
-    unsigned n = 0;
-#pragma unroll
-    for (int c = 0; c < NC; ++c)
-#pragma unroll
-        for (int g = 0; g < LG::NG; ++g) n += ((pk >> (8 * c + g)) & 1u) * (unsigned)(LG::start(g + 1) - LG::start(g));
-    return n;
+__device__ __forceinline__ unsigned group_lines(unsigned pk);
+template <>
+__device__ __forceinline__ unsigned group_lines<B200FIT_MODEL_NH3_11, 1>(unsigned pk) {   // 2 | 3 | 8 | 3 | 2
+    return 2u * __popc(pk & 0x11u) + 3u * __popc(pk & 0x0au) + 8u * __popc(pk & 0x04u);
 }
+template <>
+__device__ __forceinline__ unsigned group_lines<B200FIT_MODEL_NH3_11, 2>(unsigned pk) {
+    return 2u * __popc(pk & 0x1111u) + 3u * __popc(pk & 0x0a0au) + 8u * __popc(pk & 0x0404u);
+}
+template <>
+__device__ __forceinline__ unsigned group_lines<B200FIT_MODEL_N2HP_10, 1>(unsigned pk) {  // 1 | 3 | 3
+    return __popc(pk & 0x01u) + 3u * __popc(pk & 0x06u);
+}
+template <>
+__device__ __forceinline__ unsigned group_lines<B200FIT_MODEL_N2HP_10, 2>(unsigned pk) {
+    return __popc(pk & 0x0101u) + 3u * __popc(pk & 0x0606u);
+}
+static_assert(LineGroups<B200FIT_MODEL_NH3_11>::start(1) == 2 && LineGroups<B200FIT_MODEL_NH3_11>::start(2) == 5 &&
+                  LineGroups<B200FIT_MODEL_NH3_11>::start(3) == 13 && LineGroups<B200FIT_MODEL_NH3_11>::start(4) == 16 &&
+                  LineGroups<B200FIT_MODEL_NH3_11>::start(5) == 18 && LineGroups<B200FIT_MODEL_N2HP_10>::start(1) == 1 &&
+                  LineGroups<B200FIT_MODEL_N2HP_10>::start(2) == 4 && LineGroups<B200FIT_MODEL_N2HP_10>::start(3) == 7,
+              "group_lines hard-codes the group sizes");
 
 //
 // TEAM = warps per pixel.  TEAM = 1: a warp owns a pixel.  TEAM = EVAL_WARPS: a block owns a pixel and its warps take
@@ -1085,7 +1099,7 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
                 const double* __restrict__ params2, const unsigned* __restrict__ fill_bits, int only_empty, int expand,
                 int model_f32, double thr10, double thr20, double thr21, double* __restrict__ rss_out,
                 double* __restrict__ nsamp_out, double* __restrict__ lnk_out, signed char* __restrict__ ncomp_out,
-                int* __restrict__ mask_counts) {
+                int* __restrict__ mask_counts, const unsigned* __restrict__ ext_bits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ AuxShared sh[AUX_WARPS];
     __shared__ unsigned bits[AUX_WARPS][MASK_WORDS];
@@ -1122,6 +1136,10 @@ __global__ void __launch_bounds__(AUX_WARPS * 32)
             if (lane == 0) bits[warp][wd] = b;
         }
         __syncwarp();
+        if (ext_bits) {   // the caller's spectral mask instead of (model A > 0) | (model B > 0)  (get_rss(mask=...))
+            for (int wd = lane; wd < nwords; wd += 32) bits[warp][wd] = ext_bits[pix * MASK_WORDS + wd];
+            __syncwarp();
+        }
         int cnt = 0;
         for (int wd = lane; wd < nwords; wd += 32) cnt += __popc(bits[warp][wd]);
         cnt = warp_sum_i(cnt);
@@ -2101,6 +2119,17 @@ int b200fit_aicc_pair(b200fit_ctx* ctx, const b200fit_problem* prob, int32_t nco
                       const double* d_params1, const double* d_params2, const uint32_t* d_fill_bits,
                       int32_t only_empty, int32_t expand, int32_t model_f32, const double* thr, double* d_rss,
                       double* d_nsamp, double* d_lnk, signed char* d_ncomp, int32_t* d_mask_counts, void* stream) {
+    return b200fit_aicc_pair_masked(ctx, prob, ncomp_a, ncomp_b, d_spectra, nchan_stride, d_row_index, d_params1,
+                                    d_params2, nullptr, d_fill_bits, only_empty, expand, model_f32, thr, d_rss, d_nsamp,
+                                    d_lnk, d_ncomp, d_mask_counts, stream);
+}
+
+int b200fit_aicc_pair_masked(b200fit_ctx* ctx, const b200fit_problem* prob, int32_t ncomp_a, int32_t ncomp_b,
+                             const float* d_spectra, int64_t nchan_stride, const int64_t* d_row_index,
+                             const double* d_params1, const double* d_params2, const uint32_t* d_mask_bits,
+                             const uint32_t* d_fill_bits, int32_t only_empty, int32_t expand, int32_t model_f32,
+                             const double* thr, double* d_rss, double* d_nsamp, double* d_lnk, signed char* d_ncomp,
+                             int32_t* d_mask_counts, void* stream) {
     if (!ctx || !prob) return fail(ctx, B200FIT_E_ARG, "aicc: null context/problem");
     if (ncomp_a < 1 || ncomp_a > 2 || ncomp_b < 1 || ncomp_b > 2) return fail(ctx, B200FIT_E_ARG, "aicc: ncomp must be 1 or 2");
     DeviceProblem pr;
@@ -2119,7 +2148,7 @@ int b200fit_aicc_pair(b200fit_ctx* ctx, const b200fit_problem* prob, int32_t nco
     if (int rc = ensure_chan_tables(ctx, pr, (cudaStream_t)stream)) return rc;
     aicc_kernel<<<(unsigned)aux_blocks(ctx, pr.npix), AUX_WARPS * 32, smem, (cudaStream_t)stream>>>(
         pr, ctx->d_chan, ncomp_a, ncomp_b, d_spectra, nchan_stride, (const long long*)d_row_index, d_params1, d_params2, d_fill_bits,
-        only_empty, expand, model_f32, t10, t20, t21, d_rss, d_nsamp, d_lnk, d_ncomp, d_mask_counts);
+        only_empty, expand, model_f32, t10, t20, t21, d_rss, d_nsamp, d_lnk, d_ncomp, d_mask_counts, d_mask_bits);
     CK(cudaGetLastError());
     ctx->launches += 1;
     return B200FIT_OK;

@@ -315,11 +315,17 @@ class Engine(object):
                     mask_counts=torch.empty(npix, dtype=torch.int32, device=dev))
 
     def aicc_pass(self, prob, spectra, params1, params2, out, fill_bits=None, only_empty=False, expand=20,
-                  model_f32=True, thr=(5.0, 5.0, 5.0), row_index=None, ncomp_pair=(1, 2)):
+                  model_f32=True, thr=(5.0, 5.0, 5.0), row_index=None, ncomp_pair=(1, 2), mask_bits=None):
+        """``mask_bits`` [npix, 64] int32 device tensor (bit b of word w = channel 32 w + b): the caller's spectral
+        mask instead of the union of the two model masks (b200fit_aicc_pair_masked)."""
         thr_arr = (C.c_double * 3)(*[float(t) for t in thr])
-        rc = self.lib.b200fit_aicc_pair(self.ctx, C.byref(prob), int(ncomp_pair[0]), int(ncomp_pair[1]),
+        if mask_bits is not None:
+            assert mask_bits.dtype == torch.int32 and mask_bits.is_contiguous() and tuple(mask_bits.shape) == (
+                int(prob.npix), 64)
+        rc = self.lib.b200fit_aicc_pair_masked(self.ctx, C.byref(prob), int(ncomp_pair[0]), int(ncomp_pair[1]),
                                    _ptr(spectra), spectra.shape[1], _ptr(row_index),
-                                   _ptr(params1), _ptr(params2), _ptr(fill_bits), 1 if only_empty else 0, int(expand),
+                                   _ptr(params1), _ptr(params2), _ptr(mask_bits), _ptr(fill_bits),
+                                   1 if only_empty else 0, int(expand),
                                    1 if model_f32 else 0, C.cast(thr_arr, C.c_void_p), _ptr(out["rss"]),
                                    _ptr(out["nsamp"]), _ptr(out["lnk"]), _ptr(out["ncomp"]), _ptr(out["mask_counts"]),
                                    self._stream())
@@ -344,17 +350,21 @@ class Engine(object):
         return bits
 
     def aicc_global(self, prob, spectra, params1, params2, expand=20, model_f32=True, thr=(5.0, 5.0, 5.0),
-                    row_index=None, ncomp_pair=(1, 2)):
+                    row_index=None, ncomp_pair=(1, 2), mask_bits=None):
         """lnk10/lnk20/lnk21, rss, N and the integer ncomp map of every pixel of ONE device's pixel set, with the
         include_nosamp rule applied over that set (single-GPU composition; dist.py composes it across ranks).
-        No host synchronisation between the passes."""
+        No host synchronisation between the passes.  ``mask_bits``: see aicc_pass."""
         out = self.aicc_alloc(int(prob.npix))
         self.aicc_pass(prob, spectra, params1, params2, out, expand=expand, model_f32=model_f32, thr=thr,
-                       row_index=row_index, ncomp_pair=ncomp_pair)
+                       row_index=row_index, ncomp_pair=ncomp_pair, mask_bits=mask_bits)
         best = self.mask_argmax(out["mask_counts"])
-        bits = self.mask_bits(prob, params1, params2, best=best, model_f32=model_f32, ncomp_pair=ncomp_pair)
+        if mask_bits is None:
+            bits = self.mask_bits(prob, params1, params2, best=best, model_f32=model_f32, ncomp_pair=ncomp_pair)
+        else:   # the fill mask of the include_nosamp rule is the given mask of the pixel holding the most samples
+            bits = torch.where(best[0] > 0, mask_bits[best[1].clamp(0, max(int(prob.npix) - 1, 0))],
+                               torch.zeros(64, dtype=torch.int32, device=self.device)).contiguous()
         self.aicc_pass(prob, spectra, params1, params2, out, fill_bits=bits, only_empty=True, expand=expand,
-                       model_f32=model_f32, thr=thr, row_index=row_index, ncomp_pair=ncomp_pair)
+                       model_f32=model_f32, thr=thr, row_index=row_index, ncomp_pair=ncomp_pair, mask_bits=mask_bits)
         out["fill_bits"] = bits
         return out
 

@@ -237,3 +237,90 @@ def test_aicc_pair_new_vs_old_fit(engine, fitted_tile):
     lnkBA = out["lnk"].cpu().numpy().reshape(ny, nx, 3)[:, :, 2]
     ok = np.isfinite(lnkBA) & np.isfinite(got)
     assert np.allclose(lnkBA[ok], -got[ok], rtol=1e-10, atol=1e-10)
+
+
+def test_custom_mask_rss_and_aicc_exact(fitted_tile):
+    """UltraCube.get_rss(ncomp, mask=..., planemask=...) / get_AICc(..., mask=...) (UltraCube.py:432-451, :474-486)
+    with a caller-supplied [nchan, ny, nx] mask: the mask is given, so N is exact and rss / AICc must agree with
+    the oracle's get_rss / AICc to rounding -- including pixels whose mask is empty (include_nosamp fill from the
+    pixel holding the most samples), the dilation, and the partial update inside a planemask."""
+    from mufasa_b200.cube import SpecCube
+    from mufasa_b200.UltraCube import UltraCube
+    t = fitted_tile
+    cube = t["cube"]
+    nchan, ny, nx = cube.shape
+    uc = UltraCube(cube=SpecCube(cube, t["v"]), fittype=t["fittype"], device=0)
+    for nc, key in ((1, "p1"), (2, "p2")):
+        p = uc.load_pcube()
+        p.parcube, p.errcube = t[key].copy(), np.zeros_like(t[key])
+        p.has_fit = np.any(p.parcube != 0, axis=0)
+        p.fittype, p.npars = t["fittype"], 4 * nc
+        uc.pcubes[str(nc)] = p
+        uc._include_fit_in_mask(nc)
+    rng = np.random.default_rng(5)
+    mask = np.zeros((nchan, ny, nx), bool)
+    for y in range(ny):
+        for x in range(nx):
+            c0 = int(rng.integers(50, nchan - 150))
+            mask[c0:c0 + int(rng.integers(5, 90)), y, x] = True
+    mask[:, 0, 1] = False                                    # empty masks: filled from the max-N pixel
+    mask[:, 1, 3] = False
+    mask[0:3, 0, 0] = True                                   # dilation is clipped at the band edge
+    m1 = M.modelcube(t["v"], t["p1"], t["fittype"], dtype=np.float32)
+    m2 = M.modelcube(t["v"], t["p2"], t["fittype"], dtype=np.float32)
+    for expand in (20, 0):
+        with np.errstate(all="ignore"):
+            ref = {0: ST.rss_maps(cube, np.zeros(cube.shape), mask.copy(), expand=expand),
+                   1: ST.rss_maps(cube, m1.copy(), mask.copy(), expand=expand),
+                   2: ST.rss_maps(cube, m2.copy(), mask.copy(), expand=expand)}
+        for nc in (0, 1, 2):
+            uc._invalidate_stats()
+            rss = uc.get_rss(nc, mask=mask.copy(), expand=expand)
+            assert np.array_equal(uc.NSamp_maps[str(nc)], ref[nc][1], equal_nan=True), (expand, nc)
+            np.testing.assert_allclose(rss, ref[nc][0], rtol=1e-6, equal_nan=True)
+            aicc = uc.get_AICc(nc, mask=mask.copy(), expand=expand)
+            with np.errstate(all="ignore"):
+                np.testing.assert_allclose(aicc, ST.AICc(ref[nc][0], 4 * nc, ref[nc][1]), rtol=1e-6, atol=1e-6,
+                                           equal_nan=True)
+    # planemask: only those pixels of the stored maps change
+    uc._invalidate_stats()
+    base = uc.get_AICc(2).copy()                             # default (model) mask
+    pm = np.zeros((ny, nx), bool)
+    pm[1, :] = True
+    upd = uc.get_AICc(2, mask=mask.copy(), planemask=pm, expand=20)
+    assert np.array_equal(upd[~pm], base[~pm], equal_nan=True)
+    with np.errstate(all="ignore"):
+        r2, n2 = ST.rss_maps(cube, m2.copy(), mask.copy(), expand=20)
+        want = ST.AICc(r2[pm], 8, n2[pm])
+    np.testing.assert_allclose(upd[pm], want, rtol=1e-6, atol=1e-6, equal_nan=True)
+
+
+def test_two_cube_likelihood_with_zero_component_model(fitted_tile):
+    """calc_AICc_likelihood(ucube, 1, 0, ucube_B=other) (UltraCube.py:1120-1216): the 0-component model is y = 0
+    with p = 0 over the common mask (here: the 1-component model's own mask, expand 0)."""
+    from mufasa_b200.cube import SpecCube
+    from mufasa_b200.UltraCube import UltraCube, calc_AICc_likelihood
+    t = fitted_tile
+    cube = t["cube"]
+    ucs = []
+    for _ in range(2):
+        uc = UltraCube(cube=SpecCube(cube, t["v"]), fittype=t["fittype"], device=0)
+        p = uc.load_pcube()
+        p.parcube, p.errcube = t["p1"].copy(), np.zeros_like(t["p1"])
+        p.has_fit = np.any(p.parcube != 0, axis=0)
+        p.fittype, p.npars = t["fittype"], 4
+        uc.pcubes["1"] = p
+        ucs.append(uc)
+    got = calc_AICc_likelihood(ucs[0], 1, 0, ucube_B=ucs[1], expand=0)
+    m1 = M.modelcube(t["v"], t["p1"], t["fittype"], dtype=np.float32)
+    with np.errstate(all="ignore"):
+        mask = m1 > 0
+        r1, n1 = ST.rss_maps(cube, m1.copy(), mask.copy(), expand=0)
+        r0, n0 = ST.rss_maps(cube, np.zeros(cube.shape), mask.copy(), expand=0)
+        ref = ST.likelihood(ST.AICc(r1, 4, n1), ST.AICc(r0, 0, n0))
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    # N can differ by the edge channels of the fp64 model mask (DESIGN.md section 4): compare where the likelihood
+    # is not sensitive to them, and exactly in sign
+    assert np.nanmedian(np.abs(got[ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))) < 1e-3
+    assert np.array_equal(got[ok & (np.abs(ref) > 1)] > 0, ref[ok & (np.abs(ref) > 1)] > 0)
