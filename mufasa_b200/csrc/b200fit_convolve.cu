@@ -19,7 +19,9 @@
 // elliptical beam takes the direct K x K path (compute bound on the fp32 pipe, K^2 per output).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "b200fit_ctx.h"
 
@@ -136,10 +138,11 @@ __device__ __forceinline__ void sep_passes(const float* val, const float* fin, f
     slide<WITH_DEN>(mnum + r0 * MP + c, mden + r0 * MP + c, MP, K, sky, num, den);
 }
 
-__global__ void __launch_bounds__(CONV_THREADS)
-    convolve_sep_kernel(const float* __restrict__ cube, float* __restrict__ out, const unsigned char* __restrict__ include,
-                        int ny, int nx, int K, const float* __restrict__ kx, const float* __restrict__ ky, float ksum) {
-    extern __shared__ float smem[];
+// one 32 x 64 tile of plane ``bz`` whose first output is (y0, x0); all threads of the block
+__device__ __forceinline__ void sep_tile(const float* __restrict__ cube, float* __restrict__ out,
+                                         const unsigned char* __restrict__ include, int ny, int nx, int K,
+                                         const float* __restrict__ kx, const float* __restrict__ ky, float ksum, int bz,
+                                         int y0, int x0, float* smem) {
     const int WX = TX + K - 1, WY = TY + K - 1, pitch = WX + 1;
     float* val = smem;                       // [WY][pitch]
     float* fin = val + WY * pitch;           // [WY][pitch]
@@ -148,8 +151,7 @@ __global__ void __launch_bounds__(CONV_THREADS)
     float* skx = mden + WY * MP;             // [K + NOUT - 1]
     float* sky = skx + K + NOUT - 1;
     const size_t plane = (size_t)ny * nx;
-    const float* in = cube + blockIdx.z * plane;
-    const int y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
+    const float* in = cube + bz * plane;
     stage_weights(kx, K, skx);
     stage_weights(ky, K, sky);
     const bool mine = load_window(in, include, ny, nx, y0, x0, K, val, fin, pitch);
@@ -167,8 +169,227 @@ __global__ void __launch_bounds__(CONV_THREADS)
     const int c = threadIdx.x & 31, r0 = (threadIdx.x >> 5) * NOUT, h = K >> 1;
 #pragma unroll
     for (int o = 0; o < NOUT; ++o)
-        store_out(out + blockIdx.z * plane, ny, nx, y0 + r0 + o, x0 + c, num[o], den[o],
-                  fin[(r0 + o + h) * pitch + c + h]);
+        store_out(out + bz * plane, ny, nx, y0 + r0 + o, x0 + c, num[o], den[o], fin[(r0 + o + h) * pitch + c + h]);
+}
+
+__global__ void __launch_bounds__(CONV_THREADS)
+    convolve_sep_kernel(const float* __restrict__ cube, float* __restrict__ out, const unsigned char* __restrict__ include,
+                        int ny, int nx, int K, const float* __restrict__ kx, const float* __restrict__ ky, float ksum) {
+    extern __shared__ float smem[];
+    sep_tile(cube, out, include, ny, nx, K, kx, ky, ksum, blockIdx.z, blockIdx.y * TY, blockIdx.x * TX, smem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast separable path: planes without a pixel mask whose rows are 16-byte aligned (nx % 4 == 0), K >= 9.
+//
+// The generic kernel above spends its time on everything except the arithmetic (ncu profiles/r1n: 336 thread
+// instructions per voxel of which 70 are the FMAs; staging loop with clamped scalar loads, two stores per staged
+// value, a division per output).  Here
+//   * the (64 + K - 1) x (64 + 2 ceil4(K/2)) window of a 64 x 64 tile goes to shared memory RAW, by 16-byte
+//     cp.async copies whose source size is 0 beyond the image (hardware zero fill = boundary='fill'): one
+//     instruction per four values, no sanitising pass, no finite-flag array;
+//   * the passes run on PAIRS: vertical first, a thread owning two adjacent columns x 8 rows (one 64-bit
+//     shared-memory load feeds 8 packed FMAs, ``fma.rn.f32x2``), its result stored TRANSPOSED so that the horizontal
+//     pass -- a thread owning rows r and r + 32 x 8 columns, a warp's lanes on consecutive rows -- reads it without
+//     bank conflicts; weights sit in registers, 8 at a time, and every product the loops issue is a real one (the
+//     ramp-in / ramp-out of the 8-output window is unrolled statically per K mod 8, no zero tail);
+//   * NaNs are not looked for: a NaN under an output's kernel makes that output NaN, the write-out loop sees it and
+//     the tile is appended to a work list that the generic kernel (interpolating normalisation) redoes afterwards.
+// Each lane of a packed FMA is the IEEE fp32 operation; per output the products are summed in the same order as in
+// the generic kernel's all-finite path (j ascending, vertical after horizontal there / before here -- the two
+// orders differ in rounding only, inside the 2e-6 of the parity tests).
+// Measured on B200 (512 x 512 x 1000, K = 23; profiles/r2k_*): 0.89 ms = 2.36 TB/s of algorithmic bytes against
+// 3.14 ms of the generic kernel.  What bounds it now is instruction issue: ncu counts a packed FMA as TWO issue slots
+// (smsp__inst_executed = source-level instructions + one per FFMA2), so the 46 FMAs per output of a separable
+// 23 x 23 kernel -- x 1.19 for the halo columns of the vertical pass -- are a floor of 0.40 ms at 128 FMA slots per
+// SM and cycle, and the kernel spends 0.36 of its slots on everything else (cp.async address arithmetic,
+// shared-memory loads, the write-out).  A persistent variant with the next tile's window in flight (two window
+// buffers, 2 blocks per SM) was measured at 1.15 ms: the loads are already hidden behind the other three blocks of
+// an SM, and 16 warps per SM leave the packed-FMA chains short of independent work.
+constexpr int FT = 64;            // fast tile edge
+constexpr int FPT = FT + 4;       // pitch of the transposed intermediate and of the output staging
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src, unsigned src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// 8 consecutive outputs of a 1-D correlation with K = 8 nb + KR weights, on pairs.  ``ld(j)`` returns the packed pair of
+// inputs at offset j (0 <= j <= K + 6) from the first output; output o accumulates w[j - o] x(j) for 0 <= j - o < K,
+// j ascending.  ``w``: shared memory, 16-byte aligned, readable up to 8 nb + 7.
+template <int KR, class Load>
+__device__ __forceinline__ void slide_pairs(Load ld, const float* __restrict__ w, int nb, f32x2 (&acc)[NOUT]) {
+    static_assert(NOUT == 8, "the weight ring is 8 deep");
+    float wp[8], wc[8];
+    auto load8 = [&](int m) {
+        const float4 a = *reinterpret_cast<const float4*>(w + 8 * m), b = *reinterpret_cast<const float4*>(w + 8 * m + 4);
+        wc[0] = a.x, wc[1] = a.y, wc[2] = a.z, wc[3] = a.w, wc[4] = b.x, wc[5] = b.y, wc[6] = b.z, wc[7] = b.w;
+    };
+    load8(0);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {             // ramp-in: input u reaches outputs 0 .. u
+        const f32x2 x = ld(u);
+#pragma unroll
+        for (int o = 0; o <= u; ++o) acc[o] = fma2(pk2(wc[u - o], wc[u - o]), x, acc[o]);
+    }
+#pragma unroll 1
+    for (int m = 1; m < nb; ++m) {            // every input reaches all 8 outputs
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wp[i] = wc[i];
+        load8(m);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const f32x2 x = ld(8 * m + u);
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const float wv = (u >= o) ? wc[u - o] : wp[8 + u - o];
+                acc[o] = fma2(pk2(wv, wv), x, acc[o]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wp[i] = wc[i];
+    load8(nb);                                // weights 8 nb .. K - 1 (what follows them is never used)
+#pragma unroll
+    for (int t = 0; t < KR + 7; ++t) {        // ramp-out: input 8 nb + t reaches outputs o >= t - KR + 1
+        const f32x2 x = ld(8 * nb + t);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            if (o >= t - KR + 1) {
+                const int rel = t - o;        // weight index relative to 8 nb: -7 .. KR - 1
+                const float wv = (rel >= 0) ? wc[rel >= 0 ? rel : 0] : wp[rel < 0 ? 8 + rel : 0];
+                acc[o] = fma2(pk2(wv, wv), x, acc[o]);
+            }
+        }
+    }
+}
+
+template <int KR>
+__global__ void __launch_bounds__(CONV_THREADS, 4)
+    convolve_sep_fast_kernel(const float* __restrict__ cube, float* __restrict__ out, int ny, int nx, int K,
+                             const float* __restrict__ kx, const float* __restrict__ ky, float inv_ksum,
+                             unsigned* __restrict__ redo) {
+    extern __shared__ __align__(16) float smem[];
+    const int h = K >> 1, H4 = (h + 3) & ~3, WXA = FT + 2 * H4, WY = FT + K - 1, nb = K >> 3;
+    const int KW = (K + 15) & ~7;                      // weights + room for the last 8-wide load
+    float* raw = smem;                                  // [WY][WXA] as it lies in the plane; later the output staging
+    float* mid = raw + WY * WXA;                        // [WXA][FPT] vertically convolved, transposed
+    float* skx = mid + WXA * FPT;                       // [KW]
+    float* sky = skx + KW;
+    const size_t plane = (size_t)ny * nx;
+    const float* in = cube + blockIdx.z * plane;
+    const int y0 = blockIdx.y * FT, x0 = blockIdx.x * FT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < KW; k += CONV_THREADS) {
+        skx[k] = (k < K) ? kx[k] : 0.f;
+        sky[k] = (k < K) ? ky[k] : 0.f;
+    }
+    // 1. the window, four values per copy (a lane owns one 16-byte segment of every row its warp stages); segments
+    //    beyond the image are zero filled by the copy engine
+    {
+        const int x = x0 - H4 + 4 * lane;
+        const bool col_ok = x >= 0 && x < nx;                            // nx % 4 == 0: a segment is inside or outside
+        const float* col = in + (col_ok ? x : 0);
+        unsigned dst = (unsigned)__cvta_generic_to_shared(raw) + (unsigned)((warp * WXA + 4 * lane) * sizeof(float));
+        if (4 * lane < WXA) {
+            int y = y0 + warp - h, off = y * nx;                         // (a plane holds < 2^31 voxels: checked by the host)
+            for (int r = warp; r < WY; r += CONV_THREADS / 32) {
+                const bool ok = col_ok && y >= 0 && y < ny;
+                cp_async16(dst, ok ? col + off : in, ok ? 16u : 0u);
+                dst += (CONV_THREADS / 32) * WXA * (unsigned)sizeof(float);
+                y += CONV_THREADS / 32;
+                off += (CONV_THREADS / 32) * nx;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    // 2. vertical pass: thread = (column pair, group of 8 rows); lanes on consecutive pairs
+    {
+        const int npair = WXA >> 1;
+        for (int e = threadIdx.x; e < npair * (FT / NOUT); e += CONV_THREADS) {
+            const int rg = e / npair, cp = e - rg * npair;
+            const float* x0p = raw + (rg * NOUT) * WXA + 2 * cp;
+            f32x2 acc[NOUT];
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) acc[o] = 0ull;
+            slide_pairs<KR>([&](int j) { return *reinterpret_cast<const f32x2*>(x0p + j * WXA); }, sky, nb, acc);
+            float lo[NOUT], hi[NOUT];
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) upk2(acc[o], lo[o], hi[o]);
+            float* d0 = mid + (2 * cp) * FPT + rg * NOUT;
+            *reinterpret_cast<float4*>(d0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<float4*>(d0 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+            *reinterpret_cast<float4*>(d0 + FPT) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(d0 + FPT + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+        }
+    }
+    __syncthreads();
+    // 3. horizontal pass: warp = group of 8 output columns, lane = rows (lane, lane + 32)
+    {
+        const float* x0p = mid + (H4 - h + warp * NOUT) * FPT + lane;
+        f32x2 acc[NOUT];
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) acc[o] = 0ull;
+        slide_pairs<KR>([&](int j) { return pk2(x0p[j * FPT], x0p[j * FPT + 32]); }, skx, nb, acc);
+        float lo[NOUT], hi[NOUT];
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            upk2(acc[o], lo[o], hi[o]);
+            lo[o] *= inv_ksum;
+            hi[o] *= inv_ksum;
+        }
+        float* d0 = raw + lane * FPT + warp * NOUT;      // (the window is dead since the barrier above)
+        *reinterpret_cast<float4*>(d0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(d0 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+        *reinterpret_cast<float4*>(d0 + 32 * FPT) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(d0 + 32 * FPT + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+    }
+    __syncthreads();
+    // 4. coalesced write-out; any non-finite output sends the tile to the generic kernel
+    bool bad = false;
+    float* op = out + blockIdx.z * plane;
+#pragma unroll
+    for (int i = 0; i < (FT * FT / 4) / CONV_THREADS; ++i) {
+        const int idx = threadIdx.x + i * CONV_THREADS, row = idx >> 4, q = idx & 15;
+        const float4 v = *reinterpret_cast<const float4*>(raw + row * FPT + 4 * q);
+        const int y = y0 + row, x = x0 + 4 * q;
+        if (y < ny && x < nx) {
+            const float s = (v.x - v.x) + (v.y - v.y) + (v.z - v.z) + (v.w - v.w);   // 0 iff all four are finite
+            bad = bad || !(s == 0.f);
+            *reinterpret_cast<float4*>(op + (size_t)y * nx + x) = v;
+        }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0)
+        redo[1 + atomicAdd(redo, 1u)] = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+}
+
+// the tiles the fast kernel gave up on (those with a NaN under some output's kernel), two generic tiles each
+__global__ void __launch_bounds__(CONV_THREADS)
+    convolve_sep_redo_kernel(const float* __restrict__ cube, float* __restrict__ out, int ny, int nx, int K,
+                             const float* __restrict__ kx, const float* __restrict__ ky, float ksum,
+                             const unsigned* __restrict__ redo, int tiles_x, int tiles_y) {
+    extern __shared__ float smem[];
+    const unsigned n = redo[0];
+    for (unsigned i = blockIdx.x; i < 2 * n; i += gridDim.x) {
+        const unsigned t = redo[1 + (i >> 1)];
+        const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, bz = t / (tiles_x * tiles_y);
+        const int x0 = bx * FT + (int)(i & 1u) * TX;
+        if (x0 < nx) sep_tile(cube, out, nullptr, ny, nx, K, kx, ky, ksum, bz, by * FT, x0, smem);
+        __syncthreads();
+    }
 }
 
 // general kernel k2[K][K] (a rotated elliptical beam): each thread owns 8 vertically adjacent outputs and slides
@@ -251,7 +472,7 @@ int b200fit_convolve_planes(b200fit_ctx* ctx, const float* d_cube, int32_t nchan
     if (nchan == 0 || ny == 0 || nx == 0) return B200FIT_OK;
     const bool sep = d_kx && d_ky && !d_k2, full = d_k2 && !d_kx && !d_ky;
     if (!d_cube || !d_out || d_cube == d_out || nchan < 0 || ny < 0 || nx < 0 || ksize < 1 || ksize > CONV_KMAX ||
-        !(ksize & 1) || !(sep || full) || nchan > 65535 || !(kernel_sum > 0.0))
+        !(ksize & 1) || !(sep || full) || nchan > 65535 || !(kernel_sum > 0.0) || (long long)ny * nx >= (1ll << 31))
         return fail(ctx, B200FIT_E_ARG, "convolve_planes: bad argument");
     CK(cudaSetDevice(ctx->device));
     const size_t WX = TX + ksize - 1, WY = TY + ksize - 1, KP = ksize + NOUT - 1;
@@ -259,6 +480,47 @@ int b200fit_convolve_planes(b200fit_ctx* ctx, const float* d_cube, int32_t nchan
     if (sep) {
         const size_t smem = sizeof(float) * (2 * WY * (WX + 1) + 2 * WY * MP + 2 * KP);
         CK(cudaFuncSetAttribute(convolve_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bool fast = !d_include && ksize >= 9 && (nx % 4) == 0 && ((uintptr_t)d_cube % 16) == 0 &&
+                          ((uintptr_t)d_out % 16) == 0 && !getenv("B200FIT_CONV_GENERIC");
+        if (fast) {
+            // fast kernel over 64 x 64 tiles, then the generic one over the tiles it flagged (those holding NaNs)
+            const int h = ksize >> 1, H4 = (h + 3) & ~3, WXA = FT + 2 * H4, WYF = FT + ksize - 1, KW = (ksize + 15) & ~7;
+            const size_t fsmem = sizeof(float) * ((size_t)WYF * WXA + (size_t)WXA * FPT + 2 * KW);
+            const dim3 fgrid((nx + FT - 1) / FT, (ny + FT - 1) / FT, nchan);
+            const size_t ntiles = (size_t)fgrid.x * fgrid.y * fgrid.z;
+            if (ctx->redo_cap < ntiles + 1) {          // work list of the context, grown on demand (convolutions of one
+                if (ctx->d_redo) {                      // context are issued one at a time, on one stream)
+                    CK(cudaDeviceSynchronize());
+                    CK(cudaFree(ctx->d_redo));
+                    ctx->d_redo = nullptr, ctx->redo_cap = 0;
+                }
+                CK(cudaMalloc((void**)&ctx->d_redo, (ntiles + 1) * sizeof(unsigned)));
+                ctx->redo_cap = ntiles + 1;
+            }
+            unsigned* d_redo = ctx->d_redo;
+            CK(cudaMemsetAsync(d_redo, 0, sizeof(unsigned), (cudaStream_t)stream));
+            const float inv = (float)(1.0 / kernel_sum);
+#define B200FIT_LAUNCH_FAST(KR)                                                                                          \
+    do {                                                                                                                 \
+        CK(cudaFuncSetAttribute(convolve_sep_fast_kernel<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
+        convolve_sep_fast_kernel<KR><<<fgrid, CONV_THREADS, fsmem, (cudaStream_t)stream>>>(d_cube, d_out, ny, nx, ksize, \
+                                                                                            d_kx, d_ky, inv, d_redo);   \
+    } while (0)
+            switch (ksize & 7) {
+                case 1: B200FIT_LAUNCH_FAST(1); break;
+                case 3: B200FIT_LAUNCH_FAST(3); break;
+                case 5: B200FIT_LAUNCH_FAST(5); break;
+                default: B200FIT_LAUNCH_FAST(7); break;
+            }
+#undef B200FIT_LAUNCH_FAST
+            CK(cudaGetLastError());
+            CK(cudaFuncSetAttribute(convolve_sep_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            convolve_sep_redo_kernel<<<ctx->num_sms * 3, CONV_THREADS, smem, (cudaStream_t)stream>>>(
+                d_cube, d_out, ny, nx, ksize, d_kx, d_ky, (float)kernel_sum, d_redo, (int)fgrid.x, (int)fgrid.y);
+            CK(cudaGetLastError());
+            ctx->launches += 2;
+            return B200FIT_OK;
+        }
         convolve_sep_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(d_cube, d_out, d_include, ny, nx, ksize,
                                                                                 d_kx, d_ky, (float)kernel_sum);
     } else {

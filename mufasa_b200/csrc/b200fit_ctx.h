@@ -25,6 +25,8 @@ struct b200fit_ctx {
     std::vector<cudaEvent_t> prof_ev;         // event pool (grown on demand)
     size_t prof_used = 0;
     int prof_rounds = 0;
+    unsigned* d_redo = nullptr;               // convolution: tiles the fast separable kernel hands to the generic one
+    size_t redo_cap = 0;
 
     cudaEvent_t next_event(cudaStream_t stream) {
         if (prof_used == prof_ev.size()) {

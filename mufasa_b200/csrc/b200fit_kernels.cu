@@ -1854,6 +1854,7 @@ void b200fit_destroy(b200fit_ctx* ctx) {
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->h_count) cudaFreeHost((void*)ctx->h_count);
     if (ctx->d_chan) cudaFree(ctx->d_chan);
+    if (ctx->d_redo) cudaFree(ctx->d_redo);
     delete ctx;
 }
 

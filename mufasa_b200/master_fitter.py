@@ -2,7 +2,7 @@
 stage of ``master_2comp_fit`` is made of -- guesses from the best neighbour, a masked refit, the new-vs-old AICc
 comparison and the in-place replacement of the better pixels -- and the first stage of the pipeline, the two-step
 fit through the convolved cube.  The later stages of ``master_2comp_fit`` (``expand_fits``,
-``refit_2comp_wide`` ...) are host control flow over these same primitives and are not rebuilt here.
+``refit_2comp_wide`` ...) are host control flow over these same primitives.
 
   get_refit_guesses   master_fitter.py:1512-1595  (+ utils/neighbours.py:17-84)
   replace_bad_pix     :1403-1464
@@ -16,8 +16,9 @@ and the stages of ``master_2comp_fit`` (:583-679) that are compositions of the a
   expand_fits         :1101-1244, fit_surroundings :1247-1400, standard_2comp_fit :1668-1697,
   save_best_2comp_fit :1722-1931 (maps only: no CSV / 3-D scatter plot), get_best_2comp_model :2412-2468,
   get_best_2comp_snr_mod :2376-2409
-Not rebuilt: ``refit_2comp_wide`` (:981-1098, the recovery of widely separated components from the convolved
-residual cube); ``master_2comp_fit(recover_wide=True)`` raises NotImplementedError.
+  refit_2comp_wide    :981-1098 with get_2comp_wide_guesses :1974-2068, fit_best_2comp_residual_cnv :2071-2189,
+  get_best_2comp_residual_cnv :2192-2248, get_best_2comp_residual_SpectralCube :2251-2336,
+  get_best_2comp_residual :2339-2373 (+ moment_guess.mom_guess_wide_sep / window_moments / vmask_moments)
 """
 import logging
 import os
@@ -28,6 +29,7 @@ from scipy import ndimage as nd
 
 from . import UltraCube as UCube
 from . import guess_refine as gss_rf
+from . import moment_guess as mmg
 from . import multi_v_fit as mvf
 from . import signals
 from .exceptions import SNRMaskError, StartFitError
@@ -610,17 +612,236 @@ def save_best_2comp_fit(reg, multicore=True, from_saved_para=False, lnk21_thres=
     return reg
 
 
-def master_2comp_fit(reg, snr_min=0.0, recover_wide=False, planemask=None, updateCnvFits=True, refit_bad_pix=True,
+# ---- recovery of a second component at wide velocity separation ----------------------------------------------
+# The reference masks the residual cube in get_best_2comp_residual_SpectralCube with the branches the wrong way
+# round (master_fitter.py:2322-2332): where at least one pixel of the residual exceeds ``res_snr_cut`` the cube is
+# returned WITHOUT a mask, and get_best_2comp_residual_cnv then raises SNRMaskError because ``cube.mask is None``
+# (:2238-2242) -- refit_2comp_wide logs "No second component recovered" and returns; only a residual with NO pixel
+# above the cut gets a (trivial, all-inclusive) mask and goes on to the convolved fit.  A drop-in has to behave the
+# same, so that is the default here.  RESIDUAL_MASK_AS_DOCUMENTED = True instead does what the reference's docstrings
+# describe: the cube is masked to the (dilated) pixels whose residual peak exceeds the cut, and left unmasked -- but
+# still fitted -- when there are none.
+RESIDUAL_MASK_AS_DOCUMENTED = False
+
+
+def get_skyheader(cube_header):
+    """master_fitter.py:2523-2559: the celestial cards of a cube header."""
+    from .convolve_tools import get_celestial_hdr
+    hdr2D = get_celestial_hdr(cube_header)
+    hdr2D['NAXIS'] = 2
+    return hdr2D
+
+
+def get_best_2comp_residual(reg):
+    """master_fitter.py:2339-2373: data minus the selected model, as a cube on the data's axes."""
+    modbest = get_best_2comp_model(reg)
+    return reg.ucube.cube.with_data(reg.ucube.cube._data - modbest)
+
+
+def get_best_2comp_residual_SpectralCube(reg, masked=True, window_hwidth=3.5, res_snr_cut=5):
+    """master_fitter.py:2251-2336.  ``masked``: pixels are selected by the peak of the residual within
+    ``window_hwidth`` of the 1-component velocity over the residual's own noise (see RESIDUAL_MASK_AS_DOCUMENTED for
+    what the selection then does)."""
+    cube_res = get_best_2comp_residual(reg)
+    if masked and res_snr_cut > 0:
+        best_rms = _rms_of_residual(cube_res._data)
+        vmap = reg.ucube.pcubes['1'].parcube[0]
+        window = mmg.vmask_cube(cube_res, vmap, window_hwidth=window_hwidth)
+        import warnings
+        with warnings.catch_warnings(), np.errstate(all="ignore"):
+            warnings.simplefilter("ignore", RuntimeWarning)
+            peak = np.nanmax(np.where(window, cube_res._data, np.nan), axis=0)
+            mask_res = peak / best_rms > res_snr_cut
+        if RESIDUAL_MASK_AS_DOCUMENTED:
+            if mask_res.sum() >= 1:
+                return cube_res.with_mask(signals.binary_dilation(mask_res))
+            logger.debug("No pixel in the residual cube mask. No mask will be applied.")
+            return cube_res.with_mask(np.ones(mask_res.shape, bool))
+        if mask_res.sum() < 1:
+            logger.debug("No pixel in the residual cube mask. No mask will be applied.")
+            return cube_res.with_mask(~signals.binary_dilation(mask_res))
+    return cube_res
+
+
+def get_best_2comp_residual_cnv(reg, masked=True, window_hwidth=3.5, res_snr_cut=3):
+    """master_fitter.py:2192-2248: the residual cube smoothed and regridded by the region's convolution factor."""
+    from . import convolve_tools as cnvtool
+    cube_res_masked = get_best_2comp_residual_SpectralCube(reg, masked=masked, window_hwidth=window_hwidth,
+                                                           res_snr_cut=res_snr_cut)
+    if cube_res_masked.plane_include is None:            # the reference's ``cube.mask is None``
+        msg = "Cube_res_masked does not have a mask for res_snr_cut={}. No residual refitting will be " \
+              "performed".format(res_snr_cut)
+        logger.debug(msg)
+        raise SNRMaskError(msg)
+    return cnvtool.convolve_sky_byfactor(cube_res_masked, factor=reg.cnv_factor, edgetrim_width=None, snrmasked=False,
+                                         iterrefine=False, device=reg.device)
+
+
+def fit_best_2comp_residual_cnv(reg, window_hwidth=3.5, res_snr_cut=3, savefit=True, planemask=None):
+    """master_fitter.py:2071-2189: a 1-component fit of the convolved residual (``reg.ucube_res_cnv``) from windowed
+    moment guesses about the (convolved, or median-smoothed and regridded) 1-component velocity; pixels enter with
+    amplitude / mad_std >= ``res_snr_cut``."""
+    from scipy.signal import medfilt2d
+    from . import convolve_tools as cnvtool
+    cube_res_cnv = get_best_2comp_residual_cnv(reg, masked=True, window_hwidth=window_hwidth, res_snr_cut=res_snr_cut)
+    ncomp = 1
+    if not hasattr(reg, 'ucube_cnv'):
+        pcube1 = reg.ucube.pcubes['1']
+        vmap = medfilt2d(np.asarray(pcube1.parcube[0], dtype=np.float64), kernel_size=3)
+        vmap = cnvtool.regrid(vmap, header1=get_skyheader(reg.ucube.cube.header),
+                              header2=get_skyheader(cube_res_cnv.header))
+    else:
+        vmap = reg.ucube_cnv.pcubes['1'].parcube[0]
+    if vmap.shape != cube_res_cnv.shape[1:]:
+        raise SNRMaskError("There doesn't seem to be enough pixels to find the residual moments. the velocity map "
+                           "{} does not match the convolved residual {}".format(vmap.shape, cube_res_cnv.shape[1:]))
+    m0, m1, m2 = mmg.window_moments(cube_res_cnv, v_atpeak=vmap, window_hwidth=window_hwidth, device=reg.device)
+    gg = mmg.moment_guesses_1c(m0, m1, m2)
+    gg = gss_rf.refine_each_comp(gg, mask=np.isfinite(gg[0]))
+    if res_snr_cut > 0:
+        rms = signals.mad_std(cube_res_cnv._data, axis=0)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            maskmap = m0 / rms >= res_snr_cut
+    else:
+        maskmap = np.isfinite(m0)
+    if planemask is not None:
+        if planemask.shape == maskmap.shape:
+            maskmap = np.logical_and(maskmap, planemask)
+        else:
+            # reproject_interp (bilinear) of the dilated mask onto the convolved grid, thresholded at 0.5
+            from .utils.fits_utils import linear_pixel_map
+            grown = signals.binary_dilation(planemask, signals.disk(2)).astype(np.float64)
+            (ay, by), (ax, bx) = linear_pixel_map(reg.ucube.cube.header, cube_res_cnv.header)
+            y = ay * np.arange(maskmap.shape[0]) + by
+            x = ax * np.arange(maskmap.shape[1]) + bx
+            inside = np.logical_and.outer((y >= 0) & (y <= grown.shape[0] - 1), (x >= 0) & (x <= grown.shape[1] - 1))
+            y0 = np.clip(np.floor(y).astype(int), 0, grown.shape[0] - 2)
+            x0 = np.clip(np.floor(x).astype(int), 0, grown.shape[1] - 2)
+            fy, fx = np.clip(y - y0, 0, 1)[:, None], np.clip(x - x0, 0, 1)[None, :]
+            interp = ((1 - fy) * ((1 - fx) * grown[np.ix_(y0, x0)] + fx * grown[np.ix_(y0, x0 + 1)]) +
+                      fy * ((1 - fx) * grown[np.ix_(y0 + 1, x0)] + fx * grown[np.ix_(y0 + 1, x0 + 1)]))
+            maskmap = np.logical_and(maskmap, inside & (interp > 0.5))
+    reg.ucube_res_cnv = UCube.UltraCube(cube=cube_res_cnv, fittype=reg.fittype, device=reg.device)
+    if np.sum(maskmap) > 0:
+        try:
+            reg.ucube_res_cnv.fit_cube(ncomp=[1], simpfit=False, snr_min=0.0, guesses=gg, maskmap=maskmap)
+        except StartFitError:
+            raise StartFitError("The first fitted pixel to the convovled residual cube did not yield a fit, likely due "
+                                "to a lack of signal or poor guesses.")
+    else:
+        raise SNRMaskError("No valid pixel to refit in the residual cube with snr_min={}. Please consider trying a "
+                           "lower snr_min value".format(res_snr_cut))
+    if savefit:
+        oriParaPath = reg.ucube.paraPaths[str(ncomp)]
+        reg.ucube_res_cnv.save_fit("{}_onBestResidual.fits".format(os.path.splitext(oriParaPath)[0]), ncomp)
+
+
+def get_2comp_wide_guesses(reg, window_hwidth=3.5, snr_min=3, savefit=True, planemask=None):
+    """master_fitter.py:1974-2068: [4, ny, nx] guesses for the second, widely separated component -- the
+    1-component fit of the convolved residual where it beats noise (lnk10 > 5), regridded to the full resolution;
+    moment guesses of the unmasked residual about the 1-component velocity otherwise."""
+    from scipy.signal import medfilt2d
+    if not hasattr(reg, 'ucube_res_cnv'):
+        try:
+            fit_best_2comp_residual_cnv(reg, window_hwidth=window_hwidth, res_snr_cut=snr_min, savefit=savefit,
+                                        planemask=planemask)
+        except SNRMaskError:
+            raise SNRMaskError("No valid pixel to refit in the residual cube for snr_min={}.".format(snr_min))
+
+    def get_mom_guesses(reg):
+        cube_res = get_best_2comp_residual_SpectralCube(reg, masked=False, window_hwidth=3.5)
+        vmap = medfilt2d(np.asarray(reg.ucube.pcubes['1'].parcube[0], dtype=np.float64), kernel_size=3)
+        moms_res = mmg.vmask_moments(cube_res, vmap=vmap, window_hwidth=3.5, device=reg.device)
+        gg = mmg.moment_guesses_1c(moms_res[0], moms_res[1], moms_res[2])
+        return gss_rf.refine_each_comp(gg, mask=np.isfinite(moms_res[0]))
+
+    if not hasattr(reg, 'ucube_res_cnv') or ('1' not in reg.ucube_res_cnv.pcubes) or not hasattr(
+            reg.ucube_res_cnv.pcubes['1'], 'parcube'):
+        return get_mom_guesses(reg)
+    with np.errstate(invalid="ignore"):
+        aic1v0_mask = reg.ucube_res_cnv.get_AICc_likelihood(1, 0) > 5
+    if np.sum(aic1v0_mask) >= 1:
+        logger.info("number of good fits to convolved residual: {}".format(np.sum(aic1v0_mask)))
+        pc = reg.ucube_res_cnv.pcubes['1']
+        preguess = np.append(pc.parcube, pc.errcube, axis=0).copy()
+        preguess[:, ~aic1v0_mask] = np.nan
+        gmask = signals.binary_dilation(aic1v0_mask)
+        return gss_rf.guess_from_cnvpara(preguess, reg.ucube_res_cnv.cube.header, reg.ucube.cube.header, mask=gmask)
+    logger.info("no good fit from convolved guess, using the moment guess for the full-res refit instead")
+    return get_mom_guesses(reg)
+
+
+def refit_2comp_wide(reg, snr_min=3, method='residual', planemask=None, multicore=True, save_para=True):
+    """master_fitter.py:981-1098: where the 1-component fit beat both noise and the 2-component fit (lnk10 > 5,
+    lnk21 < -5), look for a second component far from the first -- ``method`` 'residual': in the convolved residual
+    of the best model (get_2comp_wide_guesses), 'moments': in the moments of the spectrum with its main component
+    blanked (mom_guess_wide_sep) -- refit with both and keep the refits that are likelier than the old fit."""
+    proc_name = 'refit_2comp_wide'
+    reg.log_progress(process_name=proc_name, mark_start=True)
+    for nc in (1, 2):
+        if str(nc) not in reg.ucube.pcubes:
+            if str(nc) not in reg.ucube.paraPaths:
+                reg.ucube.paraPaths[str(nc)] = '{}/{}_{}vcomp.fits'.format(reg.ucube.paraDir, reg.ucube.paraNameRoot, nc)
+            reg.ucube.load_model_fit(reg.ucube.paraPaths[str(nc)], nc)
+    lnk10, lnk20, lnk21 = reg.ucube.get_all_lnk_maps(ncomp_max=2, rest_model_mask=False)
+    if planemask is None:
+        with np.errstate(invalid="ignore"):
+            mask = np.logical_and(lnk21 < -5, lnk10 > 5)
+    else:
+        mask = planemask
+    if method == 'residual':
+        c1_guess = gss_rf.refine_each_comp(copy(reg.ucube.pcubes['1'].parcube))
+        try:
+            wide_comp_guess = get_2comp_wide_guesses(reg, window_hwidth=3.5, snr_min=snr_min, savefit=True,
+                                                     planemask=mask)
+        except SNRMaskError as e:
+            logger.warning(str(e) + " No second component recovered from the residual cube.")
+            reg.log_progress(process_name=proc_name, mark_start=False, n_attempted=0, n_success=0, finished=True)
+            return
+        except StartFitError as e:
+            logger.warning(str(e))
+            return
+        except ValueError as e:
+            logger.warning(str(e) + "Convolved residual cube is not fitted. No recovery is done for the wide "
+                                    "component.")
+            reg.log_progress(process_name=proc_name, mark_start=False, n_attempted=0, n_success=0, finished=True)
+            return
+        wide_comp_guess[:, ~mask] = np.nan
+        final_guess = np.append(c1_guess, wide_comp_guess, axis=0)
+        mask = np.logical_and(mask, np.all(np.isfinite(final_guess), axis=0))
+        final_guess = gss_rf.refine_2c_guess(final_guess)
+    elif method == 'moments':
+        final_guess = mmg.mom_guess_wide_sep(reg.ucube.cube, planemask=mask, device=reg.device)
+        mask = np.logical_and(mask, np.all(np.isfinite(final_guess), axis=0))
+    else:
+        raise Exception("the following method specified is invalid: {}".format(method))
+    mask_size = int(np.sum(mask))
+    if mask_size > 0:
+        logger.info("Attempting wide recovery over {} pixels".format(mask_size))
+        reg.log_progress(process_name=proc_name, mark_start=False, n_attempted=mask_size, n_success='in progress')
+    else:
+        logger.info("No pixel was used in attempt to recover wide component")
+        reg.log_progress(process_name=proc_name, mark_start=False, n_attempted=0, n_success=None, finished=True)
+        return
+    good_mask = replace_bad_pix(reg.ucube, mask, snr_min, final_guess, ncomp=2, simpfit=True, multicore=multicore,
+                                return_good_mask=True)
+    if save_para:
+        save_updated_paramaps(reg.ucube, ncomps=[2, 1])
+    reg.log_progress(process_name=proc_name, mark_start=False, n_attempted=None, n_success=int(good_mask.sum()),
+                     finished=True)
+    return good_mask
+
+
+def master_2comp_fit(reg, snr_min=0.0, recover_wide=True, planemask=None, updateCnvFits=True, refit_bad_pix=True,
                      refit_marg=True, max_expand_iter=None, multicore=True):
     """The reference's full 2-component pipeline (master_fitter.py:583-679): two-step fit through the convolved cube,
-    quality-assurance refits, expansion into the surroundings, products.  ``recover_wide`` (the reference's default
-    True) needs ``refit_2comp_wide``, which is not rebuilt."""
-    if recover_wide:
-        raise NotImplementedError("refit_2comp_wide is not rebuilt; call with recover_wide=False")
+    quality-assurance refits, recovery of widely separated components, expansion into the surroundings, products."""
     iter_2comp_fit(reg, snr_min=snr_min, updateCnvFits=updateCnvFits, planemask=planemask, multicore=multicore)
     recover_snr_min = min(3.0, snr_min / 3.0)
     if refit_bad_pix:
         refit_bad_2comp(reg, snr_min=recover_snr_min, lnk_thresh=-5, multicore=multicore)
+    if recover_wide:
+        refit_2comp_wide(reg, snr_min=recover_snr_min, multicore=multicore)
     if refit_marg:
         for nc in (1, 2):
             refit_marginal(reg, ncomp=nc, lnk_thresh=10, holes_only=False, multicore=multicore,

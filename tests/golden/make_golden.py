@@ -11,7 +11,8 @@ What is executed from /root/reference (through the import stubs of _ref_stubs.py
                      and -- through a real ``UltraCube`` instance holding stand-in pcubes --
                      get_all_lnk_maps :1218, get_best_2c_parcube :1283 (=> get_AICc :474, get_rss :432,
                      calc_rss :911, calc_AICc_likelihood :1120, reset_model_mask :359, has_fit :328)
-  guess_golden.npz   mufasa/moment_guess.py: moment_guesses :388, get_tex/get_tau/peakT :774-800;
+  guess_golden.npz   mufasa/moment_guess.py: moment_guesses :388, moment_guesses_1c :523, get_tex/get_tau/peakT
+                     :774-800;
                      mufasa/guess_refine.py: tautex_renorm :183
   meta_golden.json   mufasa/spec_models/meta_model.py:67-150 (limits, windows, rest value, voff_at_peak)
 Not reference-provided: the NH3 (1,1) hyperfine table (pyspeckit, absent) -- injected, see _ref_stubs.py.
@@ -212,6 +213,15 @@ def make_guess():
     out["get_tex"] = mg.get_tex(Ta, tau=0.7, nu=23.6944955)
     out["get_tau"] = mg.get_tau(Ta * 0.3, tex=6.0, nu=23.6944955)
     out["peakT"] = mg.peakT(rng.uniform(3, 12, 20) * 0 + np.linspace(3, 12, 20), np.linspace(0.1, 5, 20), nu=93.1737637)
+    # moment_guesses_1c (moment_guess.py:523-572): amplitude-like moment 0 spanning both tau/Tex regimes, the floor
+    # and a few NaNs
+    rng1 = np.random.default_rng(77)
+    m0a = rng1.uniform(0.0, 6.0, size=(5, 7))
+    m0a[0, 0], m0a[4, 6] = 1e-4, np.nan
+    m1a = rng1.uniform(-3, 3, size=(5, 7))
+    m2a = rng1.uniform(0.05, 1.5, size=(5, 7))
+    out["m1c_m0"], out["m1c_m1"], out["m1c_m2"] = m0a, m1a, m2a
+    out["m1c_out"] = mg.moment_guesses_1c(m0a.copy(), m1a.copy(), m2a.copy())
     np.savez_compressed(os.path.join(HERE, "guess_golden.npz"), **out)
 
 

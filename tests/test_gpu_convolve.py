@@ -4,6 +4,8 @@ two-step fit of iter_2comp_fit (fit the convolved cube, turn its parameters into
 
 Tolerance: the kernels accumulate in fp32 over K^2 <= 4225 terms of the fp32 cube, the oracle in fp64 --
 |gpu - oracle| <= 2e-6 * max|cube| + 2e-6 |oracle| is asserted; NaN patterns must agree exactly."""
+import os
+
 import numpy as np
 import pytest
 
@@ -60,6 +62,40 @@ def test_convolve_planes_matches_oracle(engine, nchan, ny, nx, beam):
         dinc = None if include is None else torch.from_numpy(include.astype(np.uint8)).cuda()
         out = engine.convolve_planes(d, include=dinc, **kdev).cpu().numpy()
         _close(out, oc.convolve_planes(cube, k64, include=include), np.nanmax(np.abs(cube)))
+
+
+@pytest.mark.parametrize("K,nchan,ny,nx", [(9, 3, 64, 64), (11, 2, 70, 132), (13, 2, 129, 68), (15, 3, 40, 200),
+                                            (23, 4, 150, 136), (59, 2, 96, 72), (65, 1, 130, 128)])
+def test_convolve_fast_separable_path_matches_oracle(engine, K, nchan, ny, nx):
+    """Planes with 16-byte aligned rows and no pixel mask take the fast separable kernel (cp.async window, packed
+    FMAs on pairs, static ramps for each K mod 8) with the generic kernel redoing the tiles that hold NaNs: every
+    residue of K mod 8, tiles cut by the image edge, all-finite planes, scattered NaNs and a blank corner; and the
+    result equals the generic kernel's to rounding."""
+    import os
+    import torch
+    rng = np.random.default_rng(K * 1000 + nx)
+    h = K // 2
+    kx = np.exp(-0.5 * ((np.arange(K) - h) / (K / 6.0)) ** 2)
+    ky = np.exp(-0.5 * ((np.arange(K) - h) / (K / 7.0)) ** 2)      # different widths: a transposed pass would show
+    k64 = np.outer(ky, kx)
+    kdev = dict(kx=torch.from_numpy(kx.astype(np.float32)).cuda(), ky=torch.from_numpy(ky.astype(np.float32)).cuda())
+    k64 = np.outer(ky.astype(np.float32).astype(np.float64), kx.astype(np.float32).astype(np.float64))
+    clean = rng.normal(size=(nchan, ny, nx)).astype(np.float32)
+    holes = clean.copy()
+    holes[rng.random(holes.shape) < 0.002] = np.nan
+    holes[:, : ny // 5, : nx // 4] = np.nan
+    holes[-1, -1, -1] = np.nan                                     # a NaN in the last corner of the last plane
+    for cube in (clean, holes):
+        d = torch.from_numpy(cube).cuda()
+        out = engine.convolve_planes(d, **kdev).cpu().numpy()
+        _close(out, oc.convolve_planes(cube, k64), np.nanmax(np.abs(cube)))
+        os.environ["B200FIT_CONV_GENERIC"] = "1"
+        try:
+            gen = engine.convolve_planes(d, **kdev).cpu().numpy()
+        finally:
+            del os.environ["B200FIT_CONV_GENERIC"]
+        assert np.array_equal(np.isnan(out), np.isnan(gen))
+        assert np.nanmax(np.abs(out - gen)) <= 1e-5
 
 
 def test_convolve_separable_equals_general_path(engine):
@@ -231,7 +267,7 @@ def test_region_iter_2comp_fit_from_fits_files(engine, tmp_path):
 
 
 def test_master_2comp_fit_pipeline(engine, tmp_path):
-    """The full driver (master_fitter.py:583-679, recover_wide off): two-step fit, bad-pixel and marginal refits,
+    """The full driver (master_fitter.py:583-679): two-step fit, bad-pixel and marginal refits,
     expansion into the surroundings, products on disk."""
     import os
     from mufasa_b200 import master_fitter as mf
@@ -281,7 +317,75 @@ def test_master_2comp_fit_pipeline(engine, tmp_path):
     np.testing.assert_allclose(m0[np.isfinite(m0)], m0_host[np.isfinite(m0)], rtol=1e-6, atol=1e-5)
     # and the one-call driver runs the same chain
     reg2 = mf.Region(path, "field2", paraDir=str(tmp_path / "paras2"), fittype=syn["fittype"], device=0)
-    mf.master_2comp_fit(reg2, snr_min=3.0, recover_wide=False, max_expand_iter=2)
+    mf.master_2comp_fit(reg2, snr_min=3.0, max_expand_iter=2)
     assert os.path.isfile(str(tmp_path / "paras2" / "field2_2vcomp_final.fits"))
-    with pytest.raises(NotImplementedError):
-        mf.master_2comp_fit(reg2, snr_min=3.0, recover_wide=True)
+
+
+def _wide_field(tmp_path, ny=40, nx=40, nchan=500):
+    """A field whose centre holds a second, fainter component 3 km/s from the first; everywhere the 2-component
+    fit is started from two guesses on top of the FIRST component, so it cannot find the second one."""
+    from mufasa_b200 import master_fitter as mf
+    v = synth.vaxis(nchan, 0.0724)
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    par1 = np.stack([0.3 * (xx / nx - 0.5) + 0.013, np.full((ny, nx), 0.3), np.full((ny, nx), 7.0), np.full((ny, nx), 3.0)])
+    par2 = np.stack([par1[0] + 3.0, np.full((ny, nx), 0.25), np.full((ny, nx), 6.0), np.full((ny, nx), 1.5)])
+    wide = np.hypot(yy - ny / 2, xx - nx / 2) < 12
+    m1 = T.oracle_modelcube(par1, v, "nh3_multi_v")
+    m2 = T.oracle_modelcube(np.concatenate([par1, par2]), v, "nh3_multi_v")
+    rng = np.random.default_rng(11)
+    cube = (np.where(wide[None], m2, m1) + rng.normal(0, 0.1, size=m1.shape)).astype(np.float32)
+    path = str(tmp_path / "wide.fits")
+    SpecCube(cube, v, rest_value=23.6944955e9, header=_header(ny, nx)).write(path)
+    reg = mf.Region(path, "wide", paraDir=str(tmp_path / "paras"), fittype="nh3_multi_v", device=0)
+    g1 = par1.copy()
+    g2 = np.concatenate([par1, par1])
+    g2[0] -= 0.15
+    g2[4] += 0.15
+    g2[3] *= 0.5
+    g2[7] *= 0.5
+    reg.ucube.fit_cube(ncomp=[1], simpfit=True, guesses=g1, snr_min=0.0)
+    reg.ucube.fit_cube(ncomp=[2], simpfit=True, guesses=g2, snr_min=0.0)
+    for nc in (1, 2):
+        reg.ucube.paraPaths[str(nc)] = '{}/{}_{}vcomp.fits'.format(reg.ucube.paraDir, reg.ucube.paraNameRoot, nc)
+    return reg, wide, par1, par2
+
+
+def test_refit_2comp_wide_recovers_a_distant_second_component(engine, tmp_path):
+    """refit_2comp_wide (master_fitter.py:981-1098), both methods.  'moments': guesses from the spectrum with its
+    main component blanked.  'residual': the 1-component fit of the convolved residual of the best model, regridded to
+    full resolution -- with the residual mask as the reference's docstrings describe it, and with the reference's
+    actual branches, under which a residual with significant pixels ends the stage without a refit."""
+    from mufasa_b200 import master_fitter as mf
+    reg, wide, par1, par2 = _wide_field(tmp_path)
+    p2 = reg.ucube.pcubes['2']
+    sep0 = np.abs(p2.parcube[4] - p2.parcube[0])
+    assert np.median(sep0[wide]) < 1.5                          # the badly started fit did not find the far line
+    lnk21_0 = np.array(reg.ucube.get_AICc_likelihood(2, 1))
+    # the reference's control flow: the residual cube has significant pixels -> returned without a mask -> SNRMaskError
+    assert mf.RESIDUAL_MASK_AS_DOCUMENTED is False
+    assert mf.refit_2comp_wide(reg, snr_min=3, method='residual', planemask=wide) is None
+    assert reg.progress_log[-1]["n_attempted"] == 0 and not hasattr(reg, 'ucube_res_cnv')
+    np.testing.assert_array_equal(np.abs(p2.parcube[4] - p2.parcube[0]), sep0)
+    # as documented: masked to the significant residual, convolved, fitted, regridded, refitted
+    mf.RESIDUAL_MASK_AS_DOCUMENTED = True
+    try:
+        good = mf.refit_2comp_wide(reg, snr_min=3, method='residual', planemask=wide)
+    finally:
+        mf.RESIDUAL_MASK_AS_DOCUMENTED = False
+    assert good is not None and good.shape == wide.shape and good[wide].mean() > 0.8 and not good[~wide].any()
+    assert reg.ucube_res_cnv.cube.shape[1:] == (wide.shape[0] // 2, wide.shape[1] // 2)
+    v_far = np.maximum(p2.parcube[0], p2.parcube[4])
+    assert np.median(np.abs(v_far[good] - par2[0][good])) < 0.05
+    lnk21_1 = reg.ucube.get_AICc_likelihood(2, 1)
+    assert np.all(lnk21_1[good] > lnk21_0[good]) and np.median(lnk21_1[good]) > 5
+    np.testing.assert_array_equal(lnk21_1[~wide & np.isfinite(lnk21_0)], lnk21_0[~wide & np.isfinite(lnk21_0)])
+    assert os.path.isfile(str(tmp_path / "paras" / "wide_1vcomp_onBestResidual.fits"))
+    assert os.path.isfile(str(tmp_path / "paras" / "wide_2vcomp.fits"))
+    # 'moments' on a fresh copy of the same field
+    reg_m, wide, par1, par2 = _wide_field(tmp_path)
+    good_m = mf.refit_2comp_wide(reg_m, snr_min=3, method='moments', planemask=wide, save_para=False)
+    p2m = reg_m.ucube.pcubes['2']
+    assert good_m is not None and good_m[wide].mean() > 0.5 and not good_m[~wide].any()
+    assert np.median(np.abs(np.maximum(p2m.parcube[0], p2m.parcube[4])[good_m] - par2[0][good_m])) < 0.05
+    with pytest.raises(Exception):
+        mf.refit_2comp_wide(reg_m, method='nonsense', planemask=wide)
