@@ -101,15 +101,18 @@ class PCube(object):
     def engine(self):
         return get_engine(self._device)
 
-    def rows_on_device(self, wait=True):
+    def rows_on_device(self, wait=True, max_slabs=None):
         """The cube as pixel-major rows [ny*nx, stride] fp32 on the GPU (NaN padded, velocity ascending).
 
         Uploaded ONCE per data cube and shared between the PCubes of one UltraCube (``share_device``); the reference
         instead re-reads the FITS file for every ncomp (UltraCube.py:191).  A large cube in pinned memory goes up as
-        two row slabs on a second stream (``b200fit_upload_slab`` + ``b200fit_gather_spectra`` per slab), each with
-        an event: fit jobs that only touch the first slab start while the second is still crossing PCIe
+        up to four row slabs on a second stream (``b200fit_upload_slab`` + ``b200fit_gather_spectra`` per slab), each
+        with an event: fit jobs that only touch the first slab start while the others are still crossing PCIe
         (``slab_ready``, used by Engine.fit_batch).  ``wait=True`` orders the current stream after the whole upload
-        -- what every consumer other than the batched fit wants."""
+        -- what every consumer other than the batched fit wants.  ``max_slabs`` = how many slabs to QUEUE in this
+        call (None: all that are left): host-to-device copies are served in the order they were queued, whatever
+        their stream, so a caller with small uploads of its own (guesses) queues one slab, then those, then the rest
+        (dist.SelectionJob) -- queued behind the whole cube they would arrive after it, and so would the first fit."""
         if self._dev.get("rows") is None:
             nchan, ny, nx = self.cube.shape
             eng = self.engine
@@ -129,26 +132,44 @@ class PCube(object):
                 up = eng.side_stream("h2d_cube")
                 up.wait_stream(torch.cuda.current_stream(eng.device))   # the allocation above is ordered before
                 bounds, events = [], []
-                for k in range(nslab):
-                    first, last = (k * ny // nslab) * nx, ((k + 1) * ny // nslab) * nx
-                    with torch.cuda.stream(up):
-                        staging = torch.empty((nchan, last - first), dtype=torch.float32, device=eng.device)
-                        # in pieces of ~16 MB: a copy cannot be overtaken, and the (small) upload of the guesses
-                        # issued later on another stream must not sit behind the whole slab
-                        step = max(1, (16 << 20) // (4 * (last - first)))
-                        for c0 in range(0, nchan, step):
-                            c1 = min(nchan, c0 + step)
-                            eng.upload_slab(t[c0:c1], first, last - first, staging[c0:c1])
-                        eng.gather(staging, None, flip=flip, out=rows[first:last])
-                        ev = torch.cuda.Event()
-                        ev.record(up)
-                        del staging
-                    bounds.append(last)
-                    events.append(ev)
+
+                # a short first slab (1/16 of the rows, at least SPLIT_MIN_PIXELS spectra): the fits start sooner
+                r0 = max(ny // 16, -(-eng.SPLIT_MIN_PIXELS // nx))
+                edges = [0] + [r0 + k * (ny - r0) // (nslab - 1) for k in range(nslab)]
+
+                def queue_slabs():
+                    for k in range(nslab):
+                        first, last = edges[k] * nx, edges[k + 1] * nx
+                        with torch.cuda.stream(up):
+                            staging = torch.empty((nchan, last - first), dtype=torch.float32, device=eng.device)
+                            # in pieces of ~16 MB (one 2-D copy each)
+                            step = max(1, (16 << 20) // (4 * (last - first)))
+                            for c0 in range(0, nchan, step):
+                                c1 = min(nchan, c0 + step)
+                                eng.upload_slab(t[c0:c1], first, last - first, staging[c0:c1])
+                            eng.gather(staging, None, flip=flip, out=rows[first:last])
+                            ev = torch.cuda.Event()
+                            ev.record(up)
+                            del staging
+                        bounds.append(last)
+                        events.append(ev)
+                        yield
+
                 self._dev["rows"] = rows
                 self._dev["slab_ready"] = (bounds, events)
+                self._dev["slab_queue"] = queue_slabs()
                 self._dev["host_cube"] = t                      # keeps the pinned source alive until the copies ran
             self._dev["h2d_bytes"] = t.numel() * 4
+        pending = self._dev.get("slab_queue")
+        if pending is not None:
+            n = 0
+            while max_slabs is None or wait or n < max_slabs:
+                try:
+                    next(pending)
+                except StopIteration:
+                    self._dev["slab_queue"] = None
+                    break
+                n += 1
         if wait and self._dev.get("slab_ready") is not None:
             torch.cuda.current_stream(self.engine.device).wait_event(self._dev["slab_ready"][1][-1])
         return self._dev["rows"]
