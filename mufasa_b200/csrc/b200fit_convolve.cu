@@ -231,12 +231,18 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void* src, unsign
 template <int KR, class Load>
 __device__ __forceinline__ void slide_pairs(Load ld, const float* __restrict__ w, int nb, f32x2 (&acc)[NOUT]) {
     static_assert(NOUT == 8, "the weight ring is 8 deep");
-    float wp[8], wc[8];
+    float wp[8], wc[8], wn[8];    // weights of the previous / this / the next block of 8 (loaded one block ahead)
     auto load8 = [&](int m) {
         const float4 a = *reinterpret_cast<const float4*>(w + 8 * m), b = *reinterpret_cast<const float4*>(w + 8 * m + 4);
-        wc[0] = a.x, wc[1] = a.y, wc[2] = a.z, wc[3] = a.w, wc[4] = b.x, wc[5] = b.y, wc[6] = b.z, wc[7] = b.w;
+        wn[0] = a.x, wn[1] = a.y, wn[2] = a.z, wn[3] = a.w, wn[4] = b.x, wn[5] = b.y, wn[6] = b.z, wn[7] = b.w;
+    };
+    auto shift = [&]() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wp[i] = wc[i], wc[i] = wn[i];
     };
     load8(0);
+    shift();
+    load8(1);                                 // (nb >= 1; the array is readable up to 8 nb + 7)
 #pragma unroll
     for (int u = 0; u < 8; ++u) {             // ramp-in: input u reaches outputs 0 .. u
         const f32x2 x = ld(u);
@@ -245,9 +251,8 @@ __device__ __forceinline__ void slide_pairs(Load ld, const float* __restrict__ w
     }
 #pragma unroll 1
     for (int m = 1; m < nb; ++m) {            // every input reaches all 8 outputs
-#pragma unroll
-        for (int i = 0; i < 8; ++i) wp[i] = wc[i];
-        load8(m);
+        shift();
+        load8(m + 1);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const f32x2 x = ld(8 * m + u);
@@ -258,9 +263,7 @@ __device__ __forceinline__ void slide_pairs(Load ld, const float* __restrict__ w
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) wp[i] = wc[i];
-    load8(nb);                                // weights 8 nb .. K - 1 (what follows them is never used)
+    shift();                                  // wc: weights 8 nb .. K - 1 (what follows them is never used)
 #pragma unroll
     for (int t = 0; t < KR + 7; ++t) {        // ramp-out: input 8 nb + t reaches outputs o >= t - KR + 1
         const f32x2 x = ld(8 * nb + t);
