@@ -134,6 +134,8 @@ class UltraCube(object):
                     pass
             if batch:
                 eng = batch[0]["pcube"].engine
+                for job in batch:                               # every job's guesses are queued: now the rest of the cube
+                    job["pcube"].rows_on_device(wait=False)
                 outs = eng.fit_batch(batch)
                 # the model selection needs nothing from the host: queue it right behind the fits, on the parameters
                 # as they lie on the device, and bring the fit results back on a second stream meanwhile

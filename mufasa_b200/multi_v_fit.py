@@ -164,7 +164,9 @@ def cubefit_simp_steps(cube, pcube, ncomp, guesses, multicore=None, maskmap=None
 
     data = _cube_data(cube)
     if hasattr(pcube, "rows_on_device"):
-        pcube.rows_on_device(wait=False)   # start the (asynchronous) upload + layout pass; host logic below overlaps it
+        # start the (asynchronous) upload + layout pass of the first slab; host logic below overlaps it, and the other
+        # slabs are queued behind the guesses (PCube.fiteach): host-to-device copies are served first in, first out
+        pcube.rows_on_device(wait=False, max_slabs=1)
     planemask = np.any(np.isfinite(guesses), axis=0)
     peaksnr, planemask, kwargs = handle_snr(pcube, snr_min, planemask, **kwargs)
 

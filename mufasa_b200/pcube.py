@@ -109,8 +109,8 @@ class PCube(object):
         up to four row slabs on a second stream (``b200fit_upload_slab`` + ``b200fit_gather_spectra`` per slab), each
         with an event: fit jobs that only touch the first slab start while the others are still crossing PCIe
         (``slab_ready``, used by Engine.fit_batch).  ``wait=True`` orders the current stream after the whole upload
-        -- what every consumer other than the batched fit wants.  ``max_slabs`` = how many slabs to QUEUE in this
-        call (None: all that are left): host-to-device copies are served in the order they were queued, whatever
+        -- what every consumer other than the batched fit wants.  ``max_slabs`` = how many slabs must have
+        been QUEUED when this call returns (None: all): host-to-device copies are served in the order they were queued, whatever
         their stream, so a caller with small uploads of its own (guesses) queues one slab, then those, then the rest
         (dist.SelectionJob) -- queued behind the whole cube they would arrive after it, and so would the first fit."""
         if self._dev.get("rows") is None:
@@ -161,15 +161,14 @@ class PCube(object):
                 self._dev["host_cube"] = t                      # keeps the pinned source alive until the copies ran
             self._dev["h2d_bytes"] = t.numel() * 4
         pending = self._dev.get("slab_queue")
-        if pending is not None:
-            n = 0
-            while max_slabs is None or wait or n < max_slabs:
+        if pending is not None:                 # ``max_slabs`` = how many slabs must have been queued in total
+            while max_slabs is None or wait or self._dev.get("slabs_queued", 0) < max_slabs:
                 try:
                     next(pending)
                 except StopIteration:
                     self._dev["slab_queue"] = None
                     break
-                n += 1
+                self._dev["slabs_queued"] = self._dev.get("slabs_queued", 0) + 1
         if wait and self._dev.get("slab_ready") is not None:
             torch.cuda.current_stream(self.engine.device).wait_event(self._dev["slab_ready"][1][-1])
         return self._dev["rows"]
@@ -291,7 +290,7 @@ class PCube(object):
         dev = eng.device
         prob = self._problem(fittype, ncomp, npix, list(minpars), list(maxpars), signal_cut=float(signal_cut or 0.0),
                              maxiter=maxiter)
-        rows = self.rows_on_device(wait=False)
+        rows = self.rows_on_device(wait=False, max_slabs=1)   # the other slabs follow the guesses (copies are FIFO)
         # guesses (and the pixel list) go up through pinned memory on a second stream: a copy from pageable memory
         # on the main stream would make the host wait for the cube upload queued ahead of it
         main = torch.cuda.current_stream(dev)
@@ -314,6 +313,8 @@ class PCube(object):
         g_dev.record_stream(main)
         if idx_dev is not None:
             idx_dev.record_stream(main)
+        if self._deferred is None:
+            self.rows_on_device(wait=False)     # (a batched fit queues the rest once every job's guesses are on their way)
         job = dict(prob=prob, spectra=rows, guesses=g_dev, row_index=idx_dev, pcube=self, pix=pix, ready=ready,
                    slab_ready=self._dev.get("slab_ready"))
         if self._deferred is not None:
