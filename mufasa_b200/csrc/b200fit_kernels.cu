@@ -374,6 +374,10 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int unit = (TEAM > 1) ? 0 : warp;
     const bool leader = (TEAM > 1) ? (threadIdx.x == 0) : (lane == 0);   // issues this unit's copies
+    const unsigned count = fq->count[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) fq->count[cur ^ 1] = 0;   // the list this round's solver appends to
+    // (the grid is sized for a full list: blocks without a pixel leave before any set-up)
+    if (((TEAM > 1) ? blockIdx.x : blockIdx.x * EVAL_WARPS) >= count) return;
     const unsigned row_bytes = (unsigned)(stride * sizeof(float));
     const unsigned buf_bytes = (unsigned)eval_buf_bytes<NC>(stride);
     unsigned char* const ubase = stage_smem + (size_t)unit * 2 * buf_bytes;
@@ -385,8 +389,6 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, (NC == 1) ? 5 : 4)
     load_fit_tables(pr, tb);                                // (ends with __syncthreads: the barriers are visible)
     EvalScratch<NC>& w = scratch[(TEAM > 1) ? 0 : warp];   // line records: per warp, or shared by the team
     EvalScratch<NC>& wr = scratch[warp];                    // reduction tile: always per warp
-    const unsigned count = fq->count[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) fq->count[cur ^ 1] = 0;   // the list this round's solver appends to
     const unsigned unit0 = (TEAM > 1) ? blockIdx.x : blockIdx.x * EVAL_WARPS + warp;
     const unsigned nunits = (TEAM > 1) ? gridDim.x : gridDim.x * EVAL_WARPS;
     const int nhf = pr.nhf;
@@ -683,10 +685,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 8)   // 128 regs (a few spills)
     constexpr int P = 4 * NC;
     constexpr unsigned GROUPS = SOLVE_THREADS / P;   // pixels per block and pass
     __shared__ FitTables tb;
+    // The grid is sized for a full list (it is part of a captured graph); in the late rounds most blocks have nothing
+    // to do and leave before the table load and its barrier -- this kernel's latency is what the tail of a fit waits on.
+    const unsigned count = fq->count[cur];
+    if (blockIdx.x * GROUPS >= count) return;
     load_fit_tables(pr, tb);
     const LMConfig cf{tb.lo, tb.hi, pr.ftol, pr.max_iter};
     const LaneGroup<P> g;
-    const unsigned count = fq->count[cur];
     const unsigned gsub = threadIdx.x / P;   // group of this lane within the block
     // warp-uniform trip count: all groups of a warp loop together, the ones past the end carry ``valid = false``
     for (unsigned idx0 = blockIdx.x * GROUPS; idx0 < count; idx0 += gridDim.x * GROUPS) {
@@ -1591,10 +1596,12 @@ struct FitJob {
     unsigned* lists[2] = {nullptr, nullptr};
     void* states = nullptr;
     cudaStream_t stream = nullptr;
-    unsigned egrid = 0, egrid_team = 0, sgrid = 0;
+    unsigned egrid = 0, egrid_team = 0, sgrid = 0, sgrid_small = 0;
+    unsigned seen = 0xffffffffu, small_limit = 0;   // last active count the host has seen; <= small_limit: small solver grid
     size_t esmem = 0, esmem_team = 0;   // dynamic shared memory of the evaluation kernels (staging buffers)
     bool use_graph = false;             // rounds are launched as captured groups (job_rounds)
-    cudaGraphExec_t gexec[2] = {nullptr, nullptr};   // ... one executable graph per evaluation variant
+    cudaGraphExec_t gexec[4] = {nullptr, nullptr, nullptr, nullptr};   // ... one executable graph per evaluation variant
+                                                                        //     and solver grid (index team + 2 small)
     void* wait_event = nullptr;
     int r = 0, max_rounds = 0, nchecks = 0, slot0 = 0;
     bool finished = false, prof = false;
@@ -1679,6 +1686,13 @@ static int job_begin(b200fit_ctx* ctx, FitJob& jb, void* d_workspace) {
     jb.egrid = (unsigned)egrid;
     jb.egrid_team = (unsigned)egrid_team;
     jb.sgrid = (unsigned)sgrid;
+    // Late rounds: the solver's latency is what the tail of a fit waits on, and scheduling num_sms x 32 blocks of which
+    // nearly all leave at once is a good part of it.  Once the host has SEEN (with its usual lag; counts only fall) an
+    // active count that two blocks per SM cover in one pass, the groups are launched with that grid.  Per-pixel
+    // arithmetic does not depend on the grid.
+    jb.sgrid_small = (unsigned)std::min<long long>(sgrid, (long long)ctx->num_sms * 2);
+    jb.small_limit = (unsigned)(jb.sgrid_small * sgroups);
+    jb.seen = 0xffffffffu;
     jb.max_rounds = (2 * pr.max_iter + 3 + FIT_CHECK - 1) / FIT_CHECK * FIT_CHECK;   // whole groups of rounds
     jb.r = 0;
     jb.nchecks = 0;
@@ -1688,7 +1702,7 @@ static int job_begin(b200fit_ctx* ctx, FitJob& jb, void* d_workspace) {
 
 // The two kernels of one round on the job's stream (directly, or recorded into a graph being captured there).
 template <int NC>
-static void launch_round(FitJob& jb, int cur, bool team) {
+static void launch_round(FitJob& jb, int cur, bool team, bool small = false) {
     constexpr int P = 4 * NC;
     cudaStream_t stream = jb.stream;
     auto* ek = (jb.model_id == B200FIT_MODEL_NH3_11)
@@ -1698,9 +1712,9 @@ static void launch_round(FitJob& jb, int cur, bool team) {
                            : fit_eval_kernel<NC, B200FIT_MODEL_N2HP_10, 1>);
     ek<<<team ? jb.egrid_team : jb.egrid, EVAL_WARPS * 32, team ? jb.esmem_team : jb.esmem, stream>>>(
         jb.pr, jb.d_spectra, jb.stride, jb.d_row_index, (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
-    fit_solve_kernel<NC><<<jb.sgrid, SOLVE_THREADS, 0, stream>>>(jb.pr, (PixState<P>*)jb.states, jb.lists[cur],
-                                                                 jb.lists[cur ^ 1], jb.fq, cur, jb.d_params, jb.d_perr,
-                                                                 jb.d_chi2, jb.d_err_used, jb.d_status, jb.d_counts);
+    fit_solve_kernel<NC><<<small ? jb.sgrid_small : jb.sgrid, SOLVE_THREADS, 0, stream>>>(
+        jb.pr, (PixState<P>*)jb.states, jb.lists[cur], jb.lists[cur ^ 1], jb.fq, cur, jb.d_params, jb.d_perr, jb.d_chi2,
+        jb.d_err_used, jb.d_status, jb.d_counts);
 }
 
 // One GROUP of FIT_CHECK rounds, then the (asynchronous) look at the active count.  The group is a CUDA graph,
@@ -1715,11 +1729,12 @@ static int job_rounds(b200fit_ctx* ctx, FitJob& jb) {
     static_assert(fit_team_round<NC>() % FIT_CHECK == 0, "the evaluation variant changes between groups of rounds");
     const bool team = r0 >= fit_team_round<NC>();
     if (jb.use_graph) {
-        cudaGraphExec_t& ge = jb.gexec[team ? 1 : 0];
+        const bool small = jb.seen <= jb.small_limit;
+        cudaGraphExec_t& ge = jb.gexec[(team ? 1 : 0) + (small ? 2 : 0)];
         if (!ge) {
             cudaGraph_t graph = nullptr;
             CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-            for (int r = 0; r < FIT_CHECK; ++r) launch_round<NC>(jb, r & 1, team);   // r0 is even: cur = r & 1
+            for (int r = 0; r < FIT_CHECK; ++r) launch_round<NC>(jb, r & 1, team, small);   // r0 is even: cur = r & 1
             const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
             if (ce != cudaSuccess || !graph) return fail(ctx, B200FIT_E_CUDA, "fit: stream capture of a round group", ce);
             const cudaError_t ci = cudaGraphInstantiate(&ge, graph, 0);
@@ -1741,7 +1756,7 @@ static int job_rounds(b200fit_ctx* ctx, FitJob& jb) {
             ek<<<team ? jb.egrid_team : jb.egrid, EVAL_WARPS * 32, team ? jb.esmem_team : jb.esmem, stream>>>(
                 jb.pr, jb.d_spectra, jb.stride, jb.d_row_index, (PixState<P>*)jb.states, jb.lists[cur], jb.fq, cur);
             if (jb.prof) ctx->next_event(stream);   // [2 + 2r] after the evaluation of round r
-            fit_solve_kernel<NC><<<jb.sgrid, SOLVE_THREADS, 0, stream>>>(
+            fit_solve_kernel<NC><<<(jb.seen <= jb.small_limit) ? jb.sgrid_small : jb.sgrid, SOLVE_THREADS, 0, stream>>>(
                 jb.pr, (PixState<P>*)jb.states, jb.lists[cur], jb.lists[cur ^ 1], jb.fq, cur, jb.d_params, jb.d_perr,
                 jb.d_chi2, jb.d_err_used, jb.d_status, jb.d_counts);
             ctx->launches += 2;
@@ -1758,7 +1773,8 @@ static int job_rounds(b200fit_ctx* ctx, FitJob& jb) {
         if (jb.nchecks >= FIT_RING - 2) {   // wait for the check issued (FIT_RING - 2) checks ago
             const int old = jb.slot0 + (jb.nchecks - (FIT_RING - 2)) % FIT_RING;
             CK(cudaEventSynchronize(ctx->check_ev[old]));
-            if (ctx->h_count[old] == 0) jb.finished = true;
+            jb.seen = ctx->h_count[old];
+            if (jb.seen == 0) jb.finished = true;
         }
         if (!jb.finished) {
             CK(cudaMemcpyAsync((void*)&ctx->h_count[slot], &jb.fq->count[cur ^ 1], sizeof(unsigned),
