@@ -232,6 +232,28 @@ def median_like_numpy(values):
     return lo if n % 2 else (lo + hi) / 2.0
 
 
+def copy_rows(dst, src, rows):
+    """dst[:, i] = src[:, rows[i]] for [k, n, nx] arrays, by runs of consecutive rows (slices: plain memcpy; np.take
+    along the middle axis is several times slower, and a cyclic partition owns its rows in blocks)."""
+    import numpy as np
+    rows = np.asarray(rows)
+    a = 0
+    while a < rows.size:
+        b = a + 1
+        while b < rows.size and rows[b] == rows[b - 1] + 1:
+            b += 1
+        dst[:, a:b] = src[:, int(rows[a]):int(rows[a]) + (b - a)]
+        a = b
+
+
+def vstats_of_device(t):
+    """(median, 99th, 1st percentile) of the finite, non-zero entries of a float64 device tensor."""
+    t = t.ravel()
+    t = t[torch.isfinite(t) & (t != 0)]
+    p99, p1 = percentiles_like_numpy(t, [99, 1])
+    return median_like_numpy(t), p99, p1
+
+
 def global_vstats(vmaps, device):
     """(median, 99th, 1st percentile) of the finite, non-zero velocity guesses ``vmaps`` [k, ny, nx] -- the numbers
     cubefit_simp derives its velocity window from (multi_v_fit.py:163-176) -- computed on ``device``."""
@@ -275,14 +297,24 @@ class SelectionJob(object):
         spec = SpecCube(slab, v_kms)
         self.model_f32 = spec._data.dtype == np.float32
         self.ref = ref = PCube(spec._data, spec.xarr(), header=spec.header, unit=spec.unit, device=dev)
-        # Host-to-device copies are served in the order they are queued, whatever their stream: the velocity maps of
-        # the global statistics go first (24 MB), then the FIRST slab of the cube, then this rank's guesses (staged
-        # on the host while that slab is crossing PCIe), then the other slabs -- so the fits of the first slab start
-        # when it is resident.  (Queued behind the whole cube, statistics and guesses arrived after it and nothing
-        # overlapped the upload: 474 -> 4xx ms end to end on one GPU at 1024 x 1024 x 1000, profiles/ab/.)
+        # Host-to-device copies are served in the order they are queued, whatever their stream, so they are queued in
+        # the order the first fit needs them: the velocity maps of the global statistics (24 MB), the FIRST slab of
+        # the cube, this rank's guesses (staged on the host while that slab is crossing PCIe), then the other slabs.
+        # Only then does the host wait for anything (the statistics: a sort on the GPU), and the kernels that need them
+        # follow.  (Queued behind the whole cube, statistics and guesses arrived after it and nothing overlapped the
+        # upload: 474 -> 405 ms end to end on one GPU at 1024 x 1024 x 1000, profiles/ab/e2e_cfg5_timeline.py.)
+        main = torch.cuda.current_stream(eng.device)
+        up = eng.side_stream("h2d")
+        vdev = {}
         if vstats is None:
-            vstats = {1: global_vstats(guesses1[::4], eng.device), 2: global_vstats(guesses2[::4], eng.device)}
-        self.vstats = vstats
+            for nc, full in ((1, guesses1), (2, guesses2)):
+                vstage = eng.pinned_stage(("vmaps", nc, ny, nx))
+                np.copyto(vstage.numpy(), full[::4])
+                with torch.cuda.stream(up):
+                    vdev[nc] = vstage.to(eng.device, non_blocking=True)
+                    vdev[nc].record_stream(main)
+            v_ready = torch.cuda.Event()
+            v_ready.record(up)
         if npix:
             ref.rows_on_device(wait=False, max_slabs=1)
         # The front half of cubefit_simp (multi_v_fit.py:126-190) for both models, ON THE DEVICE: the rank's rows of the
@@ -291,10 +323,25 @@ class SelectionJob(object):
         # and every pixel of the slab enters the fit -- the fit kernel itself reports a pixel with a non-finite guess
         # as "not fitted" (zeros), which is what the reference's maskmap & all-finite rule comes to.  On the host this
         # conditioning costs ~0.2 s per 1024 x 1024 map (copies, masks, clamps) and sat in front of the fits.
+        raw = {}
+        if npix:
+            for nc, full in ((1, guesses1), (2, guesses2)):
+                P = 4 * nc
+                stage = eng.pinned_stage(("rawguess", P, self.ry, nx))
+                if contiguous:
+                    np.copyto(stage.numpy(), full[:, int(rows[0]):int(rows[-1]) + 1, :])
+                else:
+                    copy_rows(stage.numpy(), full, rows)
+                with torch.cuda.stream(up):
+                    raw[nc] = stage.to(eng.device, non_blocking=True).reshape(P, npix)
+                    raw[nc].record_stream(main)
+            ref.rows_on_device(wait=False)                   # the rest of the cube follows the guesses
+        if vstats is None:
+            main.wait_event(v_ready)
+            vstats = {nc: vstats_of_device(vdev[nc]) for nc in (1, 2)}
+        self.vstats = vstats
         self.batch, self.jobs = [], {}
-        main = torch.cuda.current_stream(eng.device)
-        up = eng.side_stream("h2d")
-        for nc, full in ((1, guesses1), (2, guesses2)):
+        for nc in (1, 2):
             P = 4 * nc
             mm = MetaModel(fittype, nc)
             v_median, v_99p, v_1p = vstats[nc]
@@ -307,14 +354,8 @@ class SelectionJob(object):
             if v_1p - mm.sigmax < vmin:
                 vmin = v_1p - mm.sigmax
             lo, hi = mm.limits(vmin, vmax)
-            stage = eng.pinned_stage(("rawguess", P, self.ry, nx))
-            if contiguous:
-                np.copyto(stage.numpy(), full[:, int(rows[0]):int(rows[-1]) + 1, :])
-            else:
-                np.take(full, rows, axis=1, out=stage.numpy())
             with torch.cuda.stream(up):
-                raw = stage.to(eng.device, non_blocking=True).reshape(P, npix)
-                g_dev = eng.prepare_guesses(raw, lo, hi, mm.eps)
+                g_dev = eng.prepare_guesses(raw[nc], lo, hi, mm.eps)
                 ready = torch.cuda.Event()
                 ready.record(up)
             g_dev.record_stream(main)
@@ -324,7 +365,6 @@ class SelectionJob(object):
                                    pcube=None, pix=None, ready=ready, slab_ready=ref._dev.get("slab_ready"),
                                    lo=lo, hi=hi))
         if npix:
-            ref.rows_on_device(wait=False)                   # the rest of the cube follows the guesses
             self.prob = ref._problem(fittype, 1, npix, [-1e30] * 4, [1e30] * 4)
         else:                                                # an empty slab still answers the collectives
             v0, dv, _ = ref.xarr.v0_dv_flip
@@ -410,6 +450,22 @@ def fit_and_select(cube, v_kms, fittype, guesses1, guesses2, device=None, group=
     Returns dict(parcube1, errcube1, parcube2, errcube2, best_parcube, best_errcube, lnk10, lnk20, lnk21, ncomp) of
     [.., ny, nx] numpy arrays on rank 0 (None elsewhere) when ``gather``, else the slab's.  The arrays are views of
     a pinned staging buffer that the next call on this device reuses: copy what must outlive it."""
+    import os
+    import time
+    stamps = [time.perf_counter()] if os.environ.get("B200FIT_TIMELINE") else None
     job = SelectionJob(cube, v_kms, fittype, guesses1, guesses2, device=device, group=group, vstats=vstats,
                        partition=partition)
-    return job.to_host(job.run(gather=gather))
+    if stamps is not None:
+        stamps.append(time.perf_counter())
+    packed = job.run(gather=gather)
+    if stamps is not None:
+        stamps.append(time.perf_counter())
+        torch.cuda.synchronize()
+        stamps.append(time.perf_counter())
+    res = job.to_host(packed)
+    if stamps is not None:                     # host work + queued uploads | launches + fits | device wait | read-back
+        stamps.append(time.perf_counter())
+        import sys
+        sys.stderr.write("fit_and_select rank %d: init %.1f run %.1f wait %.1f to_host %.1f ms\n" % (
+            (job.rank,) + tuple(1e3 * (b - a) for a, b in zip(stamps[:-1], stamps[1:]))))
+    return res
