@@ -354,12 +354,14 @@ def run_b200(args):
     barrier()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = eng.launch_count()
+    host_launches0 = eng.host_launch_count()
     start.record()
     for _ in range(args.steps):
         packed = job.run()
     stop.record()
     barrier()
     launches_timed = eng.launch_count() - launches0
+    host_launches_timed = eng.host_launch_count() - host_launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = max_over_ranks(start.elapsed_time(stop)) / args.steps
     value = nspec / (ms_per_step * 1e-3)
@@ -464,6 +466,7 @@ def run_b200(args):
                         "api": "mufasa_b200.dist.fit_and_select(cube slab view, v, fittype, guesses1, guesses2): "
                                "pinned host slab in, 44 gathered maps out on rank 0; wall clock, max over ranks"},
                 "gpu_launches": int(launches_timed),
+                "host_launches": int(host_launches_timed),   # kernels outside graphs + graph launches (8 rounds each)
                 "stage_ms": {"fits_1c_2c": t_fits, "selection_assembly_gather": t_sel},
                 "roofline": roofline, "clocks": clocks,
                 "fit_stats": {"converged_2c": conv[0].item() / nspec, "maxiter_2c": conv[1].item() / nspec,

@@ -18,6 +18,8 @@ struct b200fit_ctx {
     std::vector<cudaGraphExec_t> retired;     // executable graphs of earlier fit calls, destroyed once retired_ev fired
     cudaEvent_t retired_ev = nullptr;
     unsigned long long launches = 0;          // kernels launched by this context (all entry points)
+    unsigned long long graph_kernels = 0;     // ... of which inside replayed CUDA graphs
+    unsigned long long graph_launches = 0;    // graph launches that carried them
     double* d_chan = nullptr;                 // per-channel constants of the fp64 model (3 x B200FIT_MAX_NCHAN)
     int chan_n = 0;                           // ... valid for this spectral axis: nchan, {v0, dv, nu_ref}
     double chan_key[3] = {0.0, 0.0, 0.0};

@@ -1743,6 +1743,8 @@ static int job_rounds(b200fit_ctx* ctx, FitJob& jb) {
         }
         CK(cudaGraphLaunch(ge, stream));
         ctx->launches += 2 * FIT_CHECK;
+        ctx->graph_kernels += 2 * FIT_CHECK;
+        ctx->graph_launches += 1;
         jb.r = r0 + FIT_CHECK;
     } else {
         for (int r = r0; r < r0 + FIT_CHECK; ++r) {
@@ -1879,6 +1881,9 @@ const char* b200fit_last_error(const b200fit_ctx* ctx) { return ctx ? ctx->err.c
 int b200fit_num_sms(const b200fit_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
 
 uint64_t b200fit_launch_count(const b200fit_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t b200fit_host_launch_count(const b200fit_ctx* ctx) {
+    return ctx ? ctx->launches - ctx->graph_kernels + ctx->graph_launches : 0;
+}
 
 int b200fit_set_profiling(b200fit_ctx* ctx, int32_t on) {
     if (!ctx) return B200FIT_E_ARG;

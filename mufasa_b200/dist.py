@@ -302,7 +302,7 @@ class SelectionJob(object):
         # the cube, this rank's guesses (staged on the host while that slab is crossing PCIe), then the other slabs.
         # Only then does the host wait for anything (the statistics: a sort on the GPU), and the kernels that need them
         # follow.  (Queued behind the whole cube, statistics and guesses arrived after it and nothing overlapped the
-        # upload: 474 -> 405 ms end to end on one GPU at 1024 x 1024 x 1000, profiles/ab/e2e_cfg5_timeline.py.)
+        # upload: 474 -> 402 ms end to end on one GPU at 1024 x 1024 x 1000, profiles/ab/e2e_cfg5_timeline.py.)
         main = torch.cuda.current_stream(eng.device)
         up = eng.side_stream("h2d")
         vdev = {}

@@ -89,6 +89,10 @@ class Engine(object):
     def launch_count(self):
         return int(self.lib.b200fit_launch_count(self.ctx))
 
+    def host_launch_count(self):
+        """Launches the host issued (kernels outside graphs + graph launches)."""
+        return int(self.lib.b200fit_host_launch_count(self.ctx))
+
     def set_profiling(self, on):
         self._profiling = bool(on)          # profiled fits run undivided (one event list per fit)
         self._check(self.lib.b200fit_set_profiling(self.ctx, 1 if on else 0), "b200fit_set_profiling")
