@@ -113,8 +113,10 @@ def replace_para(pcube, pcube_ref, mask, multicore=None):
     pcube.errcube[:, mask] = pcube_ref.errcube[:, mask]
     pcube.has_fit[mask] = pcube_ref.has_fit[mask]
     if getattr(pcube, "_modelcube", None) is not None:      # the reference patches the cached model cube in place
-        newmod = pcube_ref.get_modelcube(update=False)
-        pcube._modelcube[:, mask] = newmod[:, mask]
+        pix = np.flatnonzero(np.asarray(mask, bool).ravel())    # (here: only the adopted pixels are evaluated, not a
+        if pix.size:                                            #  whole second model cube)
+            nchan = pcube._modelcube.shape[0]
+            pcube._modelcube.reshape(nchan, -1)[:, pix] = pcube_ref.model_of_pixels(pix)
 
 
 def replace_rss(ucube, ucube_ref, ncomp, mask):
@@ -632,26 +634,79 @@ def get_skyheader(cube_header):
     return hdr2D
 
 
+def _best_residual_rows(reg):
+    """(residual [npix, nchan] float32 on the device, velocity ascending; engine; flip): data minus the selected model
+    per pixel, from the device-resident rows and ``b200fit_model`` -- the reference builds two host model cubes, the
+    selected one and their difference (master_fitter.py:2339-2373, 2412-2468; half a minute of numpy at
+    512 x 512 x 1000, and a cached model cube that every later ``replace_para`` would have to patch)."""
+    import torch
+    ucube = reg.ucube
+    ucube.get_all_lnk_maps(ncomp_max=2, rest_model_mask=True)
+    ref = ucube._ref_pcube if ucube._ref_pcube is not None else ucube.load_pcube()
+    eng = ref.engine
+    nchan, ny, nx = ucube.cube.shape
+    res = ref.rows_on_device()[:, :nchan].clone()
+    ncomp = torch.from_numpy(ucube.ncomp_map.astype(np.int64).ravel()).to(eng.device)
+    for nc in (1, 2):
+        sel = torch.nonzero(ncomp == nc).ravel()
+        if sel.numel() == 0:
+            continue
+        par = ucube._params_dev(nc, eng)[sel].contiguous()
+        prob = ref._problem(ucube.fittype, nc, int(sel.numel()), [-1e30] * (4 * nc), [1e30] * (4 * nc))
+        # the host recipe subtracts the model cube in the data's precision (get_modelcube has the cube's dtype)
+        model = torch.nan_to_num(eng.model(prob, par)[:, :nchan], nan=0.0).to(torch.float32)
+        res[sel] -= model
+    _, _, flip = ref.xarr.v0_dv_flip
+    return res, eng, flip
+
+
+def _rows_to_cube(rows, ny, nx, flip):
+    """[npix, nchan] device rows (velocity ascending) -> [nchan, ny, nx] numpy in the data cube's channel order."""
+    import torch
+    if flip:
+        rows = torch.flip(rows, dims=[1])
+    return np.ascontiguousarray(rows.t().cpu().numpy()).reshape(rows.shape[1], ny, nx)
+
+
+def _rms_of_rows(res):
+    """UltraCube.get_rms on device rows: 1.4826 median|r - roll(r, 2)| / sqrt(2) over the finite differences (numpy's
+    median: the mean of the two middle values of an even count)."""
+    import torch
+    diff = (res - torch.roll(res, 2, dims=1)).abs().to(torch.float64)
+    n = torch.isfinite(diff).sum(dim=1)
+    srt = torch.sort(torch.where(torch.isfinite(diff), diff, torch.full_like(diff, float("inf"))), dim=1).values
+    lo = torch.clamp((n - 1) // 2, min=0)[:, None]
+    hi = torch.clamp(n // 2, min=0)[:, None]
+    med = 0.5 * (torch.gather(srt, 1, lo) + torch.gather(srt, 1, hi))[:, 0]
+    med = torch.where(n > 0, med, torch.full_like(med, float("nan")))
+    return 1.4826 * med / 2 ** 0.5
+
+
 def get_best_2comp_residual(reg):
     """master_fitter.py:2339-2373: data minus the selected model, as a cube on the data's axes."""
-    modbest = get_best_2comp_model(reg)
-    return reg.ucube.cube.with_data(reg.ucube.cube._data - modbest)
+    res, eng, flip = _best_residual_rows(reg)
+    nchan, ny, nx = reg.ucube.cube.shape
+    return reg.ucube.cube.with_data(_rows_to_cube(res, ny, nx, flip))
 
 
 def get_best_2comp_residual_SpectralCube(reg, masked=True, window_hwidth=3.5, res_snr_cut=5):
     """master_fitter.py:2251-2336.  ``masked``: pixels are selected by the peak of the residual within
     ``window_hwidth`` of the 1-component velocity over the residual's own noise (see RESIDUAL_MASK_AS_DOCUMENTED for
     what the selection then does)."""
-    cube_res = get_best_2comp_residual(reg)
+    import torch
+    res, eng, flip = _best_residual_rows(reg)
+    nchan, ny, nx = reg.ucube.cube.shape
+    cube_res = reg.ucube.cube.with_data(_rows_to_cube(res, ny, nx, flip))
     if masked and res_snr_cut > 0:
-        best_rms = _rms_of_residual(cube_res._data)
-        vmap = reg.ucube.pcubes['1'].parcube[0]
-        window = mmg.vmask_cube(cube_res, vmap, window_hwidth=window_hwidth)
-        import warnings
-        with warnings.catch_warnings(), np.errstate(all="ignore"):
-            warnings.simplefilter("ignore", RuntimeWarning)
-            peak = np.nanmax(np.where(window, cube_res._data, np.nan), axis=0)
-            mask_res = peak / best_rms > res_snr_cut
+        best_rms = _rms_of_rows(res)
+        vmap = torch.from_numpy(np.ascontiguousarray(reg.ucube.pcubes['1'].parcube[0], dtype=np.float64).ravel()
+                                ).to(eng.device)
+        v = torch.from_numpy(np.sort(np.asarray(reg.ucube.cube.spectral_axis, dtype=np.float64))).to(eng.device)
+        window = (v[None, :] > (vmap - window_hwidth)[:, None]) & (v[None, :] < (vmap + window_hwidth)[:, None])
+        inside = window & torch.isfinite(res)
+        peak = torch.where(inside, res, torch.full_like(res, -float("inf"))).amax(dim=1).to(torch.float64)
+        peak = torch.where(inside.any(dim=1), peak, torch.full_like(peak, float("nan")))
+        mask_res = ((peak / best_rms) > res_snr_cut).cpu().numpy().reshape(ny, nx)
         if RESIDUAL_MASK_AS_DOCUMENTED:
             if mask_res.sum() >= 1:
                 return cube_res.with_mask(signals.binary_dilation(mask_res))
@@ -699,7 +754,7 @@ def fit_best_2comp_residual_cnv(reg, window_hwidth=3.5, res_snr_cut=3, savefit=T
     gg = mmg.moment_guesses_1c(m0, m1, m2)
     gg = gss_rf.refine_each_comp(gg, mask=np.isfinite(gg[0]))
     if res_snr_cut > 0:
-        rms = signals.mad_std(cube_res_cnv._data, axis=0)
+        rms = mmg.mad_std_cube(cube_res_cnv._data, device=reg.device)
         with np.errstate(invalid="ignore", divide="ignore"):
             maskmap = m0 / rms >= res_snr_cut
     else:

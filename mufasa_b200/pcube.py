@@ -381,6 +381,26 @@ class PCube(object):
         self.fit_header = hdr
         return self
 
+    def model_of_pixels(self, pix):
+        """[nchan, len(pix)] model spectra of the flat pixel indices ``pix`` (NaN where a pixel has no fit), in the data
+        cube's channel order and dtype -- what get_modelcube would hold in those columns, without the cube."""
+        P, ny, nx = self.parcube.shape
+        nchan = self.cube.shape[0]
+        pix = np.asarray(pix, dtype=np.int64)
+        dtype = self.cube.dtype if self.cube.dtype.kind == 'f' else np.float64
+        out = np.full((nchan, pix.size), np.nan, dtype=dtype)
+        par = self.parcube.reshape(P, ny * nx)[:, pix]
+        valid = np.any(par != 0, axis=0) & np.all(np.isfinite(par), axis=0)
+        if valid.any():
+            eng = self.engine
+            prob = self._problem(self.fittype, P // 4, int(valid.sum()), [-1e30] * P, [1e30] * P)
+            m = eng.model(prob, torch.from_numpy(np.ascontiguousarray(par[:, valid].T)).to(eng.device))[:, :nchan]
+            _, _, flip = self.xarr.v0_dv_flip
+            if flip:
+                m = torch.flip(m, dims=[1])
+            out[:, valid] = m.to(torch.float32 if dtype == np.float32 else torch.float64).cpu().numpy().T
+        return out
+
     def get_modelcube(self, update=False, multicore=1, mask=None):
         """Model cube from parcube (pyspeckit get_modelcube: NaN where there is no fit), dtype of the data cube,
         cached in ``_modelcube``; callers may mutate the returned array (master_fitter.py:2516-2520)."""

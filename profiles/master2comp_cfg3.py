@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""BASELINE configs[2] -- "512 x 512 x 1000 full pipeline" -- through master_fitter.master_2comp_fit (recover_wide
-off) from a FITS file on disk: two-step fit through the convolved cube, bad-pixel and marginal refits, expansion into
-the surroundings, products.  Wall-clock per stage.   usage: python profiles/master2comp_cfg3.py [ny nx nchan]"""
+"""BASELINE configs[2] -- "512 x 512 x 1000 full pipeline" -- through the stages of master_fitter.master_2comp_fit
+from a FITS file on disk: two-step fit through the convolved cube, bad-pixel, wide-separation (reference behaviour, and
+with WIDE_AS_DOCUMENTED=1 the documented masking) and marginal refits, expansion into the surroundings, products.  Wall-clock per stage.   usage: python profiles/master2comp_cfg3.py [ny nx nchan]"""
 import os
 import sys
 import tempfile
@@ -54,6 +54,10 @@ mf.iter_2comp_fit(reg, snr_min=snr_min)
 t0 = lap("iter_2comp_fit (convolve, cnv fits, full fits)", t0)
 mf.refit_bad_2comp(reg, snr_min=1.0, lnk_thresh=-5)
 t0 = lap("refit_bad_2comp", t0)
+mf.RESIDUAL_MASK_AS_DOCUMENTED = bool(os.environ.get("WIDE_AS_DOCUMENTED"))
+good = mf.refit_2comp_wide(reg, snr_min=1.0)
+t0 = lap("refit_2comp_wide (%s; refits kept: %s)" % (
+    "documented masking" if mf.RESIDUAL_MASK_AS_DOCUMENTED else "reference branches", None if good is None else int(good.sum())), t0)
 for nc in (1, 2):
     mf.refit_marginal(reg, ncomp=nc, lnk_thresh=10, holes_only=False, method='best_neighbour')
 t0 = lap("refit_marginal (1c, 2c)", t0)

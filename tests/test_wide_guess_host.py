@@ -111,3 +111,24 @@ def test_mom_guess_wide_sep_finds_both_lines():
     assert np.all(gg[0][one] > gg[4][one]) and np.abs(0.5 * (gg[0] + gg[4])[one] + 0.5).max() < 0.1
     np.testing.assert_allclose(gg[3][one], gg[7][one])
     np.testing.assert_allclose(gg[1][one], gg[5][one])
+
+
+def test_mad_std_cube_equals_the_numpy_twin():
+    from mufasa_b200 import signals
+    rng = np.random.default_rng(0)
+    for n in (50, 51):                                         # even and odd counts: numpy's median of the middle pair
+        d = rng.normal(size=(n, 4, 5)).astype(np.float32)
+        d[rng.random(d.shape) < 0.1] = np.nan
+        d[:, 0, 0] = np.nan
+        a, b = mmg.mad_std_cube(d), signals.mad_std(d, axis=0)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        np.testing.assert_array_equal(a[np.isfinite(a)], b[np.isfinite(b)])
+
+
+def test_copy_rows_by_runs():
+    from mufasa_b200.dist import copy_rows, owned_rows
+    src = np.arange(3 * 40 * 7, dtype=np.float64).reshape(3, 40, 7)
+    for rows in (owned_rows(40, 3, 1, "cyclic"), np.array([0, 1, 2, 9, 11, 12, 39]), np.arange(40), np.array([], int)):
+        dst = np.full((3, len(rows), 7), -1.0)
+        copy_rows(dst, src, rows)
+        np.testing.assert_array_equal(dst, src[:, rows])
