@@ -405,3 +405,49 @@ def test_slab_upload_and_slab_split_jobs_equal_single_upload():
             for a, b in zip(bp, bh):
                 np.testing.assert_array_equal(a, b)
             assert up.pcubes["2"].has_fit.sum() > (0.3 if maskmap is not None else 0.8) * (mask.sum() if maskmap is not None else ny * nx)
+
+
+def test_config4_scale_slab_properties():
+    """Size-independent properties at BASELINE configs[4] scale (a 192-row slab of the 1024 x 1024 x 1000 cube =
+    196 608 spectra, in pinned memory so that it goes up in slabs): the per-pixel fit results do not depend on how the
+    rows are cut into calls (whole slab == its two halves fitted separately, bit for bit, the global velocity
+    statistics being passed to both), the model selection recovers the synthetic truth, and the 1-component
+    velocities sit on the truth."""
+    import torch
+    from mufasa_b200 import _abi
+    from mufasa_b200 import dist as D
+    from mufasa_b200.engine import get_engine
+    eng = get_engine(0)
+    fittype, NY, NX, nchan, dv = synth.CONFIGS[5]
+    y0, ny = 416, 192
+
+    def gpu_modelcube(parcube, v, ft):
+        P, py, px = parcube.shape
+        prob = _abi.make_problem(ft, P // 4, len(v), py * px, v[0], v[1] - v[0], [-1e30] * P, [1e30] * P)
+        par = torch.from_numpy(np.ascontiguousarray(parcube.reshape(P, py * px).T)).to(eng.device)
+        return eng.model(prob, par)[:, :len(v)].float().cpu().numpy().T.reshape(len(v), py, px)
+
+    pinned = torch.empty((nchan, ny, NX), dtype=torch.float32).pin_memory()
+    g1, g2 = np.empty((4, ny, NX)), np.empty((8, ny, NX))
+    truth1, nct = np.empty((4, ny, NX)), np.empty((ny, NX), dtype=np.int8)
+    for a in range(0, ny, 64):
+        part = synth.make_cube(5, gpu_modelcube, rows=(y0 + a, y0 + a + 64), out=pinned.numpy()[:, a:a + 64, :])
+        g1[:, a:a + 64], g2[:, a:a + 64] = part["guess1"], part["guess2"]
+        truth1[:, a:a + 64], nct[a:a + 64] = part["truth1"], part["ncomp_true"]
+        v = part["v"]
+    vstats = {1: D.global_vstats(g1[::4], eng.device), 2: D.global_vstats(g2[::4], eng.device)}
+    whole = {k: np.array(x) for k, x in D.fit_and_select(pinned.numpy(), v, fittype, g1, g2, device=0,
+                                                          vstats=vstats).items()}
+    half = ny // 2
+    for sl in (slice(0, half), slice(half, ny)):
+        part = D.fit_and_select(np.ascontiguousarray(pinned.numpy()[:, sl]), v, fittype, g1[:, sl].copy(),
+                                g2[:, sl].copy(), device=0, vstats=vstats)
+        for key in ("parcube1", "errcube1", "parcube2", "errcube2"):
+            assert np.array_equal(part[key], whole[key][:, sl]), key
+    ncomp = whole["ncomp"].astype(int)
+    fitted = np.any(whole["parcube1"] != 0, axis=0)
+    assert fitted.mean() > 0.95
+    assert (ncomp[fitted] == nct[fitted]).mean() > 0.85
+    one = fitted & (nct == 1) & (ncomp == 1)
+    assert one.sum() > 10000
+    assert np.median(np.abs(whole["parcube1"][0][one] - truth1[0][one])) < 0.01
