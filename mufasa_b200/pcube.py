@@ -142,8 +142,9 @@ class PCube(object):
                         first, last = edges[k] * nx, edges[k + 1] * nx
                         with torch.cuda.stream(up):
                             staging = torch.empty((nchan, last - first), dtype=torch.float32, device=eng.device)
-                            # in pieces of ~16 MB (one 2-D copy each)
-                            step = max(1, (16 << 20) // (4 * (last - first)))
+                            # in pieces of ~256 MB (one 2-D copy each; small pieces only cost host time now that
+                            # nothing has to slip in between them -- the callers queue their own uploads in order)
+                            step = max(1, (256 << 20) // (4 * (last - first)))
                             for c0 in range(0, nchan, step):
                                 c1 = min(nchan, c0 + step)
                                 eng.upload_slab(t[c0:c1], first, last - first, staging[c0:c1])
