@@ -378,12 +378,8 @@ class SelectionJob(object):
             n += int(job["guesses"].numel()) * 8 + (0 if job["row_index"] is None else int(job["row_index"].numel()) * 8)
         return n
 
-    def run(self, gather=True):
-        """Both fits in flight together, the AICc selection (global include_nosamp rule) and the assembly of the
-        result block on the fit results where they lie, then ONE gather.  Returns the [44, ny, nx] block on rank 0
-        (None elsewhere), or this rank's [44, rows, nx] block when ``gather`` is False.  Device tensors; no copy
-        to the host except the 16 bytes per rank of the global arg-max."""
-        from . import _abi
+    def _fit(self):
+        """Both fits in flight together; results as {ncomp: dict(params, perr, ...)} in the slab's pixel order."""
         eng, npix = self.eng, self.npix
         outs = eng.fit_batch(self.batch) if self.batch else []
         fits = {}
@@ -403,16 +399,32 @@ class SelectionJob(object):
                 full_e[job["row_index"]] = out["perr"]
                 fits[nc] = dict(params=full_p, perr=full_e, status=out["status"], counts=out.get("counts"))
         self.fits = fits
+        return fits
+
+    def _select_and_pack(self, fits):
+        """The AICc selection (global include_nosamp rule) and the assembly of this rank's [44, rows, nx] block."""
+        from . import _abi
+        eng, npix = self.eng, self.npix
         rows = self.ref.rows_on_device() if npix else self._no_rows
         nx, owned = self.nx, self.rows
         self.sel = sel = aicc_distributed(eng, self.prob, rows, fits[1]["params"], fits[2]["params"],
                                           model_f32=self.model_f32, group=self.group,
                                           local_to_global=lambda i: int(owned[i // nx]) * nx + i % nx)
-        packed = eng.pack_selection(fits[1], fits[2], sel).reshape(_abi.PACK_FIELDS, self.ry, self.nx)
+        return eng.pack_selection(fits[1], fits[2], sel).reshape(_abi.PACK_FIELDS, self.ry, self.nx)
+
+    def _gather(self, block):
+        if dist.get_backend(self.group) != "nccl":
+            block = block.cpu()
+        return gather_rows(block, self.ny, partition=self.partition, group=self.group, dst=0)
+
+    def run(self, gather=True):
+        """Both fits in flight together, the AICc selection and the assembly of the result block on the fit results
+        where they lie, then ONE gather.  Returns the [44, ny, nx] block on rank 0 (None elsewhere), or this rank's
+        [44, rows, nx] block when ``gather`` is False.  Device tensors; no copy to the host except the 16 bytes per
+        rank of the global arg-max."""
+        packed = self._select_and_pack(self._fit())
         if gather and self.world > 1:
-            if dist.get_backend(self.group) != "nccl":
-                packed = packed.cpu()
-            packed = gather_rows(packed, self.ny, partition=self.partition, group=self.group, dst=0)
+            packed = self._gather(packed)
         return packed
 
     def to_host(self, packed):
@@ -422,6 +434,41 @@ class SelectionJob(object):
         stage = self.eng.pinned_stage(("select",) + tuple(packed.shape))
         stage.copy_(packed, non_blocking=True)
         torch.cuda.current_stream(self.eng.device).synchronize()
+        host = stage.numpy()
+        return {name: (host[a] if b - a == 1 else host[a:b]) for name, a, b in FIELDS}
+
+    def run_to_host(self, gather=True):
+        """``to_host(run())`` with the read-back split in two: the fit maps (24 of the 44) are final when the fits are,
+        so their gather and their copy to the host run on a second stream UNDER the selection pass; only the 20
+        selection maps follow it.  Same values, same pinned result buffer."""
+        eng = self.eng
+        main = torch.cuda.current_stream(eng.device)
+        side = eng.side_stream("d2h")
+        fits = self._fit()
+        nfit = FIELDS[3][2]                                    # parcube1, errcube1, parcube2, errcube2
+        collect = gather and self.world > 1
+        out_rows = self.ny if collect else self.ry
+        stage = eng.pinned_stage(("select", FIELDS[-1][2], out_rows, self.nx))
+        fits_done = torch.cuda.Event()
+        fits_done.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(fits_done)
+            part = torch.cat([fits[1]["params"].t(), fits[1]["perr"].t(), fits[2]["params"].t(), fits[2]["perr"].t()]
+                             ).reshape(nfit, self.ry, self.nx)
+            if collect:
+                part = self._gather(part)
+            if part is not None:
+                part.record_stream(side)
+                stage[:nfit].copy_(part, non_blocking=True)
+        packed = self._select_and_pack(fits)[nfit:]
+        if collect:
+            packed = self._gather(packed)
+        if packed is not None:
+            stage[nfit:].copy_(packed, non_blocking=True)
+        side.synchronize()
+        main.synchronize()
+        if packed is None:
+            return None
         host = stage.numpy()
         return {name: (host[a] if b - a == 1 else host[a:b]) for name, a, b in FIELDS}
 
@@ -457,15 +504,10 @@ def fit_and_select(cube, v_kms, fittype, guesses1, guesses2, device=None, group=
                        partition=partition)
     if stamps is not None:
         stamps.append(time.perf_counter())
-    packed = job.run(gather=gather)
-    if stamps is not None:
-        stamps.append(time.perf_counter())
-        torch.cuda.synchronize()
-        stamps.append(time.perf_counter())
-    res = job.to_host(packed)
-    if stamps is not None:                     # host work + queued uploads | launches + fits | device wait | read-back
+    res = job.run_to_host(gather=gather)
+    if stamps is not None:                     # host work + queued uploads | fits, selection, gather and read-back
         stamps.append(time.perf_counter())
         import sys
-        sys.stderr.write("fit_and_select rank %d: init %.1f run %.1f wait %.1f to_host %.1f ms\n" % (
+        sys.stderr.write("fit_and_select rank %d: init %.1f run_to_host %.1f ms\n" % (
             (job.rank,) + tuple(1e3 * (b - a) for a, b in zip(stamps[:-1], stamps[1:]))))
     return res
