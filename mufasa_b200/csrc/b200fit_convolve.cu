@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(CONV_THREADS)
 //     bank conflicts; weights sit in registers, 8 at a time, and every product the loops issue is a real one (the
 //     ramp-in / ramp-out of the 8-output window is unrolled statically per K mod 8, no zero tail);
 //   * NaNs are not looked for: a NaN under an output's kernel makes that output NaN, the write-out loop sees it and
-//     the tile is appended to a work list that the generic kernel (interpolating normalisation) redoes afterwards.
+//     the tile is appended to a work list that convolve_sep_redo_fast_kernel (interpolating normalisation: the same
+//     passes on values and on finite flags) redoes afterwards.
 // Each lane of a packed FMA is the IEEE fp32 operation; per output the products are summed in the same order as in
 // the generic kernel's all-finite path (j ascending, vertical after horizontal there / before here -- the two
 // orders differ in rounding only, inside the 2e-6 of the parity tests).
@@ -278,96 +279,85 @@ __device__ __forceinline__ void slide_pairs(Load ld, const float* __restrict__ w
     }
 }
 
-template <int KR>
-__global__ void __launch_bounds__(CONV_THREADS, 4)
-    convolve_sep_fast_kernel(const float* __restrict__ cube, float* __restrict__ out, int ny, int nx, int K,
-                             const float* __restrict__ kx, const float* __restrict__ ky, float inv_ksum,
-                             unsigned* __restrict__ redo) {
-    extern __shared__ __align__(16) float smem[];
-    const int h = K >> 1, H4 = (h + 3) & ~3, WXA = FT + 2 * H4, WY = FT + K - 1, nb = K >> 3;
-    const int KW = (K + 15) & ~7;                      // weights + room for the last 8-wide load
-    float* raw = smem;                                  // [WY][WXA] as it lies in the plane; later the output staging
-    float* mid = raw + WY * WXA;                        // [WXA][FPT] vertically convolved, transposed
-    float* skx = mid + WXA * FPT;                       // [KW]
-    float* sky = skx + KW;
-    const size_t plane = (size_t)ny * nx;
-    const float* in = cube + blockIdx.z * plane;
-    const int y0 = blockIdx.y * FT, x0 = blockIdx.x * FT;
+// ---- the phases of a fast tile (all threads of the block) -------------------------------------------------------
+struct FastGeom {
+    int h, H4, WXA, WY, nb;
+    __device__ __forceinline__ explicit FastGeom(int K) : h(K >> 1), H4((h + 3) & ~3), WXA(FT + 2 * H4), WY(FT + K - 1), nb(K >> 3) {}
+};
+
+// the window of the tile at (y0, x0) of plane ``in``, four values per copy (a lane owns one 16-byte segment of every
+// row its warp stages); segments beyond the image are zero filled by the copy engine.  One commit group.
+__device__ __forceinline__ void stage_window(const FastGeom& g, const float* __restrict__ in, int ny, int nx, int y0, int x0,
+                                             float* raw) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = threadIdx.x; k < KW; k += CONV_THREADS) {
-        skx[k] = (k < K) ? kx[k] : 0.f;
-        sky[k] = (k < K) ? ky[k] : 0.f;
-    }
-    // 1. the window, four values per copy (a lane owns one 16-byte segment of every row its warp stages); segments
-    //    beyond the image are zero filled by the copy engine
-    {
-        const int x = x0 - H4 + 4 * lane;
-        const bool col_ok = x >= 0 && x < nx;                            // nx % 4 == 0: a segment is inside or outside
-        const float* col = in + (col_ok ? x : 0);
-        unsigned dst = (unsigned)__cvta_generic_to_shared(raw) + (unsigned)((warp * WXA + 4 * lane) * sizeof(float));
-        if (4 * lane < WXA) {
-            int y = y0 + warp - h, off = y * nx;                         // (a plane holds < 2^31 voxels: checked by the host)
-            for (int r = warp; r < WY; r += CONV_THREADS / 32) {
-                const bool ok = col_ok && y >= 0 && y < ny;
-                cp_async16(dst, ok ? col + off : in, ok ? 16u : 0u);
-                dst += (CONV_THREADS / 32) * WXA * (unsigned)sizeof(float);
-                y += CONV_THREADS / 32;
-                off += (CONV_THREADS / 32) * nx;
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    // 2. vertical pass: thread = (column pair, group of 8 rows); lanes on consecutive pairs
-    {
-        const int npair = WXA >> 1;
-        for (int e = threadIdx.x; e < npair * (FT / NOUT); e += CONV_THREADS) {
-            const int rg = e / npair, cp = e - rg * npair;
-            const float* x0p = raw + (rg * NOUT) * WXA + 2 * cp;
-            f32x2 acc[NOUT];
-#pragma unroll
-            for (int o = 0; o < NOUT; ++o) acc[o] = 0ull;
-            slide_pairs<KR>([&](int j) { return *reinterpret_cast<const f32x2*>(x0p + j * WXA); }, sky, nb, acc);
-            float lo[NOUT], hi[NOUT];
-#pragma unroll
-            for (int o = 0; o < NOUT; ++o) upk2(acc[o], lo[o], hi[o]);
-            float* d0 = mid + (2 * cp) * FPT + rg * NOUT;
-            *reinterpret_cast<float4*>(d0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<float4*>(d0 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-            *reinterpret_cast<float4*>(d0 + FPT) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(d0 + FPT + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+    const int x = x0 - g.H4 + 4 * lane;
+    const bool col_ok = x >= 0 && x < nx;                            // nx % 4 == 0: a segment is inside or outside
+    const float* col = in + (col_ok ? x : 0);
+    unsigned dst = (unsigned)__cvta_generic_to_shared(raw) + (unsigned)((warp * g.WXA + 4 * lane) * sizeof(float));
+    if (4 * lane < g.WXA) {
+        int y = y0 + warp - g.h, off = y * nx;                       // (a plane holds < 2^31 voxels: checked by the host)
+        for (int r = warp; r < g.WY; r += CONV_THREADS / 32) {
+            const bool ok = col_ok && y >= 0 && y < ny;
+            cp_async16(dst, ok ? col + off : in, ok ? 16u : 0u);
+            dst += (CONV_THREADS / 32) * g.WXA * (unsigned)sizeof(float);
+            y += CONV_THREADS / 32;
+            off += (CONV_THREADS / 32) * nx;
         }
     }
-    __syncthreads();
-    // 3. horizontal pass: warp = group of 8 output columns, lane = rows (lane, lane + 32)
-    {
-        const float* x0p = mid + (H4 - h + warp * NOUT) * FPT + lane;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// vertical pass: thread = (column pair, group of 8 rows), lanes on consecutive pairs; result transposed into ``mid``
+template <int KR>
+__device__ __forceinline__ void pass_vertical(const FastGeom& g, const float* raw, float* mid, const float* sky) {
+    const int npair = g.WXA >> 1;
+    for (int e = threadIdx.x; e < npair * (FT / NOUT); e += CONV_THREADS) {
+        const int rg = e / npair, cp = e - rg * npair;
+        const float* x0p = raw + (rg * NOUT) * g.WXA + 2 * cp;
+        const int WXA = g.WXA;
         f32x2 acc[NOUT];
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) acc[o] = 0ull;
-        slide_pairs<KR>([&](int j) { return pk2(x0p[j * FPT], x0p[j * FPT + 32]); }, skx, nb, acc);
+        slide_pairs<KR>([&](int j) { return *reinterpret_cast<const f32x2*>(x0p + j * WXA); }, sky, g.nb, acc);
         float lo[NOUT], hi[NOUT];
 #pragma unroll
-        for (int o = 0; o < NOUT; ++o) {
-            upk2(acc[o], lo[o], hi[o]);
-            lo[o] *= inv_ksum;
-            hi[o] *= inv_ksum;
-        }
-        float* d0 = raw + lane * FPT + warp * NOUT;      // (the window is dead since the barrier above)
+        for (int o = 0; o < NOUT; ++o) upk2(acc[o], lo[o], hi[o]);
+        float* d0 = mid + (2 * cp) * FPT + rg * NOUT;
         *reinterpret_cast<float4*>(d0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         *reinterpret_cast<float4*>(d0 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-        *reinterpret_cast<float4*>(d0 + 32 * FPT) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(d0 + 32 * FPT + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<float4*>(d0 + FPT) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(d0 + FPT + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
     }
-    __syncthreads();
-    // 4. coalesced write-out; any non-finite output sends the tile to the generic kernel
+}
+
+// horizontal pass: warp = group of 8 output columns, lane = rows (lane, lane + 32); acc[o] = {row lane, row lane + 32}
+// of output column 8 warp + o
+template <int KR>
+__device__ __forceinline__ void pass_horizontal(const FastGeom& g, const float* mid, const float* skx, f32x2 (&acc)[NOUT]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* x0p = mid + (g.H4 - g.h + warp * NOUT) * FPT + lane;
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) acc[o] = 0ull;
+    slide_pairs<KR>([&](int j) { return pk2(x0p[j * FPT], x0p[j * FPT + 32]); }, skx, g.nb, acc);
+}
+
+// this thread's 16 outputs into the [64][FPT] staging tile
+__device__ __forceinline__ void stage_outputs(float* tile, const float (&lo)[NOUT], const float (&hi)[NOUT]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* d0 = tile + lane * FPT + warp * NOUT;
+    *reinterpret_cast<float4*>(d0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<float4*>(d0 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+    *reinterpret_cast<float4*>(d0 + 32 * FPT) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(d0 + 32 * FPT + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+}
+
+// coalesced write-out of the staging tile; returns whether this thread saw a non-finite output
+__device__ __forceinline__ bool write_tile(const float* tile, float* __restrict__ op, int ny, int nx, int y0, int x0) {
     bool bad = false;
-    float* op = out + blockIdx.z * plane;
 #pragma unroll
     for (int i = 0; i < (FT * FT / 4) / CONV_THREADS; ++i) {
         const int idx = threadIdx.x + i * CONV_THREADS, row = idx >> 4, q = idx & 15;
-        const float4 v = *reinterpret_cast<const float4*>(raw + row * FPT + 4 * q);
+        const float4 v = *reinterpret_cast<const float4*>(tile + row * FPT + 4 * q);
         const int y = y0 + row, x = x0 + 4 * q;
         if (y < ny && x < nx) {
             const float s = (v.x - v.x) + (v.y - v.y) + (v.z - v.z) + (v.w - v.w);   // 0 iff all four are finite
@@ -375,23 +365,125 @@ __global__ void __launch_bounds__(CONV_THREADS, 4)
             *reinterpret_cast<float4*>(op + (size_t)y * nx + x) = v;
         }
     }
+    return bad;
+}
+
+template <int KR>
+__global__ void __launch_bounds__(CONV_THREADS, 4)
+    convolve_sep_fast_kernel(const float* __restrict__ cube, float* __restrict__ out, int ny, int nx, int K,
+                             const float* __restrict__ kx, const float* __restrict__ ky, float inv_ksum,
+                             unsigned* __restrict__ redo) {
+    extern __shared__ __align__(16) float smem[];
+    const FastGeom g(K);
+    const int KW = (K + 15) & ~7;                      // weights + room for the last 8-wide load
+    float* raw = smem;                                  // [WY][WXA] as it lies in the plane; later the output staging
+    float* mid = raw + g.WY * g.WXA;                    // [WXA][FPT] vertically convolved, transposed
+    float* skx = mid + g.WXA * FPT;                     // [KW]
+    float* sky = skx + KW;
+    const size_t plane = (size_t)ny * nx;
+    const int y0 = blockIdx.y * FT, x0 = blockIdx.x * FT;
+    for (int k = threadIdx.x; k < KW; k += CONV_THREADS) {
+        skx[k] = (k < K) ? kx[k] : 0.f;
+        sky[k] = (k < K) ? ky[k] : 0.f;
+    }
+    stage_window(g, cube + blockIdx.z * plane, ny, nx, y0, x0, raw);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    pass_vertical<KR>(g, raw, mid, sky);
+    __syncthreads();
+    f32x2 acc[NOUT];
+    pass_horizontal<KR>(g, mid, skx, acc);
+    float lo[NOUT], hi[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+        upk2(acc[o], lo[o], hi[o]);
+        lo[o] *= inv_ksum;
+        hi[o] *= inv_ksum;
+    }
+    stage_outputs(raw, lo, hi);                         // (the window is dead since the barrier above)
+    __syncthreads();
+    // any non-finite output sends the tile to the two-accumulator kernel below
+    const bool bad = write_tile(raw, out + blockIdx.z * plane, ny, nx, y0, x0);
     if (__syncthreads_or(bad) && threadIdx.x == 0)
         redo[1 + atomicAdd(redo, 1u)] = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
 }
 
-// the tiles the fast kernel gave up on (those with a NaN under some output's kernel), two generic tiles each
-__global__ void __launch_bounds__(CONV_THREADS)
-    convolve_sep_redo_kernel(const float* __restrict__ cube, float* __restrict__ out, int ny, int nx, int K,
-                             const float* __restrict__ kx, const float* __restrict__ ky, float ksum,
-                             const unsigned* __restrict__ redo, int tiles_x, int tiles_y) {
-    extern __shared__ float smem[];
+// The tiles the fast kernel gave up on (a NaN under some output's kernel), with the interpolating normalisation of the
+// generic kernel: out = sum K v / sum K f, v = value or 0, f = 1 where the voxel is finite (and beyond the image), NaN
+// where the voxel itself is NaN or nothing finite is under the kernel.  The same passes run twice on the same buffers:
+// once on the sanitised values, once on the finite flags -- whose window is on its way in (second cp.async group)
+// while the first horizontal pass runs.  Persistent blocks over the work list.
+template <int KR>
+__global__ void __launch_bounds__(CONV_THREADS, 2)
+    convolve_sep_redo_fast_kernel(const float* __restrict__ cube, float* __restrict__ out, int ny, int nx, int K,
+                                  const float* __restrict__ kx, const float* __restrict__ ky,
+                                  const unsigned* __restrict__ redo, int tiles_x, int tiles_y) {
+    extern __shared__ __align__(16) float smem[];
+    const FastGeom g(K);
+    const int KW = (K + 15) & ~7;
+    float* raw = smem;
+    float* mid = raw + g.WY * g.WXA;
+    float* skx = mid + g.WXA * FPT;
+    float* sky = skx + KW;
+    const size_t plane = (size_t)ny * nx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < KW; k += CONV_THREADS) {
+        skx[k] = (k < K) ? kx[k] : 0.f;
+        sky[k] = (k < K) ? ky[k] : 0.f;
+    }
     const unsigned n = redo[0];
-    for (unsigned i = blockIdx.x; i < 2 * n; i += gridDim.x) {
-        const unsigned t = redo[1 + (i >> 1)];
+    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
+        const unsigned t = redo[1 + i];
         const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, bz = t / (tiles_x * tiles_y);
-        const int x0 = bx * FT + (int)(i & 1u) * TX;
-        if (x0 < nx) sep_tile(cube, out, nullptr, ny, nx, K, kx, ky, ksum, bz, by * FT, x0, smem);
+        const int y0 = by * FT, x0 = bx * FT;
+        const float* in = cube + bz * plane;
+        stage_window(g, in, ny, nx, y0, x0, raw);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        // is each of this thread's 16 outputs a finite voxel itself?  (read before the window is sanitised)
+        unsigned selfok = 0;
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            const float a = raw[(lane + g.h) * g.WXA + g.H4 + warp * NOUT + o];
+            const float b = raw[(lane + 32 + g.h) * g.WXA + g.H4 + warp * NOUT + o];
+            selfok |= (a == a ? 1u : 0u) << o;
+            selfok |= (b == b ? 1u : 0u) << (8 + o);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < g.WY * g.WXA; e += CONV_THREADS) {
+            const float v = raw[e];
+            raw[e] = (v == v) ? v : 0.f;
+        }
+        __syncthreads();
+        pass_vertical<KR>(g, raw, mid, sky);
+        __syncthreads();
+        stage_window(g, in, ny, nx, y0, x0, raw);          // the same window again, for the flags (L2-resident)
+        f32x2 num[NOUT];
+        pass_horizontal<KR>(g, mid, skx, num);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                    // every thread is done with ``mid`` and the window is in
+        for (int e = threadIdx.x; e < g.WY * g.WXA; e += CONV_THREADS) {
+            const float v = raw[e];
+            raw[e] = (v == v) ? 1.f : 0.f;                  // (zero fill beyond the image: a finite zero)
+        }
+        __syncthreads();
+        pass_vertical<KR>(g, raw, mid, sky);
+        __syncthreads();
+        f32x2 den[NOUT];
+        pass_horizontal<KR>(g, mid, skx, den);
+        float lo[NOUT], hi[NOUT];
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            float nl, nh, dl, dh;
+            upk2(num[o], nl, nh);
+            upk2(den[o], dl, dh);
+            lo[o] = (((selfok >> o) & 1u) && dl > 0.f) ? nl / dl : __int_as_float(0x7fc00000);
+            hi[o] = (((selfok >> (8 + o)) & 1u) && dh > 0.f) ? nh / dh : __int_as_float(0x7fc00000);
+        }
+        stage_outputs(raw, lo, hi);                         // (the flags are dead since the barrier above)
+        __syncthreads();
+        write_tile(raw, out + bz * plane, ny, nx, y0, x0);
+        __syncthreads();                                    // the staging tile is read: the next window may land
     }
 }
 
@@ -517,9 +609,20 @@ int b200fit_convolve_planes(b200fit_ctx* ctx, const float* d_cube, int32_t nchan
             }
 #undef B200FIT_LAUNCH_FAST
             CK(cudaGetLastError());
-            CK(cudaFuncSetAttribute(convolve_sep_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            convolve_sep_redo_kernel<<<ctx->num_sms * 3, CONV_THREADS, smem, (cudaStream_t)stream>>>(
-                d_cube, d_out, ny, nx, ksize, d_kx, d_ky, (float)kernel_sum, d_redo, (int)fgrid.x, (int)fgrid.y);
+#define B200FIT_LAUNCH_REDO(KR)                                                                                          \
+    do {                                                                                                                 \
+        CK(cudaFuncSetAttribute(convolve_sep_redo_fast_kernel<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                (int)fsmem));                                                                            \
+        convolve_sep_redo_fast_kernel<KR><<<ctx->num_sms * 2, CONV_THREADS, fsmem, (cudaStream_t)stream>>>(              \
+            d_cube, d_out, ny, nx, ksize, d_kx, d_ky, d_redo, (int)fgrid.x, (int)fgrid.y);                               \
+    } while (0)
+            switch (ksize & 7) {
+                case 1: B200FIT_LAUNCH_REDO(1); break;
+                case 3: B200FIT_LAUNCH_REDO(3); break;
+                case 5: B200FIT_LAUNCH_REDO(5); break;
+                default: B200FIT_LAUNCH_REDO(7); break;
+            }
+#undef B200FIT_LAUNCH_REDO
             CK(cudaGetLastError());
             ctx->launches += 2;
             return B200FIT_OK;
