@@ -417,7 +417,8 @@ def run_b200(args):
     t_eval = prof2["eval_ms"] * 1e-3                        # sum over the launches of one fit
     clk = peaks["sm_max_mhz"] * 1e6
     nsm = eng.num_sms
-    pk = {"fp32": nsm * 128 * 2 * clk, "xu": nsm * 16 * clk, "fp64": nsm * 64 * 2 * clk}
+    xu_measured = eng.measure_xu_peak()                    # in-repo micro-benchmark on this box
+    pk = {"fp32": nsm * 128 * 2 * clk, "xu": xu_measured, "fp64": nsm * 64 * 2 * clk}
     ach = {"fp32": f32 / t_eval, "xu": sfu / t_eval, "fp64": f64 / t_eval}
     frac_alg = {k: ach[k] / pk[k] for k in pk}
     frac_exec = {"xu": sfu_exec / t_eval / pk["xu"], "fp32": f32_exec / t_eval / pk["fp32"]}
@@ -438,8 +439,9 @@ def run_b200(args):
                                   "profiles/ (NCU_TRAFFIC.json: %.0f B at this row length; algorithmic %d B) x "
                                   "evaluations per launch of this run" % (ncu_traffic_per_eval(row_bytes),
                                                                           row_bytes + 112 + 360 + 4),
-                "peak_source": "derived: %d SMs x 16 XU lanes x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json, %s)" % (
-                    nsm, peaks["sm_max_mhz"], peaks["source"]),
+                "peak_source": "measured: b200fit_measure_xu_peak micro-benchmark on this GPU (8 independent ex2.approx "
+                               "chains per thread); derived %d SMs x 16 XU lanes x %.0f MHz = %.3f Top/s" % (
+                                   nsm, peaks["sm_max_mhz"], nsm * 16 * clk / 1e12),
                 "hbm": {"achieved": hbm_bytes / t2 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": hbm_bytes / t2 / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"]},
                 "per_launch": {"launches": launches_eval, "avg_ms": prof2["eval_ms"] / launches_eval,

@@ -59,11 +59,14 @@ int b200fit_num_sms(const b200fit_ctx* ctx);
 /* Measurement hooks (no reference analogue; bench.py's roofline and launch accounting).
  *   b200fit_launch_count: kernels launched by this context since creation.
  *   b200fit_host_launch_count: launches the HOST issued for them (a replayed CUDA graph of a round group counts once).
+ *   b200fit_measure_xu_peak: ex2.approx operations per second of this GPU (micro-benchmark: 8 independent chains per
+ *     thread, 8 blocks of 256 threads per SM) -- the measured peak of the pipe that bounds the fit's evaluation kernel.
  *   b200fit_set_profiling(on): record CUDA events around the kernels of b200fit_fit on the launching stream.
  *   b200fit_get_profile: waits for the last profiled fit and returns out[4] = {prologue ms, sum of evaluation-kernel
  *   ms, sum of solver-kernel ms, rounds launched}. */
 uint64_t b200fit_launch_count(const b200fit_ctx* ctx);
 uint64_t b200fit_host_launch_count(const b200fit_ctx* ctx);
+int b200fit_measure_xu_peak(b200fit_ctx* ctx, double* ex2_per_second, void* stream);
 int b200fit_set_profiling(b200fit_ctx* ctx, int32_t on);
 int b200fit_get_profile(b200fit_ctx* ctx, double* out);
 

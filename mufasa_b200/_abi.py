@@ -64,6 +64,7 @@ SIGNATURES = {
     "b200fit_num_sms": (C.c_int, [_vp]),
     "b200fit_launch_count": (C.c_uint64, [_vp]),
     "b200fit_host_launch_count": (C.c_uint64, [_vp]),
+    "b200fit_measure_xu_peak": (C.c_int, [_vp, C.POINTER(C.c_double), _vp]),
     "b200fit_set_profiling": (C.c_int, [_vp, _i32]),
     "b200fit_get_profile": (C.c_int, [_vp, _vp]),
     "b200fit_nchan_stride": (_i64, [_i32]),

@@ -93,6 +93,12 @@ class Engine(object):
         """Launches the host issued (kernels outside graphs + graph launches)."""
         return int(self.lib.b200fit_host_launch_count(self.ctx))
 
+    def measure_xu_peak(self):
+        """ex2.approx operations per second of this GPU (b200fit_measure_xu_peak micro-benchmark)."""
+        out = C.c_double(0.0)
+        self._check(self.lib.b200fit_measure_xu_peak(self.ctx, C.byref(out), self._stream()), "b200fit_measure_xu_peak")
+        return float(out.value)
+
     def set_profiling(self, on):
         self._profiling = bool(on)          # profiled fits run undivided (one event list per fit)
         self._check(self.lib.b200fit_set_profiling(self.ctx, 1 if on else 0), "b200fit_set_profiling")
