@@ -17,7 +17,7 @@ e2e      : the same job through the public host API, mufasa_b200.dist.fit_and_se
            rank 0; wall clock between barriers, max over ranks.
 roofline : dominant kernel = fit_eval_kernel<2> (model + analytic Jacobian + normal equations of the 2-component
            fit).  The path is compute bound.  ``frac`` is the EXECUTED fraction of the binding pipe
-           (XU: ex2 actually issued / kernel time / peak); the algorithmic figure (what the reference's arithmetic
+           (XU: ex2 actually issued / kernel time / the peak b200fit_measure_xu_peak measures on this GPU); the algorithmic figure (what the reference's arithmetic
            would need, most of which the kernel's windows skip) is reported beside it as ``frac_algorithmic``.
 cpu_baseline / --impl reference: the CPU oracle (numpy restatement of the reference's pyspeckit/mpfit path; the
            reference itself is pure Python on un-vendored pyspeckit and cannot be installed here) timed on this
