@@ -705,24 +705,21 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 8)   // 128 regs (a few spills)
         lane_load<P>(g, ps.st, cf, s);
         bool accepted = false;
         const int done = lane_step<P>(g, s, cf, valid, accepted);
-        // coefficients of the next trial point (every lane computes, lane 0 of a live group stores)
-        double p4[NC][4];
+        // coefficients of the next trial point: lanes 4c .. 4c + 3 of a group work on component c (the fp64 exp and
+        // expm1 of the Planck terms are ~6 % of this kernel's instructions per component), lane 4c of a live group stores
+        const int cmine = (NC > 1) ? (g.gl >> 2) : 0;
+        double p4[4];
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) p4[c][k] = g.bcast(s.pt, 4 * c + k);
+        for (int k = 0; k < 4; ++k) p4[k] = g.bcast(s.pt, 4 * cmine + k);
         if (!valid) continue;
         lane_store<P>(g, ps.st, s, accepted);   // results are written by fit_finalize_kernel
         if (!done) {
-#pragma unroll 1
-            for (int c = 0; c < NC; ++c) {
-                CompCoef cc;
-                comp_coefs(pr.T0c, pr.dT0, pr.Jbg0, pr.Jbg1, p4[c], cc);
-                if (g.gl == 0) {
-                    ps.in.cc[c] = cc;
-                    ps.in.v[c] = p4[c][0];
-                    ps.in.inv_sigma[c] = 1.0 / p4[c][1];
-                }
+            CompCoef cc;
+            comp_coefs(pr.T0c, pr.dT0, pr.Jbg0, pr.Jbg1, p4, cc);
+            if ((g.gl & 3) == 0) {
+                ps.in.cc[cmine] = cc;
+                ps.in.v[cmine] = p4[0];
+                ps.in.inv_sigma[cmine] = 1.0 / p4[1];
             }
             if (g.gl == 0) next_list[atomicAdd(&fq->count[cur ^ 1], 1u)] = px;
         }

@@ -267,25 +267,27 @@ __device__ __forceinline__ double lane_par(const LaneGroup<P>& g, const double (
         const double y = lane_fwd<P>(g, lrow, linv, rhs);
         const double xs = lane_bwd<P>(g, lrow, linv, y);
         const double dxs = lane_dnorm<P>(g, dg, xs);
+        // accept tests first: the Newton correction below is needed only by a group that goes on iterating (the
+        // common last iteration of a call skips its forward solve)
+        if (live) {
+            if (solved) {
+                x = xs;
+                dxnorm = dxs;
+                fp = dxnorm - delta;
+            }
+            if (it == 0 && spd && fp <= 0.1 * delta) {
+                par = 0.0;
+                xout = x;
+                live = false;
+            } else if (it > 0 && (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || it == 10)) {
+                xout = x;
+                live = false;
+            }
+        }
+        if (!g.any_in_warp(live)) break;
         // Newton correction (fp / delta) / |L^-1 (D^2 x / |D x|)|^2
         const double den = lane_newton_den<P>(g, lrow, linv, dg, xs, dxs, fixedbit);
         if (!live) continue;
-        if (solved) {
-            x = xs;
-            dxnorm = dxs;
-            fp = dxnorm - delta;
-        }
-        if (it == 0 && spd && fp <= 0.1 * delta) {
-            par = 0.0;
-            xout = x;
-            live = false;
-            continue;
-        }
-        if (it > 0 && (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || it == 10)) {
-            xout = x;
-            live = false;
-            continue;
-        }
         const double corr = solved ? (fp / delta) / den : 0.0;
         if (it == 0) {
             parl = corr;                       // 0 when H is not positive definite
