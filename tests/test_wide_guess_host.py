@@ -1,28 +1,20 @@
 """Host logic of the wide-separation recovery (mufasa/moment_guess.py:119-367, 523-701): the windowed moments in
-pyspeckit's and spectral_cube's definitions against per-pixel loops that restate those definitions [RECALLED --
-pyspeckit / spectral_cube are absent: parity unpinned], moment_guesses_1c against the golden vectors made by
+pyspeckit's and spectral_cube's definitions against the oracle's per-spectrum loops (oracle/guesses.py; they restate
+those packages' definitions [RECALLED -- pyspeckit / spectral_cube are absent: parity unpinned]), moment_guesses_1c against the golden vectors made by
 executing the reference, and mom_guess_wide_sep on a spectrum with two well separated lines."""
 import os
 
 import numpy as np
 
 from mufasa_b200 import moment_guess as mmg
+from oracle import guesses as OG
 from mufasa_b200.cube import SpecCube
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _pys_moments_loop(d, v):
-    """pyspeckit.spectrum.moments.moments(v, d, vheight=False) on the finite samples of one spectrum."""
-    ok = np.isfinite(d)
-    if not ok.any():
-        return 0.0, 0.0, 0.0
-    d, v = d[ok].astype(np.float64), v[ok]
-    tot = d.sum()
-    x = (v * d).sum() / tot
-    width = np.sqrt(np.abs(((v - x) ** 2 * d).sum() / tot))
-    amp = d.min() if abs(d.min()) > abs(d.max()) else d.max()
-    return amp, x, width
+    return OG.pyspeckit_moments(v, d)
 
 
 def _cube(seed=0, nchan=120, ny=5, nx=6):
@@ -41,12 +33,8 @@ def test_window_moments_match_the_pyspeckit_definition():
     vmap[1, 1] = np.nan                                        # no window -> pixel keeps momentcube's zeros
     m0, m1, m2 = mmg.window_moments(cube, window_hwidth=1.5, v_atpeak=vmap)
     v = cube.spectral_axis
-    for y in range(cube.shape[1]):
-        for x in range(cube.shape[2]):
-            d = cube._data[:, y, x].astype(np.float64)
-            win = (v > vmap[y, x] - 1.5) & (v < vmap[y, x] + 1.5)
-            ref = _pys_moments_loop(np.where(win, d, np.nan), v)
-            np.testing.assert_allclose([m0[y, x], m1[y, x], m2[y, x]], ref, rtol=1e-10, atol=1e-12)
+    ref = OG.window_moments_map(cube._data, v, vmap, 1.5)
+    np.testing.assert_allclose(np.array([m0, m1, m2]), ref, rtol=1e-10, atol=1e-12)
     assert m0[0, 0] == 0 and m0[1, 1] == 0
     good = np.isfinite(vmap) & (m0 != 0)
     assert np.abs(m1[good] - cen[good]).max() < 0.1            # the centroid finds the line ...
@@ -70,11 +58,10 @@ def test_vmask_moments_match_the_spectral_cube_definition():
             if not inc.any():
                 assert np.isnan(m0[y, x])
                 continue
-            tot = d[inc].sum()
-            c = (v[inc] * d[inc]).sum() / tot
-            np.testing.assert_allclose(m0[y, x], tot * dv, rtol=1e-12)
-            np.testing.assert_allclose(m1[y, x], c, rtol=1e-10, atol=1e-12)
-            np.testing.assert_allclose(m2[y, x], np.sqrt(abs(((v[inc] - c) ** 2 * d[inc]).sum() / tot)), rtol=1e-9)
+            r0, r1, r2 = OG.spectral_cube_moments(v, np.where(inc, d, np.nan))
+            np.testing.assert_allclose(m0[y, x], r0, rtol=1e-12)
+            np.testing.assert_allclose(m1[y, x], r1, rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(m2[y, x], r2, rtol=1e-9)
     assert np.array_equal(mmg.vmask_cube(cube, cen, 1.0)[:, 2, 3], (v > cen[2, 3] - 1.0) & (v < cen[2, 3] + 1.0))
 
 
