@@ -89,6 +89,12 @@ def snr_estimate(pcube, errmap, smooth=True):
     from . import signals
     cube = pcube.cube if hasattr(pcube, 'cube') else pcube
     peak = None
+    cache = getattr(pcube, "_dev", None) if errmap is None else None
+    if cache is not None and ("snr_estimate", bool(smooth)) in cache:
+        # the maps depend on the data cube only, and the PCubes of a refit share their cube's device state: the
+        # ~40 masked refits of fit_surroundings each smoothed the same 512 x 512 map again (7 ms apiece)
+        peaksnr, errmap, err_mask = cache[("snr_estimate", bool(smooth))]
+        return peaksnr.copy(), None, errmap, err_mask
     if errmap is None:
         # per-pixel MAD + peak on the GPU (b200fit_rms_snr): mad_std(cube, axis=0) and nanmax(cube, axis=0)
         r = pcube.rms_robust()
@@ -101,6 +107,8 @@ def snr_estimate(pcube, errmap, smooth=True):
         peaksnr = peak / errmap      # == nanmax(cube / errmap) for errmap > 0
     if smooth:
         peaksnr = signals.convolve_gauss2d(peaksnr, 1.0)
+    if cache is not None:
+        cache[("snr_estimate", bool(smooth))] = (peaksnr.copy(), errmap, err_mask)
     return peaksnr, None, errmap, err_mask
 
 
