@@ -101,6 +101,13 @@ class PCube(object):
     def engine(self):
         return get_engine(self._device)
 
+    @staticmethod
+    def slab_edges(ny, nx, nslab, min_pixels):
+        """Row boundaries [0, r0, ..., ny] of the ``nslab`` (>= 2) upload slabs: a short first slab (1/16 of the rows,
+        at least ``min_pixels`` spectra) so that the fits start sooner, the rest in equal parts."""
+        r0 = max(ny // 16, -(-min_pixels // nx))
+        return [0] + [r0 + k * (ny - r0) // (nslab - 1) for k in range(nslab)]
+
     def rows_on_device(self, wait=True, max_slabs=None):
         """The cube as pixel-major rows [ny*nx, stride] fp32 on the GPU (NaN padded, velocity ascending).
 
@@ -133,9 +140,7 @@ class PCube(object):
                 up.wait_stream(torch.cuda.current_stream(eng.device))   # the allocation above is ordered before
                 bounds, events = [], []
 
-                # a short first slab (1/16 of the rows, at least SPLIT_MIN_PIXELS spectra): the fits start sooner
-                r0 = max(ny // 16, -(-eng.SPLIT_MIN_PIXELS // nx))
-                edges = [0] + [r0 + k * (ny - r0) // (nslab - 1) for k in range(nslab)]
+                edges = self.slab_edges(ny, nx, nslab, eng.SPLIT_MIN_PIXELS)
 
                 def queue_slabs():
                     for k in range(nslab):

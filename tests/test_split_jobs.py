@@ -91,3 +91,18 @@ def test_slab_split_waits_for_the_right_slab():
         e.done = True
     parts = eng._split_jobs([j1, j2], [o1, o2])
     assert [int(p["prob"].ncomp) for p in parts] == [1, 2, 2] and all(p.get("wait") is None for p in parts)
+
+
+def test_upload_slab_edges():
+    """PCube.slab_edges: the slabs tile the rows in order, the first one is short but holds at least the minimum
+    number of spectra a fit part needs, for every cube shape that is split at all (>= 2 slabs)."""
+    from mufasa_b200.pcube import PCube
+    split_min = 16384
+    for ny, nx in ((1024, 1024), (128, 1024), (256, 256), (32, 1024), (53, 700), (2048, 16), (129, 257)):
+        nslab = int(max(1, min(4, ny, (ny * nx) // split_min)))
+        if nslab < 2:
+            continue
+        e = PCube.slab_edges(ny, nx, nslab, split_min)
+        assert e[0] == 0 and e[-1] == ny and len(e) == nslab + 1
+        assert all(b > a for a, b in zip(e[:-1], e[1:]))
+        assert e[1] * nx >= split_min and e[1] <= max(ny // 2, -(-split_min // nx))
